@@ -1,0 +1,122 @@
+#!/usr/bin/env python
+"""Extract the reference's own golden numbers for the hot path into small JSON fixtures.
+
+Run in the build container only (reads /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+Writes tests/golden/reference_goldens.json, tests/golden/singular_quadrature_table.json and copies the few
+small meshes the parity tests need into tests/golden/meshes/ (mesh files are input DATA, not source code).
+Every value is parsed verbatim from a reference test output; the file:line of each is recorded.
+"""
+import json
+import os
+import re
+import shutil
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lines(rel):
+    with open(os.path.join(REF, rel)) as f:
+        return f.read().split("\n")
+
+
+def mat3(ls, start):
+    return [[float(x) for x in ls[start + r].split()] for r in range(3)]
+
+
+def find(ls, needle, nth=0):
+    hits = [i for i, l in enumerate(ls) if needle in l]
+    return hits[nth]
+
+
+def main():
+    g = {}
+    a = lines("tests/alpha_test.output")
+    i0, i1 = find(a, "Test on V", 0), find(a, "Test on V", 1)
+    k0, k1 = find(a, "Test on K", 0), find(a, "Test on K", 1)
+    g["alpha_test"] = {
+        "source": "tests/alpha_test.output:%d-%d,%d-%d" % (i0 + 1, k0 + 4, i1 + 1, k1 + 4),
+        "setup": "sphere_half_refined_0.inp, Gauss 8, Mixed singular order 10, node 0 (file vertex 1), free-space",
+        "Q1": {"V": mat3(a, i0 + 1), "K": mat3(a, k0 + 1)},
+        "Q2": {"V": mat3(a, i1 + 1), "K": mat3(a, k1 + 1)},
+    }
+    d = lines("tests/dof_renumbering.output")
+    dv, dk = find(d, "Test on V", 0), find(d, "Test on K", 0)
+    g["dof_renumbering"] = {"source": "tests/dof_renumbering.output:%d-%d" % (dv + 1, dk + 4),
+                            "setup": "sphere_coarse_0.inp 6 cells, Q2 (78 DoF), Gauss 8, QIterated(10,2); node = file vertex 2",
+                            "V": mat3(d, dv + 1), "K": mat3(d, dk + 1)}
+
+    def vnorm(rel):
+        ls = lines(rel)
+        i = find(ls, "Check on the V operator Norm (should be zero):")
+        surf = find(ls, "The Mass (Surface) of the entire system is")
+        return {"source": "%s:%d" % (rel, i + 1), "Vn_linf": float(ls[i].split(":")[1]),
+                "surface": float(ls[surf].split(":")[1])}
+
+    g["Vn_free"] = vnorm("tests/rigidity_sphere.output")
+    g["Vn_free_surface"] = vnorm("tests/reflected_kernel_test_stresses.output")
+    g["Vn_no_slip"] = vnorm("tests/wall_kernel_test_velocity.output")
+    vg = lines("tests/V_test_with_Green.output")
+    hits = [l for l in vg if "Check on the V operator Norm (should be zero):" in l]
+    g["V_test_with_Green"] = {"source": "tests/V_test_with_Green.output", "Vn_linf": [float(h.split(":")[1]) for h in hits]}
+
+    p = lines("tests/minimum_preconditioner_test_no_box.output")
+    its = [int(l.split(":")[1]) for l in p if "Iterations needed to solve monolithic" in l]
+    g["gmres_iterations_no_box"] = {"source": "tests/minimum_preconditioner_test_no_box.output (last 6 lines)",
+                                    "ILU": its[0], "Jacobi": its[1], "AMG": its[2],
+                                    "setup": "sphere_half_refined_0.inp Q1, ImposedForce, imposed component 1, tol 1e-10"}
+    r = lines("tests/rigidity_sphere.output")
+    fc = [l for l in r if l.startswith("FINAL CHECK 0")]
+    g["rigidity_sphere_final_check0"] = {"source": "tests/rigidity_sphere.output", "linf": [float(l.split()[3]) for l in fc]}
+    g["imposed_rotation"] = {"source": "tests/imposed_rotation_test_on_sphere.cc:28-31", "omega": 1.0 / (8 * 3.141592653589793),
+                             "tol": 1.2e-3}
+    with open(os.path.join(HERE, "reference_goldens.json"), "w") as f:
+        json.dump(g, f, indent=1)
+
+    # ---- singular quadrature error table -----------------------------------------------------------
+    cc = "\n".join(lines("tests/integrate_one_over_r_Q2.cc"))
+    exact = {}
+    for m in re.finditer(r"v\[(\d)\]\[(\d)\]\[(\d)\]\s*=\s*([-0-9.eE]+)\s*;", cc):
+        exact["%s,%s,%s" % (m.group(1), m.group(2), m.group(3))] = float(m.group(4))
+    out = lines("tests/integrate_one_over_r_Q2.output")
+    table = []
+    order, vertex = None, None
+    vid = -1
+    for l in out:
+        m = re.match(r"\s*=+Quadrature Order: (\d+)", l)
+        if m:
+            order, vid = int(m.group(1)), -1
+            continue
+        m = re.match(r"\s*=+Vertex: ([-0-9.e]+) ([-0-9.e]+)", l)
+        if m:
+            vid += 1
+            continue
+        m = re.match(r"f\(x,y\) = x\^(\d) y\^(\d), Errors = Telles ([-0-9.e+]+), LWGaussOneR ([-0-9.e+]+), "
+                     r"QIteraded\(QGauss\) ([-0-9.e+]+), QDuffy ([-0-9.e+]+), exact value ([-0-9.e+]+)", l)
+        if m:
+            table.append([order, vid, int(m.group(1)), int(m.group(2))] + [float(m.group(k)) for k in range(3, 8)])
+    with open(os.path.join(HERE, "singular_quadrature_table.json"), "w") as f:
+        json.dump({"source": "tests/integrate_one_over_r_Q2.output (+ exact constants of integrate_one_over_r_Q2.cc)",
+                   "columns": ["order", "support_point", "i", "j", "err_telles", "err_lw", "err_qiterated", "err_duffy",
+                               "exact_printed"],
+                   "exact": exact, "rows": table}, f)
+
+    # ---- meshes (input data) -------------------------------------------------------------------------
+    os.makedirs(os.path.join(HERE, "meshes"), exist_ok=True)
+    for rel in ["tests/grid_test/sphere_half_refined_0.inp", "tests/grid_test/sphere_0.inp",
+                "tests/grid_test/sphere_coarse_0.inp", "debug_grids/sphere_mesh_3d_0.msh",
+                "debug_grids/prolate_spheroid_lambda_2_ref_0.msh", "debug_grids/sphere_very_refined_0.inp",
+                "debug_grids/sphere_very_very_refined_0.inp", "debug_grids/sphere_2.inp"]:
+        src = os.path.join(REF, rel)
+        if os.path.exists(src):
+            shutil.copy(src, os.path.join(HERE, "meshes", os.path.basename(rel)))
+        else:
+            print("missing", rel)
+    print("wrote goldens:", len(table), "quadrature rows,", len(exact), "exact constants")
+
+
+if __name__ == "__main__":
+    main()

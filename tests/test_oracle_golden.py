@@ -1,0 +1,178 @@
+"""Pins the CPU oracle (oracle/bem_oracle.py) to the reference's own golden outputs.
+Fixtures were generated from /root/reference/tests/*.output by tests/golden/make_golden.py."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bem_oracle as bo
+from conftest import GOLDEN, MESHES
+
+
+def sig6(x, ref):
+    """ref is a 6-significant-digit print of x."""
+    if ref == 0:
+        return abs(x) < 1e-12
+    return abs(x - ref) <= 0.6 * 10 ** (math.floor(math.log10(abs(ref))) - 5)
+
+
+@pytest.fixture(scope="module")
+def half_refined():
+    v, q = bo.read_inp(os.path.join(MESHES, "sphere_half_refined_0.inp"))
+    geo = bo.Geometry(v, q, 1)
+    return geo, bo.Prepass(geo, 8)
+
+
+@pytest.fixture(scope="module")
+def VK_free(half_refined):
+    geo, pre = half_refined
+    return bo.assemble_VK(geo, bo.KernelSpec(), 8, "Mixed", 10)
+
+
+def test_alpha_test_Q1(goldens, half_refined):
+    geo, _ = half_refined
+    tV, tK = bo.alpha_sums(geo, bo.KernelSpec(), 0, 8, "Mixed", 10)
+    gV, gK = np.array(goldens["alpha_test"]["Q1"]["V"]), np.array(goldens["alpha_test"]["Q1"]["K"])
+    for a in range(3):
+        for b in range(3):
+            assert sig6(tV[a, b], gV[a, b]), (a, b, tV[a, b], gV[a, b])
+            assert sig6(tK[a, b], gK[a, b]), (a, b, tK[a, b], gK[a, b])
+
+
+def test_alpha_test_Q2_diagonal(goldens):
+    # Q2 nodes by radial projection; deal.II's SphericalManifold places cell centres differently at the 1e-7
+    # level (SURVEY §8c residual risk), so only the diagonal is pinned to 6 digits here.
+    v, q = bo.read_inp(os.path.join(MESHES, "sphere_half_refined_0.inp"))
+    nodes, conn = bo.q2_from_q1(v, q, project_radius=1.0)
+    geo = bo.Geometry(nodes, conn, 2)
+    tV, tK = bo.alpha_sums(geo, bo.KernelSpec(), 0, 8, "Mixed", 10)
+    gV, gK = np.array(goldens["alpha_test"]["Q2"]["V"]), np.array(goldens["alpha_test"]["Q2"]["K"])
+    assert np.allclose(np.diag(tV), np.diag(gV), atol=2e-6)
+    assert np.allclose(np.diag(tK), np.diag(gK), atol=2e-6)
+    assert np.abs(tV - gV).max() < 5e-6 and np.abs(tK - gK).max() < 5e-6
+
+
+def test_dof_renumbering_Q2(goldens):
+    v, q = bo.read_inp(os.path.join(MESHES, "sphere_coarse_0.inp"))
+    nodes, conn = bo.q2_from_q1(v, q, project_radius=1.0)
+    geo = bo.Geometry(nodes, conn, 2)
+    tV, tK = bo.alpha_sums(geo, bo.KernelSpec(), 1, 8, "Mixed", 10)  # file vertex 2
+    gV, gK = np.array(goldens["dof_renumbering"]["V"]), np.array(goldens["dof_renumbering"]["K"])
+    for a in range(3):
+        for b in range(3):
+            assert sig6(tV[a, b], gV[a, b]), (a, b, tV[a, b], gV[a, b])
+            assert sig6(tK[a, b], gK[a, b]), (a, b, tK[a, b], gK[a, b])
+
+
+def test_surface_and_Vn_free(goldens, half_refined, VK_free):
+    geo, pre = half_refined
+    assert sig6(pre.area, goldens["Vn_free"]["surface"])
+    V, K = VK_free
+    assert sig6(np.abs(V @ pre.nhat).max(), goldens["Vn_free"]["Vn_linf"])
+
+
+@pytest.mark.parametrize("kind,key", [(bo.FREE_SURFACE, "Vn_free_surface"), (bo.NO_SLIP, "Vn_no_slip")])
+def test_Vn_image_kernels(goldens, half_refined, kind, key):
+    geo, pre = half_refined
+    V, K = bo.assemble_VK(geo, bo.KernelSpec(kind, 0.0, 1, (0, 1.4, 0)), 8, "Mixed", 10)
+    assert sig6(np.abs(V @ pre.nhat).max(), goldens[key]["Vn_linf"])
+
+
+def test_V_test_with_Green_cycle0(goldens):
+    v, q = bo.read_inp(os.path.join(MESHES, "sphere_0.inp"))
+    geo = bo.Geometry(v, q, 1)
+    pre = bo.Prepass(geo, 8)
+    assert abs(pre.area - 8.0) < 1e-6
+    # parameters of that test: Gauss 8? the golden 0.0294664 was reproduced with singular order 5 / Gauss 8
+    for so in (5, 10):
+        V, K = bo.assemble_VK(geo, bo.KernelSpec(), 8, "Mixed", so)
+        if sig6(np.abs(V @ pre.nhat).max(), goldens["V_test_with_Green"]["Vn_linf"][0]):
+            return
+    pytest.fail("||V n|| of the 6-cell sphere not reproduced")
+
+
+def test_corrections_and_gmres_counts(goldens, half_refined, VK_free):
+    geo, pre = half_refined
+    V, K = VK_free
+    Vc, _ = bo.correct_V(V, pre)
+    Kc = bo.correct_K(K, geo.N)
+    # "Check on the V operator Norm post (should be one) pure: 1"; "check with versor vector: l_infty 1"
+    assert abs((Vc @ pre.nhat) @ pre.nhat / geo.N - 1) < 1e-12
+    for k in range(3):
+        assert abs(np.abs(Kc[:, k * geo.N:(k + 1) * geo.N].sum(1)).max() - 1) < 1e-12
+    A, b = bo.monolithic(Vc, Kc, pre, "ImposedForce", 1)
+    n = 3 * geo.N
+    D = np.diag(A).copy()
+    D[n:] = 1.0
+    _, its, _, ok = bo.gmres(lambda v: A @ v, b, prec=lambda v: v / D, tol=1e-10)
+    assert ok and its == goldens["gmres_iterations_no_box"]["Jacobi"]
+    Pm = np.eye(n + 6)
+    Pm[:n, :n] = A[:n, :n]
+    x, its, _, ok = bo.gmres(lambda v: A @ v, b, prec=bo.lu_solve_factory(Pm), tol=1e-10)
+    assert ok and its == goldens["gmres_iterations_no_box"]["ILU"] == goldens["gmres_iterations_no_box"]["AMG"]
+    assert np.abs(A @ x - b).max() < 1e-9
+    # rotation mobility 1/(8 pi) within 1.2e-3 (tests/imposed_rotation_test_on_sphere.cc:28-31)
+    A, b = bo.monolithic(Vc, Kc, pre, "ImposedForce", 3)
+    x = np.linalg.solve(A, b)
+    assert abs(x[n + 3] - goldens["imposed_rotation"]["omega"]) < goldens["imposed_rotation"]["tol"]
+    assert abs(abs(x[n + 3] - goldens["imposed_rotation"]["omega"]) - 1.085e-3) < 5e-6
+
+
+def test_singular_quadrature_table():
+    """All 1 377 rows of tests/integrate_one_over_r_Q2.output: |exact - rule| for Telles / Lachat-Watson /
+    QIterated / Duffy, orders 3..19, nine Q2 support points, monomials x^i y^j."""
+    with open(os.path.join(GOLDEN, "singular_quadrature_table.json")) as f:
+        T = json.load(f)
+    exact = T["exact"]
+    us = bo.UNIT_SUPPORT[2]
+    cache = {}
+    bad = 0
+    for (order, sp, i, j, e_t, e_lw, e_it, e_du, ex_print) in T["rows"]:
+        key = (order, sp)
+        if key not in cache:
+            s = us[sp]
+            cache[key] = (bo.telles2(order, s), bo.lw_point(order, s, True), bo.qiterated2(order, 2),
+                          bo.qsplit_duffy(order, s, 1.0))
+        s = us[sp]
+        ex = exact["%d,%d,%d" % (i, j, sp)]
+        errs = []
+        for k, (P, W) in enumerate(cache[key]):
+            dx, dy = P[:, 0] - s[0], P[:, 1] - s[1]
+            R = np.sqrt(dx * dx + dy * dy)
+            f = dx ** i * dy ** j
+            val = (f * W).sum() if k == 1 else (f / R * W).sum()
+            errs.append(abs(ex - val))
+        for got, ref in zip(errs, (e_t, e_lw, e_it, e_du)):
+            # printed with 6 significant digits; values at rounding-noise level (<1e-14) are not comparable
+            if ref < 1e-13:
+                ok = got < 1e-12
+            else:
+                ok = abs(got - ref) <= 2e-5 * ref + 2e-15
+            bad += (not ok)
+            assert ok, (order, sp, i, j, errs, (e_t, e_lw, e_it, e_du))
+    assert bad == 0
+
+
+def test_kernel_units_vanish_on_wall():
+    """tests/reflected_kernel_test_{G,W}.cc, wall_kernel_test_{G,W}.cc: image kernels vanish on the wall."""
+    rng = np.random.default_rng(0)
+    for o in range(3):
+        x = rng.uniform(-1, 1, 3)
+        wall = np.zeros(3)
+        wall[o] = 1.4
+        x[o] = 0.3
+        y = rng.uniform(-2, 2, 3)
+        y[o] = wall[o]  # evaluation point on the wall
+        xim = x.copy()
+        xim[o] -= 2 * (x[o] - wall[o])
+        R, Rim = y - x, y - xim
+        # no-slip: all of G vanishes on the wall
+        assert np.abs(bo.G_ns(R[None], Rim[None], o)).max() < 1e-12
+        # free surface, exactly as tests/reflected_kernel_test_G.cc:16-36 / _W.cc: the valuation point lies on
+        # the wall, so R_image == R and row `o` of G and W cancels
+        assert np.abs(bo.G_fs(R[None], R[None], o)[0, o, :]).max() < 1e-6
+        assert np.abs(bo.W_fs(R[None], R[None], o)[0, o]).max() < 1e-6
+        # physical version: normal velocity due to a tangential force vanishes on the symmetry plane
+        assert abs(bo.G_fs(R[None], Rim[None], o)[0, o, o]) < 1e-12
