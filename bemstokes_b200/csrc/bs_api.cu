@@ -1,0 +1,880 @@
+// extern "C" entry points of libbemstokes_b200 (see include/bemstokes_b200.h for the contract and the
+// reference file:line each one replaces).  Exceptions never cross the ABI.
+#include "bs_internal.h"
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+namespace bs {
+const std::string &get_last_error();
+
+struct Extra {  // per-context extras kept out of the header
+  DBuf<int> d_node_of_pos;
+  DBuf<double> vin, vout, vin2;
+  DBuf<int> ir, ic;
+  DBuf<unsigned char> d_flag;
+  DBuf<double> dev_ref;  // device scratch in reference ordering
+};
+static Extra &extra(Context &c) {
+  if (!c.extra) c.extra = new Extra();
+  return *static_cast<Extra *>(c.extra);
+}
+static void drop_extra(Context &c) {
+  delete static_cast<Extra *>(c.extra);
+  c.extra = nullptr;
+}
+
+struct Timer {
+  Context &c;
+  double &acc;
+  Timer(Context &c_, double &a) : c(c_), acc(a) { cudaEventRecord(c.ev0, c.stream); }
+  ~Timer() {
+    cudaEventRecord(c.ev1, c.stream);
+    cudaEventSynchronize(c.ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c.ev0, c.ev1);
+    acc += ms;
+  }
+};
+
+// reference-ordered vector (host or device per pointer mode) -> full internal device vector
+static void to_internal(Context &c, const double *ref, int nextra, double *d_int, bool force_host = false) {
+  Extra &e = extra(c);
+  const size_t n = c.n3() + nextra;
+  const double *src = ref;
+  if (force_host || c.pointer_mode == BS_PTR_HOST) {
+    e.dev_ref.alloc(std::max(e.dev_ref.n, n));
+    BS_CUDA(cudaMemcpyAsync(e.dev_ref.p, ref, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    src = e.dev_ref.p;
+  }
+  perm_in(c, src, d_int, e.d_node_of_pos.p, nextra);
+}
+// internal entries [lo,hi) of a full-indexed internal device vector -> reference-ordered vector
+static void from_internal(Context &c, const double *d_int_full, int nextra, double *ref, size_t lo, size_t hi,
+                          bool force_host = false) {
+  Extra &e = extra(c);
+  const size_t n = c.n3() + nextra;
+  if (force_host || c.pointer_mode == BS_PTR_HOST) {
+    if (lo == 0 && hi == n) {
+      e.dev_ref.alloc(std::max(e.dev_ref.n, n));
+      perm_out(c, d_int_full, e.dev_ref.p, e.d_node_of_pos.p, nextra, lo, hi);
+      BS_CUDA(cudaMemcpyAsync(ref, e.dev_ref.p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+      BS_CUDA(cudaStreamSynchronize(c.stream));
+    } else {
+      std::vector<double> h(hi - lo);
+      BS_CUDA(cudaMemcpyAsync(h.data(), d_int_full + lo, (hi - lo) * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+      BS_CUDA(cudaStreamSynchronize(c.stream));
+      for (size_t i = lo; i < hi; ++i) {
+        if (i < c.n3()) ref[(size_t)c.node_of_pos[i / 3] + (i % 3) * c.N] = h[i - lo];
+        else ref[i] = h[i - lo];
+      }
+    }
+  } else {
+    perm_out(c, d_int_full, ref, e.d_node_of_pos.p, nextra, lo, hi);
+  }
+}
+
+static void alloc_matrix(Context &c, DBuf<double> &store, DMat &M, size_t rows, size_t cols) {
+  store.alloc((c.rows_loc + MAX_RIGID) * c.ld + 2);
+  store.zero(c.stream);
+  M.p = store.p;
+  M.rows = rows;
+  M.cols = cols;
+  M.ld = c.ld;
+  M.owned = true;
+}
+
+static int nextra_of(Context &c, int which) { return which == BS_MAT_A ? c.num_rigid : 0; }
+
+}  // namespace bs
+
+using namespace bs;
+
+#define BS_API_BEGIN try {
+#define BS_API_END                                  \
+  }                                                 \
+  catch (const bs::Error &e) {                      \
+    bs::set_last_error(e.what());                   \
+    return e.code;                                  \
+  }                                                 \
+  catch (const std::exception &e) {                 \
+    bs::set_last_error(e.what());                   \
+    return BS_ERR_INVALID;                          \
+  }                                                 \
+  return BS_OK;
+
+static Context &ctx_of(bs_context *h) {
+  if (!h) throw Error(BS_ERR_INVALID, "null context");
+  Context &c = h->c;
+  BS_CUDA(cudaSetDevice(c.device));
+  return c;
+}
+
+extern "C" {
+
+const char *bs_last_error(void) { return bs::get_last_error().c_str(); }
+int bs_version(void) { return 100; }
+
+int bs_create(bs_context **out, int device, int fe_degree, int map_degree) {
+  BS_API_BEGIN
+  BS_REQUIRE(out != nullptr, "null output pointer");
+  BS_REQUIRE((fe_degree == 1 || fe_degree == 2) && (map_degree == 1 || map_degree == 2), "FE degrees must be 1 or 2");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    throw Error(BS_ERR_NO_DEVICE, "no CUDA device visible: libbemstokes_b200 has no CPU fallback");
+  BS_REQUIRE(device >= 0 && device < ndev, "device ordinal out of range");
+  cudaDeviceProp prop;
+  BS_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    throw Error(BS_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                      ", this library is built for sm_100a (B200) only");
+  BS_CUDA(cudaSetDevice(device));
+  bs_context *h = new bs_context();
+  Context &c = h->c;
+  c.device = device;
+  c.fe_degree = fe_degree;
+  c.map_degree = map_degree;
+  c.na = n_shape(fe_degree);
+  c.na_map = n_shape(map_degree);
+  c.sm_count = prop.multiProcessorCount;
+  BS_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+  c.own_stream = true;
+  BS_CUDA(cudaEventCreate(&c.ev0));
+  BS_CUDA(cudaEventCreate(&c.ev1));
+  *out = h;
+  BS_API_END
+}
+
+int bs_destroy(bs_context *h) {
+  BS_API_BEGIN
+  if (!h) return BS_OK;
+  Context &c = h->c;
+  cudaSetDevice(c.device);
+  cudaStreamSynchronize(c.stream);
+  drop_extra(c);
+  if (c.ev0) cudaEventDestroy(c.ev0);
+  if (c.ev1) cudaEventDestroy(c.ev1);
+  if (c.own_stream && c.stream) cudaStreamDestroy(c.stream);
+  delete h;
+  BS_API_END
+}
+
+int bs_set_pointer_mode(bs_context *h, int mode) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(mode == BS_PTR_HOST || mode == BS_PTR_DEVICE, "bad pointer mode");
+  c.pointer_mode = mode;
+  BS_API_END
+}
+
+int bs_set_stream(bs_context *h, void *s) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_CUDA(cudaStreamSynchronize(c.stream));
+  if (c.own_stream) cudaStreamDestroy(c.stream);
+  if (s) {
+    c.stream = (cudaStream_t)s;
+    c.own_stream = false;
+  } else {
+    BS_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    c.own_stream = true;
+  }
+  BS_API_END
+}
+
+int bs_set_partition(bs_context *h, int rank, int nranks, const int *owner_of_node, int n_nodes) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
+  BS_REQUIRE(!c.have_geometry, "bs_set_partition must precede bs_set_geometry");
+  c.rank = rank;
+  c.nranks = nranks;
+  c.owner_in.clear();
+  if (owner_of_node) c.owner_in.assign(owner_of_node, owner_of_node + n_nodes);
+  BS_API_END
+}
+
+int bs_get_owned_nodes(bs_context *h, int *n_owned, int *owned) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(c.have_geometry, "geometry not set");
+  if (n_owned) *n_owned = c.p1 - c.p0;
+  if (owned)
+    for (int p = c.p0; p < c.p1; ++p) owned[p - c.p0] = c.node_of_pos[p];
+  BS_API_END
+}
+
+int bs_set_geometry(bs_context *h, int n_map_nodes, const double *euler_vec, int ncell, const int *conn_map, int n_nodes,
+                    const int *conn_stokes, const int *material_id) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(n_map_nodes > 0 && ncell > 0 && n_nodes > 0 && euler_vec && conn_map && conn_stokes, "bad geometry arguments");
+  c.Nmap = n_map_nodes;
+  c.N = n_nodes;
+  c.ncell = ncell;
+  c.map_nodes.resize((size_t)3 * n_map_nodes);
+  for (int i = 0; i < n_map_nodes; ++i)
+    for (int d = 0; d < 3; ++d) c.map_nodes[(size_t)3 * i + d] = euler_vec[(size_t)i + (size_t)d * n_map_nodes];
+  c.conn_map.assign(conn_map, conn_map + (size_t)ncell * c.na_map);
+  c.conn.assign(conn_stokes, conn_stokes + (size_t)ncell * c.na);
+  c.material.assign(ncell, 0);
+  if (material_id) c.material.assign(material_id, material_id + ncell);
+  build_geometry(c);
+  extra(c).d_node_of_pos.upload(c.node_of_pos, c.stream);
+  c.ld = ((c.n3() + MAX_RIGID + 15) / 16) * 16;
+  // a new geometry invalidates matrices
+  c.V = DMat();
+  c.K = DMat();
+  c.A = DMat();
+  if (c.have_quadrature) build_tables(c);
+  BS_API_END
+}
+
+int bs_make_gauss_1d(int n, double *x, double *w) {
+  try {
+    std::vector<double> xs, ws;
+    gauss_legendre_01(n, xs, ws);
+    for (int i = 0; i < n; ++i) {
+      x[i] = xs[i];
+      w[i] = ws[i];
+    }
+    return n;
+  } catch (const std::exception &e) {
+    bs::set_last_error(e.what());
+    return BS_ERR_INVALID;
+  }
+}
+
+int bs_make_singular_rule(int kind, int order, int fe_degree, int local_index, int capacity, double *xi, double *w) {
+  try {
+    Rule2D r = make_singular_rule(kind, order, fe_degree, local_index);
+    if (xi && w) {
+      if (capacity < r.size()) throw Error(BS_ERR_INVALID, "capacity too small for the rule");
+      std::copy(r.xi.begin(), r.xi.end(), xi);
+      std::copy(r.w.begin(), r.w.end(), w);
+    }
+    return r.size();
+  } catch (const bs::Error &e) {
+    bs::set_last_error(e.what());
+    return e.code;
+  } catch (const std::exception &e) {
+    bs::set_last_error(e.what());
+    return BS_ERR_INVALID;
+  }
+}
+
+int bs_set_quadrature(bs_context *h, int n1d, const double *x1d, const double *w1d) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(n1d >= 1 && n1d <= 32, "regular quadrature order must be in [1,32]");
+  if (x1d && w1d) {
+    c.x1d.assign(x1d, x1d + n1d);
+    c.w1d.assign(w1d, w1d + n1d);
+  } else {
+    gauss_legendre_01(n1d, c.x1d, c.w1d);
+  }
+  c.reg = tensor_rule(c.x1d, c.w1d);
+  c.have_quadrature = true;
+  if (c.have_geometry) build_tables(c);
+  BS_API_END
+}
+
+int bs_set_singular_quadrature(bs_context *h, int kind, int order) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  c.sing.clear();
+  for (int a = 0; a < c.na; ++a) c.sing.push_back(make_singular_rule(kind, order, c.fe_degree, a));
+  c.have_singular = true;
+  if (c.have_geometry && c.have_quadrature) build_tables(c);
+  BS_API_END
+}
+
+int bs_set_singular_rule(bs_context *h, int a, int nq, const double *xi, const double *w) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(a >= 0 && a < c.na && nq > 0 && xi && w, "bad singular rule arguments");
+  if ((int)c.sing.size() != c.na) c.sing.assign(c.na, Rule2D());
+  c.sing[a].xi.assign(xi, xi + 2 * (size_t)nq);
+  c.sing[a].w.assign(w, w + nq);
+  c.have_singular = true;
+  for (int b = 0; b < c.na; ++b) c.have_singular = c.have_singular && c.sing[b].size() > 0;
+  if (c.have_singular && c.have_geometry && c.have_quadrature) build_tables(c);
+  BS_API_END
+}
+
+int bs_set_kernel(bs_context *h, int type, double eps, int wall_orientation, const double *wall_position) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(type >= 0 && type <= 2, "unknown kernel type");
+  BS_REQUIRE(wall_orientation >= 0 && wall_orientation < 3, "wall orientation must be 0,1,2");
+  const bool retile = (type == BS_KERNEL_FREE) != (c.kp.type == BS_KERNEL_FREE);
+  c.kp.type = type;
+  c.kp.eps = eps;
+  c.kp.o = wall_orientation;
+  c.kp.wall_pos = wall_position ? wall_position[wall_orientation] : 0.0;
+  if (retile && c.have_geometry && c.have_quadrature) build_tables(c);
+  BS_API_END
+}
+
+int bs_assemble_VK(bs_context *h) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(c.have_geometry && c.have_quadrature && c.have_singular, "geometry, quadrature and singular quadrature must be set");
+  alloc_matrix(c, c.storeV, c.V, c.rows_loc, c.n3());
+  alloc_matrix(c, c.storeK, c.K, c.rows_loc, c.n3());
+  c.A = DMat();
+  c.A_aliases_V = false;
+  {
+    Timer t(c, c.stats.geometry_ms);
+    launch_cell_geometry(c);
+  }
+  {
+    Timer t(c, c.stats.assemble_regular_ms);
+    launch_assembly_regular(c);
+  }
+  {
+    Timer t(c, c.stats.assemble_singular_ms);
+    launch_assembly_singular(c);
+  }
+  BS_CUDA(cudaStreamSynchronize(c.stream));
+  BS_API_END
+}
+
+static void set_projector(Context &c, const double *nhat, const double *Mnhat, double l2) {
+  BS_REQUIRE(nhat && Mnhat && l2 > 0, "projector data missing");
+  c.d_nhat.alloc(c.n3() + 2);
+  c.d_Mnhat.alloc(c.n3() + 2);
+  to_internal(c, nhat, 0, c.d_nhat.p, true);
+  to_internal(c, Mnhat, 0, c.d_Mnhat.p, true);
+  c.l2gamma = l2;
+  c.have_projector = true;
+}
+
+int bs_correct_V(bs_context *h, const double *nhat, const double *Mnhat, double l2gamma, double *Vn_out) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(c.V.valid(), "V not assembled");
+  Timer t(c, c.stats.correct_ms);
+  set_projector(c, nhat, Mnhat, l2gamma);
+  Extra &e = extra(c);
+  e.vout.alloc(std::max(e.vout.n, c.n3() + MAX_RIGID + 2));
+  double *vn_loc = e.vout.p + 3 * (size_t)c.p0;
+  gemv(c, c.V, c.d_nhat.p, vn_loc);
+  if (Vn_out) from_internal(c, e.vout.p, 0, Vn_out, 3 * (size_t)c.p0, 3 * (size_t)c.p1, true);
+  // u = nhat - V nhat on the owned rows
+  e.vin.alloc(std::max(e.vin.n, c.n3() + MAX_RIGID + 2));
+  sub(c, c.d_nhat.p + 3 * (size_t)c.p0, vn_loc, e.vin.p, c.rows_loc);
+  rank1_update(c, c.V, e.vin.p, c.d_Mnhat.p, 1.0 / l2gamma);
+  BS_CUDA(cudaStreamSynchronize(c.stream));
+  BS_API_END
+}
+
+int bs_correct_K(bs_context *h, int use_internal_alpha) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(c.K.valid(), "K not assembled");
+  Timer t(c, c.stats.correct_ms);
+  const size_t n = c.n3();
+  const size_t ldx = (n + 2) & ~(size_t)1;
+  std::vector<double> E(3 * ldx, 0.0);
+  for (size_t p = 0; p < (size_t)c.N; ++p)
+    for (int k = 0; k < 3; ++k) E[k * ldx + 3 * p + k] = 1.0;
+  Extra &e = extra(c);
+  e.vin2.upload(E, c.stream);
+  e.vout.alloc(std::max(e.vout.n, 3 * c.rows_loc + 2));
+  gemv_multi(c, c.K, 3, e.vin2.p, ldx, e.vout.p, c.rows_loc);
+  k_correct_diag(c, c.K, e.vout.p, use_internal_alpha);
+  BS_CUDA(cudaStreamSynchronize(c.stream));
+  BS_API_END
+}
+
+int bs_build_monolithic(bs_context *h, const unsigned char *col_is_K, int num_rigid, const double *N_rigid,
+                        const double *N_rigid_dual, const double *nhat, const double *Mnhat, double l2gamma, int grid_type,
+                        int imposed_component, double scaling, const double *shape_vel, int keep_VK, double *rhs_out) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(c.V.valid() && c.K.valid(), "V and K must be assembled (and corrected) first");
+  BS_REQUIRE(num_rigid >= 0 && num_rigid <= MAX_RIGID, "num_rigid out of range");
+  BS_REQUIRE(num_rigid == 0 || (N_rigid && N_rigid_dual), "rigid modes missing");
+  Timer t(c, c.stats.monolithic_ms);
+  set_projector(c, nhat, Mnhat, l2gamma);
+  Extra &e = extra(c);
+  const size_t n = c.n3();
+  const int nr = num_rigid;
+  const int nvec = nr + 1;  // rigid modes + shape velocity
+  c.num_rigid = nr;
+  c.mono_size = n + nr;
+  const bool last = (c.rank == c.nranks - 1);
+  // ---- P N_r and P u_shape on the host (O(n) work, inputs of the boundary), then K * panel on the device
+  const size_t ldx = (n + 2) & ~(size_t)1;
+  std::vector<double> X((size_t)nvec * ldx, 0.0);
+  auto project_into = [&](const double *v, double *dst_int) {
+    double d = 0;
+    for (size_t i = 0; i < n; ++i) d += Mnhat[i] * v[i];
+    d /= l2gamma;
+    for (size_t p = 0; p < (size_t)c.N; ++p)
+      for (int k = 0; k < 3; ++k) {
+        const size_t ref = (size_t)c.node_of_pos[p] + (size_t)k * c.N;
+        dst_int[3 * p + k] = v[ref] - d * nhat[ref];
+      }
+  };
+  for (int r = 0; r < nr; ++r) project_into(N_rigid + (size_t)r * n, &X[(size_t)r * ldx]);
+  const bool use_shape = (grid_type == BS_GRID_REAL && shape_vel != nullptr);
+  if (use_shape) project_into(shape_vel, &X[(size_t)nr * ldx]);
+  e.vin2.upload(X, c.stream);
+  e.vout.alloc(std::max(e.vout.n, (size_t)nvec * c.rows_loc + 2));
+  gemv_multi(c, c.K, nvec, e.vin2.p, ldx, e.vout.p, c.rows_loc);
+  // second projection needs the full vectors: gather slices
+  std::vector<double> Y((size_t)nvec * n, 0.0);
+  {
+    DBuf<double> full;
+    full.alloc(n + 2);
+    std::vector<double> tmp(n);
+    for (int v = 0; v < nvec; ++v) {
+      exchange(c, BS_MAT_K, e.vout.p + (size_t)v * c.rows_loc, full.p + (c.nranks == 1 ? 0 : 0));
+      if (c.nranks == 1) {
+        BS_CUDA(cudaMemcpyAsync(tmp.data(), full.p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+      } else {
+        BS_CUDA(cudaMemcpyAsync(tmp.data(), full.p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+      }
+      BS_CUDA(cudaStreamSynchronize(c.stream));
+      // internal -> apply P in internal ordering
+      double d = 0;
+      std::vector<double> &mn = tmp;  // alias for clarity
+      (void)mn;
+      for (size_t p = 0; p < (size_t)c.N; ++p)
+        for (int k = 0; k < 3; ++k) d += Mnhat[(size_t)c.node_of_pos[p] + (size_t)k * c.N] * tmp[3 * p + k];
+      d /= l2gamma;
+      for (size_t p = 0; p < (size_t)c.N; ++p)
+        for (int k = 0; k < 3; ++k)
+          Y[(size_t)v * n + 3 * p + k] = tmp[3 * p + k] - d * nhat[(size_t)c.node_of_pos[p] + (size_t)k * c.N];
+    }
+  }
+  // ---- matrix
+  if (keep_VK) {
+    alloc_matrix(c, c.storeA, c.A, c.rows_loc + (last ? nr : 0), n + nr);
+    c.A_aliases_V = false;
+  } else {
+    c.A = c.V;
+    c.A.rows = c.rows_loc + (last ? nr : 0);
+    c.A.cols = n + nr;
+    c.A.owned = false;
+    c.A_aliases_V = true;
+  }
+  const unsigned char *d_flag = nullptr;
+  if (col_is_K) {
+    std::vector<unsigned char> f(n);
+    for (size_t p = 0; p < (size_t)c.N; ++p)
+      for (int k = 0; k < 3; ++k) f[3 * p + k] = col_is_K[(size_t)c.node_of_pos[p] + (size_t)k * c.N];
+    e.d_flag.upload(f, c.stream);
+    d_flag = e.d_flag.p;
+  }
+  {
+    DMat Vv = c.V;
+    Vv.rows = c.rows_loc;
+    Vv.cols = n;
+    select_columns(c, c.A, Vv, c.K, d_flag, c.A_aliases_V);
+  }
+  // rigid columns A(i, 3N+r) = -scaling * tmpN[r][i]  (ref: bem_stokes.cc:3247-3251)
+  DBuf<double> colbuf;
+  colbuf.alloc(c.rows_loc + 2);
+  DMat Arows = c.A;
+  Arows.rows = c.rows_loc;
+  for (int r = 0; r < nr; ++r) {
+    BS_CUDA(cudaMemcpyAsync(colbuf.p, &Y[(size_t)r * n + 3 * (size_t)c.p0], c.rows_loc * sizeof(double), cudaMemcpyHostToDevice,
+                            c.stream));
+    set_column(c, Arows, n + r, colbuf.p, -scaling);
+    BS_CUDA(cudaStreamSynchronize(c.stream));
+  }
+  // rigid rows (ref: 3297-3339), stored after the last rank's node rows
+  std::vector<double> rhs_int(n + nr, 0.0);
+  if (use_shape)
+    for (size_t i = 0; i < n; ++i) rhs_int[i] = Y[(size_t)nr * n + i];
+  if (nr > 0) {
+    std::vector<double> rows((size_t)nr * c.ld, 0.0);
+    for (int r = 0; r < nr; ++r) {
+      if (grid_type != BS_GRID_REAL) {
+        rhs_int[n + r] = (r == imposed_component) ? 1.0 : 0.0;
+        if (grid_type == BS_GRID_IMPOSED_VELOCITY) {
+          rows[(size_t)r * c.ld + n + r] = scaling;
+        } else {
+          for (size_t p = 0; p < (size_t)c.N; ++p)
+            for (int k = 0; k < 3; ++k)
+              rows[(size_t)r * c.ld + 3 * p + k] = N_rigid_dual[(size_t)r * n + c.node_of_pos[p] + (size_t)k * c.N];
+        }
+      } else {
+        for (size_t p = 0; p < (size_t)c.N; ++p)
+          for (int k = 0; k < 3; ++k)
+            rows[(size_t)r * c.ld + 3 * p + k] = scaling * N_rigid_dual[(size_t)r * n + c.node_of_pos[p] + (size_t)k * c.N];
+      }
+    }
+    if (last)
+      BS_CUDA(cudaMemcpyAsync(c.A.p + c.rows_loc * c.ld, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice,
+                              c.stream));
+    BS_CUDA(cudaStreamSynchronize(c.stream));
+  }
+  if (rhs_out) {
+    for (size_t p = 0; p < (size_t)c.N; ++p)
+      for (int k = 0; k < 3; ++k) rhs_out[(size_t)c.node_of_pos[p] + (size_t)k * c.N] = rhs_int[3 * p + k];
+    for (int r = 0; r < nr; ++r) rhs_out[n + r] = rhs_int[n + r];
+  }
+  c.has_rigid_rows = last && nr > 0;
+  BS_API_END
+}
+
+int bs_matrix_size(bs_context *h, int which, int *rows, int *cols) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  const size_t m = c.full_vec_len(which);
+  if (rows) *rows = (int)m;
+  if (cols) *cols = (int)m;
+  BS_API_END
+}
+
+int bs_vmult(bs_context *h, int which, const double *x, double *y) { return bs_vmult_multi(h, which, 1, x, y); }
+
+int bs_vmult_multi(bs_context *h, int which, int nrhs, const double *X, double *Y) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(which >= 0 && which <= 2 && nrhs >= 1 && X && Y, "bad vmult arguments");
+  const DMat &M = which == BS_MAT_V ? c.V : (which == BS_MAT_K ? c.K : c.A);
+  BS_REQUIRE(M.valid(), "matrix not available");
+  if (which != BS_MAT_A && c.A_aliases_V && which == BS_MAT_V)
+    throw Error(BS_ERR_INVALID, "V was consumed by bs_build_monolithic(keep_VK=0)");
+  Extra &e = extra(c);
+  const int nx = nextra_of(c, which);
+  const size_t m = c.full_vec_len(which), mloc = c.local_vec_len(which);
+  const size_t ldx = (m + 2) & ~(size_t)1;
+  e.vin.alloc(std::max(e.vin.n, (size_t)nrhs * ldx));
+  e.vout.alloc(std::max(e.vout.n, (size_t)nrhs * ldx));
+  for (int k = 0; k < nrhs; ++k) to_internal(c, X + (size_t)k * m, nx, e.vin.p + (size_t)k * ldx);
+  const size_t off = c.slice_offset(which);
+  {
+    cudaEventRecord(c.ev0, c.stream);
+    if (nrhs == 1) gemv(c, M, e.vin.p, e.vout.p + off);
+    else gemv_multi(c, M, nrhs, e.vin.p, ldx, e.vout.p + off, ldx);
+    cudaEventRecord(c.ev1, c.stream);
+  }
+  for (int k = 0; k < nrhs; ++k) from_internal(c, e.vout.p + (size_t)k * ldx, nx, Y + (size_t)k * m, off, off + mloc);
+  BS_CUDA(cudaStreamSynchronize(c.stream));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c.ev0, c.ev1);
+  c.stats.vmult_ms_last = ms;
+  BS_API_END
+}
+
+int bs_get_entries(bs_context *h, int which, int n, const int *rows, const int *cols, double *out) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  const DMat &M = which == BS_MAT_V ? c.V : (which == BS_MAT_K ? c.K : c.A);
+  BS_REQUIRE(M.valid(), "matrix not available");
+  BS_REQUIRE(n >= 0 && rows && cols && out, "bad arguments");
+  const int N = c.N, n3 = 3 * N;
+  std::vector<int> ir(n), ic(n);
+  auto to_int = [&](int ref) {
+    if (ref >= n3) return ref;
+    return 3 * c.pos_of_node[ref % N] + ref / N;
+  };
+  for (int k = 0; k < n; ++k) {
+    BS_REQUIRE(rows[k] >= 0 && rows[k] < (int)c.full_vec_len(which) && cols[k] >= 0 && cols[k] < (int)c.full_vec_len(which),
+               "entry index out of range");
+    const int r = to_int(rows[k]) - 3 * c.p0;
+    BS_REQUIRE(r >= 0 && r < (int)M.rows, "row not owned by this rank");
+    ir[k] = r;
+    ic[k] = to_int(cols[k]);
+  }
+  Extra &e = extra(c);
+  e.ir.upload(ir, c.stream);
+  e.ic.upload(ic, c.stream);
+  e.vout.alloc(std::max(e.vout.n, (size_t)n + 2));
+  gather_entries(c, M, n, e.ir.p, e.ic.p, e.vout.p);
+  BS_CUDA(cudaMemcpyAsync(out, e.vout.p, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  BS_CUDA(cudaStreamSynchronize(c.stream));
+  BS_API_END
+}
+
+int bs_tangential_projector(bs_context *h, const double *in, double *out) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(c.have_projector, "projector data not set (bs_correct_V / bs_build_monolithic)");
+  Extra &e = extra(c);
+  const size_t n = c.n3();
+  e.vin.alloc(std::max(e.vin.n, n + 2));
+  to_internal(c, in, 0, e.vin.p);
+  const double d = dot(c, c.d_Mnhat.p, e.vin.p, n);
+  axpy(c, -d / c.l2gamma, c.d_nhat.p, e.vin.p, n);
+  from_internal(c, e.vin.p, 0, out, 0, n);
+  BS_CUDA(cudaStreamSynchronize(c.stream));
+  BS_API_END
+}
+
+int bs_precond_setup(bs_context *h, int which, int kind, int param) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  const DMat &M = which == BS_MAT_V ? c.V : (which == BS_MAT_K ? c.K : c.A);
+  BS_REQUIRE(kind == BS_PREC_NONE || M.valid(), "matrix not available");
+  Timer t(c, c.stats.precond_setup_ms);
+  c.prec_which = which;
+  const size_t mloc = c.local_vec_len(which);
+  const size_t off = c.slice_offset(which);
+  if (kind == BS_PREC_JACOBI) {
+    c.d_prec_diag.alloc(mloc + 2);
+    extract_diag(c, M, off, c.d_prec_diag.p);
+    std::vector<double> d(mloc);
+    BS_CUDA(cudaMemcpyAsync(d.data(), c.d_prec_diag.p, mloc * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    BS_CUDA(cudaStreamSynchronize(c.stream));
+    for (auto &v : d) v = (v != 0.0) ? 1.0 / v : 1.0;
+    BS_CUDA(cudaMemcpyAsync(c.d_prec_diag.p, d.data(), mloc * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    BS_CUDA(cudaStreamSynchronize(c.stream));
+  } else if (kind == BS_PREC_DIRECT || kind == BS_PREC_BLOCK_DIRECT || kind == BS_PREC_BAND) {
+    size_t nb;
+    if (kind == BS_PREC_BLOCK_DIRECT) nb = c.rows_loc;  // node rows of this rank; rigid unknowns pass through
+    else {
+      BS_REQUIRE(c.nranks == 1, "full direct / band preconditioner needs the whole matrix on one GPU; use BS_PREC_BLOCK_DIRECT");
+      nb = mloc;
+    }
+    c.lu_n = nb;
+    c.d_lu.alloc(nb * nb + 2);
+    c.d_piv.alloc(nb + 2);
+    BS_CUDA(cudaMemcpy2DAsync(c.d_lu.p, nb * sizeof(double), M.p + off, M.ld * sizeof(double), nb * sizeof(double), nb,
+                              cudaMemcpyDeviceToDevice, c.stream));
+    if (kind == BS_PREC_BAND) {
+      // ref: assemble_monolithic_preconditioner, bem_stokes.cc:3437-3475 (entries with |i-j| beyond the band dropped)
+      std::vector<double> hm(nb * nb);
+      BS_CUDA(cudaMemcpyAsync(hm.data(), c.d_lu.p, nb * nb * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+      BS_CUDA(cudaStreamSynchronize(c.stream));
+      // the band is defined in the reference ordering; translate through the permutation
+      auto ref_of = [&](size_t i) { return i < c.n3() ? (size_t)c.node_of_pos[i / 3] + (i % 3) * c.N : i; };
+      for (size_t i = 0; i < nb; ++i)
+        for (size_t j = 0; j < nb; ++j) {
+          const long long ri = (long long)ref_of(i), rj = (long long)ref_of(j);
+          const long long lo = ri > param ? ri - param : 0, hi = ri + param;
+          if (!(rj >= lo && rj < hi)) hm[i * nb + j] = 0.0;
+        }
+      BS_CUDA(cudaMemcpyAsync(c.d_lu.p, hm.data(), nb * nb * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+      BS_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    lu_factor(c, c.d_lu.p, nb, nb, c.d_piv.p);
+    BS_CUDA(cudaStreamSynchronize(c.stream));
+  } else {
+    BS_REQUIRE(kind == BS_PREC_NONE, "unknown preconditioner kind");
+  }
+  c.prec_kind = kind;
+  BS_API_END
+}
+
+int bs_precond_vmult(bs_context *h, const double *x, double *y) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  Extra &e = extra(c);
+  const int which = c.prec_which;
+  const int nx = nextra_of(c, which);
+  const size_t m = c.full_vec_len(which), mloc = c.local_vec_len(which), off = c.slice_offset(which);
+  e.vin.alloc(std::max(e.vin.n, m + 2));
+  e.vout.alloc(std::max(e.vout.n, m + 2));
+  to_internal(c, x, nx, e.vin.p);
+  apply_precond(c, e.vin.p + off, e.vout.p + off);
+  from_internal(c, e.vout.p, nx, y, off, off + mloc);
+  BS_CUDA(cudaStreamSynchronize(c.stream));
+  BS_API_END
+}
+
+int bs_gmres(bs_context *h, int which, const double *b, double *x, double tol_abs, int max_steps, int max_n_tmp_vectors,
+             int *iterations, double *final_residual) {
+  int rc = BS_OK;
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(b && x, "null vectors");
+  BS_REQUIRE(c.prec_kind == BS_PREC_NONE || c.prec_which == which, "preconditioner was set up for another matrix");
+  Timer t(c, c.stats.solve_ms);
+  Extra &e = extra(c);
+  const int nx = nextra_of(c, which);
+  const size_t m = c.full_vec_len(which), mloc = c.local_vec_len(which), off = c.slice_offset(which);
+  DBuf<double> db, dx;
+  db.alloc(m + 2);
+  dx.alloc(m + 2);
+  to_internal(c, b, nx, db.p);
+  to_internal(c, x, nx, dx.p);
+  (void)e;
+  rc = gmres(c, which, db.p + off, dx.p + off, tol_abs, max_steps, max_n_tmp_vectors, iterations, final_residual);
+  from_internal(c, dx.p, nx, x, off, off + mloc);
+  BS_CUDA(cudaStreamSynchronize(c.stream));
+  if (rc == BS_ERR_NOT_CONVERGED) bs::set_last_error("GMRES did not converge within max_steps");
+  }
+  catch (const bs::Error &e) {
+    bs::set_last_error(e.what());
+    return e.code;
+  }
+  catch (const std::exception &e) {
+    bs::set_last_error(e.what());
+    return BS_ERR_INVALID;
+  }
+  return rc;
+}
+
+int bs_gmres_multi(bs_context *h, int which, int nrhs, const double *B, double *X, double tol_abs, int max_steps,
+                   int max_n_tmp_vectors, int *iterations, double *final_residuals) {
+  int worst = BS_OK;
+  bs_context *ctx = h;
+  if (!ctx) return BS_ERR_INVALID;
+  const size_t m = ctx->c.full_vec_len(which);
+  for (int k = 0; k < nrhs; ++k) {
+    int rc = bs_gmres(h, which, B + (size_t)k * m, X + (size_t)k * m, tol_abs, max_steps, max_n_tmp_vectors,
+                      iterations ? iterations + k : nullptr, final_residuals ? final_residuals + k : nullptr);
+    if (rc != BS_OK) worst = rc;
+    if (rc != BS_OK && rc != BS_ERR_NOT_CONVERGED) return rc;
+  }
+  return worst;
+}
+
+int bs_direct_solve(bs_context *h, int which, const double *b, double *x) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(c.nranks == 1, "bs_direct_solve needs the whole matrix on one GPU");
+  const DMat &M = which == BS_MAT_V ? c.V : (which == BS_MAT_K ? c.K : c.A);
+  BS_REQUIRE(M.valid(), "matrix not available");
+  Timer t(c, c.stats.solve_ms);
+  const int nx = nextra_of(c, which);
+  const size_t m = c.full_vec_len(which);
+  DBuf<double> lu, dx;
+  DBuf<int> piv;
+  lu.alloc(m * m + 2);
+  piv.alloc(m + 2);
+  dx.alloc(m + 2);
+  BS_CUDA(cudaMemcpy2DAsync(lu.p, m * sizeof(double), M.p, M.ld * sizeof(double), m * sizeof(double), m,
+                            cudaMemcpyDeviceToDevice, c.stream));
+  lu_factor(c, lu.p, m, m, piv.p);
+  to_internal(c, b, nx, dx.p);
+  lu_solve(c, lu.p, m, m, piv.p, dx.p);
+  from_internal(c, dx.p, nx, x, 0, m);
+  BS_CUDA(cudaStreamSynchronize(c.stream));
+  BS_API_END
+}
+
+int bs_kernel_eval(int device, int type, double eps, int o, int npts, const double *p, const double *pim, double *G,
+                   double *W) {
+  BS_API_BEGIN
+  BS_REQUIRE(npts > 0 && p, "bad arguments");
+  BS_REQUIRE(type >= 0 && type <= 2 && o >= 0 && o < 3, "bad kernel type / orientation");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    throw Error(BS_ERR_NO_DEVICE, "no CUDA device visible: libbemstokes_b200 has no CPU fallback");
+  BS_CUDA(cudaSetDevice(device));
+  DBuf<double> dp, dq, dG, dW;
+  dp.upload(p, (size_t)3 * npts, 0);
+  if (pim) dq.upload(pim, (size_t)3 * npts, 0);
+  if (G) dG.alloc((size_t)9 * npts);
+  if (W) dW.alloc((size_t)27 * npts);
+  kernel_eval_device(type, eps, o, npts, dp.p, pim ? dq.p : nullptr, dG.p, dW.p, 0);
+  if (G) BS_CUDA(cudaMemcpy(G, dG.p, sizeof(double) * 9 * npts, cudaMemcpyDeviceToHost));
+  if (W) BS_CUDA(cudaMemcpy(W, dW.p, sizeof(double) * 27 * npts, cudaMemcpyDeviceToHost));
+  BS_CUDA(cudaDeviceSynchronize());
+  BS_API_END
+}
+
+int bs_set_comm(bs_context *h, bs_allgatherv_fn ag, bs_allreduce_sum_fn ar, void *user) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  c.cb_allgatherv = ag;
+  c.cb_allreduce = ar;
+  c.cb_user = user;
+  BS_API_END
+}
+
+int bs_get_exchange_buffer(bs_context *h, void **dev_ptr, size_t *bytes) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  const size_t n = c.n3() + MAX_RIGID + 2;
+  c.d_xchg.alloc(std::max(c.d_xchg.n, n));
+  if (dev_ptr) *dev_ptr = c.d_xchg.p;
+  if (bytes) *bytes = c.d_xchg.n * sizeof(double);
+  BS_API_END
+}
+
+int bs_set_peer_buffers(bs_context *h, int nranks, void *const *peer_xbuf, void *const *peer_flags) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(nranks == c.nranks, "nranks mismatch");
+  c.peer_xbuf.assign(peer_xbuf, peer_xbuf + nranks);
+  c.peer_flags.clear();
+  if (peer_flags) c.peer_flags.assign(peer_flags, peer_flags + nranks);
+  BS_API_END
+}
+
+int bs_get_stats(bs_context *h, bs_stats *out) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(out != nullptr, "null output");
+  *out = c.stats;
+  BS_API_END
+}
+int bs_reset_stats(bs_context *h) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  c.stats = bs_stats{};
+  BS_API_END
+}
+
+int bs_bench_vmult(bs_context *h, int which, int repeats, double *ms_per_call) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  const DMat &M = which == BS_MAT_V ? c.V : (which == BS_MAT_K ? c.K : c.A);
+  BS_REQUIRE(M.valid() && repeats > 0, "matrix not available");
+  Extra &e = extra(c);
+  const size_t m = c.full_vec_len(which);
+  e.vin.alloc(std::max(e.vin.n, m + 2));
+  e.vout.alloc(std::max(e.vout.n, m + 2));
+  fill(c, e.vin.p, 1.0, m);
+  gemv(c, M, e.vin.p, e.vout.p);  // warm-up
+  cudaEventRecord(c.ev0, c.stream);
+  for (int i = 0; i < repeats; ++i) gemv(c, M, e.vin.p, e.vout.p);
+  cudaEventRecord(c.ev1, c.stream);
+  BS_CUDA(cudaEventSynchronize(c.ev1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c.ev0, c.ev1);
+  if (ms_per_call) *ms_per_call = ms / repeats;
+  BS_API_END
+}
+
+}  // extern "C"
+
+// ---- FP64 FMA-chain microbenchmark: the denominator of the assembly roofline (not in MEASURED_PEAKS.json) ----
+__global__ void k_fp64_peak(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, b = 1e-7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+    a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" int bs_bench_fp64_peak(int device, double *tflops) {
+  BS_API_BEGIN
+  BS_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  BS_CUDA(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 4, threads = 512, iters = 1 << 15;
+  DBuf<double> out;
+  out.alloc((size_t)blocks * threads);
+  cudaEvent_t e0, e1;
+  BS_CUDA(cudaEventCreate(&e0));
+  BS_CUDA(cudaEventCreate(&e1));
+  k_fp64_peak<<<blocks, threads>>>(out.p, 1 << 10);
+  double best = 0;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0);
+    k_fp64_peak<<<blocks, threads>>>(out.p, iters);
+    cudaEventRecord(e1);
+    BS_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double fl = 2.0 * 8 * (double)iters * blocks * threads;
+    best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (tflops) *tflops = best;
+  BS_API_END
+}

@@ -1,0 +1,533 @@
+// Collocation assembly of V (single layer) and K (double layer) on sm_100a — replaces the (cell, node, q)
+// loop nest of BEMProblem::assemble_stokes_system (ref: source/bem_stokes.cc:2871-3000).
+//
+//   K0  k_cell_geometry      FEValues::reinit for every cell with the regular rule: y_q, n_q*JxW_q, JxW_q
+//   K1  k_assemble_regular   CTA tile = 128 collocation nodes (one per thread) x one column block of TJ
+//                            nodes; the cells touching the block are streamed through shared memory by
+//                            bulk-async copies (TMA engine, mbarrier-tracked, double buffered); per-thread
+//                            register accumulators over q, per-CTA shared-memory accumulators over cells,
+//                            one coalesced vectorised write of the finished V/K tile (no atomics, no
+//                            read-modify-write of HBM, deterministic summation order).
+//   K2  k_assemble_singular  one warp per owned collocation node: the cells containing the node are
+//                            integrated with the singular rule of that local index (geometry evaluated on
+//                            the fly) and added to the node's three rows.
+#include "bs_internal.h"
+#include "bs_green.cuh"
+
+namespace bs {
+
+void count_launch(Context &c, int n) { c.stats.kernel_launches += n; }
+
+// ---------------------------------------------------------------------------------------------------------
+// small PTX wrappers: mbarrier + bulk async copy global -> shared
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K0: per-cell quadrature data with the regular rule.  cellq[cell][7][nq_pad] = y(3), n*JxW(3), JxW
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_cell_geometry(int ncell, int nq, int nq_pad, int nam, const int *__restrict__ conn_map,
+                                const double *__restrict__ map_nodes, const double *__restrict__ tab /*[nq][nam][3]*/,
+                                const double *__restrict__ w, double *__restrict__ cellq) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)ncell * nq) return;
+  const int cell = (int)(gid / nq), q = (int)(gid % nq);
+  double y[3] = {0, 0, 0}, t1[3] = {0, 0, 0}, t2[3] = {0, 0, 0};
+  for (int a = 0; a < nam; ++a) {
+    const int m = conn_map[(size_t)cell * nam + a];
+    const double ph = tab[((size_t)q * nam + a) * 3], dx = tab[((size_t)q * nam + a) * 3 + 1],
+                 dy = tab[((size_t)q * nam + a) * 3 + 2];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const double X = map_nodes[(size_t)3 * m + d];
+      y[d] = fma(ph, X, y[d]);
+      t1[d] = fma(dx, X, t1[d]);
+      t2[d] = fma(dy, X, t2[d]);
+    }
+  }
+  const double nx = t1[1] * t2[2] - t1[2] * t2[1], ny = t1[2] * t2[0] - t1[0] * t2[2], nz = t1[0] * t2[1] - t1[1] * t2[0];
+  const double J = sqrt(nx * nx + ny * ny + nz * nz);
+  double *o = cellq + (size_t)cell * 7 * nq_pad;
+  o[0 * nq_pad + q] = y[0];
+  o[1 * nq_pad + q] = y[1];
+  o[2 * nq_pad + q] = y[2];
+  o[3 * nq_pad + q] = w[q] * nx;  // n*JxW = (nn/|nn|) * w|nn|
+  o[4 * nq_pad + q] = w[q] * ny;
+  o[5 * nq_pad + q] = w[q] * nz;
+  o[6 * nq_pad + q] = w[q] * J;
+}
+
+void launch_cell_geometry(Context &c) {
+  c.d_cellq.alloc((size_t)c.ncell * 7 * c.nq_pad);
+  c.d_cellq.zero(c.stream);
+  DBuf<double> dw;
+  dw.upload(c.reg.w, c.stream);
+  const long long total = (long long)c.ncell * c.nq;
+  const int bs_ = 256;
+  k_cell_geometry<<<(unsigned)((total + bs_ - 1) / bs_), bs_, 0, c.stream>>>(c.ncell, c.nq, c.nq_pad, c.na_map, c.d_conn_map.p,
+                                                                            c.d_map_nodes.p, c.d_map_tab_reg.p, dw.p,
+                                                                            c.d_cellq.p);
+  BS_CUDA(cudaGetLastError());
+  count_launch(c);
+  BS_CUDA(cudaStreamSynchronize(c.stream));  // dw goes out of scope
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1: regular pass
+// ---------------------------------------------------------------------------------------------------------
+struct RegParams {
+  int p0, p1, N;            // owned row positions [p0,p1), number of nodes
+  int nq, nq_pad, tj;
+  const double *support;    // [N][3]
+  const int *conn_pos;      // [ncell][NA]
+  const double *cellq;      // [ncell][7][nq_pad]
+  const double *phi;        // [nq][NA]
+  const int *blk_cell_ptr, *blk_cells;
+  const signed char *blk_slots;
+  double *V, *K;
+  size_t ld;
+  KernelParams kp;
+};
+
+constexpr int ACC_LD = TI + 1;  // padded row-node stride of the shared accumulators (bank-conflict free both ways)
+
+size_t assembly_smem_bytes(int na, int nv, int tj, int nq_pad) {
+  return (size_t)2 * nv * tj * ACC_LD * 8 + (size_t)2 * 7 * nq_pad * 8 + (size_t)nq_pad * na * 8 + 64;
+}
+
+int choose_tj(int na, int kernel_type, int nq_pad) {
+  const int nv = (kernel_type == BS_KERNEL_FREE) ? 6 : 9;
+  const size_t budget = 227 * 1024;
+  int tj = 2;
+  for (int t = 2; t <= 32; t += 2)
+    if (assembly_smem_bytes(na, nv, t, nq_pad) <= budget) tj = t;
+  return tj;
+}
+
+// index of (i,j) in the stored value vector
+template <int NV>
+__device__ __forceinline__ int vidx(int i, int j) {
+  if (NV == 9) return 3 * i + j;
+  const int a = i < j ? i : j, b = i < j ? j : i;
+  return a == 0 ? b : (a == 1 ? 2 + b : 5);  // (0,0)=0 (0,1)=1 (0,2)=2 (1,1)=3 (1,2)=4 (2,2)=5
+}
+
+template <int NA, int KT, bool SPLIT>
+__global__ void __launch_bounds__(TI, 1) k_assemble_regular(const RegParams P) {
+  constexpr int NV = GreenTraits<KT>::NV;
+  constexpr int NV2 = 2 * NV;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tj = P.tj, nq = P.nq, nqp = P.nq_pad;
+  double *cellbuf = reinterpret_cast<double *>(smem_raw);                   // [2][7][nqp]
+  double *phi_s = cellbuf + (size_t)2 * 7 * nqp;                            // [nq][NA]
+  double *acc_s = phi_s + (size_t)nqp * NA;                                 // [tj][NV2][ACC_LD]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(acc_s + (size_t)tj * NV2 * ACC_LD);  // [2]
+
+  const int t = threadIdx.x;
+  const int blk = blockIdx.x;
+  const int p = P.p0 + blockIdx.y * TI + t;
+  const bool row_ok = p < P.p1;
+  const int cs = P.blk_cell_ptr[blk], ce = P.blk_cell_ptr[blk + 1];
+  const uint32_t cell_bytes = (uint32_t)(7 * nqp * sizeof(double));
+
+  if (t == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = t; i < nq * NA; i += TI) phi_s[i] = P.phi[i];
+  for (int i = t; i < tj * NV2 * ACC_LD; i += TI) acc_s[i] = 0.0;
+  __syncthreads();
+  if (t == 0 && cs < ce) {
+    mbar_expect_tx(&bars[0], cell_bytes);
+    bulk_g2s(cellbuf, P.cellq + (size_t)P.blk_cells[cs] * 7 * nqp, cell_bytes, &bars[0]);
+  }
+  double x[3] = {0, 0, 0};
+  if (row_ok) {
+    x[0] = P.support[(size_t)3 * p];
+    x[1] = P.support[(size_t)3 * p + 1];
+    x[2] = P.support[(size_t)3 * p + 2];
+  }
+  double xim[3] = {x[0], x[1], x[2]};
+  if (KT != BS_KERNEL_FREE) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      if (d == P.kp.o) xim[d] = x[d] - 2.0 * (x[d] - P.kp.wall_pos);  // ref: bem_stokes.cc:2918-2919
+  }
+  const double eps = P.kp.eps;
+  const int o = P.kp.o;
+
+  for (int kc = cs; kc < ce; ++kc) {
+    const int it = kc - cs;
+    const int buf = it & 1;
+    if (t == 0 && kc + 1 < ce) {
+      mbar_expect_tx(&bars[buf ^ 1], cell_bytes);
+      bulk_g2s(cellbuf + (size_t)(buf ^ 1) * 7 * nqp, P.cellq + (size_t)P.blk_cells[kc + 1] * 7 * nqp, cell_bytes,
+               &bars[buf ^ 1]);
+    }
+    const int cell = P.blk_cells[kc];
+    int slot[NA];
+    bool sing = false;
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      slot[a] = P.blk_slots[(size_t)kc * NA + a];
+      sing |= (P.conn_pos[(size_t)cell * NA + a] == p);
+    }
+    mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
+    const double *cq = cellbuf + (size_t)buf * 7 * nqp;
+    if (row_ok && !sing) {  // singular (node in cell) pairs are integrated by K2 (ref: 2885-2908)
+#pragma unroll
+      for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
+        constexpr int NACC = SPLIT ? NV : NV2;
+        double acc[NA][NACC];
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+#pragma unroll
+          for (int v = 0; v < NACC; ++v) acc[a][v] = 0.0;
+#pragma unroll 2
+        for (int q = 0; q < nq; ++q) {
+          double R[3], Rim[3], nJ[3], g[NV], k[NV];
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            const double yq = cq[d * nqp + q];
+            R[d] = yq - x[d];
+            Rim[d] = yq - xim[d];
+            nJ[d] = cq[(3 + d) * nqp + q];
+          }
+          green_eval<KT>(R, Rim, nJ, cq[6 * nqp + q], eps, o, g, k);
+#pragma unroll
+          for (int a = 0; a < NA; ++a) {
+            const double ph = phi_s[q * NA + a];
+            if (!SPLIT) {
+#pragma unroll
+              for (int v = 0; v < NV; ++v) {
+                acc[a][v] = fma(g[v], ph, acc[a][v]);
+                acc[a][NV + v] = fma(k[v], ph, acc[a][NV + v]);
+              }
+            } else {
+#pragma unroll
+              for (int v = 0; v < NV; ++v) acc[a][v] = fma(part == 0 ? g[v] : k[v], ph, acc[a][v]);
+            }
+          }
+        }
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+          if (slot[a] >= 0) {
+            double *dst = acc_s + ((size_t)slot[a] * NV2 + (SPLIT ? part * NV : 0)) * ACC_LD + t;
+#pragma unroll
+            for (int v = 0; v < NACC; ++v) dst[(size_t)v * ACC_LD] += acc[a][v];
+          }
+        }
+      }
+    }
+    __syncthreads();  // everyone is done with cellbuf[buf] before it is refilled two iterations later
+  }
+
+  // ---- write the finished tile: rows 3*(p-p0)+i, columns 3*(blk*tj+slot)+j, 16-byte stores along columns ----
+  const int ncols_tile = 3 * tj;                      // even
+  const int col0 = 3 * blk * tj;
+  const int ncols_valid = min(ncols_tile, 3 * P.N - col0);
+  const int rows_tile = min(TI, P.p1 - (P.p0 + (int)blockIdx.y * TI));
+  const int half = ncols_tile / 2;
+  const int total = rows_tile * 3 * half;
+  for (int e = t; e < total; e += TI) {
+    const int rr = e / half, cp = (e - rr * half) * 2;   // rr = 3*rowlocal + i
+    if (cp >= ncols_valid) continue;
+    const int rl = rr / 3, i = rr - 3 * rl;
+    const int s0 = cp / 3, j0 = cp - 3 * s0;
+    const int c1 = cp + 1, s1 = c1 / 3, j1 = c1 - 3 * s1;
+    const double *a0 = acc_s + ((size_t)s0 * NV2 + vidx<NV>(i, j0)) * ACC_LD + rl;
+    const double *a1 = acc_s + ((size_t)s1 * NV2 + vidx<NV>(i, j1)) * ACC_LD + rl;
+    const size_t row = (size_t)3 * (blockIdx.y * TI + rl) + i;
+    const size_t off = row * P.ld + col0 + cp;
+    if (c1 < ncols_valid) {
+      *reinterpret_cast<double2 *>(P.V + off) = make_double2(a0[0], a1[0]);
+      *reinterpret_cast<double2 *>(P.K + off) = make_double2(a0[(size_t)NV * ACC_LD], a1[(size_t)NV * ACC_LD]);
+    } else {
+      P.V[off] = a0[0];
+      P.K[off] = a0[(size_t)NV * ACC_LD];
+    }
+  }
+}
+
+template <int NA, int KT, bool SPLIT>
+static void launch_reg(Context &c, const RegParams &P, dim3 grid, size_t smem) {
+  auto kern = k_assemble_regular<NA, KT, SPLIT>;
+  BS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, TI, smem, c.stream>>>(P);
+  BS_CUDA(cudaGetLastError());
+}
+
+void launch_assembly_regular(Context &c) {
+  RegParams P;
+  P.p0 = c.p0;
+  P.p1 = c.p1;
+  P.N = c.N;
+  P.nq = c.nq;
+  P.nq_pad = c.nq_pad;
+  P.tj = c.blocks.tj;
+  P.support = c.d_support.p;
+  P.conn_pos = c.d_conn_pos.p;
+  P.cellq = c.d_cellq.p;
+  P.phi = c.d_phi_reg.p;
+  P.blk_cell_ptr = c.d_blk_cell_ptr.p;
+  P.blk_cells = c.d_blk_cells.p;
+  P.blk_slots = c.d_blk_slots.p;
+  P.V = c.V.p;
+  P.K = c.K.p;
+  P.ld = c.ld;
+  P.kp = c.kp;
+  const int nrow_tiles = (c.p1 - c.p0 + TI - 1) / TI;
+  if (nrow_tiles == 0) return;
+  BS_REQUIRE(nrow_tiles <= 65535, "too many row tiles per rank");
+  dim3 grid(c.blocks.nblocks, nrow_tiles);
+  const int nv = (c.kp.type == BS_KERNEL_FREE) ? 6 : 9;
+  const size_t smem = assembly_smem_bytes(c.na, nv, c.blocks.tj, c.nq_pad);
+  const bool q2 = (c.na == 9);
+  switch (c.kp.type) {
+    case BS_KERNEL_FREE:
+      if (q2) launch_reg<9, BS_KERNEL_FREE, true>(c, P, grid, smem);
+      else launch_reg<4, BS_KERNEL_FREE, false>(c, P, grid, smem);
+      break;
+    case BS_KERNEL_FREE_SURFACE:
+      if (q2) launch_reg<9, BS_KERNEL_FREE_SURFACE, true>(c, P, grid, smem);
+      else launch_reg<4, BS_KERNEL_FREE_SURFACE, true>(c, P, grid, smem);
+      break;
+    case BS_KERNEL_NO_SLIP:
+      if (q2) launch_reg<9, BS_KERNEL_NO_SLIP, true>(c, P, grid, smem);
+      else launch_reg<4, BS_KERNEL_NO_SLIP, true>(c, P, grid, smem);
+      break;
+    default:
+      throw Error(BS_ERR_INVALID, "unknown kernel type");
+  }
+  count_launch(c);
+  c.stats.pairs_regular += (long long)(c.p1 - c.p0) * c.ncell * c.nq;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2: singular pass — one warp per owned node, lanes over the points of the singular rule
+// ---------------------------------------------------------------------------------------------------------
+struct SingParams {
+  int p0, p1, N, na, nam;
+  const double *support, *map_nodes;
+  const int *conn_pos, *conn_map;
+  const int *patch_ptr, *patch_cell, *patch_local;
+  const double *tab;          // records of (na + 3*nam + 1) doubles
+  const int *sing_off, *sing_nq;
+  double *V, *K;
+  size_t ld;
+  KernelParams kp;
+};
+
+constexpr int SING_WARPS = 4;
+
+template <int NA, int NAM, int KT>
+__global__ void __launch_bounds__(32 * SING_WARPS) k_assemble_singular(const SingParams P) {
+  constexpr int NV = GreenTraits<KT>::NV;
+  constexpr int NV2 = 2 * NV;
+  constexpr int CH = (NA == 4) ? 4 : 3;          // shape functions per register chunk
+  constexpr int REC = NA + 3 * NAM + 1;
+  __shared__ double red[SING_WARPS][CH * NV2];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int p = P.p0 + blockIdx.x * SING_WARPS + wid;
+  if (p >= P.p1) return;
+  const double x[3] = {P.support[(size_t)3 * p], P.support[(size_t)3 * p + 1], P.support[(size_t)3 * p + 2]};
+  double xim[3] = {x[0], x[1], x[2]};
+  if (KT != BS_KERNEL_FREE) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      if (d == P.kp.o) xim[d] = x[d] - 2.0 * (x[d] - P.kp.wall_pos);
+  }
+  const size_t row0 = (size_t)3 * (p - P.p0);
+  for (int e = P.patch_ptr[p]; e < P.patch_ptr[p + 1]; ++e) {
+    const int cell = P.patch_cell[e], al = P.patch_local[e];
+    const int off = P.sing_off[al], nqs = P.sing_nq[al];
+    double X[NAM][3];
+#pragma unroll
+    for (int a = 0; a < NAM; ++a) {
+      const int m = P.conn_map[(size_t)cell * NAM + a];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) X[a][d] = P.map_nodes[(size_t)3 * m + d];
+    }
+    for (int a0 = 0; a0 < NA; a0 += CH) {
+      double acc[CH][NV2];
+#pragma unroll
+      for (int a = 0; a < CH; ++a)
+#pragma unroll
+        for (int v = 0; v < NV2; ++v) acc[a][v] = 0.0;
+      for (int q = lane; q < nqs; q += 32) {
+        const double *rec = P.tab + (size_t)(off + q) * REC;
+        double y[3] = {0, 0, 0}, t1[3] = {0, 0, 0}, t2[3] = {0, 0, 0};
+#pragma unroll
+        for (int a = 0; a < NAM; ++a) {
+          const double ph = rec[NA + 3 * a], dx = rec[NA + 3 * a + 1], dy = rec[NA + 3 * a + 2];
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            y[d] = fma(ph, X[a][d], y[d]);
+            t1[d] = fma(dx, X[a][d], t1[d]);
+            t2[d] = fma(dy, X[a][d], t2[d]);
+          }
+        }
+        const double w = rec[NA + 3 * NAM];
+        const double nx = t1[1] * t2[2] - t1[2] * t2[1], ny = t1[2] * t2[0] - t1[0] * t2[2],
+                     nz = t1[0] * t2[1] - t1[1] * t2[0];
+        const double JxW = w * sqrt(nx * nx + ny * ny + nz * nz);
+        const double nJ[3] = {w * nx, w * ny, w * nz};
+        double R[3], Rim[3], g[NV], k[NV];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          R[d] = y[d] - x[d];
+          Rim[d] = y[d] - xim[d];
+        }
+        green_eval<KT>(R, Rim, nJ, JxW, P.kp.eps, P.kp.o, g, k);
+#pragma unroll
+        for (int a = 0; a < CH; ++a) {
+          if (a0 + a < NA) {
+            const double ph = rec[a0 + a];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+              acc[a][v] = fma(g[v], ph, acc[a][v]);
+              acc[a][NV + v] = fma(k[v], ph, acc[a][NV + v]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < CH; ++a)
+#pragma unroll
+        for (int v = 0; v < NV2; ++v) {
+          double s = acc[a][v];
+#pragma unroll
+          for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+          if (lane == 0) red[wid][a * NV2 + v] = s;
+        }
+      __syncwarp();
+      // scatter-add: CH shape functions x 3 x 3 entries x 2 matrices
+      for (int idx = lane; idx < CH * 18; idx += 32) {
+        const int a = idx / 18, r = idx - a * 18;
+        const int mat = r / 9, ij = r - mat * 9, i = ij / 3, j = ij - 3 * i;
+        if (a0 + a < NA) {
+          const int cpos = P.conn_pos[(size_t)cell * NA + a0 + a];
+          const double val = red[wid][a * NV2 + mat * NV + vidx<NV>(i, j)];
+          double *M = mat == 0 ? P.V : P.K;
+          M[(row0 + i) * P.ld + (size_t)3 * cpos + j] += val;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <int NA, int NAM, int KT>
+static void launch_sing(Context &c, const SingParams &P) {
+  const int n = c.p1 - c.p0;
+  if (n <= 0) return;
+  k_assemble_singular<NA, NAM, KT><<<(n + SING_WARPS - 1) / SING_WARPS, 32 * SING_WARPS, 0, c.stream>>>(P);
+  BS_CUDA(cudaGetLastError());
+}
+
+template <int KT>
+static void launch_sing_kt(Context &c, const SingParams &P) {
+  if (c.na == 4 && c.na_map == 4) launch_sing<4, 4, KT>(c, P);
+  else if (c.na == 4 && c.na_map == 9) launch_sing<4, 9, KT>(c, P);
+  else if (c.na == 9 && c.na_map == 4) launch_sing<9, 4, KT>(c, P);
+  else launch_sing<9, 9, KT>(c, P);
+}
+
+void launch_assembly_singular(Context &c) {
+  BS_REQUIRE(c.have_singular, "singular quadrature not set");
+  SingParams P;
+  P.p0 = c.p0;
+  P.p1 = c.p1;
+  P.N = c.N;
+  P.na = c.na;
+  P.nam = c.na_map;
+  P.support = c.d_support.p;
+  P.map_nodes = c.d_map_nodes.p;
+  P.conn_pos = c.d_conn_pos.p;
+  P.conn_map = c.d_conn_map.p;
+  P.patch_ptr = c.d_patch_ptr.p;
+  P.patch_cell = c.d_patch_cell.p;
+  P.patch_local = c.d_patch_local.p;
+  P.tab = c.d_sing_tab.p;
+  P.sing_off = c.d_sing_off.p;
+  P.sing_nq = c.d_sing_nq.p;
+  P.V = c.V.p;
+  P.K = c.K.p;
+  P.ld = c.ld;
+  P.kp = c.kp;
+  switch (c.kp.type) {
+    case BS_KERNEL_FREE: launch_sing_kt<BS_KERNEL_FREE>(c, P); break;
+    case BS_KERNEL_FREE_SURFACE: launch_sing_kt<BS_KERNEL_FREE_SURFACE>(c, P); break;
+    case BS_KERNEL_NO_SLIP: launch_sing_kt<BS_KERNEL_NO_SLIP>(c, P); break;
+    default: throw Error(BS_ERR_INVALID, "unknown kernel type");
+  }
+  count_launch(c);
+  long long pairs = 0;
+  for (int a = 0; a < c.na; ++a) pairs += c.sing_nq[a];
+  c.stats.pairs_singular += pairs * c.ncell;  // every cell has one singular node per local index
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// bs_kernel_eval: G (9) and W (27) through the same device functions (W_ijk = S_ij with n = e_k, sign restored)
+// ---------------------------------------------------------------------------------------------------------
+template <int KT>
+__device__ void eval_one(const double *p, const double *pim, double eps, int o, double *G, double *W) {
+  constexpr int NV = GreenTraits<KT>::NV;
+  double R[3] = {p[0], p[1], p[2]}, Q[3] = {pim[0], pim[1], pim[2]};
+  for (int kk = 0; kk < 3; ++kk) {
+    double nJ[3] = {kk == 0 ? 1.0 : 0.0, kk == 1 ? 1.0 : 0.0, kk == 2 ? 1.0 : 0.0};
+    double g[NV], k[NV];
+    green_eval<KT>(R, Q, nJ, 1.0, eps, o, g, k);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        if (G && kk == 0) G[3 * i + j] = g[vidx<NV>(i, j)];
+        if (W) W[9 * i + 3 * j + kk] = -k[vidx<NV>(i, j)];
+      }
+  }
+}
+
+__global__ void k_kernel_eval(int type, double eps, int o, int npts, const double *p, const double *pim, double *G,
+                              double *W) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npts) return;
+  double *Gi = G ? G + 9 * (size_t)i : nullptr, *Wi = W ? W + 27 * (size_t)i : nullptr;
+  const double *pi_ = pim ? pim + 3 * (size_t)i : p + 3 * (size_t)i;
+  if (type == BS_KERNEL_FREE) eval_one<BS_KERNEL_FREE>(p + 3 * (size_t)i, pi_, eps, o, Gi, Wi);
+  else if (type == BS_KERNEL_FREE_SURFACE) eval_one<BS_KERNEL_FREE_SURFACE>(p + 3 * (size_t)i, pi_, eps, o, Gi, Wi);
+  else eval_one<BS_KERNEL_NO_SLIP>(p + 3 * (size_t)i, pi_, eps, o, Gi, Wi);
+}
+
+void kernel_eval_device(int type, double eps, int o, int npts, const double *d_p, const double *d_pim, double *d_G,
+                        double *d_W, cudaStream_t s) {
+  k_kernel_eval<<<(npts + 127) / 128, 128, 0, s>>>(type, eps, o, npts, d_p, d_pim, d_G, d_W);
+  BS_CUDA(cudaGetLastError());
+}
+
+}  // namespace bs

@@ -1,0 +1,449 @@
+// Host-side logic of the hot path: quadrature rules with deal.II semantics, FE_Q shape tables, locality
+// ordering / row partition, column-block and singular-patch tables.  Integer / O(N) work only; all
+// floating-point assembly work happens in bs_assembly.cu on the device.
+#include "bs_internal.h"
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+namespace bs {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string &m) { g_last_error = m; }
+const std::string &get_last_error() { return g_last_error; }
+
+// ---------------------------------------------------------------------------------------------------------
+// 1-D Gauss-Legendre on [0,1] (deal.II QGauss<1>): Newton on Legendre polynomials
+// ---------------------------------------------------------------------------------------------------------
+void gauss_legendre_01(int n, std::vector<double> &x, std::vector<double> &w) {
+  BS_REQUIRE(n >= 1 && n <= 256, "gauss order out of range");
+  x.assign(n, 0.0);
+  w.assign(n, 0.0);
+  const long double pi = 3.14159265358979323846264338327950288L;
+  for (int i = 0; i < (n + 1) / 2; ++i) {
+    long double z = cosl(pi * (i + 0.75L) / (n + 0.5L));
+    long double pp = 0;
+    for (int it = 0; it < 100; ++it) {
+      long double p1 = 1.0L, p2 = 0.0L;
+      for (int j = 1; j <= n; ++j) {
+        long double p3 = p2;
+        p2 = p1;
+        p1 = ((2.0L * j - 1.0L) * z * p2 - (j - 1.0L) * p3) / j;
+      }
+      pp = n * (z * p1 - p2) / (z * z - 1.0L);
+      long double z1 = z;
+      z = z1 - p1 / pp;
+      if (fabsl(z - z1) < 1e-19L) break;
+    }
+    long double wi = 2.0L / ((1.0L - z * z) * pp * pp);
+    x[i] = (double)((1.0L - z) / 2.0L);
+    x[n - 1 - i] = (double)((1.0L + z) / 2.0L);
+    w[i] = w[n - 1 - i] = (double)(wi / 2.0L);
+  }
+}
+
+Rule2D tensor_rule2(const std::vector<double> &x1, const std::vector<double> &w1, const std::vector<double> &x2,
+                    const std::vector<double> &w2) {
+  Rule2D r;
+  for (size_t j = 0; j < x2.size(); ++j)
+    for (size_t i = 0; i < x1.size(); ++i) {  // first coordinate fastest
+      r.xi.push_back(x1[i]);
+      r.xi.push_back(x2[j]);
+      r.w.push_back(w1[i] * w2[j]);
+    }
+  return r;
+}
+Rule2D tensor_rule(const std::vector<double> &x1, const std::vector<double> &w1) { return tensor_rule2(x1, w1, x1, w1); }
+
+// QGaussOneOverR<2>(n, vertex_index, factor_out_singular_weight=true): Lachat-Watson
+static Rule2D lw_vertex(int n, int v) {
+  std::vector<double> x, w;
+  gauss_legendre_01(n, x, w);
+  Rule2D g = tensor_rule(x, w);
+  const double pi4 = M_PI / 4.0;
+  const int m = g.size();
+  Rule2D r;
+  r.xi.resize(4 * m);
+  r.w.resize(2 * m);
+  for (int q = 0; q < m; ++q) {
+    double u = g.xi[2 * q], t = g.xi[2 * q + 1];
+    double px = u, py = u * std::tan(pi4 * t);
+    double ww = g.w[q] * pi4 / std::cos(pi4 * t);
+    ww *= std::sqrt(px * px + py * py);
+    r.xi[2 * q] = px;
+    r.xi[2 * q + 1] = py;
+    r.w[q] = ww;
+    r.xi[2 * (m + q)] = py;
+    r.xi[2 * (m + q) + 1] = px;
+    r.w[m + q] = ww;
+  }
+  double theta = 0;
+  if (v == 1) theta = M_PI / 2;
+  if (v == 2) theta = -M_PI / 2;
+  if (v == 3) theta = M_PI;
+  if (v != 0) {
+    double c = std::cos(theta), s = std::sin(theta);
+    for (int q = 0; q < 2 * m; ++q) {
+      double X = r.xi[2 * q] - .5, Y = r.xi[2 * q + 1] - .5;
+      r.xi[2 * q] = c * X - s * Y + .5;
+      r.xi[2 * q + 1] = s * X + c * Y + .5;
+    }
+  }
+  return r;
+}
+
+// QGaussOneOverR<2>(n, Point<2> singularity, true)
+static Rule2D lw_point(int n, double sx, double sy) {
+  Rule2D quads[4] = {lw_vertex(n, 3), lw_vertex(n, 2), lw_vertex(n, 1), lw_vertex(n, 0)};
+  const double ox[4] = {0, sx, 0, sx}, oy[4] = {0, 0, sy, sy};
+  const double vx[4] = {0, 1, 0, 1}, vy[4] = {0, 0, 1, 1};
+  Rule2D r;
+  for (int b = 0; b < 4; ++b) {
+    double dx = std::fabs(sx - vx[b]), dy = std::fabs(sy - vy[b]);
+    double area = dx * dy;
+    if (area > 1e-8)
+      for (int q = 0; q < quads[b].size(); ++q) {
+        r.xi.push_back(ox[b] + dx * quads[b].xi[2 * q]);
+        r.xi.push_back(oy[b] + dy * quads[b].xi[2 * q + 1]);
+        r.w.push_back(quads[b].w[q] * area);
+      }
+  }
+  return r;
+}
+
+// QTelles<1>(n, s)
+static void telles_1d(int n, double s, std::vector<double> &xo, std::vector<double> &wo) {
+  std::vector<double> x, w;
+  gauss_legendre_01(n, x, w);
+  xo.clear();
+  wo.clear();
+  const double eb = 2 * s - 1, es = eb * eb - 1;
+  const double gb = std::cbrt(eb * es + std::fabs(es)) + std::cbrt(eb * es - std::fabs(es)) + eb;
+  for (int q = 0; q < n; ++q) {
+    if (!(std::fabs(x[q] - s) > 1e-10)) continue;
+    double g = 2 * x[q] - 1;
+    double d = g - gb;
+    double eta = (d * d * d + gb * (gb * gb + 3)) / (1 + 3 * gb * gb);
+    double J = 3 * d * d / (1 + 3 * gb * gb);
+    xo.push_back((eta + 1) / 2);
+    wo.push_back(J * w[q]);
+  }
+}
+
+// QSplit<2>(QDuffy(n, 1.), s)
+static Rule2D qsplit_duffy(int n, double sx, double sy) {
+  std::vector<double> x, w;
+  gauss_legendre_01(n, x, w);
+  Rule2D g = tensor_rule(x, w);
+  const double vx[4] = {0, 1, 0, 1}, vy[4] = {0, 0, 1, 1};
+  const int f[4][2] = {{0, 2}, {1, 3}, {0, 1}, {2, 3}};
+  Rule2D r;
+  for (int k = 0; k < 4; ++k) {
+    double b00 = vx[f[k][0]] - sx, b10 = vy[f[k][0]] - sy;  // first column
+    double b01 = vx[f[k][1]] - sx, b11 = vy[f[k][1]] - sy;  // second column
+    double J = std::fabs(b00 * b11 - b01 * b10);
+    if (J < 1e-12) continue;
+    for (int q = 0; q < g.size(); ++q) {
+      double xh = g.xi[2 * q], yh = g.xi[2 * q + 1];
+      double X = xh * (1 - yh), Y = xh * yh;  // beta = 1
+      r.xi.push_back(sx + b00 * X + b01 * Y);
+      r.xi.push_back(sy + b10 * X + b11 * Y);
+      r.w.push_back(g.w[q] * xh * J);
+    }
+  }
+  return r;
+}
+
+static Rule2D qiterated(int n, int k) {
+  std::vector<double> x, w, xs, ws;
+  gauss_legendre_01(n, x, w);
+  for (int i = 0; i < k; ++i)
+    for (int q = 0; q < n; ++q) {
+      xs.push_back((x[q] + i) / k);
+      ws.push_back(w[q] / k);
+    }
+  return tensor_rule(xs, ws);
+}
+
+int n_shape(int degree) { return degree == 1 ? 4 : 9; }
+
+void unit_support_point(int degree, int a, double &sx, double &sy) {
+  static const double q1[4][2] = {{0, 0}, {1, 0}, {0, 1}, {1, 1}};
+  static const double q2[9][2] = {{0, 0}, {1, 0}, {0, 1}, {1, 1}, {0, .5}, {1, .5}, {.5, 0}, {.5, 1}, {.5, .5}};
+  if (degree == 1) {
+    sx = q1[a][0];
+    sy = q1[a][1];
+  } else {
+    sx = q2[a][0];
+    sy = q2[a][1];
+  }
+}
+
+// ref: BEMProblem<3>::get_singular_quadrature, source/bem_stokes.cc:4912-4957
+Rule2D make_singular_rule(int kind, int order, int fe_degree, int a) {
+  BS_REQUIRE(fe_degree == 1 || fe_degree == 2, "fe_degree must be 1 or 2");
+  BS_REQUIRE(a >= 0 && a < n_shape(fe_degree), "local index out of range");
+  BS_REQUIRE(order >= 1 && order <= 64, "singular quadrature order out of range");
+  double sx, sy;
+  unit_support_point(fe_degree, a, sx, sy);
+  if (kind == BS_SING_MIXED) return fe_degree > 1 ? qiterated(order, fe_degree) : lw_point(order, sx, sy);
+  if (kind == BS_SING_DUFFY) return qsplit_duffy(order, sx, sy);
+  if (kind == BS_SING_TELLES) {
+    std::vector<double> x1, w1, x2, w2;
+    telles_1d(order, sx, x1, w1);
+    telles_1d(order, sy, x2, w2);
+    return tensor_rule2(x1, w1, x2, w2);
+  }
+  throw Error(BS_ERR_INVALID, "unknown singular quadrature kind");
+}
+
+static void lagrange_1d(int degree, double x, double *l, double *d) {
+  if (degree == 1) {
+    l[0] = 1 - x;
+    l[1] = x;
+    d[0] = -1;
+    d[1] = 1;
+  } else {
+    l[0] = 2 * (x - .5) * (x - 1);
+    l[1] = -4 * x * (x - 1);
+    l[2] = 2 * x * (x - .5);
+    d[0] = 4 * x - 3;
+    d[1] = -8 * x + 4;
+    d[2] = 4 * x - 1;
+  }
+}
+
+void shape_eval(int degree, double x, double y, double *phi, double *dphi) {
+  double lx[3], dx[3], ly[3], dy[3];
+  lagrange_1d(degree, x, lx, dx);
+  lagrange_1d(degree, y, ly, dy);
+  const int na = n_shape(degree);
+  for (int a = 0; a < na; ++a) {
+    double sx, sy;
+    unit_support_point(degree, a, sx, sy);
+    int ix = (int)std::lround(sx * degree), iy = (int)std::lround(sy * degree);
+    phi[a] = lx[ix] * ly[iy];
+    if (dphi) {
+      dphi[2 * a] = dx[ix] * ly[iy];
+      dphi[2 * a + 1] = lx[ix] * dy[iy];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// geometry: support points, locality order, partition
+// ---------------------------------------------------------------------------------------------------------
+static inline uint64_t spread3(uint64_t v) {
+  v &= 0x1fffffULL;
+  v = (v | v << 32) & 0x1f00000000ffffULL;
+  v = (v | v << 16) & 0x1f0000ff0000ffULL;
+  v = (v | v << 8) & 0x100f00f00f00f00fULL;
+  v = (v | v << 4) & 0x10c30c30c30c30c3ULL;
+  v = (v | v << 2) & 0x1249249249249249ULL;
+  return v;
+}
+
+void build_geometry(Context &c) {
+  const int N = c.N, na = c.na, nam = c.na_map;
+  // support points = mapped unit support points (ref: DoFTools::map_dofs_to_support_points, bem_stokes.cc:2855)
+  c.support.assign((size_t)3 * N, 0.0);
+  std::vector<double> phi((size_t)na * nam);
+  for (int a = 0; a < na; ++a) {
+    double sx, sy;
+    unit_support_point(c.fe_degree, a, sx, sy);
+    shape_eval(c.map_degree, sx, sy, &phi[(size_t)a * nam], nullptr);
+  }
+  std::vector<char> seen(N, 0);
+  for (int cell = 0; cell < c.ncell; ++cell)
+    for (int a = 0; a < na; ++a) {
+      int i = c.conn[(size_t)cell * na + a];
+      BS_REQUIRE(i >= 0 && i < N, "conn_stokes entry out of range");
+      if (seen[i]) continue;
+      seen[i] = 1;
+      double p[3] = {0, 0, 0};
+      for (int b = 0; b < nam; ++b) {
+        int m = c.conn_map[(size_t)cell * nam + b];
+        BS_REQUIRE(m >= 0 && m < c.Nmap, "conn_map entry out of range");
+        for (int d = 0; d < 3; ++d) p[d] += phi[(size_t)a * nam + b] * c.map_nodes[(size_t)3 * m + d];
+      }
+      for (int d = 0; d < 3; ++d) c.support[(size_t)3 * i + d] = p[d];
+    }
+  for (int i = 0; i < N; ++i) BS_REQUIRE(seen[i], "node without a cell");
+
+  // Morton order of the support points -> spatially compact column blocks and row partitions
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int i = 0; i < N; ++i)
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = std::min(lo[d], c.support[(size_t)3 * i + d]);
+      hi[d] = std::max(hi[d], c.support[(size_t)3 * i + d]);
+    }
+  double ext = std::max({hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2], 1e-300});
+  std::vector<uint64_t> code(N);
+  for (int i = 0; i < N; ++i) {
+    uint64_t k = 0;
+    for (int d = 0; d < 3; ++d) {
+      double t = (c.support[(size_t)3 * i + d] - lo[d]) / ext;
+      uint64_t q = (uint64_t)std::min(2097151.0, std::max(0.0, t * 2097151.0));
+      k |= spread3(q) << d;
+    }
+    code[i] = k;
+  }
+  std::vector<int> owner(N, 0);
+  const bool user_owner = !c.owner_in.empty();
+  if (user_owner) {
+    BS_REQUIRE((int)c.owner_in.size() == N, "owner_of_node length != n_nodes");
+    owner = c.owner_in;
+    for (int i = 0; i < N; ++i) BS_REQUIRE(owner[i] >= 0 && owner[i] < c.nranks, "owner_of_node out of range");
+  }
+  c.node_of_pos.resize(N);
+  std::iota(c.node_of_pos.begin(), c.node_of_pos.end(), 0);
+  std::stable_sort(c.node_of_pos.begin(), c.node_of_pos.end(), [&](int a, int b) {
+    if (owner[a] != owner[b]) return owner[a] < owner[b];
+    return code[a] < code[b];
+  });
+  c.pos_of_node.resize(N);
+  for (int p = 0; p < N; ++p) c.pos_of_node[c.node_of_pos[p]] = p;
+  c.part_start.assign(c.nranks + 1, 0);
+  if (user_owner) {
+    for (int i = 0; i < N; ++i) c.part_start[owner[i] + 1]++;
+    for (int r = 0; r < c.nranks; ++r) c.part_start[r + 1] += c.part_start[r];
+  } else {
+    for (int r = 0; r <= c.nranks; ++r) c.part_start[r] = (int)(((long long)N * r) / c.nranks);
+  }
+  c.p0 = c.part_start[c.rank];
+  c.p1 = c.part_start[c.rank + 1];
+  c.rows_loc = (size_t)3 * (c.p1 - c.p0);
+
+  // upload
+  std::vector<double> sup_int((size_t)3 * N);
+  for (int p = 0; p < N; ++p)
+    for (int d = 0; d < 3; ++d) sup_int[(size_t)3 * p + d] = c.support[(size_t)3 * c.node_of_pos[p] + d];
+  c.d_support.upload(sup_int, c.stream);
+  c.d_map_nodes.upload(c.map_nodes, c.stream);
+  std::vector<int> conn_pos(c.conn.size());
+  for (size_t k = 0; k < c.conn.size(); ++k) conn_pos[k] = c.pos_of_node[c.conn[k]];
+  c.d_conn_pos.upload(conn_pos, c.stream);
+  c.d_conn_map.upload(c.conn_map, c.stream);
+
+  // patches (cells containing a node + FIRST local index, ref: bem_stokes.cc:2885-2895) by internal position
+  std::vector<int> cnt(N + 1, 0);
+  for (int cell = 0; cell < c.ncell; ++cell)
+    for (int a = 0; a < na; ++a) {
+      int p = conn_pos[(size_t)cell * na + a];
+      bool first = true;
+      for (int b = 0; b < a; ++b)
+        if (conn_pos[(size_t)cell * na + b] == p) first = false;
+      if (first) cnt[p + 1]++;
+    }
+  for (int p = 0; p < N; ++p) cnt[p + 1] += cnt[p];
+  std::vector<int> pc(cnt[N]), pl(cnt[N]), fill(cnt.begin(), cnt.end() - 1);
+  for (int cell = 0; cell < c.ncell; ++cell)
+    for (int a = 0; a < na; ++a) {
+      int p = conn_pos[(size_t)cell * na + a];
+      bool first = true;
+      for (int b = 0; b < a; ++b)
+        if (conn_pos[(size_t)cell * na + b] == p) first = false;
+      if (!first) continue;
+      pc[fill[p]] = cell;
+      pl[fill[p]] = a;
+      fill[p]++;
+    }
+  c.d_patch_ptr.upload(cnt, c.stream);
+  c.d_patch_cell.upload(pc, c.stream);
+  c.d_patch_local.upload(pl, c.stream);
+  BS_CUDA(cudaStreamSynchronize(c.stream));
+  c.have_geometry = true;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tables depending on quadrature: regular shape tables, column blocks, singular rule tables
+// ---------------------------------------------------------------------------------------------------------
+void build_tables(Context &c) {
+  BS_REQUIRE(c.have_geometry && c.have_quadrature, "geometry and quadrature must be set first");
+  const int na = c.na, nam = c.na_map, nq = c.reg.size();
+  c.nq = nq;
+  c.nq_pad = (nq + 1) & ~1;  // keep every 7*nq_pad*8-byte cell record a multiple of 16 B for bulk copies
+  std::vector<double> phi((size_t)nq * na), tab((size_t)nq * nam * 3);
+  std::vector<double> ph(MAX_NA), dph(2 * MAX_NA);
+  for (int q = 0; q < nq; ++q) {
+    shape_eval(c.fe_degree, c.reg.xi[2 * q], c.reg.xi[2 * q + 1], ph.data(), nullptr);
+    for (int a = 0; a < na; ++a) phi[(size_t)q * na + a] = ph[a];
+    shape_eval(c.map_degree, c.reg.xi[2 * q], c.reg.xi[2 * q + 1], ph.data(), dph.data());
+    for (int a = 0; a < nam; ++a) {
+      tab[((size_t)q * nam + a) * 3 + 0] = ph[a];
+      tab[((size_t)q * nam + a) * 3 + 1] = dph[2 * a];
+      tab[((size_t)q * nam + a) * 3 + 2] = dph[2 * a + 1];
+    }
+  }
+  c.d_phi_reg.upload(phi, c.stream);
+  c.d_map_tab_reg.upload(tab, c.stream);
+
+  // column blocks: tj consecutive column positions; cell list = union of their patches, in ascending cell id
+  ColumnBlocks &B = c.blocks;
+  B.tj = choose_tj(na, c.kp.type, c.nq_pad);
+  B.nblocks = (c.N + B.tj - 1) / B.tj;
+  B.cell_ptr.assign(1, 0);
+  B.cells.clear();
+  B.slots.clear();
+  B.max_cells = 0;
+  std::vector<std::vector<int>> cells_of_block(B.nblocks);
+  for (int cell = 0; cell < c.ncell; ++cell) {
+    int last = -1;
+    // a cell belongs to the block of each of its nodes
+    int blks[MAX_NA];
+    int nb = 0;
+    for (int a = 0; a < na; ++a) {
+      int b = c.pos_of_node[c.conn[(size_t)cell * na + a]] / B.tj;
+      bool dup = false;
+      for (int k = 0; k < nb; ++k) dup |= (blks[k] == b);
+      if (!dup) blks[nb++] = b;
+    }
+    (void)last;
+    for (int k = 0; k < nb; ++k) cells_of_block[blks[k]].push_back(cell);
+  }
+  for (int b = 0; b < B.nblocks; ++b) {
+    for (int cell : cells_of_block[b]) {
+      B.cells.push_back(cell);
+      for (int a = 0; a < na; ++a) {
+        int p = c.pos_of_node[c.conn[(size_t)cell * na + a]];
+        B.slots.push_back((p / B.tj == b) ? (signed char)(p % B.tj) : (signed char)-1);
+      }
+    }
+    B.cell_ptr.push_back((int)B.cells.size());
+    B.max_cells = std::max(B.max_cells, (int)cells_of_block[b].size());
+  }
+  c.d_blk_cell_ptr.upload(B.cell_ptr, c.stream);
+  c.d_blk_cells.upload(B.cells, c.stream);
+  c.d_blk_slots.upload(B.slots, c.stream);
+
+  // singular rule tables: per rule, per point: phi[na], then (phi_map, dphi_x, dphi_y)[na_map], then weight
+  if (c.have_singular) {
+    BS_REQUIRE((int)c.sing.size() == na, "one singular rule per scalar local index required");
+    const int rec = na + 3 * nam + 1;
+    std::vector<double> st;
+    c.sing_off.assign(na, 0);
+    c.sing_nq.assign(na, 0);
+    for (int a = 0; a < na; ++a) {
+      c.sing_off[a] = (int)(st.size() / rec);
+      c.sing_nq[a] = c.sing[a].size();
+      for (int q = 0; q < c.sing[a].size(); ++q) {
+        double x = c.sing[a].xi[2 * q], y = c.sing[a].xi[2 * q + 1];
+        shape_eval(c.fe_degree, x, y, ph.data(), nullptr);
+        for (int b = 0; b < na; ++b) st.push_back(ph[b]);
+        shape_eval(c.map_degree, x, y, ph.data(), dph.data());
+        for (int b = 0; b < nam; ++b) {
+          st.push_back(ph[b]);
+          st.push_back(dph[2 * b]);
+          st.push_back(dph[2 * b + 1]);
+        }
+        st.push_back(c.sing[a].w[q]);
+      }
+    }
+    c.d_sing_tab.upload(st, c.stream);
+    c.d_sing_off.upload(c.sing_off, c.stream);
+    c.d_sing_nq.upload(c.sing_nq, c.stream);
+  }
+  BS_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+}  // namespace bs

@@ -1,0 +1,262 @@
+// Internal declarations of libbemstokes_b200 (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <stdexcept>
+#include "../../include/bemstokes_b200.h"
+
+namespace bs {
+
+// ---------------------------------------------------------------------------------------------------------
+// errors: C++ exceptions inside, status codes at the ABI
+// ---------------------------------------------------------------------------------------------------------
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+void set_last_error(const std::string &m);
+
+#define BS_CUDA(call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      throw bs::Error(BS_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " at " + __FILE__ + \
+                                       ":" + std::to_string(__LINE__));                                 \
+  } while (0)
+#define BS_REQUIRE(cond, msg)                                          \
+  do {                                                                 \
+    if (!(cond)) throw bs::Error(BS_ERR_INVALID, std::string(msg));    \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// device buffer
+// ---------------------------------------------------------------------------------------------------------
+template <class T>
+struct DBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  DBuf() = default;
+  DBuf(const DBuf &) = delete;
+  DBuf &operator=(const DBuf &) = delete;
+  ~DBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void alloc(size_t count) {
+    if (count == n && p) return;
+    release();
+    if (count) BS_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+    n = count;
+  }
+  void upload(const std::vector<T> &h, cudaStream_t s) {
+    alloc(h.size());
+    if (h.size()) BS_CUDA(cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void upload(const T *h, size_t count, cudaStream_t s) {
+    alloc(count);
+    if (count) BS_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void zero(cudaStream_t s) {
+    if (n) BS_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+  }
+};
+
+// Row-block of a dense matrix, row-major, leading dimension ld (doubles), internal (node-major) ordering.
+struct DMat {
+  double *p = nullptr;
+  size_t rows = 0, cols = 0, ld = 0;
+  bool owned = false;
+  bool valid() const { return p != nullptr; }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// host-side rule / shape tables
+// ---------------------------------------------------------------------------------------------------------
+struct Rule2D {
+  std::vector<double> xi;  // [nq][2]
+  std::vector<double> w;   // [nq]
+  int size() const { return (int)w.size(); }
+};
+void gauss_legendre_01(int n, std::vector<double> &x, std::vector<double> &w);
+Rule2D tensor_rule(const std::vector<double> &x1, const std::vector<double> &w1);
+Rule2D make_singular_rule(int kind, int order, int fe_degree, int local_index);
+int n_shape(int degree);
+void unit_support_point(int degree, int a, double &sx, double &sy);
+// phi[a], dphi[a][2] of scalar FE_Q(degree) at (x,y), deal.II dof order
+void shape_eval(int degree, double x, double y, double *phi, double *dphi);
+
+// ---------------------------------------------------------------------------------------------------------
+// Green-kernel parameters (device-visible POD)
+// ---------------------------------------------------------------------------------------------------------
+struct KernelParams {
+  int type = BS_KERNEL_FREE;
+  double eps = 0.0;
+  int o = 1;             // wall orientation
+  double wall_pos = 0.0; // wall_positions[0][o]
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// assembly tiling constants
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TI = 128;       // row nodes per CTA (one per thread)
+constexpr int MAX_NA = 9;     // Q2
+constexpr int MAX_RIGID = 7;
+
+struct ColumnBlocks {
+  int tj = 0;                       // column nodes per block
+  int nblocks = 0;
+  std::vector<int> cell_ptr;        // [nblocks+1]
+  std::vector<int> cells;           // concatenated cell ids
+  std::vector<signed char> slots;   // [ncells_total][na] slot in block or -1
+  int max_cells = 0;
+};
+
+struct Context {
+  int device = 0;
+  int fe_degree = 1, map_degree = 1;
+  int na = 4, na_map = 4;
+  int pointer_mode = BS_PTR_HOST;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+
+  // partition
+  int rank = 0, nranks = 1;
+  std::vector<int> owner_in;        // user supplied owner_of_node (may be empty)
+  // geometry (host copies)
+  int N = 0, Nmap = 0, ncell = 0;
+  std::vector<double> map_nodes;    // [Nmap][3]
+  std::vector<int> conn_map, conn;  // original ids
+  std::vector<int> material;
+  std::vector<double> support;      // [N][3] original order
+  std::vector<int> pos_of_node;     // original node id -> internal position
+  std::vector<int> node_of_pos;     // internal position -> original node id
+  std::vector<int> part_start;      // [nranks+1] internal position ranges
+  int p0 = 0, p1 = 0;               // my node-position range
+  bool have_geometry = false;
+
+  // quadrature
+  std::vector<double> x1d, w1d;
+  Rule2D reg;
+  std::vector<Rule2D> sing;         // per scalar local index
+  bool have_quadrature = false, have_singular = false;
+  KernelParams kp;
+
+  // device geometry
+  DBuf<double> d_support;           // [N][3] internal order
+  DBuf<double> d_map_nodes;         // [Nmap][3]
+  DBuf<int> d_conn_pos;             // [ncell][na] internal positions
+  DBuf<int> d_conn_map;             // [ncell][na_map]
+  DBuf<double> d_cellq;             // [ncell][7][nq_pad]
+  DBuf<double> d_phi_reg;           // [nq][na]
+  DBuf<double> d_map_tab_reg;       // [nq][na_map][3]  (phi, dphi_x, dphi_y)
+  int nq = 0, nq_pad = 0;
+  ColumnBlocks blocks;
+  DBuf<int> d_blk_cell_ptr, d_blk_cells;
+  DBuf<signed char> d_blk_slots;
+  // singular pass tables
+  DBuf<int> d_patch_ptr, d_patch_cell, d_patch_local;   // per internal position (CSR)
+  DBuf<double> d_sing_tab;          // concatenated per rule: [nqs][ (na + 3*na_map + 1) ]
+  std::vector<int> sing_off, sing_nq;
+  DBuf<int> d_sing_off, d_sing_nq;
+
+  // matrices (row block of this rank, internal ordering)
+  size_t ld = 0;                    // leading dimension (doubles)
+  size_t rows_loc = 0;              // 3*(p1-p0)
+  DBuf<double> storeV, storeK, storeA;
+  DMat V, K, A;
+  int num_rigid = 0;
+  bool A_aliases_V = false;
+  bool has_rigid_rows = false;      // this rank stores the rigid rows (last rank)
+  size_t mono_size = 0;             // 3N + num_rigid
+
+  // projector data (internal ordering, full length 3N)
+  DBuf<double> d_nhat, d_Mnhat;
+  double l2gamma = 0.0;
+  bool have_projector = false;
+
+  // preconditioner
+  int prec_kind = BS_PREC_NONE;
+  int prec_which = BS_MAT_A;
+  DBuf<double> d_prec_diag;         // Jacobi
+  DBuf<double> d_lu;                // LU factors (full matrix, single GPU) or local diagonal block
+  DBuf<int> d_piv;
+  size_t lu_n = 0;
+
+  // comm
+  bs_allgatherv_fn cb_allgatherv = nullptr;
+  bs_allreduce_sum_fn cb_allreduce = nullptr;
+  void *cb_user = nullptr;
+  std::vector<void *> peer_xbuf, peer_flags;
+  DBuf<double> d_xchg;              // replicated vector buffer (exchange target)
+  DBuf<unsigned long long> d_flags;
+
+  // scratch
+  DBuf<double> d_tmp0, d_tmp1, d_tmp2, d_tmp3;
+  DBuf<double> d_small;             // small reductions
+  double *h_pinned = nullptr;       // pinned host scratch
+  size_t h_pinned_n = 0;
+
+  void *extra = nullptr;            // bs_api.cu private scratch
+  bs_stats stats{};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  size_t n3() const { return (size_t)3 * N; }
+  size_t local_vec_len(int which) const;     // length of this rank's slice of a `which` vector
+  size_t full_vec_len(int which) const;
+  size_t slice_offset(int which) const;      // offset of my slice in the full internal vector
+};
+
+// ---- geometry / tables (bs_host.cu) ---------------------------------------------------------------------
+void build_geometry(Context &c);
+void build_tables(Context &c);          // after geometry + quadrature known
+// ---- assembly (bs_assembly.cu) ---------------------------------------------------------------------------
+void launch_cell_geometry(Context &c);
+void launch_assembly_regular(Context &c);
+void launch_assembly_singular(Context &c);
+size_t assembly_smem_bytes(int na, int nv, int tj, int nq_pad);
+int choose_tj(int na, int kernel_type, int nq_pad);
+void kernel_eval_device(int type, double eps, int o, int npts, const double *d_p, const double *d_pim, double *d_G,
+                        double *d_W, cudaStream_t s);
+// ---- linear algebra (bs_linalg.cu) ------------------------------------------------------------------------
+void gemv(Context &c, const DMat &M, const double *x, double *y);                  // y[rows] = M x
+void gemv_multi(Context &c, const DMat &M, int nrhs, const double *X, size_t ldx, double *Y, size_t ldy);
+void rank1_update(Context &c, DMat &M, const double *u, const double *w, double scale);  // M += scale u w^T
+void perm_in(Context &c, const double *src_dev, double *dst_int, const int *d_node_of_pos, int nextra);
+void perm_out(Context &c, const double *src_int, double *dst_dev, const int *d_node_of_pos, int nextra, size_t lo, size_t hi);
+double dot(Context &c, const double *a, const double *b, size_t n);                // device sync + host result
+void multi_dot(Context &c, const double *basis, size_t ldb, int k, const double *w, size_t n, double *d_out);
+void multi_axpy(Context &c, const double *basis, size_t ldb, int k, const double *d_coef, double sign, double *w, size_t n);
+void axpy(Context &c, double a, const double *x, double *y, size_t n);
+void scal(Context &c, double a, double *x, size_t n);
+void scal_dev_inv(Context &c, const double *d_s, double *x, const double *src, size_t n);  // x = src / *d_s
+void copy(Context &c, const double *src, double *dst, size_t n);
+void sub(Context &c, const double *a, const double *b, double *out, size_t n);      // out = a - b
+void mul_elem(Context &c, const double *a, const double *d, double *out, size_t n); // out = a*d
+void fill(Context &c, double *x, double v, size_t n);
+void k_correct_diag(Context &c, DMat &K, const double *Ck /*[3][rows] internal*/, int use_internal_alpha);
+void extract_diag(Context &c, const DMat &M, size_t row_offset, double *d_out);
+void select_columns(Context &c, DMat &A, const DMat &V, const DMat &K, const unsigned char *d_flag, bool alias);
+void set_column(Context &c, DMat &A, size_t col, const double *v, double scale);
+void gather_entries(Context &c, const DMat &M, int n, const int *d_r, const int *d_c, double *d_out);
+// ---- solvers (bs_solve.cu) --------------------------------------------------------------------------------
+void lu_factor(Context &c, double *A, size_t n, size_t ld, int *piv);
+void lu_solve(Context &c, const double *LU, size_t n, size_t ld, const int *piv, double *x /* in/out */);
+void apply_operator(Context &c, int which, const double *x_full, double *y_loc);
+void exchange(Context &c, int which, const double *y_loc, double *x_full);
+void apply_precond(Context &c, const double *in_loc, double *out_loc);
+int gmres(Context &c, int which, const double *d_b_loc, double *d_x_loc, double tol, int max_steps, int max_tmp,
+          int *iters, double *final_res);
+void count_launch(Context &c, int n = 1);
+
+}  // namespace bs
+
+struct bs_context {
+  bs::Context c;
+};

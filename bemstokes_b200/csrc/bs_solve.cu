@@ -1,0 +1,419 @@
+// Device solvers: left-preconditioned restarted GMRES with deal.II SolverGMRES semantics (ref call sites
+// source/bem_stokes.cc:4116, 4332; semantics SURVEY A.7), dense blocked LU with partial pivoting (replaces
+// TrilinosWrappers::SolverDirect / Amesos KLU behind DirectPreconditioner, source/direct_preconditioner.cc).
+#include "bs_internal.h"
+#include <cmath>
+#include <algorithm>
+
+namespace bs {
+
+size_t Context::full_vec_len(int which) const { return which == BS_MAT_A ? n3() + num_rigid : n3(); }
+size_t Context::slice_offset(int) const { return (size_t)3 * p0; }
+size_t Context::local_vec_len(int which) const {
+  return rows_loc + ((which == BS_MAT_A && rank == nranks - 1) ? (size_t)num_rigid : 0);
+}
+
+static const DMat &mat_of(Context &c, int which) {
+  const DMat &M = which == BS_MAT_V ? c.V : (which == BS_MAT_K ? c.K : c.A);
+  BS_REQUIRE(M.valid(), which == BS_MAT_A ? "monolithic matrix not built" : "matrix not assembled");
+  return M;
+}
+
+void apply_operator(Context &c, int which, const double *x_full, double *y_loc) { gemv(c, mat_of(c, which), x_full, y_loc); }
+
+// slice of every rank -> replicated full vector (the Epetra Import of the reference's vmult)
+void exchange(Context &c, int which, const double *y_loc, double *x_full) {
+  const size_t mloc = c.local_vec_len(which);
+  if (c.nranks == 1) {
+    if (y_loc != x_full) copy(c, y_loc, x_full, mloc);
+    return;
+  }
+  BS_REQUIRE(c.cb_allgatherv != nullptr, "nranks > 1 but no communicator callbacks set (bs_set_comm)");
+  std::vector<int> counts(c.nranks), displs(c.nranks);
+  for (int r = 0; r < c.nranks; ++r) {
+    counts[r] = 3 * (c.part_start[r + 1] - c.part_start[r]) + ((which == BS_MAT_A && r == c.nranks - 1) ? c.num_rigid : 0);
+    displs[r] = 3 * c.part_start[r];
+  }
+  int rc = c.cb_allgatherv(c.cb_user, y_loc, (int)mloc, x_full, counts.data(), displs.data(), (void *)c.stream);
+  if (rc != 0) throw Error(BS_ERR_COMM, "allgatherv callback failed");
+}
+
+static void allreduce(Context &c, double *d_buf, int count) {
+  if (c.nranks == 1) return;
+  BS_REQUIRE(c.cb_allreduce != nullptr, "nranks > 1 but no communicator callbacks set (bs_set_comm)");
+  int rc = c.cb_allreduce(c.cb_user, d_buf, count, (void *)c.stream);
+  if (rc != 0) throw Error(BS_ERR_COMM, "allreduce callback failed");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// LU with partial pivoting, blocked right-looking, everything on the device
+// ---------------------------------------------------------------------------------------------------------
+constexpr int LU_NB = 32;
+
+// factorise the panel A[k0:n, k0:k0+nb] with one CTA; piv[k0+j] = absolute pivot row
+__global__ void __launch_bounds__(1024) k_lu_panel(double *A, size_t ld, int n, int k0, int nb, int *piv) {
+  __shared__ double s_val[32];
+  __shared__ int s_idx[32];
+  __shared__ int s_piv;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int j = 0; j < nb; ++j) {
+    const int col = k0 + j;
+    // pivot search
+    double best = -1.0;
+    int bi = col;
+    for (int r = col + tid; r < n; r += blockDim.x) {
+      const double v = fabs(A[(size_t)r * ld + col]);
+      if (v > best) {
+        best = v;
+        bi = r;
+      }
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, m);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
+      if (ov > best || (ov == best && oi < bi)) {
+        best = ov;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      s_val[wid] = best;
+      s_idx[wid] = bi;
+    }
+    __syncthreads();
+    if (wid == 0) {
+      best = (lane < (blockDim.x >> 5)) ? s_val[lane] : -1.0;
+      bi = (lane < (blockDim.x >> 5)) ? s_idx[lane] : 0x7fffffff;
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, m);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
+        if (ov > best || (ov == best && oi < bi)) {
+          best = ov;
+          bi = oi;
+        }
+      }
+      if (lane == 0) {
+        s_piv = bi;
+        piv[col] = bi;
+      }
+    }
+    __syncthreads();
+    const int pr = s_piv;
+    // swap rows col <-> pr inside the panel
+    if (pr != col && tid < nb) {
+      const double a = A[(size_t)col * ld + k0 + tid], b = A[(size_t)pr * ld + k0 + tid];
+      A[(size_t)col * ld + k0 + tid] = b;
+      A[(size_t)pr * ld + k0 + tid] = a;
+    }
+    __syncthreads();
+    const double dinv = 1.0 / A[(size_t)col * ld + col];
+    // scale column and update the rest of the panel: thread <-> row
+    for (int r = col + 1 + tid; r < n; r += blockDim.x) {
+      double *row = A + (size_t)r * ld;
+      const double l = row[col] * dinv;
+      row[col] = l;
+      for (int jj = j + 1; jj < nb; ++jj) row[k0 + jj] = fma(-l, A[(size_t)col * ld + k0 + jj], row[k0 + jj]);
+    }
+    __syncthreads();
+  }
+}
+
+// apply the panel's row swaps to columns outside the panel
+__global__ void k_lu_swap(double *A, size_t ld, int n, int k0, int nb, const int *piv) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n || (c >= k0 && c < k0 + nb)) return;
+  for (int j = 0; j < nb; ++j) {
+    const int r = k0 + j, pr = piv[r];
+    if (pr != r) {
+      const double a = A[(size_t)r * ld + c], b = A[(size_t)pr * ld + c];
+      A[(size_t)r * ld + c] = b;
+      A[(size_t)pr * ld + c] = a;
+    }
+  }
+}
+
+// U12 = L11^{-1} A12 : one thread per column of A12
+__global__ void k_lu_trsm(double *A, size_t ld, int n, int k0, int nb) {
+  __shared__ double L[LU_NB][LU_NB + 1];
+  for (int i = threadIdx.x; i < nb * nb; i += blockDim.x) L[i / nb][i % nb] = A[(size_t)(k0 + i / nb) * ld + k0 + i % nb];
+  __syncthreads();
+  const int c = k0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  double u[LU_NB];
+#pragma unroll
+  for (int i = 0; i < LU_NB; ++i) u[i] = (i < nb) ? A[(size_t)(k0 + i) * ld + c] : 0.0;
+#pragma unroll
+  for (int i = 0; i < LU_NB; ++i) {
+#pragma unroll
+    for (int j = 0; j < i; ++j) u[i] = fma(-L[i][j], u[j], u[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < LU_NB; ++i)
+    if (i < nb) A[(size_t)(k0 + i) * ld + c] = u[i];
+}
+
+// A22 -= L21 * U12 ; 64x64 tile per CTA, 256 threads, 4x4 per thread, k = nb <= 32
+__global__ void __launch_bounds__(256) k_lu_gemm(double *A, size_t ld, int n, int k0, int nb) {
+  __shared__ double Ls[64][LU_NB + 1];
+  __shared__ double Us[LU_NB][64 + 2];
+  const int r0 = k0 + nb + blockIdx.y * 64, c0 = k0 + nb + blockIdx.x * 64;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 64 * nb; i += 256) {
+    const int r = i / nb, k = i % nb;
+    Ls[r][k] = (r0 + r < n) ? A[(size_t)(r0 + r) * ld + k0 + k] : 0.0;
+  }
+  for (int i = tid; i < nb * 64; i += 256) {
+    const int k = i / 64, cc = i % 64;
+    Us[k][cc] = (c0 + cc < n) ? A[(size_t)(k0 + k) * ld + c0 + cc] : 0.0;
+  }
+  __syncthreads();
+  const int tr = (tid / 16) * 4, tc = (tid % 16) * 4;
+  double acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+  for (int k = 0; k < nb; ++k) {
+    double l[4], u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) l[i] = Ls[tr + i][k];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) u[j] = Us[k][tc + j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fma(l[i], u[j], acc[i][j]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = r0 + tr + i, cc = c0 + tc + j;
+      if (r < n && cc < n) A[(size_t)r * ld + cc] -= acc[i][j];
+    }
+}
+
+void lu_factor(Context &c, double *A, size_t n_, size_t ld, int *piv) {
+  const int n = (int)n_;
+  for (int k0 = 0; k0 < n; k0 += LU_NB) {
+    const int nb = std::min(LU_NB, n - k0);
+    k_lu_panel<<<1, 1024, 0, c.stream>>>(A, ld, n, k0, nb, piv);
+    k_lu_swap<<<(n + 255) / 256, 256, 0, c.stream>>>(A, ld, n, k0, nb, piv);
+    count_launch(c, 2);
+    const int rem = n - k0 - nb;
+    if (rem > 0) {
+      k_lu_trsm<<<(rem + 127) / 128, 128, 0, c.stream>>>(A, ld, n, k0, nb);
+      const int tiles = (rem + 63) / 64;
+      k_lu_gemm<<<dim3(tiles, tiles), 256, 0, c.stream>>>(A, ld, n, k0, nb);
+      count_launch(c, 2);
+    }
+  }
+  BS_CUDA(cudaGetLastError());
+}
+
+// x <- P x (sequential swaps, tiny kernel), then blocked forward / backward substitution
+__global__ void k_apply_piv(double *x, const int *piv, int n) {
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    for (int i = 0; i < n; ++i) {
+      const int p = piv[i];
+      if (p != i) {
+        const double t = x[i];
+        x[i] = x[p];
+        x[p] = t;
+      }
+    }
+}
+// solve the diagonal block (unit lower or upper) for rows [k0,k0+nb) with one warp
+__global__ void k_tri_diag(const double *LU, size_t ld, int k0, int nb, double *x, int upper) {
+  __shared__ double xs[LU_NB];
+  const int lane = threadIdx.x;
+  if (lane < nb) xs[lane] = x[k0 + lane];
+  __syncwarp();
+  if (!upper) {
+    for (int j = 0; j < nb; ++j) {
+      const double xj = xs[j];
+      if (lane > j && lane < nb) xs[lane] = fma(-LU[(size_t)(k0 + lane) * ld + k0 + j], xj, xs[lane]);
+      __syncwarp();
+    }
+  } else {
+    for (int j = nb - 1; j >= 0; --j) {
+      if (lane == j) xs[j] = xs[j] / LU[(size_t)(k0 + j) * ld + k0 + j];
+      __syncwarp();
+      const double xj = xs[j];
+      if (lane < j) xs[lane] = fma(-LU[(size_t)(k0 + lane) * ld + k0 + j], xj, xs[lane]);
+      __syncwarp();
+    }
+  }
+  if (lane < nb) x[k0 + lane] = xs[lane];
+}
+// x[r] -= sum_{j<nb} LU[r][k0+j] * x[k0+j] for r in [r_lo, r_hi): one warp per row
+__global__ void k_tri_update(const double *LU, size_t ld, int k0, int nb, double *x, int r_lo, int r_hi) {
+  const int r = r_lo + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= r_hi) return;
+  double s = (lane < nb) ? LU[(size_t)r * ld + k0 + lane] * x[k0 + lane] : 0.0;
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  if (lane == 0) x[r] -= s;
+}
+
+void lu_solve(Context &c, const double *LU, size_t n_, size_t ld, const int *piv, double *x) {
+  const int n = (int)n_;
+  k_apply_piv<<<1, 32, 0, c.stream>>>(x, piv, n);
+  count_launch(c);
+  for (int k0 = 0; k0 < n; k0 += LU_NB) {
+    const int nb = std::min(LU_NB, n - k0);
+    k_tri_diag<<<1, 32, 0, c.stream>>>(LU, ld, k0, nb, x, 0);
+    const int rem = n - k0 - nb;
+    if (rem > 0) k_tri_update<<<(rem + 7) / 8, 256, 0, c.stream>>>(LU, ld, k0, nb, x, k0 + nb, n);
+    count_launch(c, 2);
+  }
+  for (int k0 = ((n - 1) / LU_NB) * LU_NB; k0 >= 0; k0 -= LU_NB) {
+    const int nb = std::min(LU_NB, n - k0);
+    k_tri_diag<<<1, 32, 0, c.stream>>>(LU, ld, k0, nb, x, 1);
+    if (k0 > 0) k_tri_update<<<(k0 + 7) / 8, 256, 0, c.stream>>>(LU, ld, k0, nb, x, 0, k0);
+    count_launch(c, 2);
+  }
+  BS_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// preconditioner application on the local slice
+// ---------------------------------------------------------------------------------------------------------
+void apply_precond(Context &c, const double *in_loc, double *out_loc) {
+  const size_t mloc = c.local_vec_len(c.prec_which);
+  switch (c.prec_kind) {
+    case BS_PREC_NONE:
+      copy(c, in_loc, out_loc, mloc);
+      break;
+    case BS_PREC_JACOBI:
+      mul_elem(c, in_loc, c.d_prec_diag.p, out_loc, mloc);
+      break;
+    case BS_PREC_DIRECT:
+    case BS_PREC_BLOCK_DIRECT:
+    case BS_PREC_BAND:
+      copy(c, in_loc, out_loc, mloc);  // entries beyond the factorised block pass through (identity)
+      lu_solve(c, c.d_lu.p, c.lu_n, c.lu_n, c.d_piv.p, out_loc);
+      break;
+    default:
+      throw Error(BS_ERR_INVALID, "unknown preconditioner kind");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// GMRES
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_scale_inv_norm(const double *s2, const double *src, double *dst, size_t n) {
+  const double a = rsqrt(*s2);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i] * a;
+}
+
+int gmres(Context &c, int which, const double *d_b, double *d_x, double tol, int max_steps, int max_tmp, int *iters,
+          double *final_res) {
+  BS_REQUIRE(max_tmp >= 3, "max_n_tmp_vectors must be >= 3");
+  const int m = max_tmp - 2;  // restart length (deal.II: n_tmp_vectors - 2 inner iterations)
+  const size_t mloc = c.local_vec_len(which), mfull = c.full_vec_len(which);
+  DBuf<double> basis, w, z, coef;
+  basis.alloc((size_t)(m + 1) * mloc + 2);
+  w.alloc(mloc + 2);
+  z.alloc(mloc + 2);
+  coef.alloc((size_t)2 * (m + 2));
+  c.d_xchg.alloc(std::max(c.d_xchg.n, mfull + 2));
+  double *xfull = c.d_xchg.p;
+  std::vector<double> hbuf(2 * (m + 2)), H((size_t)(m + 1) * m, 0.0), gamma(m + 1), ci(m), si(m), h(m + 2), yk(m);
+  int its = 0;
+  double rho = 0.0;
+  bool converged = false;
+  auto norm2 = [&](const double *v) {
+    multi_dot(c, v, 0, 1, v, mloc, coef.p);
+    allreduce(c, coef.p, 1);
+    double s2;
+    BS_CUDA(cudaMemcpyAsync(&s2, coef.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    BS_CUDA(cudaStreamSynchronize(c.stream));
+    return s2;
+  };
+  while (true) {
+    // r0 = M^{-1} (b - A x)
+    exchange(c, which, d_x, xfull);
+    apply_operator(c, which, xfull, w.p);
+    sub(c, d_b, w.p, w.p, mloc);
+    apply_precond(c, w.p, z.p);
+    const double s2 = norm2(z.p);
+    rho = std::sqrt(s2);
+    if (rho <= tol) {
+      converged = true;
+      break;
+    }
+    if (its >= max_steps) break;
+    k_scale_inv_norm<<<(unsigned)std::min<size_t>((mloc + 255) / 256, 1184), 256, 0, c.stream>>>(coef.p, z.p, basis.p, mloc);
+    count_launch(c);
+    std::fill(gamma.begin(), gamma.end(), 0.0);
+    gamma[0] = rho;
+    int dim = 0;
+    bool stop = false;
+    for (int inner = 0; inner < m && !stop; ++inner) {
+      ++its;
+      exchange(c, which, basis.p + (size_t)inner * mloc, xfull);
+      apply_operator(c, which, xfull, w.p);
+      apply_precond(c, w.p, z.p);
+      dim = inner + 1;
+      // classical Gram-Schmidt applied twice (one fused multi-dot + one fused multi-axpy per pass): the
+      // reference's modified Gram-Schmidt with its re-orthogonalisation safeguard, without per-vector reductions
+      multi_dot(c, basis.p, mloc, dim, z.p, mloc, coef.p);
+      allreduce(c, coef.p, dim);
+      multi_axpy(c, basis.p, mloc, dim, coef.p, -1.0, z.p, mloc);
+      multi_dot(c, basis.p, mloc, dim, z.p, mloc, coef.p + (m + 2));
+      allreduce(c, coef.p + (m + 2), dim);
+      multi_axpy(c, basis.p, mloc, dim, coef.p + (m + 2), -1.0, z.p, mloc);
+      multi_dot(c, z.p, 0, 1, z.p, mloc, coef.p + dim);
+      allreduce(c, coef.p + dim, 1);
+      BS_CUDA(cudaMemcpyAsync(hbuf.data(), coef.p, sizeof(double) * 2 * (m + 2), cudaMemcpyDeviceToHost, c.stream));
+      BS_CUDA(cudaStreamSynchronize(c.stream));
+      for (int i = 0; i < dim; ++i) h[i] = hbuf[i] + hbuf[m + 2 + i];
+      const double s = std::sqrt(hbuf[dim]);
+      h[dim] = s;
+      k_scale_inv_norm<<<(unsigned)std::min<size_t>((mloc + 255) / 256, 1184), 256, 0, c.stream>>>(
+          coef.p + dim, z.p, basis.p + (size_t)(inner + 1) * mloc, mloc);
+      count_launch(c);
+      // Givens rotations (deal.II SolverGMRES::givens_rotation)
+      for (int i = 0; i < inner; ++i) {
+        const double t = h[i];
+        h[i] = ci[i] * t + si[i] * h[i + 1];
+        h[i + 1] = -si[i] * t + ci[i] * h[i + 1];
+      }
+      const double r = std::hypot(h[inner], h[inner + 1]);
+      ci[inner] = h[inner] / r;
+      si[inner] = h[inner + 1] / r;
+      h[inner] = r;
+      gamma[inner + 1] = -si[inner] * gamma[inner];
+      gamma[inner] = ci[inner] * gamma[inner];
+      for (int i = 0; i < dim; ++i) H[(size_t)i * m + inner] = h[i];
+      rho = std::fabs(gamma[dim]);
+      if (rho <= tol) {
+        converged = true;
+        stop = true;
+      } else if (its >= max_steps) {
+        stop = true;
+      }
+    }
+    // back substitution H y = gamma, x += sum y_i v_i
+    for (int i = dim - 1; i >= 0; --i) {
+      double s = gamma[i];
+      for (int j = i + 1; j < dim; ++j) s -= H[(size_t)i * m + j] * yk[j];
+      yk[i] = s / H[(size_t)i * m + i];
+    }
+    if (dim > 0) {
+      BS_CUDA(cudaMemcpyAsync(coef.p, yk.data(), sizeof(double) * dim, cudaMemcpyHostToDevice, c.stream));
+      multi_axpy(c, basis.p, mloc, dim, coef.p, 1.0, d_x, mloc);
+      BS_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    if (converged || its >= max_steps) break;
+  }
+  if (iters) *iters = its;
+  if (final_res) *final_res = rho;
+  return converged ? BS_OK : BS_ERR_NOT_CONVERGED;
+}
+
+}  // namespace bs

@@ -1,0 +1,406 @@
+"""Host-side mirror of the reference's hot-path interface, driving the C-ABI.
+
+`BEMProblem` keeps the member names of BEMStokes::BEMProblem<3> (include/bem_stokes.h:106-660) that the hot
+path and the reference's tests touch: assemble_stokes_system, solve_system, dirichlet_to_neumann_operator,
+tangential_projector_body, V_matrix / K_matrix / monolithic_system_matrix (vmult + element reads),
+monolithic_rhs / monolithic_solution, stokes_forces, rigid_velocities, rigid_total_forces, and the parameter
+names of declare_parameters (source/bem_stokes.cc:207-476) as attributes.  `DirectPreconditioner` mirrors
+include/direct_preconditioner.h:27-51, the kernel classes mirror include/kernel.h, free_surface_kernel.h and
+no_slip_wall_kernel.h.  All arithmetic happens in libbemstokes_b200.so on the GPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib, check
+from .mesh import QuadMesh
+from .prepass import Prepass, gauss_1d
+
+
+def _dp(a):
+    return a.ctypes.data_as(_lib.c_double_p)
+
+
+def _ip(a):
+    return a.ctypes.data_as(_lib.c_int_p)
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+_SING = {"Mixed": _lib.SING_MIXED, "Duffy": _lib.SING_DUFFY, "Telles": _lib.SING_TELLES}
+_GRID = {"Real": _lib.GRID_REAL, "ImposedForce": _lib.GRID_IMPOSED_FORCE, "ImposedVelocity": _lib.GRID_IMPOSED_VELOCITY}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Green kernels (point evaluation on the device through the same functions the assembly kernels inline)
+# ---------------------------------------------------------------------------------------------------------------
+class StokesKernel:
+    """ref: include/kernel.h StokesKernel<3>: value_tens (G, rank 2), value_tens2 (W, rank 3)."""
+    _type = _lib.KERNEL_FREE
+
+    def __init__(self, eps=0.0, device=0):
+        self.epsilon, self.device, self.wall_orientation = eps, device, 1
+
+    def set_wall_orientation(self, o):
+        self.wall_orientation = int(o)
+
+    def _eval(self, p, p_image, want_w):
+        p = np.ascontiguousarray(np.atleast_2d(p), dtype=np.float64)
+        q = p if p_image is None else np.ascontiguousarray(np.atleast_2d(p_image), dtype=np.float64)
+        n = p.shape[0]
+        G = np.zeros((n, 3, 3))
+        W = np.zeros((n, 3, 3, 3)) if want_w else None
+        check(lib.bs_kernel_eval(self.device, self._type, self.epsilon, self.wall_orientation, n, _dp(p), _dp(q),
+                                 _dp(G), _dp(W) if want_w else None))
+        return G, W
+
+    def value_tens(self, p):
+        G, _ = self._eval(p, None, False)
+        return G[0] if np.ndim(p) == 1 else G
+
+    def value_tens2(self, p):
+        _, W = self._eval(p, None, True)
+        return W[0] if np.ndim(p) == 1 else W
+
+
+class FreeSurfaceStokesKernel(StokesKernel):
+    """ref: include/free_surface_kernel.h: value_tens_image / value_tens_image2."""
+    _type = _lib.KERNEL_FREE_SURFACE
+
+    def value_tens_image(self, p, p_image):
+        G, _ = self._eval(p, p_image, False)
+        return G[0] if np.ndim(p) == 1 else G
+
+    def value_tens_image2(self, p, p_image):
+        _, W = self._eval(p, p_image, True)
+        return W[0] if np.ndim(p) == 1 else W
+
+
+class NoSlipWallStokesKernel(FreeSurfaceStokesKernel):
+    """ref: include/no_slip_wall_kernel.h."""
+    _type = _lib.KERNEL_NO_SLIP
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# matrix / preconditioner objects with the deal.II vmult concept
+# ---------------------------------------------------------------------------------------------------------------
+class DeviceMatrix:
+    """Anything with vmult(dst, src) — what SolverGMRES::solve requires (include/operator.h:22-66)."""
+
+    def __init__(self, problem, which):
+        self._p, self.which = problem, which
+
+    def m(self):
+        r = C.c_int()
+        check(lib.bs_matrix_size(self._p._ctx, self.which, C.byref(r), None))
+        return r.value
+
+    n = m
+
+    def vmult(self, dst, src):
+        src = np.ascontiguousarray(src, dtype=np.float64)
+        assert dst.dtype == np.float64 and dst.flags.c_contiguous and dst.shape == src.shape
+        if src.ndim == 1:
+            check(lib.bs_vmult(self._p._ctx, self.which, _vp(src), _vp(dst)))
+        else:
+            check(lib.bs_vmult_multi(self._p._ctx, self.which, src.shape[0], _vp(src), _vp(dst)))
+        return dst
+
+    def __matmul__(self, x):
+        return self.vmult(np.zeros(np.shape(x)), x)
+
+    def __call__(self, i, j):
+        """Element read, like TrilinosWrappers::SparseMatrix::operator()(i,j)."""
+        return float(self.entries([i], [j])[0])
+
+    def entries(self, rows, cols):
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        out = np.zeros(len(rows))
+        check(lib.bs_get_entries(self._p._ctx, self.which, len(rows), _ip(rows), _ip(cols), _dp(out)))
+        return out
+
+    def to_dense(self):
+        """Whole matrix on the host in reference ordering (parity tests, 'Save matrices as txt files')."""
+        n = self.m()
+        r, c = np.meshgrid(np.arange(n, dtype=np.int32), np.arange(n, dtype=np.int32), indexing="ij")
+        return self.entries(r.reshape(-1), c.reshape(-1)).reshape(n, n)
+
+
+class DirectPreconditioner:
+    """ref: include/direct_preconditioner.h:27-51 — set_up(SolverControl, AdditionalData), initialize(matrix),
+    vmult(dst, src).  The LU lives on the device (dense blocked LU with partial pivoting)."""
+
+    def __init__(self):
+        self._matrix = None
+        self.kind = _lib.PREC_DIRECT
+
+    def set_up(self, solver_control=None, additional_data=None):
+        self.solver_control = solver_control
+
+    def initialize(self, matrix, block_only=False):
+        self._matrix = matrix
+        self.kind = _lib.PREC_BLOCK_DIRECT if block_only else _lib.PREC_DIRECT
+        check(lib.bs_precond_setup(matrix._p._ctx, matrix.which, self.kind, 0))
+
+    def vmult(self, dst, src):
+        src = np.ascontiguousarray(src, dtype=np.float64)
+        check(lib.bs_precond_vmult(self._matrix._p._ctx, _vp(src), _vp(dst)))
+        return dst
+
+
+class SolverControl:
+    def __init__(self, max_steps=1000, tolerance=1e-10):
+        self.max_steps, self.tolerance = max_steps, tolerance
+        self._last_step, self._last_value = 0, 0.0
+
+    def last_step(self):
+        return self._last_step
+
+    def last_value(self):
+        return self._last_value
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class BEMProblem:
+    def __init__(self, device=0, rank=0, nranks=1):
+        self.device, self.this_mpi_process, self.n_mpi_processes = device, rank, nranks
+        # parameters (names follow declare_parameters, bem_stokes.cc:207-476)
+        self.fe_degree = 1
+        self.map_degree = None            # default: isoparametric
+        self.quadrature_order = 8         # "Internal Quadrature" gauss order
+        self.singular_quadrature_type = "Mixed"
+        self.singular_quadrature_order = 5
+        self.reflect_kernel = False
+        self.no_slip_kernel = False
+        self.epsilon = 0.0
+        self.wall_spans_0 = (10.0, 0.0, 10.0)
+        self.wall_position_0 = (0.0, 0.0, 0.0)
+        self.grid_type = "Real"
+        self.imposed_component = 1
+        self.assemble_scaling = 1.0
+        self.use_internal_alpha = False
+        self.monolithic_bool = True
+        self.solve_directly = True
+        self.preconditioner_type = "Direct"
+        self.bandwith_preconditioner = False
+        self.bandwith = 100
+        self.gmres_restart = 100
+        self.solver_control = SolverControl(1000, 1e-10)
+        self.force_pole = (0.0, 0.0, 0.0)
+        self.keep_VK = True
+        self.num_rigid = 6
+        self._ctx = None
+        self.mesh = None
+        self.direct_trilinos_preconditioner = DirectPreconditioner()
+        self.reassemble_preconditoner = False
+        self.shape_velocities = None
+
+    # ---- geometry ---------------------------------------------------------------------------------------
+    def set_mesh(self, mesh: QuadMesh, map_mesh: QuadMesh = None):
+        """read_domain + reinit + euler vector in one step: the unknown-space mesh and (optionally) a separate
+        mapping-space mesh (MappingFEField(map_dh, euler_vec), bem_stokes.cc:1851)."""
+        self.mesh = mesh
+        self.map_mesh = mesh if map_mesh is None else map_mesh
+        self.fe_degree = mesh.degree
+        self.map_degree = self.map_mesh.degree
+        return self
+
+    def reinit(self):
+        if self._ctx is not None:
+            check(lib.bs_destroy(self._ctx))
+        ctx = _lib.ctx_p()
+        check(lib.bs_create(C.byref(ctx), self.device, self.fe_degree, self.map_degree))
+        self._ctx = ctx
+        if self.n_mpi_processes > 1:
+            check(lib.bs_set_partition(ctx, self.this_mpi_process, self.n_mpi_processes, None, self.mesh.n_nodes))
+        mm = self.map_mesh
+        euler = np.ascontiguousarray(mm.nodes.T.reshape(-1))  # component-major euler_vec
+        check(lib.bs_set_geometry(ctx, mm.n_nodes, _dp(euler), self.mesh.n_cells, _ip(mm.conn), self.mesh.n_nodes,
+                                  _ip(self.mesh.conn), None))
+        check(lib.bs_set_quadrature(ctx, self.quadrature_order, None, None))
+        check(lib.bs_set_singular_quadrature(ctx, _SING[self.singular_quadrature_type], self.singular_quadrature_order))
+        self._set_kernel()
+        self.N = self.mesh.n_nodes
+        self.n_dofs = 3 * self.N
+        self.V_matrix = DeviceMatrix(self, _lib.MAT_V)
+        self.K_matrix = DeviceMatrix(self, _lib.MAT_K)
+        self.monolithic_system_matrix = DeviceMatrix(self, _lib.MAT_A)
+        if self.shape_velocities is None or len(self.shape_velocities) != self.n_dofs:
+            self.shape_velocities = np.zeros(self.n_dofs)
+        return self
+
+    def _set_kernel(self):
+        # ref: kernel_wall_orientation = last axis with wall_spans[0][axis]==0 (bem_stokes.cc:2861-2866)
+        o = 1
+        for i in range(3):
+            if self.wall_spans_0[i] == 0:
+                o = i
+        self.kernel_wall_orientation = o
+        ktype = _lib.KERNEL_FREE
+        if self.reflect_kernel:
+            ktype = _lib.KERNEL_FREE_SURFACE
+        elif self.no_slip_kernel:
+            ktype = _lib.KERNEL_NO_SLIP
+        wp = np.asarray(self.wall_position_0, dtype=np.float64)
+        check(lib.bs_set_kernel(self._ctx, ktype, self.epsilon, o, _dp(wp)))
+
+    def owned_nodes(self):
+        n = C.c_int()
+        out = np.zeros(self.N, dtype=np.int32)
+        check(lib.bs_get_owned_nodes(self._ctx, C.byref(n), _ip(out)))
+        return out[:n.value].copy()
+
+    # ---- pre-pass (host) --------------------------------------------------------------------------------
+    def compute_center_of_mass_and_rigid_modes(self, frame=0):
+        self._pre = Prepass(self.map_mesh.nodes, self.map_mesh.conn.astype(np.int64), self.map_degree, self.N,
+                            self.mesh.conn.astype(np.int64), self.fe_degree, self.quadrature_order, self.force_pole)
+        self.Mass_Matrix = self._pre.M
+        self.N_rigid = self._pre.N_rigid
+        self.N_rigid_dual = self._pre.N_rigid_dual
+        self.support_points = self._pre.support_points
+        self.surface = self._pre.area
+        return self
+
+    def compute_normal_vector(self):
+        p = self._pre
+        self.normal_vector = p.normal_vector
+        self.normal_vector_pure = p.normal_vector_pure
+        self.M_normal_vector_pure = p.M_normal_vector_pure
+        self.l2normGamma_pure = p.l2normGamma_pure
+        return self
+
+    # ---- assembly -----------------------------------------------------------------------------------------
+    def assemble_stokes_system(self, correction_on_V=True):
+        """ref: BEMProblem::assemble_stokes_system (bem_stokes.cc:2840-3435)."""
+        ctx = self._ctx
+        self._set_kernel()
+        check(lib.bs_assemble_VK(ctx))
+        nh = np.ascontiguousarray(self.normal_vector_pure)
+        mn = np.ascontiguousarray(self.M_normal_vector_pure)
+        self.V_x_normals_body = np.zeros(self.n_dofs)
+        if correction_on_V:
+            check(lib.bs_correct_V(ctx, _dp(nh), _dp(mn), self.l2normGamma_pure, _dp(self.V_x_normals_body)))
+        else:
+            self.V_matrix.vmult(self.V_x_normals_body, nh)
+        check(lib.bs_correct_K(ctx, 1 if self.use_internal_alpha else 0))
+        if self.monolithic_bool:
+            nr = self.num_rigid
+            self.monolithic_rhs = np.zeros(self.n_dofs + nr)
+            Nr = np.ascontiguousarray(self.N_rigid[:nr])
+            Nd = np.ascontiguousarray(self.N_rigid_dual[:nr])
+            sv = np.ascontiguousarray(self.shape_velocities, dtype=np.float64)
+            check(lib.bs_build_monolithic(ctx, None, nr, _dp(Nr), _dp(Nd), _dp(nh), _dp(mn), self.l2normGamma_pure,
+                                          _GRID[self.grid_type], self.imposed_component, self.assemble_scaling, _dp(sv),
+                                          1 if self.keep_VK else 0, _dp(self.monolithic_rhs)))
+            if getattr(self, "monolithic_solution", None) is None or len(self.monolithic_solution) != self.n_dofs + nr:
+                self.monolithic_solution = np.zeros(self.n_dofs + nr)
+        return self
+
+    def tangential_projector_body(self, input_vel, output_vel=None):
+        out = np.zeros(self.n_dofs) if output_vel is None else output_vel
+        src = np.ascontiguousarray(input_vel, dtype=np.float64)
+        check(lib.bs_tangential_projector(self._ctx, _vp(src), _vp(out)))
+        return out
+
+    # ---- solve --------------------------------------------------------------------------------------------
+    def _setup_preconditioner(self, which):
+        t = self.preconditioner_type
+        if t == "Jacobi":
+            check(lib.bs_precond_setup(self._ctx, which, _lib.PREC_JACOBI, 0))
+        elif t in ("Direct",):
+            if self.direct_trilinos_preconditioner._matrix is None or self.reassemble_preconditoner:
+                self.direct_trilinos_preconditioner.initialize(DeviceMatrix(self, which))
+                self.reassemble_preconditoner = False
+        elif t in ("ILU", "AMG"):
+            # on these dense matrices ILU(0) is the exact LU and ML collapses to a direct coarse solve
+            kind = _lib.PREC_BAND if self.bandwith_preconditioner else _lib.PREC_DIRECT
+            check(lib.bs_precond_setup(self._ctx, which, kind, int(self.bandwith)))
+        elif t in ("None", None):
+            check(lib.bs_precond_setup(self._ctx, which, _lib.PREC_NONE, 0))
+        else:
+            raise ValueError("preconditioner %r is not part of the B200 hot path (SOR/SSOR are Trilinos specific)" % t)
+
+    def gmres(self, which, x, b):
+        its, res = C.c_int(), C.c_double()
+        rc = lib.bs_gmres(self._ctx, which, _vp(b), _vp(x), self.solver_control.tolerance, self.solver_control.max_steps,
+                          self.gmres_restart, C.byref(its), C.byref(res))
+        self.solver_control._last_step, self.solver_control._last_value = its.value, res.value
+        check(rc)
+        return its.value
+
+    def solve_system(self, monolithic_booly=True):
+        """ref: BEMProblem::solve_system (bem_stokes.cc:4158-4508)."""
+        n, nr = self.n_dofs, self.num_rigid
+        if monolithic_booly:
+            b = np.ascontiguousarray(self.monolithic_rhs)
+            x = self.monolithic_solution
+            if self.solve_directly:
+                check(lib.bs_direct_solve(self._ctx, _lib.MAT_A, _vp(b), _vp(x)))
+                self.solver_control._last_step = 1
+            else:
+                self._setup_preconditioner(_lib.MAT_A)
+                its = self.gmres(_lib.MAT_A, x, b)
+                if its > 100:
+                    self.reassemble_preconditoner = True
+            r = self.monolithic_system_matrix @ x - b
+            self.final_check_0 = (float(np.abs(r).max()), float(np.linalg.norm(r)))
+            self.stokes_forces = x[:n].copy()
+            self.rigid_velocities = x[n:n + nr].copy() * self.assemble_scaling
+        else:
+            self.solve_dn()
+        self.rigid_total_forces = np.array([self.stokes_forces @ self.N_rigid_dual[r] for r in range(nr)])
+        return self
+
+    def dirichlet_to_neumann_operator(self, input_vel, output_force=None):
+        """DN(u) = P V^{-1} (P K P u)   (ref: bem_stokes.cc:4072-4129)."""
+        v1 = self.tangential_projector_body(input_vel)
+        v2 = self.K_matrix @ v1
+        v1 = self.tangential_projector_body(v2)
+        f = np.zeros(self.n_dofs)
+        if self.solve_directly:
+            check(lib.bs_direct_solve(self._ctx, _lib.MAT_V, _vp(v1), _vp(f)))
+        else:
+            self._setup_preconditioner(_lib.MAT_V)
+            self.gmres(_lib.MAT_V, f, v1)
+        out = self.tangential_projector_body(f, output_force)
+        return out
+
+    def solve_dn(self):
+        """solve_system(false): resistance problem through the DN operator (bem_stokes.cc:4163-4258)."""
+        nr = self.num_rigid
+        DN = [self.dirichlet_to_neumann_operator(self.N_rigid[r]) for r in range(nr)]
+        F = np.array([[self.N_rigid_dual[i] @ DN[j] for j in range(nr)] for i in range(nr)])
+        self.final_matrix = F
+        rhs = -np.array([self.N_rigid_dual[i] @ self.dirichlet_to_neumann_operator(self.shape_velocities)
+                         for i in range(nr)]) if np.any(self.shape_velocities) else np.zeros(nr)
+        if not np.any(rhs):
+            self.rigid_velocities = np.zeros(nr)
+            self.stokes_forces = np.zeros(self.n_dofs)
+            return
+        U = np.linalg.solve(F, rhs)
+        self.rigid_velocities = U
+        self.stokes_forces = sum(U[r] * DN[r] for r in range(nr)) + self.dirichlet_to_neumann_operator(self.shape_velocities)
+
+    # ---- stats ------------------------------------------------------------------------------------------------
+    def stats(self):
+        s = _lib.BsStats()
+        check(lib.bs_get_stats(self._ctx, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in s._fields_}
+
+    def reset_stats(self):
+        check(lib.bs_reset_stats(self._ctx))
+
+    def close(self):
+        if self._ctx is not None:
+            check(lib.bs_destroy(self._ctx))
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,177 @@
+/* bemstokes_b200.h — C-ABI of the B200-native BEMStokes hot path.
+ *
+ * Drop-in boundary for ONE path of mathLab/BEMStokes: collocation assembly of the dense single-layer (V) and
+ * double-layer (K) Stokes matrices and the GMRES / direct solve of the monolithic rigid-body system.
+ * Everything behind these entry points runs on the GPU (sm_100a); there is no CPU fallback.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative bs_status otherwise; bs_last_error() gives the text
+ *    (the reference throws deal.II exceptions, caught in source/main.cc:48-71).
+ *  - all pointers are caller-owned HOST arrays borrowed for the duration of the call, unless the context was
+ *    switched to BS_PTR_DEVICE with bs_set_pointer_mode (then the x/y/b vectors of vmult/gmres/precond are
+ *    device pointers in the same reference ordering).
+ *  - vectors use the reference's component-major ordering: dof (node i, component c) = i + c*N
+ *    (DoFRenumbering::component_wise, source/bem_stokes.cc:1593); the monolithic vector appends the
+ *    num_rigid (6, +1 with torque) rigid unknowns at 3N.. (bem_stokes.cc:3247-3251).  The library permutes
+ *    to its own node-major, locality-sorted device layout internally.
+ *  - one context per rank/GPU; a context is not re-entrant.
+ *
+ * "ref:" = file:line under the reference tree that the entry point replaces.
+ */
+#ifndef BEMSTOKES_B200_H
+#define BEMSTOKES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bs_context bs_context;
+
+typedef enum {
+  BS_OK = 0,
+  BS_ERR_INVALID = -1,     /* bad argument / call order */
+  BS_ERR_CUDA = -2,        /* CUDA runtime failure (message has the CUDA error string) */
+  BS_ERR_NO_DEVICE = -3,   /* no sm_100 device: the product path has no CPU fallback */
+  BS_ERR_NOT_CONVERGED = -4, /* SolverControl::NoConvergence equivalent */
+  BS_ERR_UNSUPPORTED = -5,
+  BS_ERR_COMM = -6
+} bs_status;
+
+typedef enum { BS_KERNEL_FREE = 0, BS_KERNEL_FREE_SURFACE = 1, BS_KERNEL_NO_SLIP = 2 } bs_kernel_type;
+typedef enum { BS_SING_MIXED = 0, BS_SING_DUFFY = 1, BS_SING_TELLES = 2 } bs_singular_kind;
+typedef enum { BS_MAT_V = 0, BS_MAT_K = 1, BS_MAT_A = 2 } bs_matrix_id;
+typedef enum { BS_PREC_NONE = 0, BS_PREC_JACOBI = 1, BS_PREC_DIRECT = 2, BS_PREC_BLOCK_DIRECT = 3, BS_PREC_BAND = 4 } bs_precond_kind;
+typedef enum { BS_GRID_REAL = 0, BS_GRID_IMPOSED_FORCE = 1, BS_GRID_IMPOSED_VELOCITY = 2 } bs_grid_type;
+typedef enum { BS_PTR_HOST = 0, BS_PTR_DEVICE = 1 } bs_pointer_mode;
+
+const char *bs_last_error(void);
+int bs_version(void);
+
+/* ---- life cycle ------------------------------------------------------------------------------------ */
+/* ref: BEMProblem<3>::BEMProblem (source/bem_stokes.cc:138-205), fe_stokes / fe_map (bem_stokes.h:414-419).
+ * fe_degree, map_degree in {1,2}.  device = CUDA ordinal. */
+int bs_create(bs_context **ctx, int device, int fe_degree, int map_degree);
+int bs_destroy(bs_context *ctx);
+int bs_set_pointer_mode(bs_context *ctx, int mode);
+/* cudaStream_t (as void*) all work of this context is ordered on; NULL = a private non-blocking stream. */
+int bs_set_stream(bs_context *ctx, void *cuda_stream);
+
+/* ---- row partition (ref: this_cpu_set, bem_stokes.cc:1599-1634; assembly filter 2877) ---------------- */
+/* owner_of_node[N] gives the owning rank of every node (same array on every rank) or NULL for the
+ * library's balanced split of its locality order.  Must be called before bs_set_geometry when nranks>1. */
+int bs_set_partition(bs_context *ctx, int rank, int nranks, const int *owner_of_node, int n_nodes);
+int bs_get_owned_nodes(bs_context *ctx, int *n_owned, int *owned_nodes /* capacity N, may be NULL */);
+
+/* ---- inputs ----------------------------------------------------------------------------------------- */
+/* ref: euler_vec + map_dh / dh_stokes connectivity (bem_stokes.cc:1819, 1851, 2874 get_dof_indices).
+ * euler_vec: 3*n_map_nodes, component-major.  conn_*: per cell the scalar node ids in deal.II local order
+ * (Q1: 4 lexicographic vertices; Q2: 4 vertices, 4 edge mid-points (x=0,x=1,y=0,y=1), centre).
+ * material_id[ncell] may be NULL (all body, material 0; bem_stokes.cc:515-521). */
+int bs_set_geometry(bs_context *ctx, int n_map_nodes, const double *euler_vec, int ncell, const int *conn_map,
+                    int n_nodes, const int *conn_stokes, const int *material_id);
+/* ref: "Internal Quadrature" ParsedQuadrature (bem_stokes.cc:151): tensor product of a 1-D rule on [0,1],
+ * first coordinate fastest.  x1d == NULL -> Gauss-Legendre of order n1d built by the library. */
+int bs_set_quadrature(bs_context *ctx, int n1d, const double *x1d, const double *w1d);
+/* ref: get_singular_quadrature (bem_stokes.cc:4912-4957): rule family + order, built by the library with
+ * deal.II semantics (QGaussOneOverR / QIterated / QSplit(QDuffy) / QTelles). */
+int bs_set_singular_quadrature(bs_context *ctx, int kind, int order);
+/* Alternative: hand over the rule of local scalar index a as deal.II built it (points on [0,1]^2). */
+int bs_set_singular_rule(bs_context *ctx, int local_index, int nq, const double *xi, const double *w);
+/* ref: stokes_kernel / fs_stokes_kernel / ns_stokes_kernel + reflect_kernel / no_slip_kernel dispatch
+ * (bem_stokes.cc:5027-5069), wall orientation/position (2861-2870, 2918-2919). */
+int bs_set_kernel(bs_context *ctx, int type, double epsilon, int wall_orientation, const double *wall_position);
+
+/* Host helpers with deal.II semantics (so a stand-alone host needs no deal.II). Return the number of
+ * points written; xi is [n][2]. capacity in points. */
+int bs_make_gauss_1d(int n, double *x, double *w);
+int bs_make_singular_rule(int kind, int order, int fe_degree, int local_index, int capacity, double *xi, double *w);
+
+/* ---- assembly (ref: BEMProblem::assemble_stokes_system, bem_stokes.cc:2840-3435) ----------------------- */
+/* K1 (regular Gauss pass) + K2 (singular pass) -> row-block of V and K on the device (2871-3000). */
+int bs_assemble_VK(bs_context *ctx);
+/* V <- V + (nhat - V nhat)(M nhat)^T / l2 on owned rows (3004-3036). nhat = normal_vector_pure,
+ * Mnhat = M_normal_vector_pure, l2 = l2normGamma_pure.  Vn_out (3N, may be NULL) receives V*nhat
+ * computed BEFORE the correction ("Check on the V operator Norm"). */
+int bs_correct_V(bs_context *ctx, const double *nhat, const double *Mnhat, double l2gamma, double *Vn_out);
+/* K(i+jN, i+kN) -= (K e_k)[i+jN]; += delta_jk unless use_internal_alpha (3044-3098). */
+int bs_correct_K(bs_context *ctx, int use_internal_alpha);
+/* Monolithic matrix + rhs (3120-3357) for a problem without hanging-node constraints.
+ * col_is_K[3N] (NULL = all V): column j of A is -K(:,j) when set, V(:,j) otherwise (the reference derives it
+ * from the body / wall index sets, 3194-3245).  N_rigid, N_rigid_dual: num_rigid x 3N row-major.
+ * shape_vel (3N, may be NULL) is used for grid_type Real.  rhs_out: 3N+num_rigid.
+ * keep_VK = 0 lets A alias V's storage (memory at scale), 1 keeps V intact. */
+int bs_build_monolithic(bs_context *ctx, const unsigned char *col_is_K, int num_rigid, const double *N_rigid,
+                        const double *N_rigid_dual, const double *nhat, const double *Mnhat, double l2gamma,
+                        int grid_type, int imposed_component, double scaling, const double *shape_vel,
+                        int keep_VK, double *rhs_out);
+
+/* ---- operators (ref: TrilinosWrappers::SparseMatrix::vmult call sites) -------------------- */
+int bs_matrix_size(bs_context *ctx, int which, int *rows, int *cols);
+int bs_vmult(bs_context *ctx, int which, const double *x, double *y);
+/* X, Y: nrhs vectors stored one after another (nrhs x size). */
+int bs_vmult_multi(bs_context *ctx, int which, int nrhs, const double *X, double *Y);
+/* ref: V_matrix(i,j) / K_matrix(i,j) / monolithic_system_matrix(i,i) element reads (3196-3243, 4355-4361,
+ * 3412-3413).  rows/cols in reference ordering; rows must be owned by this rank. */
+int bs_get_entries(bs_context *ctx, int which, int n, const int *rows, const int *cols, double *out);
+/* tangential_projector_body (4142-4151) with the nhat/Mnhat/l2 given to bs_build_monolithic/correct_V. */
+int bs_tangential_projector(bs_context *ctx, const double *in, double *out);
+
+/* ---- preconditioner (ref: DirectPreconditioner, source/direct_preconditioner.cc:10-23; Jacobi 4296-4300;
+ *      band copy assemble_monolithic_preconditioner 3437-3505) ---------------------------------------- */
+int bs_precond_setup(bs_context *ctx, int which, int kind, int bandwidth_or_block);
+int bs_precond_vmult(bs_context *ctx, const double *x, double *y);
+
+/* ---- solvers (ref: solve_system 4158-4508; deal.II SolverGMRES semantics) ----------------- */
+/* Left-preconditioned restarted GMRES, x is the initial guess on entry.  max_n_tmp_vectors as
+ * gmres_additional_data (restart length = max_n_tmp_vectors-2).  Returns BS_ERR_NOT_CONVERGED after
+ * max_steps like SolverControl. */
+int bs_gmres(bs_context *ctx, int which, const double *b, double *x, double tol_abs, int max_steps,
+             int max_n_tmp_vectors, int *iterations, double *final_residual);
+/* nrhs independent systems (the 6 rigid-body resistance problems), B and X nrhs x size. */
+int bs_gmres_multi(bs_context *ctx, int which, int nrhs, const double *B, double *X, double tol_abs, int max_steps,
+                   int max_n_tmp_vectors, int *iterations, double *final_residuals);
+/* ref: TrilinosWrappers::SolverDirect (4261-4267): dense LU with partial pivoting on the device. */
+int bs_direct_solve(bs_context *ctx, int which, const double *b, double *x);
+
+/* ---- kernel point evaluation (ref: StokesKernel::value_tens / value_tens2 kernel.cc:61-104,
+ *      FreeSurfaceStokesKernel::value_tens_image(2), NoSlipWallStokesKernel::value_tens_image(2)) -------
+ * Evaluated by the same device functions the assembly kernels use.  p, p_image: npts x 3.
+ * G_out: npts x 9 (may be NULL), W_out: npts x 27 (may be NULL). */
+int bs_kernel_eval(int device, int type, double epsilon, int wall_orientation, int npts, const double *p,
+                   const double *p_image, double *G_out, double *W_out);
+
+/* ---- multi-GPU plumbing -------------------------------------------------------------------------------
+ * The library does not own a communicator; the host passes the exchange steps of the solve as callbacks
+ * (the reference gets them from Epetra: Import in vmult, Allreduce in dots).  Buffers are
+ * device pointers; the callback must order its work on `stream`.  allgatherv gathers counts[r] doubles of
+ * every rank into recv at displs[r]. */
+typedef int (*bs_allgatherv_fn)(void *user, const double *send, int sendcount, double *recv, const int *counts,
+                                const int *displs, void *stream);
+typedef int (*bs_allreduce_sum_fn)(void *user, double *buf, int count, void *stream);
+int bs_set_comm(bs_context *ctx, bs_allgatherv_fn allgatherv, bs_allreduce_sum_fn allreduce, void *user);
+/* Peer-memory exchange: peer_xbuf[r] = device pointer (mapped in this process) of rank r's replicated
+ * Krylov-vector buffer; the GEMV epilogue stores its slice straight into every peer (NVLink P2P). */
+int bs_get_exchange_buffer(bs_context *ctx, void **dev_ptr, size_t *bytes);
+int bs_set_peer_buffers(bs_context *ctx, int nranks, void *const *peer_xbuf, void *const *peer_flags);
+
+/* ---- timers / counters (ref: Teuchos timers bem_stokes.cc:19-23) ---------------------------------------- */
+typedef struct {
+  double assemble_regular_ms, assemble_singular_ms, geometry_ms, correct_ms, monolithic_ms;
+  double precond_setup_ms, solve_ms, vmult_ms_last;
+  long long kernel_launches; /* number of this library's kernels launched since bs_reset_stats */
+  long long pairs_regular, pairs_singular;
+} bs_stats;
+int bs_get_stats(bs_context *ctx, bs_stats *out);
+int bs_reset_stats(bs_context *ctx);
+
+/* ---- benchmarking helpers: device-resident repeat loops timed with CUDA events on the context stream ---- */
+int bs_bench_vmult(bs_context *ctx, int which, int repeats, double *ms_per_call);
+int bs_bench_fp64_peak(int device, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEMSTOKES_B200_H */
