@@ -57,9 +57,10 @@ def read_mesh(path):
     return read_inp(path) if str(path).endswith(".inp") else read_msh(path)
 
 
-def cubesphere(r, degree=1, scale=(1.0, 1.0, 1.0)):
-    """6 * 4^r quads; every node projected radially to the unit sphere, then scaled per axis (prolate: x*2)."""
-    m = 2 ** r
+def cubesphere(r=None, degree=1, scale=(1.0, 1.0, 1.0), m=None):
+    """6 * m^2 quads (m = 2^r unless given); every node projected radially to the unit sphere, then scaled per
+    axis (prolate: x*2)."""
+    m = 2 ** r if m is None else int(m)
     sub = m * degree
     L = sub + 1
     unit = Q1_UNIT if degree == 1 else Q2_UNIT

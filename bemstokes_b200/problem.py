@@ -103,10 +103,13 @@ class DeviceMatrix:
     def vmult(self, dst, src):
         src = np.ascontiguousarray(src, dtype=np.float64)
         assert dst.dtype == np.float64 and dst.flags.c_contiguous and dst.shape == src.shape
+        if self._p.n_mpi_processes > 1:
+            dst[...] = 0.0  # every rank writes its owned rows only; the host sums the slices
         if src.ndim == 1:
             check(lib.bs_vmult(self._p._ctx, self.which, _vp(src), _vp(dst)))
         else:
             check(lib.bs_vmult_multi(self._p._ctx, self.which, src.shape[0], _vp(src), _vp(dst)))
+        self._p._allsum(dst)
         return dst
 
     def __matmul__(self, x):
@@ -166,8 +169,9 @@ class SolverControl:
 
 # ---------------------------------------------------------------------------------------------------------------
 class BEMProblem:
-    def __init__(self, device=0, rank=0, nranks=1):
+    def __init__(self, device=0, rank=0, nranks=1, comm=None, stream=None):
         self.device, self.this_mpi_process, self.n_mpi_processes = device, rank, nranks
+        self.comm, self.stream = comm, stream
         # parameters (names follow declare_parameters, bem_stokes.cc:207-476)
         self.fe_degree = 1
         self.map_degree = None            # default: isoparametric
@@ -215,8 +219,13 @@ class BEMProblem:
         ctx = _lib.ctx_p()
         check(lib.bs_create(C.byref(ctx), self.device, self.fe_degree, self.map_degree))
         self._ctx = ctx
+        if self.stream is not None:
+            check(lib.bs_set_stream(ctx, C.c_void_p(self.stream)))
         if self.n_mpi_processes > 1:
             check(lib.bs_set_partition(ctx, self.this_mpi_process, self.n_mpi_processes, None, self.mesh.n_nodes))
+            if self.comm is None:
+                raise ValueError("nranks > 1 needs a communicator (bemstokes_b200.comm.TorchComm)")
+            self.comm.attach(ctx)
         mm = self.map_mesh
         euler = np.ascontiguousarray(mm.nodes.T.reshape(-1))  # component-major euler_vec
         check(lib.bs_set_geometry(ctx, mm.n_nodes, _dp(euler), self.mesh.n_cells, _ip(mm.conn), self.mesh.n_nodes,
@@ -248,11 +257,31 @@ class BEMProblem:
         wp = np.asarray(self.wall_position_0, dtype=np.float64)
         check(lib.bs_set_kernel(self._ctx, ktype, self.epsilon, o, _dp(wp)))
 
+    def _allsum(self, arr):
+        """Sum host arrays over ranks (replicated host vectors out of rank-owned slices); no-op on one rank."""
+        if self.n_mpi_processes > 1:
+            import torch
+            import torch.distributed as dist
+            dev = self.comm.device if self.comm is not None and self.comm.device is not None else "cpu"
+            t = torch.from_numpy(arr).to(dev)
+            dist.all_reduce(t, group=getattr(self.comm, "group", None))
+            arr[...] = t.cpu().numpy()
+        return arr
+
     def owned_nodes(self):
         n = C.c_int()
         out = np.zeros(self.N, dtype=np.int32)
         check(lib.bs_get_owned_nodes(self._ctx, C.byref(n), _ip(out)))
         return out[:n.value].copy()
+
+    def _owned_mask(self, nr):
+        own = np.zeros(self.n_dofs + nr, dtype=bool)
+        nodes = self.owned_nodes()
+        for c in range(3):
+            own[nodes + c * self.N] = True
+        if self.this_mpi_process == self.n_mpi_processes - 1:
+            own[self.n_dofs:] = True
+        return own
 
     # ---- pre-pass (host) --------------------------------------------------------------------------------
     def compute_center_of_mass_and_rigid_modes(self, frame=0):
@@ -343,7 +372,11 @@ class BEMProblem:
                 self.solver_control._last_step = 1
             else:
                 self._setup_preconditioner(_lib.MAT_A)
+                if self.n_mpi_processes > 1:
+                    own = self._owned_mask(nr)
+                    x[~own] = 0.0
                 its = self.gmres(_lib.MAT_A, x, b)
+                self._allsum(x)
                 if its > 100:
                     self.reassemble_preconditoner = True
             r = self.monolithic_system_matrix @ x - b

@@ -176,3 +176,37 @@ def test_kernel_units_vanish_on_wall():
         assert np.abs(bo.W_fs(R[None], R[None], o)[0, o]).max() < 1e-6
         # physical version: normal velocity due to a tangential force vanishes on the symmetry plane
         assert abs(bo.G_fs(R[None], Rim[None], o)[0, o, o]) < 1e-12
+
+
+def test_c_port_matches_numpy_oracle(half_refined):
+    """oracle/bem_port.c (the timed CPU baseline) against the pinned NumPy oracle, entry by entry."""
+    from oracle import port
+    geo, pre = half_refined
+    for kind in (bo.FREE, bo.FREE_SURFACE, bo.NO_SLIP):
+        ker = bo.KernelSpec(kind, 0.0, 1, (0, 1.4, 0))
+        V, K, pairs = port.assemble_VK(geo, ker, 8, "Mixed", 10, 10, 60)
+        Vo, Ko = bo.assemble_VK(geo, ker, 8, "Mixed", 10, rows=np.arange(10, 60))
+        assert np.abs(V - Vo).max() <= 1e-13 * np.abs(Vo).max()
+        assert np.abs(K - Ko).max() <= 2e-12 * np.abs(Ko).max()
+    n2, c2 = bo.cubesphere(1, 2)
+    g2 = bo.Geometry(n2, c2, 2)
+    V, K, _ = port.assemble_VK(g2, bo.KernelSpec(), 6, "Mixed", 6)
+    Vo, Ko = bo.assemble_VK(g2, bo.KernelSpec(), 6, "Mixed", 6)
+    assert np.abs(V - Vo).max() <= 1e-13 * np.abs(Vo).max() and np.abs(K - Ko).max() <= 2e-12 * np.abs(Ko).max()
+    A = np.random.default_rng(0).uniform(-1, 1, (50, 70))
+    x = np.random.default_rng(1).uniform(-1, 1, 70)
+    assert np.abs(port.gemv(A, x) - A @ x).max() < 1e-12
+
+
+def test_c_port_gmres_counts(goldens, half_refined, VK_free):
+    from oracle import port
+    geo, pre = half_refined
+    V, K = VK_free
+    Vc, _ = bo.correct_V(V, pre)
+    A, b = bo.monolithic(Vc, bo.correct_K(K, geo.N), pre, "ImposedForce", 1)
+    D = np.diag(A).copy()
+    D[3 * geo.N:] = 1.0
+    x, its, res, ok = port.gmres(A, b, diag_inv=1 / D)
+    assert ok and its == goldens["gmres_iterations_no_box"]["Jacobi"]
+    x, its, res, ok = port.gmres(A, b)
+    assert ok and its == 40
