@@ -26,7 +26,8 @@ class BsStats(C.Structure):
     _fields_ = [("assemble_regular_ms", C.c_double), ("assemble_singular_ms", C.c_double), ("geometry_ms", C.c_double),
                 ("correct_ms", C.c_double), ("monolithic_ms", C.c_double), ("precond_setup_ms", C.c_double),
                 ("solve_ms", C.c_double), ("vmult_ms_last", C.c_double), ("kernel_launches", C.c_longlong),
-                ("pairs_regular", C.c_longlong), ("pairs_singular", C.c_longlong)]
+                ("pairs_regular", C.c_longlong), ("pairs_singular", C.c_longlong),
+                ("n_cell_blocks", C.c_longlong), ("n_colours", C.c_longlong), ("node_touch_ratio", C.c_double)]
 
 
 ALLGATHERV_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, c_int_p, c_int_p, C.c_void_p)
@@ -62,6 +63,7 @@ SIGNATURES = {
     "bs_precond_setup": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int]),
     "bs_precond_vmult": (C.c_int, [ctx_p, C.c_void_p, C.c_void_p]),
     "bs_gmres": (C.c_int, [ctx_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, c_int_p, c_double_p]),
+    "bs_set_gmres_orthogonalization": (C.c_int, [ctx_p, C.c_int]),
     "bs_gmres_multi": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, c_int_p,
                                  c_double_p]),
     "bs_direct_solve": (C.c_int, [ctx_p, C.c_int, C.c_void_p, C.c_void_p]),
@@ -88,6 +90,7 @@ MAT_V, MAT_K, MAT_A = 0, 1, 2
 PREC_NONE, PREC_JACOBI, PREC_DIRECT, PREC_BLOCK_DIRECT, PREC_BAND = 0, 1, 2, 3, 4
 GRID_REAL, GRID_IMPOSED_FORCE, GRID_IMPOSED_VELOCITY = 0, 1, 2
 PTR_HOST, PTR_DEVICE = 0, 1
+ORTHO_CGS2, ORTHO_MGS = 0, 1
 ERR_NOT_CONVERGED = -4
 ERR_NO_DEVICE = -3
 

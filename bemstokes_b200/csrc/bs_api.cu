@@ -76,7 +76,11 @@ static void from_internal(Context &c, const double *d_int_full, int nextra, doub
 
 static void alloc_matrix(Context &c, DBuf<double> &store, DMat &M, size_t rows, size_t cols) {
   store.alloc((c.rows_loc + MAX_RIGID) * c.ld + 2);
-  store.zero(c.stream);
+  // the assembly writes every (row, column < 3N) entry exactly once before anything reads it; only the padding
+  // columns [3N, ld) and the MAX_RIGID spare rows have to be cleared
+  if (c.rows_loc)
+    BS_CUDA(cudaMemset2DAsync(store.p + c.n3(), c.ld * sizeof(double), 0, (c.ld - c.n3()) * sizeof(double), c.rows_loc, c.stream));
+  BS_CUDA(cudaMemsetAsync(store.p + c.rows_loc * c.ld, 0, (MAX_RIGID * c.ld + 2) * sizeof(double), c.stream));
   M.p = store.p;
   M.rows = rows;
   M.cols = cols;
@@ -713,6 +717,14 @@ int bs_gmres(bs_context *h, int which, const double *b, double *x, double tol_ab
   return rc;
 }
 
+int bs_set_gmres_orthogonalization(bs_context *h, int kind) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(kind == BS_ORTHO_CGS2 || kind == BS_ORTHO_MGS, "unknown orthogonalisation");
+  c.gmres_ortho = kind;
+  BS_API_END
+}
+
 int bs_gmres_multi(bs_context *h, int which, int nrhs, const double *B, double *X, double tol_abs, int max_steps,
                    int max_n_tmp_vectors, int *iterations, double *final_residuals) {
   int worst = BS_OK;
@@ -806,6 +818,9 @@ int bs_get_stats(bs_context *h, bs_stats *out) {
   BS_API_BEGIN
   Context &c = ctx_of(h);
   BS_REQUIRE(out != nullptr, "null output");
+  c.stats.n_cell_blocks = c.blocks.nblocks;
+  c.stats.n_colours = c.blocks.colour_start.empty() ? 0 : (long long)c.blocks.colour_start.size() - 1;
+  c.stats.node_touch_ratio = c.blocks.node_touch_ratio;
   *out = c.stats;
   BS_API_END
 }

@@ -107,9 +107,13 @@ struct RegParams {
   const double *support;    // [N][3]
   const int *conn_pos;      // [ncell][NA]
   const double *cellq;      // [ncell][7][nq_pad]
-  const double *phi;        // [nq][NA]
+  const double *l1d;        // [n1d][NB1] 1-D Lagrange values at the 1-D rule points (NB1 = degree+1)
+  int n1d;
   const int *blk_cell_ptr, *blk_cells;
   const signed char *blk_slots;
+  const int *blk_nodes;            // [nblocks][tj] node position per slot, -1 unused
+  const unsigned char *blk_first;  // [nblocks][tj] first-touch flag
+  int blk_begin;                   // first block of the colour being launched
   double *V, *K;
   size_t ld;
   KernelParams kp;
@@ -138,20 +142,37 @@ __device__ __forceinline__ int vidx(int i, int j) {
   return a == 0 ? b : (a == 1 ? 2 + b : 5);  // (0,0)=0 (0,1)=1 (0,2)=2 (1,1)=3 (1,2)=4 (2,2)=5
 }
 
-template <int NA, int KT, bool SPLIT>
-__global__ void __launch_bounds__(TI, 1) k_assemble_regular(const RegParams P) {
+// 1-D node index (ix, iy) of scalar shape function a: phi_a(q) = l_ix(x_q) * l_iy(y_q)  (deal.II FE_Q order)
+template <int NA>
+__device__ __forceinline__ constexpr int shape_ix(int a) {
+  return NA == 4 ? (a & 1) : (a == 0 ? 0 : a == 1 ? 2 : a == 2 ? 0 : a == 3 ? 2 : a == 4 ? 0 : a == 5 ? 2 : 1);
+}
+template <int NA>
+__device__ __forceinline__ constexpr int shape_iy(int a) {
+  return NA == 4 ? (a >> 1) : (a == 0 ? 0 : a == 1 ? 0 : a == 2 ? 2 : a == 3 ? 2 : a == 4 ? 1 : a == 5 ? 1 : a == 6 ? 0 : a == 7 ? 2 : 1);
+}
+
+// Regular pass.  TI collocation nodes per CTA, QS threads per node (each takes every QS-th row of the tensor
+// rule), so a CTA has TI*QS threads.  Per cell: sum-factorised accumulation over the tensor-product rule
+// (x-direction into NB1 temporaries per value, y-direction once per quadrature row), pair-wise shuffle
+// combine, then add into the shared [value][slot][row] tile.
+template <int NA, int KT, bool SPLIT, int QS>
+__global__ void __launch_bounds__(TI *QS, 1) k_assemble_regular(const RegParams P) {
   constexpr int NV = GreenTraits<KT>::NV;
   constexpr int NV2 = 2 * NV;
+  constexpr int NB1 = (NA == 4) ? 2 : 3;
+  constexpr int NT = TI * QS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int tj = P.tj, nq = P.nq, nqp = P.nq_pad;
+  const int tj = P.tj, nq = P.nq, nqp = P.nq_pad, n1 = P.n1d;
   double *cellbuf = reinterpret_cast<double *>(smem_raw);                   // [2][7][nqp]
-  double *phi_s = cellbuf + (size_t)2 * 7 * nqp;                            // [nq][NA]
-  double *acc_s = phi_s + (size_t)nqp * NA;                                 // [tj][NV2][ACC_LD]
+  double *l1d_s = cellbuf + (size_t)2 * 7 * nqp;                            // [n1][NB1] 1-D shape values
+  double *acc_s = l1d_s + (size_t)nqp * NA;                                 // [NV2][tj][ACC_LD]
   uint64_t *bars = reinterpret_cast<uint64_t *>(acc_s + (size_t)tj * NV2 * ACC_LD);  // [2]
 
   const int t = threadIdx.x;
-  const int blk = blockIdx.x;
-  const int p = P.p0 + blockIdx.y * TI + t;
+  const int rl = t / QS, part = t - rl * QS;
+  const int blk = P.blk_begin + blockIdx.x;
+  const int p = P.p0 + blockIdx.y * TI + rl;
   const bool row_ok = p < P.p1;
   const int cs = P.blk_cell_ptr[blk], ce = P.blk_cell_ptr[blk + 1];
   const uint32_t cell_bytes = (uint32_t)(7 * nqp * sizeof(double));
@@ -161,8 +182,8 @@ __global__ void __launch_bounds__(TI, 1) k_assemble_regular(const RegParams P) {
     mbar_init(&bars[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = t; i < nq * NA; i += TI) phi_s[i] = P.phi[i];
-  for (int i = t; i < tj * NV2 * ACC_LD; i += TI) acc_s[i] = 0.0;
+  for (int i = t; i < n1 * NB1; i += NT) l1d_s[i] = P.l1d[i];
+  for (int i = t; i < tj * NV2 * ACC_LD; i += NT) acc_s[i] = 0.0;
   __syncthreads();
   if (t == 0 && cs < ce) {
     mbar_expect_tx(&bars[0], cell_bytes);
@@ -201,47 +222,71 @@ __global__ void __launch_bounds__(TI, 1) k_assemble_regular(const RegParams P) {
     }
     mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
     const double *cq = cellbuf + (size_t)buf * 7 * nqp;
-    if (row_ok && !sing) {  // singular (node in cell) pairs are integrated by K2 (ref: 2885-2908)
+    const bool ok = row_ok && !sing;  // singular (node in cell) pairs are integrated by K2 (ref: 2885-2908)
+    const unsigned okmask = __ballot_sync(0xffffffffu, ok);   // both threads of a row agree
+    if (ok) {
 #pragma unroll
-      for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
+      for (int pass = 0; pass < (SPLIT ? 2 : 1); ++pass) {
         constexpr int NACC = SPLIT ? NV : NV2;
         double acc[NA][NACC];
 #pragma unroll
         for (int a = 0; a < NA; ++a)
 #pragma unroll
           for (int v = 0; v < NACC; ++v) acc[a][v] = 0.0;
+        for (int qy = part; qy < n1; qy += QS) {
+          double tmp[NB1][NACC];
+#pragma unroll
+          for (int b = 0; b < NB1; ++b)
+#pragma unroll
+            for (int v = 0; v < NACC; ++v) tmp[b][v] = 0.0;
+          const int q0 = qy * n1;
 #pragma unroll 2
-        for (int q = 0; q < nq; ++q) {
-          double R[3], Rim[3], nJ[3], g[NV], k[NV];
+          for (int qx = 0; qx < n1; ++qx) {
+            const int q = q0 + qx;
+            double R[3], Rim[3], nJ[3], g[NV], k[NV];
 #pragma unroll
-          for (int d = 0; d < 3; ++d) {
-            const double yq = cq[d * nqp + q];
-            R[d] = yq - x[d];
-            Rim[d] = yq - xim[d];
-            nJ[d] = cq[(3 + d) * nqp + q];
-          }
-          green_eval<KT>(R, Rim, nJ, cq[6 * nqp + q], eps, o, g, k);
+            for (int d = 0; d < 3; ++d) {
+              const double yq = cq[d * nqp + q];
+              R[d] = yq - x[d];
+              Rim[d] = yq - xim[d];
+              nJ[d] = cq[(3 + d) * nqp + q];
+            }
+            green_eval<KT>(R, Rim, nJ, cq[6 * nqp + q], eps, o, g, k);
 #pragma unroll
-          for (int a = 0; a < NA; ++a) {
-            const double ph = phi_s[q * NA + a];
-            if (!SPLIT) {
+            for (int b = 0; b < NB1; ++b) {
+              const double l = l1d_s[qx * NB1 + b];
+              if (!SPLIT) {
 #pragma unroll
-              for (int v = 0; v < NV; ++v) {
-                acc[a][v] = fma(g[v], ph, acc[a][v]);
-                acc[a][NV + v] = fma(k[v], ph, acc[a][NV + v]);
+                for (int v = 0; v < NV; ++v) {
+                  tmp[b][v] = fma(g[v], l, tmp[b][v]);
+                  tmp[b][NV + v] = fma(k[v], l, tmp[b][NV + v]);
+                }
+              } else {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) tmp[b][v] = fma(pass == 0 ? g[v] : k[v], l, tmp[b][v]);
               }
-            } else {
-#pragma unroll
-              for (int v = 0; v < NV; ++v) acc[a][v] = fma(part == 0 ? g[v] : k[v], ph, acc[a][v]);
             }
           }
+#pragma unroll
+          for (int a = 0; a < NA; ++a) {
+            const double l = l1d_s[qy * NB1 + shape_iy<NA>(a)];
+#pragma unroll
+            for (int v = 0; v < NACC; ++v) acc[a][v] = fma(tmp[shape_ix<NA>(a)][v], l, acc[a][v]);
+          }
         }
+        // combine the QS partial sums of a row (adjacent lanes), then lane `part` adds its share of the shape
+        // functions into the shared tile [value][slot][row]: conflict-free here and in the write-out
 #pragma unroll
         for (int a = 0; a < NA; ++a) {
-          if (slot[a] >= 0) {
-            double *dst = acc_s + ((size_t)slot[a] * NV2 + (SPLIT ? part * NV : 0)) * ACC_LD + t;
 #pragma unroll
-            for (int v = 0; v < NACC; ++v) dst[(size_t)v * ACC_LD] += acc[a][v];
+          for (int v = 0; v < NACC; ++v) {
+#pragma unroll
+            for (int m = 1; m < QS; m <<= 1) acc[a][v] += __shfl_xor_sync(okmask, acc[a][v], m);
+          }
+          if ((a % QS) == part) {
+            double *dst = acc_s + ((size_t)(SPLIT ? pass * NV : 0) * tj + slot[a]) * ACC_LD + rl;
+#pragma unroll
+            for (int v = 0; v < NACC; ++v) dst[(size_t)v * tj * ACC_LD] += acc[a][v];
           }
         }
       }
@@ -249,39 +294,58 @@ __global__ void __launch_bounds__(TI, 1) k_assemble_regular(const RegParams P) {
     __syncthreads();  // everyone is done with cellbuf[buf] before it is refilled two iterations later
   }
 
-  // ---- write the finished tile: rows 3*(p-p0)+i, columns 3*(blk*tj+slot)+j, 16-byte stores along columns ----
-  const int ncols_tile = 3 * tj;                      // even
-  const int col0 = 3 * blk * tj;
-  const int ncols_valid = min(ncols_tile, 3 * P.N - col0);
+  // ---- combine the tile with global memory: rows 3*(p-p0)+i, columns 3*node(slot)+j.  The first colour that
+  // touches a node column stores, later colours (launched after this one) add: fixed summation order.
   const int rows_tile = min(TI, P.p1 - (P.p0 + (int)blockIdx.y * TI));
-  const int half = ncols_tile / 2;
-  const int total = rows_tile * 3 * half;
-  for (int e = t; e < total; e += TI) {
-    const int rr = e / half, cp = (e - rr * half) * 2;   // rr = 3*rowlocal + i
-    if (cp >= ncols_valid) continue;
-    const int rl = rr / 3, i = rr - 3 * rl;
-    const int s0 = cp / 3, j0 = cp - 3 * s0;
-    const int c1 = cp + 1, s1 = c1 / 3, j1 = c1 - 3 * s1;
-    const double *a0 = acc_s + ((size_t)s0 * NV2 + vidx<NV>(i, j0)) * ACC_LD + rl;
-    const double *a1 = acc_s + ((size_t)s1 * NV2 + vidx<NV>(i, j1)) * ACC_LD + rl;
-    const size_t row = (size_t)3 * (blockIdx.y * TI + rl) + i;
-    const size_t off = row * P.ld + col0 + cp;
-    if (c1 < ncols_valid) {
-      *reinterpret_cast<double2 *>(P.V + off) = make_double2(a0[0], a1[0]);
-      *reinterpret_cast<double2 *>(P.K + off) = make_double2(a0[(size_t)NV * ACC_LD], a1[(size_t)NV * ACC_LD]);
+  const int *nodes = P.blk_nodes + (size_t)blk * tj;
+  const unsigned char *first = P.blk_first + (size_t)blk * tj;
+  const int total = rows_tile * 3 * tj;
+  for (int e = t; e < total; e += NT) {
+    const int rr = e / tj, sl = e - rr * tj;   // rr = 3*rowlocal + i
+    const int node = nodes[sl];
+    if (node < 0) continue;
+    const int r_ = rr / 3, i = rr - 3 * r_;
+    const size_t off = ((size_t)3 * (blockIdx.y * TI + r_) + i) * P.ld + (size_t)3 * node;
+    const double *as = acc_s + (size_t)sl * ACC_LD + r_;
+    double v[3], k[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      v[j] = as[(size_t)vidx<NV>(i, j) * tj * ACC_LD];
+      k[j] = as[(size_t)(NV + vidx<NV>(i, j)) * tj * ACC_LD];
+    }
+    if (first[sl]) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        P.V[off + j] = v[j];
+        P.K[off + j] = k[j];
+      }
     } else {
-      P.V[off] = a0[0];
-      P.K[off] = a0[(size_t)NV * ACC_LD];
+      // fire-and-forget L2 reductions: no load latency on the critical path.  Blocks of one colour never share a
+      // node and colours are separate launches, so each address receives its addends in a fixed order.
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(P.V + off + j), "d"(v[j]) : "memory");
+        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(P.K + off + j), "d"(k[j]) : "memory");
+      }
     }
   }
 }
 
+constexpr int REG_QS = 2;
+
 template <int NA, int KT, bool SPLIT>
-static void launch_reg(Context &c, const RegParams &P, dim3 grid, size_t smem) {
-  auto kern = k_assemble_regular<NA, KT, SPLIT>;
+static void launch_reg(Context &c, RegParams P, int nrow_tiles, size_t smem) {
+  auto kern = k_assemble_regular<NA, KT, SPLIT, REG_QS>;
   BS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid, TI, smem, c.stream>>>(P);
-  BS_CUDA(cudaGetLastError());
+  const std::vector<int> &cs = c.blocks.colour_start;
+  for (size_t k = 0; k + 1 < cs.size(); ++k) {  // one launch per colour, stream order = summation order
+    const int nb = cs[k + 1] - cs[k];
+    if (nb <= 0) continue;
+    P.blk_begin = cs[k];
+    kern<<<dim3(nb, nrow_tiles), TI * REG_QS, smem, c.stream>>>(P);
+    BS_CUDA(cudaGetLastError());
+    count_launch(c);
+  }
 }
 
 void launch_assembly_regular(Context &c) {
@@ -291,14 +355,18 @@ void launch_assembly_regular(Context &c) {
   P.N = c.N;
   P.nq = c.nq;
   P.nq_pad = c.nq_pad;
+  P.n1d = (int)c.x1d.size();
   P.tj = c.blocks.tj;
   P.support = c.d_support.p;
   P.conn_pos = c.d_conn_pos.p;
   P.cellq = c.d_cellq.p;
-  P.phi = c.d_phi_reg.p;
+  P.l1d = c.d_l1d.p;
   P.blk_cell_ptr = c.d_blk_cell_ptr.p;
   P.blk_cells = c.d_blk_cells.p;
   P.blk_slots = c.d_blk_slots.p;
+  P.blk_nodes = c.d_blk_nodes.p;
+  P.blk_first = c.d_blk_first.p;
+  P.blk_begin = 0;
   P.V = c.V.p;
   P.K = c.K.p;
   P.ld = c.ld;
@@ -306,7 +374,7 @@ void launch_assembly_regular(Context &c) {
   const int nrow_tiles = (c.p1 - c.p0 + TI - 1) / TI;
   if (nrow_tiles == 0) return;
   BS_REQUIRE(nrow_tiles <= 65535, "too many row tiles per rank");
-  dim3 grid(c.blocks.nblocks, nrow_tiles);
+  const int grid = nrow_tiles;
   const int nv = (c.kp.type == BS_KERNEL_FREE) ? 6 : 9;
   const size_t smem = assembly_smem_bytes(c.na, nv, c.blocks.tj, c.nq_pad);
   const bool q2 = (c.na == 9);
@@ -326,7 +394,6 @@ void launch_assembly_regular(Context &c) {
     default:
       throw Error(BS_ERR_INVALID, "unknown kernel type");
   }
-  count_launch(c);
   c.stats.pairs_regular += (long long)(c.p1 - c.p0) * c.ncell * c.nq;
 }
 

@@ -377,44 +377,149 @@ void build_tables(Context &c) {
   }
   c.d_phi_reg.upload(phi, c.stream);
   c.d_map_tab_reg.upload(tab, c.stream);
+  {  // 1-D factors of the tensor-product shape functions: phi_a(q) = l_ix(a)(x_qx) * l_iy(a)(x_qy)
+    const int n1 = (int)c.x1d.size(), nb1 = c.fe_degree + 1;
+    std::vector<double> l1((size_t)n1 * nb1);
+    for (int i = 0; i < n1; ++i) {
+      double l[3], d[3];
+      lagrange_1d(c.fe_degree, c.x1d[i], l, d);
+      for (int b = 0; b < nb1; ++b) l1[(size_t)i * nb1 + b] = l[b];
+    }
+    c.d_l1d.upload(l1, c.stream);
+  }
 
-  // column blocks: tj consecutive column positions; cell list = union of their patches, in ascending cell id
+  // ---- cell blocks --------------------------------------------------------------------------------------
+  // Disjoint, spatially compact clusters of cells touching at most tj distinct nodes each: every (row node,
+  // cell) pair is integrated exactly once.  Blocks that share a node get different colours; colours are
+  // launched one after another, so the partial tiles of a shared node column are combined in a fixed order
+  // (first colour stores, later colours read-modify-write) without atomics.
   ColumnBlocks &B = c.blocks;
   B.tj = choose_tj(na, c.kp.type, c.nq_pad);
-  B.nblocks = (c.N + B.tj - 1) / B.tj;
+  const int tj = B.tj;
+  BS_REQUIRE(tj >= na, "shared memory too small for one cell per block");
+  std::vector<int> cpos((size_t)c.ncell * na);
+  for (size_t k = 0; k < cpos.size(); ++k) cpos[k] = c.pos_of_node[c.conn[k]];
+  // node -> cells (by position)
+  std::vector<int> nptr(c.N + 1, 0);
+  for (size_t k = 0; k < cpos.size(); ++k) nptr[cpos[k] + 1]++;
+  for (int i = 0; i < c.N; ++i) nptr[i + 1] += nptr[i];
+  std::vector<int> ncells(nptr[c.N]), nfill(nptr.begin(), nptr.end() - 1);
+  for (int cell = 0; cell < c.ncell; ++cell)
+    for (int a = 0; a < na; ++a) ncells[nfill[cpos[(size_t)cell * na + a]]++] = cell;
+  // seed order: cells sorted by their smallest node position (the node order is a Morton curve)
+  std::vector<int> corder(c.ncell);
+  std::iota(corder.begin(), corder.end(), 0);
+  std::vector<int> ckey(c.ncell);
+  for (int cell = 0; cell < c.ncell; ++cell) {
+    int m = cpos[(size_t)cell * na];
+    for (int a = 1; a < na; ++a) m = std::min(m, cpos[(size_t)cell * na + a]);
+    ckey[cell] = m;
+  }
+  std::stable_sort(corder.begin(), corder.end(), [&](int x, int y) { return ckey[x] < ckey[y]; });
+  std::vector<int> block_of(c.ncell, -1);
+  std::vector<std::vector<int>> bcells, bnodes;
+  std::vector<int> mark(c.N, -1);  // mark[node] == current block id when the node is in the block
+  for (int seed : corder) {
+    if (block_of[seed] >= 0) continue;
+    const int b = (int)bcells.size();
+    bcells.emplace_back();
+    bnodes.emplace_back();
+    auto add_cell = [&](int cell) {
+      block_of[cell] = b;
+      bcells[b].push_back(cell);
+      for (int a = 0; a < na; ++a) {
+        const int p = cpos[(size_t)cell * na + a];
+        if (mark[p] != b) {
+          mark[p] = b;
+          bnodes[b].push_back(p);
+        }
+      }
+    };
+    add_cell(seed);
+    while (true) {
+      // candidate = unassigned neighbour cell adding the fewest new nodes (ties: most shared nodes, lowest key)
+      int best = -1, best_new = 1 << 30, best_key = 1 << 30;
+      for (size_t in = 0; in < bnodes[b].size(); ++in) {
+        const int p = bnodes[b][in];
+        for (int e = nptr[p]; e < nptr[p + 1]; ++e) {
+          const int cell = ncells[e];
+          if (block_of[cell] >= 0) continue;
+          int nn = 0;
+          for (int a = 0; a < na; ++a) nn += (mark[cpos[(size_t)cell * na + a]] != b);
+          if (nn < best_new || (nn == best_new && ckey[cell] < best_key)) {
+            best = cell;
+            best_new = nn;
+            best_key = ckey[cell];
+          }
+        }
+      }
+      if (best < 0 || (int)bnodes[b].size() + best_new > tj) break;
+      add_cell(best);
+    }
+  }
+  B.nblocks = (int)bcells.size();
+  // greedy colouring of the block conflict graph (blocks sharing a node)
+  std::vector<std::vector<int>> blocks_of_node(c.N);
+  for (int b = 0; b < B.nblocks; ++b)
+    for (int p : bnodes[b]) blocks_of_node[p].push_back(b);
+  std::vector<int> colour(B.nblocks, -1);
+  int ncol = 0;
+  {
+    std::vector<int> used;
+    for (int b = 0; b < B.nblocks; ++b) {
+      used.assign(ncol + 1, 0);
+      for (int p : bnodes[b])
+        for (int ob : blocks_of_node[p])
+          if (colour[ob] >= 0) used[colour[ob]] = 1;
+      int k = 0;
+      while (k < ncol && used[k]) ++k;
+      colour[b] = k;
+      ncol = std::max(ncol, k + 1);
+    }
+  }
+  // emit blocks grouped by colour; first-touch flag = lowest colour among the blocks sharing the node
+  std::vector<int> border(B.nblocks);
+  std::iota(border.begin(), border.end(), 0);
+  std::stable_sort(border.begin(), border.end(), [&](int x, int y) { return colour[x] < colour[y]; });
+  B.colour_start.assign(ncol + 1, 0);
+  for (int b = 0; b < B.nblocks; ++b) B.colour_start[colour[b] + 1]++;
+  for (int k = 0; k < ncol; ++k) B.colour_start[k + 1] += B.colour_start[k];
   B.cell_ptr.assign(1, 0);
   B.cells.clear();
   B.slots.clear();
+  B.nodes.assign((size_t)B.nblocks * tj, -1);
+  B.first.assign((size_t)B.nblocks * tj, 0);
   B.max_cells = 0;
-  std::vector<std::vector<int>> cells_of_block(B.nblocks);
-  for (int cell = 0; cell < c.ncell; ++cell) {
-    int last = -1;
-    // a cell belongs to the block of each of its nodes
-    int blks[MAX_NA];
-    int nb = 0;
-    for (int a = 0; a < na; ++a) {
-      int b = c.pos_of_node[c.conn[(size_t)cell * na + a]] / B.tj;
-      bool dup = false;
-      for (int k = 0; k < nb; ++k) dup |= (blks[k] == b);
-      if (!dup) blks[nb++] = b;
+  long long touched = 0;
+  for (int nb = 0; nb < B.nblocks; ++nb) {
+    const int b = border[nb];
+    std::vector<int> nodes = bnodes[b];
+    std::sort(nodes.begin(), nodes.end());  // ascending positions: runs of consecutive columns coalesce
+    touched += (long long)nodes.size();
+    for (size_t sidx = 0; sidx < nodes.size(); ++sidx) {
+      const int p = nodes[sidx];
+      B.nodes[(size_t)nb * tj + sidx] = p;
+      int minc = colour[b];
+      for (int ob : blocks_of_node[p]) minc = std::min(minc, colour[ob]);
+      B.first[(size_t)nb * tj + sidx] = (minc == colour[b]) ? 1 : 0;
     }
-    (void)last;
-    for (int k = 0; k < nb; ++k) cells_of_block[blks[k]].push_back(cell);
-  }
-  for (int b = 0; b < B.nblocks; ++b) {
-    for (int cell : cells_of_block[b]) {
+    for (int cell : bcells[b]) {
       B.cells.push_back(cell);
       for (int a = 0; a < na; ++a) {
-        int p = c.pos_of_node[c.conn[(size_t)cell * na + a]];
-        B.slots.push_back((p / B.tj == b) ? (signed char)(p % B.tj) : (signed char)-1);
+        const int p = cpos[(size_t)cell * na + a];
+        const int sidx = (int)(std::lower_bound(nodes.begin(), nodes.end(), p) - nodes.begin());
+        B.slots.push_back((signed char)sidx);
       }
     }
     B.cell_ptr.push_back((int)B.cells.size());
-    B.max_cells = std::max(B.max_cells, (int)cells_of_block[b].size());
+    B.max_cells = std::max(B.max_cells, (int)bcells[b].size());
   }
+  B.node_touch_ratio = (double)touched / std::max(1, c.N);
   c.d_blk_cell_ptr.upload(B.cell_ptr, c.stream);
   c.d_blk_cells.upload(B.cells, c.stream);
   c.d_blk_slots.upload(B.slots, c.stream);
+  c.d_blk_nodes.upload(B.nodes, c.stream);
+  c.d_blk_first.upload(B.first, c.stream);
 
   // singular rule tables: per rule, per point: phi[na], then (phi_map, dphi_x, dphi_y)[na_map], then weight
   if (c.have_singular) {

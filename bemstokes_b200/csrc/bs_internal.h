@@ -113,8 +113,12 @@ struct ColumnBlocks {
   int nblocks = 0;
   std::vector<int> cell_ptr;        // [nblocks+1]
   std::vector<int> cells;           // concatenated cell ids
-  std::vector<signed char> slots;   // [ncells_total][na] slot in block or -1
+  std::vector<signed char> slots;   // [ncells_total][na] slot of the cell's node in its block
+  std::vector<int> nodes;           // [nblocks][tj] node position of every slot (-1 = unused)
+  std::vector<unsigned char> first; // [nblocks][tj] 1 = this block's colour is the first to touch the node column
+  std::vector<int> colour_start;    // [ncolours+1] block ranges per colour (blocks are sorted by colour)
   int max_cells = 0;
+  double node_touch_ratio = 0;      // sum over blocks of touched nodes / N  (tile traffic amplification)
 };
 
 struct Context {
@@ -155,11 +159,14 @@ struct Context {
   DBuf<int> d_conn_map;             // [ncell][na_map]
   DBuf<double> d_cellq;             // [ncell][7][nq_pad]
   DBuf<double> d_phi_reg;           // [nq][na]
+  DBuf<double> d_l1d;               // [n1d][degree+1] 1-D Lagrange values at the 1-D rule points
   DBuf<double> d_map_tab_reg;       // [nq][na_map][3]  (phi, dphi_x, dphi_y)
   int nq = 0, nq_pad = 0;
   ColumnBlocks blocks;
   DBuf<int> d_blk_cell_ptr, d_blk_cells;
   DBuf<signed char> d_blk_slots;
+  DBuf<int> d_blk_nodes;
+  DBuf<unsigned char> d_blk_first;
   // singular pass tables
   DBuf<int> d_patch_ptr, d_patch_cell, d_patch_local;   // per internal position (CSR)
   DBuf<double> d_sing_tab;          // concatenated per rule: [nqs][ (na + 3*na_map + 1) ]
@@ -181,6 +188,7 @@ struct Context {
   double l2gamma = 0.0;
   bool have_projector = false;
 
+  int gmres_ortho = BS_ORTHO_CGS2;
   // preconditioner
   int prec_kind = BS_PREC_NONE;
   int prec_which = BS_MAT_A;

@@ -319,7 +319,8 @@ int gmres(Context &c, int which, const double *d_b, double *d_x, double tol, int
   basis.alloc((size_t)(m + 1) * mloc + 2);
   w.alloc(mloc + 2);
   z.alloc(mloc + 2);
-  coef.alloc((size_t)2 * (m + 2));
+  coef.alloc((size_t)2 * (m + 2) + 2);
+  double *nrm_scratch = coef.p + 2 * (m + 2);
   c.d_xchg.alloc(std::max(c.d_xchg.n, mfull + 2));
   double *xfull = c.d_xchg.p;
   std::vector<double> hbuf(2 * (m + 2)), H((size_t)(m + 1) * m, 0.0), gamma(m + 1), ci(m), si(m), h(m + 2), yk(m);
@@ -327,10 +328,10 @@ int gmres(Context &c, int which, const double *d_b, double *d_x, double tol, int
   double rho = 0.0;
   bool converged = false;
   auto norm2 = [&](const double *v) {
-    multi_dot(c, v, 0, 1, v, mloc, coef.p);
-    allreduce(c, coef.p, 1);
+    multi_dot(c, v, 0, 1, v, mloc, nrm_scratch);
+    allreduce(c, nrm_scratch, 1);
     double s2;
-    BS_CUDA(cudaMemcpyAsync(&s2, coef.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    BS_CUDA(cudaMemcpyAsync(&s2, nrm_scratch, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     BS_CUDA(cudaStreamSynchronize(c.stream));
     return s2;
   };
@@ -347,7 +348,7 @@ int gmres(Context &c, int which, const double *d_b, double *d_x, double tol, int
       break;
     }
     if (its >= max_steps) break;
-    k_scale_inv_norm<<<(unsigned)std::min<size_t>((mloc + 255) / 256, 1184), 256, 0, c.stream>>>(coef.p, z.p, basis.p, mloc);
+    k_scale_inv_norm<<<(unsigned)std::min<size_t>((mloc + 255) / 256, 1184), 256, 0, c.stream>>>(nrm_scratch, z.p, basis.p, mloc);
     count_launch(c);
     std::fill(gamma.begin(), gamma.end(), 0.0);
     gamma[0] = rho;
@@ -359,14 +360,42 @@ int gmres(Context &c, int which, const double *d_b, double *d_x, double tol, int
       apply_operator(c, which, xfull, w.p);
       apply_precond(c, w.p, z.p);
       dim = inner + 1;
-      // classical Gram-Schmidt applied twice (one fused multi-dot + one fused multi-axpy per pass): the
-      // reference's modified Gram-Schmidt with its re-orthogonalisation safeguard, without per-vector reductions
-      multi_dot(c, basis.p, mloc, dim, z.p, mloc, coef.p);
-      allreduce(c, coef.p, dim);
-      multi_axpy(c, basis.p, mloc, dim, coef.p, -1.0, z.p, mloc);
-      multi_dot(c, basis.p, mloc, dim, z.p, mloc, coef.p + (m + 2));
-      allreduce(c, coef.p + (m + 2), dim);
-      multi_axpy(c, basis.p, mloc, dim, coef.p + (m + 2), -1.0, z.p, mloc);
+      if (c.gmres_ortho == BS_ORTHO_CGS2) {
+        // classical Gram-Schmidt applied twice (one fused multi-dot + one fused multi-axpy per pass, one
+        // reduction each): orthogonal to machine precision, so the re-orthogonalisation safeguard of the
+        // reference's modified Gram-Schmidt is built in
+        multi_dot(c, basis.p, mloc, dim, z.p, mloc, coef.p);
+        allreduce(c, coef.p, dim);
+        multi_axpy(c, basis.p, mloc, dim, coef.p, -1.0, z.p, mloc);
+        multi_dot(c, basis.p, mloc, dim, z.p, mloc, coef.p + (m + 2));
+        allreduce(c, coef.p + (m + 2), dim);
+        multi_axpy(c, basis.p, mloc, dim, coef.p + (m + 2), -1.0, z.p, mloc);
+      } else {
+        // deal.II SolverGMRES::modified_gram_schmidt verbatim: sequential projections, and at every 5th
+        // iteration a second pass if the vector lost more than 10*sqrt(eps) of its norm
+        const bool check = (its % 5 == 0);
+        double norm_start2 = 0.0;
+        if (check) norm_start2 = norm2(z.p);
+        BS_CUDA(cudaMemsetAsync(coef.p + (m + 2), 0, sizeof(double) * (m + 2), c.stream));
+        for (int i = 0; i < dim; ++i) {
+          multi_dot(c, basis.p + (size_t)i * mloc, mloc, 1, z.p, mloc, coef.p + (m + 2) + i);
+          allreduce(c, coef.p + (m + 2) + i, 1);
+          multi_axpy(c, basis.p + (size_t)i * mloc, mloc, 1, coef.p + (m + 2) + i, -1.0, z.p, mloc);
+        }
+        BS_CUDA(cudaMemcpyAsync(coef.p, coef.p + (m + 2), sizeof(double) * dim, cudaMemcpyDeviceToDevice, c.stream));
+        BS_CUDA(cudaMemsetAsync(coef.p + (m + 2), 0, sizeof(double) * (m + 2), c.stream));
+        bool reorth = false;
+        if (check) {
+          const double nv2 = norm2(z.p);
+          reorth = !(std::sqrt(nv2) > 10.0 * std::sqrt(norm_start2) * std::sqrt(2.220446049250313e-16));
+        }
+        if (reorth)
+          for (int i = 0; i < dim; ++i) {
+            multi_dot(c, basis.p + (size_t)i * mloc, mloc, 1, z.p, mloc, coef.p + (m + 2) + i);
+            allreduce(c, coef.p + (m + 2) + i, 1);
+            multi_axpy(c, basis.p + (size_t)i * mloc, mloc, 1, coef.p + (m + 2) + i, -1.0, z.p, mloc);
+          }
+      }
       multi_dot(c, z.p, 0, 1, z.p, mloc, coef.p + dim);
       allreduce(c, coef.p + dim, 1);
       BS_CUDA(cudaMemcpyAsync(hbuf.data(), coef.p, sizeof(double) * 2 * (m + 2), cudaMemcpyDeviceToHost, c.stream));

@@ -193,6 +193,7 @@ class BEMProblem:
         self.bandwith_preconditioner = False
         self.bandwith = 100
         self.gmres_restart = 100
+        self.gmres_orthogonalization = "CGS2"   # "MGS" = deal.II's modified Gram-Schmidt verbatim
         self.solver_control = SolverControl(1000, 1e-10)
         self.force_pole = (0.0, 0.0, 0.0)
         self.keep_VK = True
@@ -355,6 +356,8 @@ class BEMProblem:
 
     def gmres(self, which, x, b):
         its, res = C.c_int(), C.c_double()
+        check(lib.bs_set_gmres_orthogonalization(
+            self._ctx, _lib.ORTHO_MGS if self.gmres_orthogonalization == "MGS" else _lib.ORTHO_CGS2))
         rc = lib.bs_gmres(self._ctx, which, _vp(b), _vp(x), self.solver_control.tolerance, self.solver_control.max_steps,
                           self.gmres_restart, C.byref(its), C.byref(res))
         self.solver_control._last_step, self.solver_control._last_value = its.value, res.value

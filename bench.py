@@ -258,6 +258,8 @@ def run_ours(args):
                           "assemble_singular": st["assemble_singular_ms"] / args.steps, "cell_geometry": st["geometry_ms"] / args.steps,
                           "corrections": st["correct_ms"] / args.steps, "monolithic": st["monolithic_ms"] / args.steps,
                           "gmres": solve_ms},
+            "tiling": {"cell_blocks": int(st["n_cell_blocks"]), "colours": int(st["n_colours"]),
+                       "node_touch_ratio": st["node_touch_ratio"]},
             "drag_over_6pi": (drag / (6 * math.pi)) if drag is not None else None,
             "clocks": clocks,
             "e2e": {"value": entries / e2e_asm_s / 1e9, "unit": "Gentries/s", "time_to_solution_s": e2e_tts_s,

@@ -46,6 +46,12 @@ typedef enum { BS_MAT_V = 0, BS_MAT_K = 1, BS_MAT_A = 2 } bs_matrix_id;
 typedef enum { BS_PREC_NONE = 0, BS_PREC_JACOBI = 1, BS_PREC_DIRECT = 2, BS_PREC_BLOCK_DIRECT = 3, BS_PREC_BAND = 4 } bs_precond_kind;
 typedef enum { BS_GRID_REAL = 0, BS_GRID_IMPOSED_FORCE = 1, BS_GRID_IMPOSED_VELOCITY = 2 } bs_grid_type;
 typedef enum { BS_PTR_HOST = 0, BS_PTR_DEVICE = 1 } bs_pointer_mode;
+/* Arnoldi orthogonalisation: BS_ORTHO_MGS = deal.II's modified Gram-Schmidt verbatim (sequential projections,
+ * conditional second pass every 5th iteration; one reduction per basis vector); BS_ORTHO_CGS2 (default) =
+ * classical Gram-Schmidt twice with two fused reductions per iteration.  Identical in exact arithmetic; CGS2 keeps
+ * the basis orthogonal to machine precision, so its iteration count can be one lower when the reference's residual
+ * estimate sits just above the tolerance. */
+typedef enum { BS_ORTHO_CGS2 = 0, BS_ORTHO_MGS = 1 } bs_ortho_kind;
 
 const char *bs_last_error(void);
 int bs_version(void);
@@ -130,6 +136,7 @@ int bs_precond_vmult(bs_context *ctx, const double *x, double *y);
  * max_steps like SolverControl. */
 int bs_gmres(bs_context *ctx, int which, const double *b, double *x, double tol_abs, int max_steps,
              int max_n_tmp_vectors, int *iterations, double *final_residual);
+int bs_set_gmres_orthogonalization(bs_context *ctx, int kind);
 /* nrhs independent systems (the 6 rigid-body resistance problems), B and X nrhs x size. */
 int bs_gmres_multi(bs_context *ctx, int which, int nrhs, const double *B, double *X, double tol_abs, int max_steps,
                    int max_n_tmp_vectors, int *iterations, double *final_residuals);
@@ -163,6 +170,9 @@ typedef struct {
   double precond_setup_ms, solve_ms, vmult_ms_last;
   long long kernel_launches; /* number of this library's kernels launched since bs_reset_stats */
   long long pairs_regular, pairs_singular;
+  /* tiling of the regular pass: disjoint cell blocks, colours (launches), tile traffic amplification */
+  long long n_cell_blocks, n_colours;
+  double node_touch_ratio;
 } bs_stats;
 int bs_get_stats(bs_context *ctx, bs_stats *out);
 int bs_reset_stats(bs_context *ctx);
