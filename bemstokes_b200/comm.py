@@ -19,6 +19,10 @@ class _DevPtr:
 
 
 def dev_tensor(ptr, n, device):
+    """float64 tensor aliasing `n` doubles at `ptr` (device memory on a CUDA device, host memory on 'cpu')."""
+    if device is None or torch.device(device).type == "cpu":
+        buf = (C.c_double * n).from_address(int(ptr))
+        return torch.from_numpy(np.ctypeslib.as_array(buf))
     return torch.as_tensor(_DevPtr(ptr, n), device=device)
 
 

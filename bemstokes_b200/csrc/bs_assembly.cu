@@ -14,7 +14,13 @@
 #include "bs_internal.h"
 #include "bs_green.cuh"
 
+#ifndef BS_QX_UNROLL
+#define BS_QX_UNROLL 2
+#endif
+
 namespace bs {
+
+constexpr int QX_UNROLL = BS_QX_UNROLL;  // quadrature points of one rule row in flight per thread
 
 void count_launch(Context &c, int n) { c.stats.kernel_launches += n; }
 
@@ -122,12 +128,12 @@ struct RegParams {
 constexpr int ACC_LD = TI + 1;  // padded row-node stride of the shared accumulators (bank-conflict free both ways)
 
 size_t assembly_smem_bytes(int na, int nv, int tj, int nq_pad) {
-  return (size_t)2 * nv * tj * ACC_LD * 8 + (size_t)2 * 7 * nq_pad * 8 + (size_t)nq_pad * na * 8 + 64;
+  return (size_t)2 * nv * tj * ACC_LD * 8 + (size_t)2 * 7 * nq_pad * 8 + (size_t)nq_pad * na * 8 + 64;  // dynamic part
 }
 
 int choose_tj(int na, int kernel_type, int nq_pad) {
   const int nv = (kernel_type == BS_KERNEL_FREE) ? 6 : 9;
-  const size_t budget = 227 * 1024;
+  const size_t budget = 227 * 1024 - 2048;  // minus the static block-metadata arrays
   int tj = 2;
   for (int t = 2; t <= 32; t += 2)
     if (assembly_smem_bytes(na, nv, t, nq_pad) <= budget) tj = t;
@@ -152,25 +158,103 @@ __device__ __forceinline__ constexpr int shape_iy(int a) {
   return NA == 4 ? (a >> 1) : (a == 0 ? 0 : a == 1 ? 0 : a == 2 ? 2 : a == 3 ? 2 : a == 4 ? 1 : a == 5 ? 1 : a == 6 ? 0 : a == 7 ? 2 : 1);
 }
 
-// Regular pass.  TI collocation nodes per CTA, QS threads per node (each takes every QS-th row of the tensor
-// rule), so a CTA has TI*QS threads.  Per cell: sum-factorised accumulation over the tensor-product rule
-// (x-direction into NB1 temporaries per value, y-direction once per quadrature row), pair-wise shuffle
-// combine, then add into the shared [value][slot][row] tile.
-template <int NA, int KT, bool SPLIT, int QS>
-__global__ void __launch_bounds__(TI *QS, 1) k_assemble_regular(const RegParams P) {
+// One (row, cell) integration over this thread's share of the tensor rule.  MODE 0: single layer only, 1: double
+// layer only, 2: both.  Sum-factorised: x-direction into NB1 temporaries per value, y-direction once per row of
+// the rule; then the QS partial sums of a row (adjacent lanes) are combined by shuffles and lane `part` adds its
+// share of the shape functions into the shared tile [value][slot][row].
+template <int NA, int KT, int MODE, int QS, bool HAS_EPS>
+__device__ __forceinline__ void cell_pass(const double *__restrict__ cq, const double *__restrict__ l1d_s, int n1, int nqp,
+                                          const double (&x)[3], const double (&xim)[3], double eps, int o, bool ok,
+                                          int part, const int (&slot)[NA], double *__restrict__ acc_s, int tj, int rl) {
+  constexpr int NV = GreenTraits<KT>::NV;
+  constexpr int NB1 = (NA == 4) ? 2 : 3;
+  constexpr int NACC = (MODE == 2) ? 2 * NV : NV;
+  constexpr int VOFF = (MODE == 1) ? NV : 0;
+  double acc[NA][NACC];
+#pragma unroll
+  for (int a = 0; a < NA; ++a)
+#pragma unroll
+    for (int v = 0; v < NACC; ++v) acc[a][v] = 0.0;
+  for (int qy = part; ok && qy < n1; qy += QS) {
+    double tmp[NB1][NACC];
+#pragma unroll
+    for (int b = 0; b < NB1; ++b)
+#pragma unroll
+      for (int v = 0; v < NACC; ++v) tmp[b][v] = 0.0;
+    const int q0 = qy * n1;
+#pragma unroll QX_UNROLL
+    for (int qx = 0; qx < n1; ++qx) {
+      const int q = q0 + qx;
+      double R[3], Rim[3], nJ[3], g[NV], k[NV];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const double yq = cq[d * nqp + q];
+        R[d] = yq - x[d];
+        Rim[d] = yq - xim[d];
+        nJ[d] = cq[(3 + d) * nqp + q];
+      }
+      green_eval<KT>(R, Rim, nJ, cq[6 * nqp + q], HAS_EPS ? eps : 0.0, o, g, k);
+#pragma unroll
+      for (int b = 0; b < NB1; ++b) {
+        const double l = l1d_s[qx * NB1 + b];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          if (MODE == 2) {
+            tmp[b][v] = fma(g[v], l, tmp[b][v]);
+            tmp[b][NV + v] = fma(k[v], l, tmp[b][NV + v]);
+          } else {
+            tmp[b][v] = fma(MODE == 0 ? g[v] : k[v], l, tmp[b][v]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      const double l = l1d_s[qy * NB1 + shape_iy<NA>(a)];
+#pragma unroll
+      for (int v = 0; v < NACC; ++v) acc[a][v] = fma(tmp[shape_ix<NA>(a)][v], l, acc[a][v]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < NA; ++a) {
+#pragma unroll
+    for (int v = 0; v < NACC; ++v) {
+#pragma unroll
+      for (int m = 1; m < QS; m <<= 1) acc[a][v] += __shfl_xor_sync(0xffffffffu, acc[a][v], m);
+    }
+    if ((a % QS) == part) {
+      double *dst = acc_s + ((size_t)VOFF * tj + slot[a]) * ACC_LD + rl;
+#pragma unroll
+      for (int v = 0; v < NACC; ++v) dst[(size_t)v * tj * ACC_LD] += acc[a][v];
+    }
+  }
+}
+
+// Regular pass.  TI collocation nodes per CTA; QS threads per node share the rows of the tensor rule, and with
+// VS == 2 a second set of warps integrates the double layer while the first integrates the single layer
+// (half the accumulator registers per thread -> twice the resident warps).  A CTA has TI*QS*VS threads.
+constexpr int MAXC = 32;  // cells per block (a block touches at most tj <= 32 nodes)
+
+template <int NA, int KT, bool SPLIT, int QS, int VS, bool HAS_EPS>
+__global__ void __launch_bounds__(TI *QS *VS, 1) k_assemble_regular(const RegParams P) {
   constexpr int NV = GreenTraits<KT>::NV;
   constexpr int NV2 = 2 * NV;
   constexpr int NB1 = (NA == 4) ? 2 : 3;
-  constexpr int NT = TI * QS;
+  constexpr int NT = TI * QS * VS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int tj = P.tj, nq = P.nq, nqp = P.nq_pad, n1 = P.n1d;
+  const int tj = P.tj, nqp = P.nq_pad, n1 = P.n1d;
   double *cellbuf = reinterpret_cast<double *>(smem_raw);                   // [2][7][nqp]
   double *l1d_s = cellbuf + (size_t)2 * 7 * nqp;                            // [n1][NB1] 1-D shape values
   double *acc_s = l1d_s + (size_t)nqp * NA;                                 // [NV2][tj][ACC_LD]
   uint64_t *bars = reinterpret_cast<uint64_t *>(acc_s + (size_t)tj * NV2 * ACC_LD);  // [2]
+  __shared__ int s_cells[MAXC];          // block metadata staged once: no dependent global loads per cell
+  __shared__ int s_conn[MAXC * NA];
+  __shared__ signed char s_slots[MAXC * NA];
 
   const int t = threadIdx.x;
-  const int rl = t / QS, part = t - rl * QS;
+  const int vpart = (VS == 2) ? t / (TI * QS) : 0;   // warp-uniform role: 0 single layer, 1 double layer
+  const int tt = t - vpart * (TI * QS);
+  const int rl = tt / QS, part = tt - rl * QS;
   const int blk = P.blk_begin + blockIdx.x;
   const int p = P.p0 + blockIdx.y * TI + rl;
   const bool row_ok = p < P.p1;
@@ -183,11 +267,17 @@ __global__ void __launch_bounds__(TI *QS, 1) k_assemble_regular(const RegParams 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = t; i < n1 * NB1; i += NT) l1d_s[i] = P.l1d[i];
+  for (int i = t; i < (ce - cs) * NA; i += NT) {
+    const int cell = P.blk_cells[cs + i / NA];
+    if (i % NA == 0) s_cells[i / NA] = cell;
+    s_conn[i] = P.conn_pos[(size_t)cell * NA + i % NA];
+    s_slots[i] = P.blk_slots[(size_t)cs * NA + i];
+  }
   for (int i = t; i < tj * NV2 * ACC_LD; i += NT) acc_s[i] = 0.0;
   __syncthreads();
   if (t == 0 && cs < ce) {
     mbar_expect_tx(&bars[0], cell_bytes);
-    bulk_g2s(cellbuf, P.cellq + (size_t)P.blk_cells[cs] * 7 * nqp, cell_bytes, &bars[0]);
+    bulk_g2s(cellbuf, P.cellq + (size_t)s_cells[0] * 7 * nqp, cell_bytes, &bars[0]);
   }
   double x[3] = {0, 0, 0};
   if (row_ok) {
@@ -201,7 +291,7 @@ __global__ void __launch_bounds__(TI *QS, 1) k_assemble_regular(const RegParams 
     for (int d = 0; d < 3; ++d)
       if (d == P.kp.o) xim[d] = x[d] - 2.0 * (x[d] - P.kp.wall_pos);  // ref: bem_stokes.cc:2918-2919
   }
-  const double eps = P.kp.eps;
+  const double eps = HAS_EPS ? P.kp.eps : 0.0;
   const int o = P.kp.o;
 
   for (int kc = cs; kc < ce; ++kc) {
@@ -209,87 +299,27 @@ __global__ void __launch_bounds__(TI *QS, 1) k_assemble_regular(const RegParams 
     const int buf = it & 1;
     if (t == 0 && kc + 1 < ce) {
       mbar_expect_tx(&bars[buf ^ 1], cell_bytes);
-      bulk_g2s(cellbuf + (size_t)(buf ^ 1) * 7 * nqp, P.cellq + (size_t)P.blk_cells[kc + 1] * 7 * nqp, cell_bytes,
+      bulk_g2s(cellbuf + (size_t)(buf ^ 1) * 7 * nqp, P.cellq + (size_t)s_cells[it + 1] * 7 * nqp, cell_bytes,
                &bars[buf ^ 1]);
     }
-    const int cell = P.blk_cells[kc];
     int slot[NA];
     bool sing = false;
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
-      slot[a] = P.blk_slots[(size_t)kc * NA + a];
-      sing |= (P.conn_pos[(size_t)cell * NA + a] == p);
+      slot[a] = s_slots[it * NA + a];
+      sing |= (s_conn[it * NA + a] == p);
     }
     mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
     const double *cq = cellbuf + (size_t)buf * 7 * nqp;
     const bool ok = row_ok && !sing;  // singular (node in cell) pairs are integrated by K2 (ref: 2885-2908)
-    const unsigned okmask = __ballot_sync(0xffffffffu, ok);   // both threads of a row agree
-    if (ok) {
-#pragma unroll
-      for (int pass = 0; pass < (SPLIT ? 2 : 1); ++pass) {
-        constexpr int NACC = SPLIT ? NV : NV2;
-        double acc[NA][NACC];
-#pragma unroll
-        for (int a = 0; a < NA; ++a)
-#pragma unroll
-          for (int v = 0; v < NACC; ++v) acc[a][v] = 0.0;
-        for (int qy = part; qy < n1; qy += QS) {
-          double tmp[NB1][NACC];
-#pragma unroll
-          for (int b = 0; b < NB1; ++b)
-#pragma unroll
-            for (int v = 0; v < NACC; ++v) tmp[b][v] = 0.0;
-          const int q0 = qy * n1;
-#pragma unroll 2
-          for (int qx = 0; qx < n1; ++qx) {
-            const int q = q0 + qx;
-            double R[3], Rim[3], nJ[3], g[NV], k[NV];
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-              const double yq = cq[d * nqp + q];
-              R[d] = yq - x[d];
-              Rim[d] = yq - xim[d];
-              nJ[d] = cq[(3 + d) * nqp + q];
-            }
-            green_eval<KT>(R, Rim, nJ, cq[6 * nqp + q], eps, o, g, k);
-#pragma unroll
-            for (int b = 0; b < NB1; ++b) {
-              const double l = l1d_s[qx * NB1 + b];
-              if (!SPLIT) {
-#pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                  tmp[b][v] = fma(g[v], l, tmp[b][v]);
-                  tmp[b][NV + v] = fma(k[v], l, tmp[b][NV + v]);
-                }
-              } else {
-#pragma unroll
-                for (int v = 0; v < NV; ++v) tmp[b][v] = fma(pass == 0 ? g[v] : k[v], l, tmp[b][v]);
-              }
-            }
-          }
-#pragma unroll
-          for (int a = 0; a < NA; ++a) {
-            const double l = l1d_s[qy * NB1 + shape_iy<NA>(a)];
-#pragma unroll
-            for (int v = 0; v < NACC; ++v) acc[a][v] = fma(tmp[shape_ix<NA>(a)][v], l, acc[a][v]);
-          }
-        }
-        // combine the QS partial sums of a row (adjacent lanes), then lane `part` adds its share of the shape
-        // functions into the shared tile [value][slot][row]: conflict-free here and in the write-out
-#pragma unroll
-        for (int a = 0; a < NA; ++a) {
-#pragma unroll
-          for (int v = 0; v < NACC; ++v) {
-#pragma unroll
-            for (int m = 1; m < QS; m <<= 1) acc[a][v] += __shfl_xor_sync(okmask, acc[a][v], m);
-          }
-          if ((a % QS) == part) {
-            double *dst = acc_s + ((size_t)(SPLIT ? pass * NV : 0) * tj + slot[a]) * ACC_LD + rl;
-#pragma unroll
-            for (int v = 0; v < NACC; ++v) dst[(size_t)v * tj * ACC_LD] += acc[a][v];
-          }
-        }
-      }
+    if (VS == 2) {
+      if (vpart == 0) cell_pass<NA, KT, 0, QS, HAS_EPS>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
+      else cell_pass<NA, KT, 1, QS, HAS_EPS>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
+    } else if (SPLIT) {
+      cell_pass<NA, KT, 0, QS, HAS_EPS>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
+      cell_pass<NA, KT, 1, QS, HAS_EPS>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
+    } else {
+      cell_pass<NA, KT, 2, QS, HAS_EPS>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
     }
     __syncthreads();  // everyone is done with cellbuf[buf] before it is refilled two iterations later
   }
@@ -331,18 +361,17 @@ __global__ void __launch_bounds__(TI *QS, 1) k_assemble_regular(const RegParams 
   }
 }
 
-constexpr int REG_QS = 2;
-
-template <int NA, int KT, bool SPLIT>
+template <int NA, int KT, bool SPLIT, int QS, int VS>
 static void launch_reg(Context &c, RegParams P, int nrow_tiles, size_t smem) {
-  auto kern = k_assemble_regular<NA, KT, SPLIT, REG_QS>;
+  BS_REQUIRE(c.blocks.max_cells <= MAXC, "cell block larger than MAXC");
+  auto kern = (c.kp.eps == 0.0) ? k_assemble_regular<NA, KT, SPLIT, QS, VS, false> : k_assemble_regular<NA, KT, SPLIT, QS, VS, true>;
   BS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const std::vector<int> &cs = c.blocks.colour_start;
   for (size_t k = 0; k + 1 < cs.size(); ++k) {  // one launch per colour, stream order = summation order
     const int nb = cs[k + 1] - cs[k];
     if (nb <= 0) continue;
     P.blk_begin = cs[k];
-    kern<<<dim3(nb, nrow_tiles), TI * REG_QS, smem, c.stream>>>(P);
+    kern<<<dim3(nb, nrow_tiles), TI * QS * VS, smem, c.stream>>>(P);
     BS_CUDA(cudaGetLastError());
     count_launch(c);
   }
@@ -379,17 +408,18 @@ void launch_assembly_regular(Context &c) {
   const size_t smem = assembly_smem_bytes(c.na, nv, c.blocks.tj, c.nq_pad);
   const bool q2 = (c.na == 9);
   switch (c.kp.type) {
+    // <NA, kernel, two sequential passes?, threads per row over q, thread sets over {V,K}>
     case BS_KERNEL_FREE:
-      if (q2) launch_reg<9, BS_KERNEL_FREE, true>(c, P, grid, smem);
-      else launch_reg<4, BS_KERNEL_FREE, false>(c, P, grid, smem);
+      if (q2) launch_reg<9, BS_KERNEL_FREE, false, 1, 2>(c, P, grid, smem);      // 256 threads
+      else launch_reg<4, BS_KERNEL_FREE, false, 2, 1>(c, P, grid, smem);         // 256 threads (V/K thread split measured slower)
       break;
     case BS_KERNEL_FREE_SURFACE:
-      if (q2) launch_reg<9, BS_KERNEL_FREE_SURFACE, true>(c, P, grid, smem);
-      else launch_reg<4, BS_KERNEL_FREE_SURFACE, true>(c, P, grid, smem);
+      if (q2) launch_reg<9, BS_KERNEL_FREE_SURFACE, false, 1, 2>(c, P, grid, smem);
+      else launch_reg<4, BS_KERNEL_FREE_SURFACE, true, 2, 1>(c, P, grid, smem);
       break;
     case BS_KERNEL_NO_SLIP:
-      if (q2) launch_reg<9, BS_KERNEL_NO_SLIP, true>(c, P, grid, smem);
-      else launch_reg<4, BS_KERNEL_NO_SLIP, true>(c, P, grid, smem);
+      if (q2) launch_reg<9, BS_KERNEL_NO_SLIP, false, 1, 2>(c, P, grid, smem);
+      else launch_reg<4, BS_KERNEL_NO_SLIP, true, 2, 1>(c, P, grid, smem);
       break;
     default:
       throw Error(BS_ERR_INVALID, "unknown kernel type");

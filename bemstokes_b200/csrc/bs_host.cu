@@ -453,7 +453,7 @@ void build_tables(Context &c) {
           }
         }
       }
-      if (best < 0 || (int)bnodes[b].size() + best_new > tj) break;
+      if (best < 0 || (int)bnodes[b].size() + best_new > tj || (int)bcells[b].size() >= 32) break;
       add_cell(best);
     }
   }

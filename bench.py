@@ -91,9 +91,8 @@ class ClockSampler:
             for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        hi = sorted(sm)[len(sm) // 2:] if sm else []
-        return {"sm_mhz": float(np.median(hi)) if hi else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_mhz_min": min(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def pairs_count(n_rows_nodes, ncell, nq, sing_pts_per_cell):
