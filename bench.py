@@ -119,9 +119,14 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     comm = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
         from bemstokes_b200.comm import TorchComm
         comm = TorchComm(device=dev)
+        # one explicit stream for the library's kernels AND torch's collectives (the legacy default stream is
+        # not ordered against the library's non-blocking stream)
+        side = torch.cuda.Stream(device=dev)
+        torch.cuda.set_stream(side)
     wl = workload(args, world)
     mesh = bb.cubesphere(degree=wl["degree"], m=wl["m"])
     N, ncell = mesh.n_nodes, mesh.n_cells
@@ -344,7 +349,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="q1", choices=["q1", "q2"])
-    ap.add_argument("--m", type=int, default=0, help="cube-sphere subdivisions per face edge (default 64*N^(1/4))")
+    ap.add_argument("--subdiv", dest="m", type=int, default=0, help="cube-sphere subdivisions per face edge (default 64*N^(1/4))")
     ap.add_argument("--refine", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
