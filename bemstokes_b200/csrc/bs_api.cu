@@ -214,6 +214,18 @@ int bs_set_geometry(bs_context *h, int n_map_nodes, const double *euler_vec, int
   BS_API_BEGIN
   Context &c = ctx_of(h);
   BS_REQUIRE(n_map_nodes > 0 && ncell > 0 && n_nodes > 0 && euler_vec && conn_map && conn_stokes, "bad geometry arguments");
+  // Moving geometry on an unchanged mesh (the reference's per-frame compute_euler_vector, bem_stokes.cc:5677-5687):
+  // keep ordering, partition, cell blocks, tables and matrix storage; only the coordinates are new.
+  if (c.have_geometry && c.Nmap == n_map_nodes && c.N == n_nodes && c.ncell == ncell &&
+      std::equal(c.conn_map.begin(), c.conn_map.end(), conn_map) && std::equal(c.conn.begin(), c.conn.end(), conn_stokes)) {
+    for (int i = 0; i < n_map_nodes; ++i)
+      for (int d = 0; d < 3; ++d) c.map_nodes[(size_t)3 * i + d] = euler_vec[(size_t)i + (size_t)d * n_map_nodes];
+    update_coordinates(c);
+    c.V = DMat();
+    c.K = DMat();
+    c.A = DMat();
+    return BS_OK;
+  }
   c.Nmap = n_map_nodes;
   c.N = n_nodes;
   c.ncell = ncell;
@@ -863,6 +875,41 @@ __global__ void k_fp64_peak(double *out, int iters) {
     a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+extern "C" int bs_bench_fp64_sustained(int device, double seconds, double *tflops) {
+  BS_API_BEGIN
+  BS_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  BS_CUDA(cudaGetDeviceProperties(&prop, device));
+  const int blocks = prop.multiProcessorCount * 4, threads = 512, iters = 1 << 15;
+  DBuf<double> out;
+  out.alloc((size_t)blocks * threads);
+  cudaEvent_t e0, e1;
+  BS_CUDA(cudaEventCreate(&e0));
+  BS_CUDA(cudaEventCreate(&e1));
+  // back-to-back launches for `seconds` (power-capped clocks), rate of the second half
+  k_fp64_peak<<<blocks, threads>>>(out.p, iters);
+  BS_CUDA(cudaDeviceSynchronize());
+  const double fl = 2.0 * 8 * (double)iters * blocks * threads;
+  cudaEventRecord(e0);
+  k_fp64_peak<<<blocks, threads>>>(out.p, iters);
+  cudaEventRecord(e1);
+  BS_CUDA(cudaEventSynchronize(e1));
+  float ms1 = 0;
+  cudaEventElapsedTime(&ms1, e0, e1);
+  const int n = std::max(4, (int)(seconds * 1e3 / std::max(ms1, 0.01f)));
+  for (int i = 0; i < n / 2; ++i) k_fp64_peak<<<blocks, threads>>>(out.p, iters);
+  cudaEventRecord(e0);
+  for (int i = 0; i < n / 2; ++i) k_fp64_peak<<<blocks, threads>>>(out.p, iters);
+  cudaEventRecord(e1);
+  BS_CUDA(cudaEventSynchronize(e1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (tflops) *tflops = fl * (n / 2) / (ms * 1e-3) / 1e12;
+  BS_API_END
 }
 
 extern "C" int bs_bench_fp64_peak(int device, double *tflops) {

@@ -243,7 +243,19 @@ static inline uint64_t spread3(uint64_t v) {
   return v;
 }
 
-void build_geometry(Context &c) {
+static void compute_support(Context &c);
+
+void update_coordinates(Context &c) {
+  compute_support(c);
+  std::vector<double> sup_int((size_t)3 * c.N);
+  for (int p = 0; p < c.N; ++p)
+    for (int d = 0; d < 3; ++d) sup_int[(size_t)3 * p + d] = c.support[(size_t)3 * c.node_of_pos[p] + d];
+  c.d_support.upload(sup_int, c.stream);
+  c.d_map_nodes.upload(c.map_nodes, c.stream);
+  BS_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+static void compute_support(Context &c) {
   const int N = c.N, na = c.na, nam = c.na_map;
   // support points = mapped unit support points (ref: DoFTools::map_dofs_to_support_points, bem_stokes.cc:2855)
   c.support.assign((size_t)3 * N, 0.0);
@@ -269,6 +281,11 @@ void build_geometry(Context &c) {
       for (int d = 0; d < 3; ++d) c.support[(size_t)3 * i + d] = p[d];
     }
   for (int i = 0; i < N; ++i) BS_REQUIRE(seen[i], "node without a cell");
+}
+
+void build_geometry(Context &c) {
+  const int N = c.N, na = c.na;
+  compute_support(c);
 
   // Morton order of the support points -> spatially compact column blocks and row partitions
   double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};

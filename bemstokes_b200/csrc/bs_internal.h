@@ -223,6 +223,7 @@ struct Context {
 
 // ---- geometry / tables (bs_host.cu) ---------------------------------------------------------------------
 void build_geometry(Context &c);
+void update_coordinates(Context &c);    // same mesh, new map_nodes
 void build_tables(Context &c);          // after geometry + quadrature known
 // ---- assembly (bs_assembly.cu) ---------------------------------------------------------------------------
 void launch_cell_geometry(Context &c);

@@ -243,6 +243,18 @@ class BEMProblem:
             self.shape_velocities = np.zeros(self.n_dofs)
         return self
 
+    def update_geometry(self, mesh=None, map_mesh=None):
+        """New coordinates on the same connectivity (the reference's per-frame compute_euler_vector): keeps the
+        context, ordering, cell blocks and matrix storage."""
+        if mesh is not None:
+            self.mesh = mesh
+            self.map_mesh = mesh if map_mesh is None else map_mesh
+        mm = self.map_mesh
+        euler = np.ascontiguousarray(mm.nodes.T.reshape(-1))
+        check(lib.bs_set_geometry(self._ctx, mm.n_nodes, _dp(euler), self.mesh.n_cells, _ip(mm.conn), self.mesh.n_nodes,
+                                  _ip(self.mesh.conn), None))
+        return self
+
     def _set_kernel(self):
         # ref: kernel_wall_orientation = last axis with wall_spans[0][axis]==0 (bem_stokes.cc:2861-2866)
         o = 1

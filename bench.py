@@ -160,7 +160,7 @@ def run_ours(args):
     def step_e2e():
         """host buffers in (geometry, quadrature, normals, rigid modes), host result out"""
         t0 = time.perf_counter()
-        p.reinit()                       # bs_create + bs_set_geometry (H2D) + tables
+        p.update_geometry()              # bs_set_geometry: host euler vector -> device (per-frame flow of the reference)
         check(lib.bs_assemble_VK(p._ctx))
         vn = np.zeros(n)
         nh = np.ascontiguousarray(p.normal_vector_pure)
@@ -225,8 +225,9 @@ def run_ours(args):
     rows_loc = 3 * n_own + (6 if rank == world - 1 else 0)
     if rank == 0:
         peaks, peak_src = load_peaks()
-        fp64 = C.c_double()
-        check(lib.bs_bench_fp64_peak(local, C.byref(fp64)))
+        fp64, fp64_burst = C.c_double(), C.c_double()
+        check(lib.bs_bench_fp64_peak(local, C.byref(fp64_burst)))
+        check(lib.bs_bench_fp64_sustained(local, 1.0, C.byref(fp64)))  # K1 runs for 100s of ms under the power cap
         na = 4 if wl["degree"] == 1 else 9
         nq = wl["quad"] ** 2
         sing_pts = sum(lib.bs_make_singular_rule(_lib.SING_MIXED, wl["sing"], wl["degree"], a, 0, None, None) for a in range(na))
@@ -242,7 +243,8 @@ def run_ours(args):
                    "algorithmic_bytes_per_launch": 8.0 * rows_loc * (n + 6), "launch_ms": mv_ms}
         roof_asm = {"kernel": "k_assemble_regular", "bound": "fp64", "achieved": asm_tflops / world, "peak": fp64.value,
                     "unit": "TFLOP/s", "frac": asm_tflops / world / fp64.value, "traffic": None,
-                    "peak_source": "measured in this run by an 8-chain DFMA microbenchmark (bs_bench_fp64_peak)",
+                    "peak_source": "measured in this run: 8-chain DFMA microbenchmark sustained for 1 s under the power cap "
+                                   "(bs_bench_fp64_sustained); burst figure in fp64_peak_tflops_burst",
                     "algorithmic_flops_per_pair": f_pair, "pairs_regular": pr, "pairs_singular": ps, "launch_ms": asm_ms}
         dominant_is_asm = asm_ms >= solve_ms
         line = {
@@ -272,7 +274,7 @@ def run_ours(args):
             "gpu_launches": int(st["kernel_launches"]),
             "roofline": roof_asm if dominant_is_asm else roof_mv,
             "roofline_secondary": roof_mv if dominant_is_asm else roof_asm,
-            "fp64_peak_tflops_measured": fp64.value,
+            "fp64_peak_tflops_measured": fp64.value, "fp64_peak_tflops_burst": fp64_burst.value,
         }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(wl, sample_seconds=args.cpu_seconds)

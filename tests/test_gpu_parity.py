@@ -327,3 +327,23 @@ def test_multi_rhs_vmult(half):
     Kd = p.K_matrix.to_dense()
     assert np.abs(Y - X @ Kd.T).max() < 1e-12
     p.close()
+
+
+def test_update_geometry_same_mesh():
+    """Per-frame flow of the reference (compute_euler_vector on an unchanged triangulation): new coordinates through
+    bs_set_geometry on the same context must give the same matrices as a fresh context."""
+    m0 = bb.cubesphere(2, 1)
+    p = make_problem(m0, quadrature_order=6, singular_quadrature_order=8)
+    V0, K0 = raw_VK(p)
+    moved = bb.QuadMesh(m0.nodes * np.array([1.3, 0.9, 1.1]) + np.array([0.1, -0.2, 0.05]), m0.conn, 1)
+    p.update_geometry(moved)
+    V1, K1 = raw_VK(p)
+    q = make_problem(moved, quadrature_order=6, singular_quadrature_order=8)
+    V2, K2 = raw_VK(q)
+    assert np.abs(V1 - V0).max() > 1e-3          # the geometry really changed
+    assert rel_rows(V1, V2) < 1e-14 and rel_rows(K1, K2) < 1e-14
+    geo = bo.Geometry(moved.nodes, moved.conn.astype(np.int64), 1)
+    Vo, Ko = bo.assemble_VK(geo, bo.KernelSpec(), 6, "Mixed", 8)
+    assert rel_rows(V1, Vo) < ENTRY_TOL and rel_rows(K1, Ko) < ENTRY_TOL
+    p.close()
+    q.close()
