@@ -739,17 +739,37 @@ int bs_set_gmres_orthogonalization(bs_context *h, int kind) {
 
 int bs_gmres_multi(bs_context *h, int which, int nrhs, const double *B, double *X, double tol_abs, int max_steps,
                    int max_n_tmp_vectors, int *iterations, double *final_residuals) {
-  int worst = BS_OK;
-  bs_context *ctx = h;
-  if (!ctx) return BS_ERR_INVALID;
-  const size_t m = ctx->c.full_vec_len(which);
+  int rc = BS_OK;
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(B && X && nrhs >= 1, "bad arguments");
+  BS_REQUIRE(c.prec_kind == BS_PREC_NONE || c.prec_which == which, "preconditioner was set up for another matrix");
+  Timer t(c, c.stats.solve_ms);
+  const int nx = nextra_of(c, which);
+  const size_t m = c.full_vec_len(which), mloc = c.local_vec_len(which), off = c.slice_offset(which);
+  const size_t ldv = (m + 3) & ~(size_t)1;
+  DBuf<double> db, dx;
+  db.alloc((size_t)nrhs * ldv);
+  dx.alloc((size_t)nrhs * ldv);
   for (int k = 0; k < nrhs; ++k) {
-    int rc = bs_gmres(h, which, B + (size_t)k * m, X + (size_t)k * m, tol_abs, max_steps, max_n_tmp_vectors,
-                      iterations ? iterations + k : nullptr, final_residuals ? final_residuals + k : nullptr);
-    if (rc != BS_OK) worst = rc;
-    if (rc != BS_OK && rc != BS_ERR_NOT_CONVERGED) return rc;
+    to_internal(c, B + (size_t)k * m, nx, db.p + (size_t)k * ldv);
+    to_internal(c, X + (size_t)k * m, nx, dx.p + (size_t)k * ldv);
   }
-  return worst;
+  rc = gmres_batched(c, which, nrhs, db.p + off, dx.p + off, ldv, tol_abs, max_steps, max_n_tmp_vectors, iterations,
+                     final_residuals);
+  for (int k = 0; k < nrhs; ++k) from_internal(c, dx.p + (size_t)k * ldv, nx, X + (size_t)k * m, off, off + mloc);
+  BS_CUDA(cudaStreamSynchronize(c.stream));
+  if (rc == BS_ERR_NOT_CONVERGED) bs::set_last_error("GMRES did not converge within max_steps for at least one right-hand side");
+  }
+  catch (const bs::Error &e) {
+    bs::set_last_error(e.what());
+    return e.code;
+  }
+  catch (const std::exception &e) {
+    bs::set_last_error(e.what());
+    return BS_ERR_INVALID;
+  }
+  return rc;
 }
 
 int bs_direct_solve(bs_context *h, int which, const double *b, double *x) {

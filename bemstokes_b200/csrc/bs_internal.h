@@ -262,6 +262,8 @@ void exchange(Context &c, int which, const double *y_loc, double *x_full);
 void apply_precond(Context &c, const double *in_loc, double *out_loc);
 int gmres(Context &c, int which, const double *d_b_loc, double *d_x_loc, double tol, int max_steps, int max_tmp,
           int *iters, double *final_res);
+int gmres_batched(Context &c, int which, int nrhs, const double *d_B, double *d_X, size_t ldv, double tol, int max_steps,
+                  int max_tmp, int *iters, double *final_res);
 void count_launch(Context &c, int n = 1);
 
 }  // namespace bs

@@ -79,12 +79,14 @@ void gemv(Context &c, const DMat &M, const double *x, double *y) {
   count_launch(c);
 }
 
-// multi-RHS: Y[k][r] = sum_c A[r][c] X[k][c], NR right-hand sides per pass, 2 rows per warp
+// multi-RHS: Y[k][r] = sum_c A[r][c] X[k][c], NR right-hand sides per pass.  Every matrix element is read once
+// from HBM and used NR times; 4 rows per warp so that the x values (L1/L2 resident) are re-used from registers.
+constexpr int GEMVM_RPW = 4;
 template <int NR>
 __global__ void __launch_bounds__(32 * GEMV_WARPS) k_gemv_multi(const double *__restrict__ A, size_t ld, size_t rows,
                                                                 size_t cols, const double *__restrict__ X, size_t ldx,
                                                                 double *__restrict__ Y, size_t ldy) {
-  constexpr int RPW = 2;
+  constexpr int RPW = GEMVM_RPW;
   const int lane = threadIdx.x & 31;
   const size_t warp = (size_t)blockIdx.x * GEMV_WARPS + (threadIdx.x >> 5);
   const size_t r0 = warp * RPW;
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(32 * GEMV_WARPS) k_gemv_multi(const double *__
 
 template <int NR>
 static void launch_gemv_multi(Context &c, const DMat &M, const double *X, size_t ldx, double *Y, size_t ldy) {
-  const size_t warps = (M.rows + 1) / 2;
+  const size_t warps = (M.rows + GEMVM_RPW - 1) / GEMVM_RPW;
   const unsigned grid = (unsigned)((warps + GEMV_WARPS - 1) / GEMV_WARPS);
   k_gemv_multi<NR><<<grid, 32 * GEMV_WARPS, 0, c.stream>>>(M.p, M.ld, M.rows, M.cols, X, ldx, Y, ldy);
   BS_CUDA(cudaGetLastError());

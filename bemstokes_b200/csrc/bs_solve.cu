@@ -310,139 +310,224 @@ __global__ void k_scale_inv_norm(const double *s2, const double *src, double *ds
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i] * a;
 }
 
-int gmres(Context &c, int which, const double *d_b, double *d_x, double tol, int max_steps, int max_tmp, int *iters,
-          double *final_res) {
+// Orthogonalise z against basis[0..dim) and leave  coef[0..dim) (+ coef[m+2 .. m+2+dim) second-pass part) and
+// coef[dim] = ||z||^2 on the device.  No host synchronisation in CGS2 mode.
+static void orthogonalize(Context &c, const double *basis, size_t mloc, int dim, double *z, double *coef, int m, int its,
+                          double *nrm_scratch) {
+  if (c.gmres_ortho == BS_ORTHO_CGS2) {
+    // classical Gram-Schmidt applied twice (one fused multi-dot + one fused multi-axpy per pass, one reduction
+    // each): orthogonal to machine precision, so the re-orthogonalisation safeguard of the reference's modified
+    // Gram-Schmidt is built in
+    multi_dot(c, basis, mloc, dim, z, mloc, coef);
+    allreduce(c, coef, dim);
+    multi_axpy(c, basis, mloc, dim, coef, -1.0, z, mloc);
+    multi_dot(c, basis, mloc, dim, z, mloc, coef + (m + 2));
+    allreduce(c, coef + (m + 2), dim);
+    multi_axpy(c, basis, mloc, dim, coef + (m + 2), -1.0, z, mloc);
+  } else {
+    // deal.II SolverGMRES::modified_gram_schmidt verbatim: sequential projections, and at every 5th iteration a
+    // second pass if the vector lost more than 10*sqrt(eps) of its norm
+    auto norm2 = [&](const double *v) {
+      multi_dot(c, v, 0, 1, v, mloc, nrm_scratch);
+      allreduce(c, nrm_scratch, 1);
+      double s2;
+      BS_CUDA(cudaMemcpyAsync(&s2, nrm_scratch, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+      BS_CUDA(cudaStreamSynchronize(c.stream));
+      return s2;
+    };
+    const bool check = (its % 5 == 0);
+    double norm_start2 = 0.0;
+    if (check) norm_start2 = norm2(z);
+    BS_CUDA(cudaMemsetAsync(coef + (m + 2), 0, sizeof(double) * (m + 2), c.stream));
+    for (int i = 0; i < dim; ++i) {
+      multi_dot(c, basis + (size_t)i * mloc, mloc, 1, z, mloc, coef + (m + 2) + i);
+      allreduce(c, coef + (m + 2) + i, 1);
+      multi_axpy(c, basis + (size_t)i * mloc, mloc, 1, coef + (m + 2) + i, -1.0, z, mloc);
+    }
+    BS_CUDA(cudaMemcpyAsync(coef, coef + (m + 2), sizeof(double) * dim, cudaMemcpyDeviceToDevice, c.stream));
+    BS_CUDA(cudaMemsetAsync(coef + (m + 2), 0, sizeof(double) * (m + 2), c.stream));
+    bool reorth = false;
+    if (check) {
+      const double nv2 = norm2(z);
+      reorth = !(std::sqrt(nv2) > 10.0 * std::sqrt(norm_start2) * std::sqrt(2.220446049250313e-16));
+    }
+    if (reorth)
+      for (int i = 0; i < dim; ++i) {
+        multi_dot(c, basis + (size_t)i * mloc, mloc, 1, z, mloc, coef + (m + 2) + i);
+        allreduce(c, coef + (m + 2) + i, 1);
+        multi_axpy(c, basis + (size_t)i * mloc, mloc, 1, coef + (m + 2) + i, -1.0, z, mloc);
+      }
+  }
+  multi_dot(c, z, 0, 1, z, mloc, coef + dim);
+  allreduce(c, coef + dim, 1);
+}
+
+// nrhs independent GMRES recurrences advanced in lockstep: ONE pass over the matrix per iteration serves all
+// right-hand sides (multi-RHS GEMV), everything else is per system.  deal.II SolverGMRES semantics per system
+// (left preconditioning, Givens, absolute tolerance on the preconditioned residual, restart max_tmp-2).
+int gmres_batched(Context &c, int which, int nrhs, const double *d_B, double *d_X, size_t ldv, double tol, int max_steps,
+                  int max_tmp, int *iters, double *final_res) {
   BS_REQUIRE(max_tmp >= 3, "max_n_tmp_vectors must be >= 3");
+  BS_REQUIRE(nrhs >= 1, "nrhs must be positive");
   const int m = max_tmp - 2;  // restart length (deal.II: n_tmp_vectors - 2 inner iterations)
   const size_t mloc = c.local_vec_len(which), mfull = c.full_vec_len(which);
-  DBuf<double> basis, w, z, coef;
-  basis.alloc((size_t)(m + 1) * mloc + 2);
-  w.alloc(mloc + 2);
-  z.alloc(mloc + 2);
-  coef.alloc((size_t)2 * (m + 2) + 2);
-  double *nrm_scratch = coef.p + 2 * (m + 2);
-  c.d_xchg.alloc(std::max(c.d_xchg.n, mfull + 2));
-  double *xfull = c.d_xchg.p;
-  std::vector<double> hbuf(2 * (m + 2)), H((size_t)(m + 1) * m, 0.0), gamma(m + 1), ci(m), si(m), h(m + 2), yk(m);
-  int its = 0;
-  double rho = 0.0;
-  bool converged = false;
-  auto norm2 = [&](const double *v) {
-    multi_dot(c, v, 0, 1, v, mloc, nrm_scratch);
-    allreduce(c, nrm_scratch, 1);
-    double s2;
-    BS_CUDA(cudaMemcpyAsync(&s2, nrm_scratch, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
-    BS_CUDA(cudaStreamSynchronize(c.stream));
-    return s2;
+  const size_t ldw = (mloc + 3) & ~(size_t)1, ldx = (mfull + 3) & ~(size_t)1;
+  const size_t CS = (size_t)2 * (m + 2) + 2;
+  const DMat &M = mat_of(c, which);
+  DBuf<double> basis, w, z, coef, xfull;
+  basis.alloc((size_t)nrhs * (m + 1) * mloc + 2);
+  w.alloc((size_t)nrhs * ldw);
+  z.alloc((size_t)nrhs * ldw);
+  coef.alloc((size_t)nrhs * CS);
+  xfull.alloc((size_t)nrhs * ldx);
+  struct Sys {
+    std::vector<double> H, gamma, ci, si, h, yk;
+    int its = 0, dim = 0;
+    double rho = 0;
+    bool active = true, converged = false;
   };
-  while (true) {
-    // r0 = M^{-1} (b - A x)
-    exchange(c, which, d_x, xfull);
-    apply_operator(c, which, xfull, w.p);
-    sub(c, d_b, w.p, w.p, mloc);
-    apply_precond(c, w.p, z.p);
-    const double s2 = norm2(z.p);
-    rho = std::sqrt(s2);
-    if (rho <= tol) {
-      converged = true;
-      break;
-    }
-    if (its >= max_steps) break;
-    k_scale_inv_norm<<<(unsigned)std::min<size_t>((mloc + 255) / 256, 1184), 256, 0, c.stream>>>(nrm_scratch, z.p, basis.p, mloc);
-    count_launch(c);
-    std::fill(gamma.begin(), gamma.end(), 0.0);
-    gamma[0] = rho;
-    int dim = 0;
-    bool stop = false;
-    for (int inner = 0; inner < m && !stop; ++inner) {
-      ++its;
-      exchange(c, which, basis.p + (size_t)inner * mloc, xfull);
-      apply_operator(c, which, xfull, w.p);
-      apply_precond(c, w.p, z.p);
-      dim = inner + 1;
-      if (c.gmres_ortho == BS_ORTHO_CGS2) {
-        // classical Gram-Schmidt applied twice (one fused multi-dot + one fused multi-axpy per pass, one
-        // reduction each): orthogonal to machine precision, so the re-orthogonalisation safeguard of the
-        // reference's modified Gram-Schmidt is built in
-        multi_dot(c, basis.p, mloc, dim, z.p, mloc, coef.p);
-        allreduce(c, coef.p, dim);
-        multi_axpy(c, basis.p, mloc, dim, coef.p, -1.0, z.p, mloc);
-        multi_dot(c, basis.p, mloc, dim, z.p, mloc, coef.p + (m + 2));
-        allreduce(c, coef.p + (m + 2), dim);
-        multi_axpy(c, basis.p, mloc, dim, coef.p + (m + 2), -1.0, z.p, mloc);
-      } else {
-        // deal.II SolverGMRES::modified_gram_schmidt verbatim: sequential projections, and at every 5th
-        // iteration a second pass if the vector lost more than 10*sqrt(eps) of its norm
-        const bool check = (its % 5 == 0);
-        double norm_start2 = 0.0;
-        if (check) norm_start2 = norm2(z.p);
-        BS_CUDA(cudaMemsetAsync(coef.p + (m + 2), 0, sizeof(double) * (m + 2), c.stream));
-        for (int i = 0; i < dim; ++i) {
-          multi_dot(c, basis.p + (size_t)i * mloc, mloc, 1, z.p, mloc, coef.p + (m + 2) + i);
-          allreduce(c, coef.p + (m + 2) + i, 1);
-          multi_axpy(c, basis.p + (size_t)i * mloc, mloc, 1, coef.p + (m + 2) + i, -1.0, z.p, mloc);
-        }
-        BS_CUDA(cudaMemcpyAsync(coef.p, coef.p + (m + 2), sizeof(double) * dim, cudaMemcpyDeviceToDevice, c.stream));
-        BS_CUDA(cudaMemsetAsync(coef.p + (m + 2), 0, sizeof(double) * (m + 2), c.stream));
-        bool reorth = false;
-        if (check) {
-          const double nv2 = norm2(z.p);
-          reorth = !(std::sqrt(nv2) > 10.0 * std::sqrt(norm_start2) * std::sqrt(2.220446049250313e-16));
-        }
-        if (reorth)
-          for (int i = 0; i < dim; ++i) {
-            multi_dot(c, basis.p + (size_t)i * mloc, mloc, 1, z.p, mloc, coef.p + (m + 2) + i);
-            allreduce(c, coef.p + (m + 2) + i, 1);
-            multi_axpy(c, basis.p + (size_t)i * mloc, mloc, 1, coef.p + (m + 2) + i, -1.0, z.p, mloc);
-          }
-      }
-      multi_dot(c, z.p, 0, 1, z.p, mloc, coef.p + dim);
-      allreduce(c, coef.p + dim, 1);
-      BS_CUDA(cudaMemcpyAsync(hbuf.data(), coef.p, sizeof(double) * 2 * (m + 2), cudaMemcpyDeviceToHost, c.stream));
-      BS_CUDA(cudaStreamSynchronize(c.stream));
-      for (int i = 0; i < dim; ++i) h[i] = hbuf[i] + hbuf[m + 2 + i];
-      const double s = std::sqrt(hbuf[dim]);
-      h[dim] = s;
-      k_scale_inv_norm<<<(unsigned)std::min<size_t>((mloc + 255) / 256, 1184), 256, 0, c.stream>>>(
-          coef.p + dim, z.p, basis.p + (size_t)(inner + 1) * mloc, mloc);
-      count_launch(c);
-      // Givens rotations (deal.II SolverGMRES::givens_rotation)
-      for (int i = 0; i < inner; ++i) {
-        const double t = h[i];
-        h[i] = ci[i] * t + si[i] * h[i + 1];
-        h[i + 1] = -si[i] * t + ci[i] * h[i + 1];
-      }
-      const double r = std::hypot(h[inner], h[inner + 1]);
-      ci[inner] = h[inner] / r;
-      si[inner] = h[inner + 1] / r;
-      h[inner] = r;
-      gamma[inner + 1] = -si[inner] * gamma[inner];
-      gamma[inner] = ci[inner] * gamma[inner];
-      for (int i = 0; i < dim; ++i) H[(size_t)i * m + inner] = h[i];
-      rho = std::fabs(gamma[dim]);
-      if (rho <= tol) {
-        converged = true;
-        stop = true;
-      } else if (its >= max_steps) {
-        stop = true;
-      }
-    }
-    // back substitution H y = gamma, x += sum y_i v_i
+  std::vector<Sys> S(nrhs);
+  for (auto &sy : S) {
+    sy.H.assign((size_t)(m + 1) * m, 0.0);
+    sy.gamma.assign(m + 1, 0.0);
+    sy.ci.assign(m, 0.0);
+    sy.si.assign(m, 0.0);
+    sy.h.assign(m + 2, 0.0);
+    sy.yk.assign(m, 0.0);
+  }
+  std::vector<double> hbuf((size_t)nrhs * CS);
+  auto Bs = [&](int s) { return basis.p + (size_t)s * (m + 1) * mloc; };
+  auto Cf = [&](int s) { return coef.p + (size_t)s * CS; };
+  auto matvec_all = [&](const std::vector<int> &act, const std::vector<const double *> &src) {
+    // replicated copies of the sources, then one sweep over the matrix for all of them
+    for (size_t k = 0; k < act.size(); ++k) exchange(c, which, src[k], xfull.p + k * ldx);
+    if (act.size() == 1) gemv(c, M, xfull.p, w.p);
+    else gemv_multi(c, M, (int)act.size(), xfull.p, ldx, w.p, ldw);
+  };
+  auto finish = [&](int s) {  // back substitution H y = gamma, x += sum y_i v_i
+    Sys &sy = S[s];
+    const int dim = sy.dim;
     for (int i = dim - 1; i >= 0; --i) {
-      double s = gamma[i];
-      for (int j = i + 1; j < dim; ++j) s -= H[(size_t)i * m + j] * yk[j];
-      yk[i] = s / H[(size_t)i * m + i];
+      double t = sy.gamma[i];
+      for (int j = i + 1; j < dim; ++j) t -= sy.H[(size_t)i * m + j] * sy.yk[j];
+      sy.yk[i] = t / sy.H[(size_t)i * m + i];
     }
     if (dim > 0) {
-      BS_CUDA(cudaMemcpyAsync(coef.p, yk.data(), sizeof(double) * dim, cudaMemcpyHostToDevice, c.stream));
-      multi_axpy(c, basis.p, mloc, dim, coef.p, 1.0, d_x, mloc);
+      BS_CUDA(cudaMemcpyAsync(Cf(s), sy.yk.data(), sizeof(double) * dim, cudaMemcpyHostToDevice, c.stream));
+      multi_axpy(c, Bs(s), mloc, dim, Cf(s), 1.0, d_X + (size_t)s * ldv, mloc);
       BS_CUDA(cudaStreamSynchronize(c.stream));
     }
-    if (converged || its >= max_steps) break;
+    sy.dim = 0;
+  };
+  const unsigned sgrid = (unsigned)std::min<size_t>((mloc + 255) / 256, 1184);
+
+  while (true) {
+    std::vector<int> act;
+    for (int s = 0; s < nrhs; ++s)
+      if (S[s].active) act.push_back(s);
+    if (act.empty()) break;
+    // ---- r0 = M^{-1} (b - A x) for every active system
+    std::vector<const double *> src;
+    for (int s : act) src.push_back(d_X + (size_t)s * ldv);
+    matvec_all(act, src);
+    for (size_t k = 0; k < act.size(); ++k) {
+      const int s = act[k];
+      sub(c, d_B + (size_t)s * ldv, w.p + k * ldw, w.p + k * ldw, mloc);
+      apply_precond(c, w.p + k * ldw, z.p + k * ldw);
+      multi_dot(c, z.p + k * ldw, 0, 1, z.p + k * ldw, mloc, Cf(s) + CS - 1);
+      allreduce(c, Cf(s) + CS - 1, 1);
+    }
+    BS_CUDA(cudaMemcpyAsync(hbuf.data(), coef.p, sizeof(double) * nrhs * CS, cudaMemcpyDeviceToHost, c.stream));
+    BS_CUDA(cudaStreamSynchronize(c.stream));
+    for (size_t k = 0; k < act.size(); ++k) {
+      const int s = act[k];
+      Sys &sy = S[s];
+      sy.rho = std::sqrt(hbuf[(size_t)s * CS + CS - 1]);
+      if (sy.rho <= tol) {
+        sy.converged = true;
+        sy.active = false;
+        continue;
+      }
+      if (sy.its >= max_steps) {
+        sy.active = false;
+        continue;
+      }
+      k_scale_inv_norm<<<sgrid, 256, 0, c.stream>>>(Cf(s) + CS - 1, z.p + k * ldw, Bs(s), mloc);
+      count_launch(c);
+      std::fill(sy.gamma.begin(), sy.gamma.end(), 0.0);
+      sy.gamma[0] = sy.rho;
+      sy.dim = 0;
+    }
+    // ---- Arnoldi, all still-active systems share the inner index
+    for (int inner = 0; inner < m; ++inner) {
+      act.clear();
+      for (int s = 0; s < nrhs; ++s)
+        if (S[s].active) act.push_back(s);
+      if (act.empty()) break;
+      src.clear();
+      for (int s : act) src.push_back(Bs(s) + (size_t)inner * mloc);
+      matvec_all(act, src);
+      const int dim = inner + 1;
+      for (size_t k = 0; k < act.size(); ++k) {
+        const int s = act[k];
+        ++S[s].its;
+        apply_precond(c, w.p + k * ldw, z.p + k * ldw);
+        orthogonalize(c, Bs(s), mloc, dim, z.p + k * ldw, Cf(s), m, S[s].its, Cf(s) + CS - 2);
+      }
+      BS_CUDA(cudaMemcpyAsync(hbuf.data(), coef.p, sizeof(double) * nrhs * CS, cudaMemcpyDeviceToHost, c.stream));
+      BS_CUDA(cudaStreamSynchronize(c.stream));
+      for (size_t k = 0; k < act.size(); ++k) {
+        const int s = act[k];
+        Sys &sy = S[s];
+        const double *hb = &hbuf[(size_t)s * CS];
+        std::vector<double> &h = sy.h;
+        for (int i = 0; i < dim; ++i) h[i] = hb[i] + hb[m + 2 + i];
+        h[dim] = std::sqrt(hb[dim]);
+        k_scale_inv_norm<<<sgrid, 256, 0, c.stream>>>(Cf(s) + dim, z.p + k * ldw, Bs(s) + (size_t)(inner + 1) * mloc, mloc);
+        count_launch(c);
+        // Givens rotations (deal.II SolverGMRES::givens_rotation)
+        for (int i = 0; i < inner; ++i) {
+          const double t = h[i];
+          h[i] = sy.ci[i] * t + sy.si[i] * h[i + 1];
+          h[i + 1] = -sy.si[i] * t + sy.ci[i] * h[i + 1];
+        }
+        const double r = std::hypot(h[inner], h[inner + 1]);
+        sy.ci[inner] = h[inner] / r;
+        sy.si[inner] = h[inner + 1] / r;
+        h[inner] = r;
+        sy.gamma[inner + 1] = -sy.si[inner] * sy.gamma[inner];
+        sy.gamma[inner] = sy.ci[inner] * sy.gamma[inner];
+        for (int i = 0; i < dim; ++i) sy.H[(size_t)i * m + inner] = h[i];
+        sy.dim = dim;
+        sy.rho = std::fabs(sy.gamma[dim]);
+        if (sy.rho <= tol) {
+          sy.converged = true;
+          sy.active = false;
+        } else if (sy.its >= max_steps) {
+          sy.active = false;
+        }
+      }
+      // the scale kernels above read coef: make sure they ran before the next iteration overwrites it (stream order
+      // guarantees it), then finalise the systems that just stopped
+      for (int s : act)
+        if (!S[s].active) finish(s);
+    }
+    // restart: systems that are still active fold their Krylov correction into x and start over
+    for (int s = 0; s < nrhs; ++s)
+      if (S[s].active) finish(s);
   }
-  if (iters) *iters = its;
-  if (final_res) *final_res = rho;
-  return converged ? BS_OK : BS_ERR_NOT_CONVERGED;
+  int rc = BS_OK;
+  for (int s = 0; s < nrhs; ++s) {
+    if (iters) iters[s] = S[s].its;
+    if (final_res) final_res[s] = S[s].rho;
+    if (!S[s].converged) rc = BS_ERR_NOT_CONVERGED;
+  }
+  return rc;
+}
+
+int gmres(Context &c, int which, const double *d_b, double *d_x, double tol, int max_steps, int max_tmp, int *iters,
+          double *final_res) {
+  return gmres_batched(c, which, 1, d_b, d_x, 0, tol, max_steps, max_tmp, iters, final_res);
 }
 
 }  // namespace bs

@@ -376,6 +376,37 @@ class BEMProblem:
         check(rc)
         return its.value
 
+    def gmres_multi(self, which, X, B):
+        """nrhs systems advanced in lockstep on the device (one multi-RHS sweep over the matrix per iteration)."""
+        nrhs = B.shape[0]
+        its = (C.c_int * nrhs)()
+        res = (C.c_double * nrhs)()
+        check(lib.bs_set_gmres_orthogonalization(
+            self._ctx, _lib.ORTHO_MGS if self.gmres_orthogonalization == "MGS" else _lib.ORTHO_CGS2))
+        rc = lib.bs_gmres_multi(self._ctx, which, nrhs, _vp(B), _vp(X), self.solver_control.tolerance,
+                                self.solver_control.max_steps, self.gmres_restart, its, res)
+        self.last_steps = [its[k] for k in range(nrhs)]
+        self.last_values = [res[k] for k in range(nrhs)]
+        self.solver_control._last_step, self.solver_control._last_value = max(self.last_steps), max(self.last_values)
+        check(rc)
+        return self.last_steps
+
+    def resistance_matrix(self):
+        """Full 6x6 rigid-body resistance matrix with the six right-hand sides solved as one batch (BASELINE config
+        'prolate spheroid ... 6 batched RHS'; the reference's tests/rigidity_sphere.cc:60-86 does six sequential solves
+        of the ImposedVelocity system with rhs = unit vector on rigid row r).  Column r = forces/torques for unit
+        rigid velocity r."""
+        assert self.grid_type == "ImposedVelocity" and self.n_mpi_processes == 1
+        n, nr = self.n_dofs, self.num_rigid
+        B = np.zeros((nr, n + nr))
+        for r in range(nr):
+            B[r, n + r] = 1.0
+        X = np.zeros_like(B)
+        self._setup_preconditioner(_lib.MAT_A)
+        self.gmres_multi(_lib.MAT_A, X, B)
+        self.batched_solutions = X
+        return np.array([[X[r, :n] @ self.N_rigid_dual[i] for r in range(nr)] for i in range(nr)])
+
     def solve_system(self, monolithic_booly=True):
         """ref: BEMProblem::solve_system (bem_stokes.cc:4158-4508)."""
         n, nr = self.n_dofs, self.num_rigid

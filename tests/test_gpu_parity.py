@@ -347,3 +347,42 @@ def test_update_geometry_same_mesh():
     assert rel_rows(V1, Vo) < ENTRY_TOL and rel_rows(K1, Ko) < ENTRY_TOL
     p.close()
     q.close()
+
+
+def test_config_C2_prolate_six_batched_rhs():
+    """BASELINE config 2: prolate spheroid lambda=2 (1 538 nodes), full 6x6 resistance matrix from 6 batched
+    right-hand sides, against the oracle's direct solve of the same systems (C port for the oracle matrices)."""
+    from oracle import port
+    m = bb.read_mesh(os.path.join(MESHES, "prolate_spheroid_lambda_2_ref_0.msh"))
+    assert m.n_nodes == 1538 and m.n_cells == 1536
+    p = make_problem(m, grid_type="ImposedVelocity", imposed_component=0, solve_directly=False, preconditioner_type="None")
+    p.assemble_stokes_system(True)
+    R = p.resistance_matrix()
+    assert len(set(p.last_steps)) >= 1 and max(p.last_steps) < 120
+    geo = bo.Geometry(m.nodes, m.conn.astype(np.int64), 1)
+    Vo, Ko, _ = port.assemble_VK(geo, bo.KernelSpec(), 8, "Mixed", 10)
+    pre = bo.Prepass(geo, 8)
+    Vc, _ = bo.correct_V(Vo, pre)
+    Ao, _ = bo.monolithic(Vc, bo.correct_K(Ko, geo.N), pre, "ImposedVelocity", 0)
+    n = 3 * geo.N
+    assert rel_rows(p.monolithic_system_matrix.entries(*[a.reshape(-1) for a in np.meshgrid(
+        np.arange(0, n + 6, 97, dtype=np.int32), np.arange(n + 6, dtype=np.int32), indexing="ij")]).reshape(-1, n + 6),
+        Ao[::97]) < 5e-12
+    Bm = np.zeros((n + 6, 6))
+    Bm[n:, :] = np.eye(6)
+    Xo = np.linalg.solve(Ao, Bm)
+    Ro = np.array([[Xo[:n, r] @ pre.N_rigid_dual[i] for r in range(6)] for i in range(6)])
+    assert np.abs(R - Ro).max() <= 1e-7 * np.abs(Ro).max()
+    for r in range(6):
+        assert np.abs(p.batched_solutions[r] - Xo[:, r]).max() <= 1e-6 * np.abs(Xo[:, r]).max()
+    # physics: resistance matrix symmetric positive, translation along the long axis is the easiest
+    assert np.abs(R - R.T).max() < 2e-2 * np.abs(R).max()
+    assert 0 < R[0, 0] < R[1, 1] and abs(R[1, 1] - R[2, 2]) < 1e-2 * R[1, 1]
+    # batched == sequential
+    p.monolithic_rhs[:] = 0
+    p.monolithic_rhs[n + 2] = 1
+    p.monolithic_solution[:] = 0
+    p.solve_system(True)
+    assert p.solver_control.last_step() == p.last_steps[2]
+    assert np.abs(p.monolithic_solution - p.batched_solutions[2]).max() <= 1e-12 * np.abs(p.monolithic_solution).max()
+    p.close()
