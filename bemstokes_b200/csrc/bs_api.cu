@@ -863,6 +863,28 @@ int bs_reset_stats(bs_context *h) {
   BS_API_END
 }
 
+int bs_bench_vmult_multi(bs_context *h, int which, int nrhs, int repeats, double *ms_per_call) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  const DMat &M = which == BS_MAT_V ? c.V : (which == BS_MAT_K ? c.K : c.A);
+  BS_REQUIRE(M.valid() && repeats > 0 && nrhs >= 1, "matrix not available");
+  Extra &e = extra(c);
+  const size_t m = c.full_vec_len(which);
+  const size_t ldx = (m + 3) & ~(size_t)1;
+  e.vin.alloc(std::max(e.vin.n, (size_t)nrhs * ldx));
+  e.vout.alloc(std::max(e.vout.n, (size_t)nrhs * ldx));
+  fill(c, e.vin.p, 1.0, (size_t)nrhs * ldx);
+  gemv_multi(c, M, nrhs, e.vin.p, ldx, e.vout.p, ldx);  // warm-up
+  cudaEventRecord(c.ev0, c.stream);
+  for (int i = 0; i < repeats; ++i) gemv_multi(c, M, nrhs, e.vin.p, ldx, e.vout.p, ldx);
+  cudaEventRecord(c.ev1, c.stream);
+  BS_CUDA(cudaEventSynchronize(c.ev1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c.ev0, c.ev1);
+  if (ms_per_call) *ms_per_call = ms / repeats;
+  BS_API_END
+}
+
 int bs_bench_vmult(bs_context *h, int which, int repeats, double *ms_per_call) {
   BS_API_BEGIN
   Context &c = ctx_of(h);

@@ -80,13 +80,12 @@ void gemv(Context &c, const DMat &M, const double *x, double *y) {
 }
 
 // multi-RHS: Y[k][r] = sum_c A[r][c] X[k][c], NR right-hand sides per pass.  Every matrix element is read once
-// from HBM and used NR times; 4 rows per warp so that the x values (L1/L2 resident) are re-used from registers.
-constexpr int GEMVM_RPW = 4;
-template <int NR>
+// from HBM and used NR times; RPW rows per warp re-use the (L1/L2 resident) x values from registers, U column
+// steps are in flight per lane.
+template <int NR, int RPW, int U>
 __global__ void __launch_bounds__(32 * GEMV_WARPS) k_gemv_multi(const double *__restrict__ A, size_t ld, size_t rows,
                                                                 size_t cols, const double *__restrict__ X, size_t ldx,
                                                                 double *__restrict__ Y, size_t ldy) {
-  constexpr int RPW = GEMVM_RPW;
   const int lane = threadIdx.x & 31;
   const size_t warp = (size_t)blockIdx.x * GEMV_WARPS + (threadIdx.x >> 5);
   const size_t r0 = warp * RPW;
@@ -100,8 +99,23 @@ __global__ void __launch_bounds__(32 * GEMV_WARPS) k_gemv_multi(const double *__
 #pragma unroll
     for (int k = 0; k < NR; ++k) acc[r][k] = 0.0;
   const size_t cols2 = cols & ~(size_t)1;
-#pragma unroll 2
-  for (size_t c = (size_t)lane * 2; c < cols2; c += 64) {
+  size_t c = (size_t)lane * 2;
+  for (; c + (U - 1) * 64 < cols2; c += U * 64) {
+    double2 av[U][RPW];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) av[u][r] = ld_stream2(a[r] + c + u * 64);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int k = 0; k < NR; ++k) {
+        const double2 xv = *reinterpret_cast<const double2 *>(X + (size_t)k * ldx + c + u * 64);
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) acc[r][k] = fma(av[u][r].x, xv.x, fma(av[u][r].y, xv.y, acc[r][k]));
+      }
+  }
+  for (; c < cols2; c += 64) {
     double2 av[RPW];
 #pragma unroll
     for (int r = 0; r < RPW; ++r) av[r] = ld_stream2(a[r] + c);
@@ -129,11 +143,19 @@ __global__ void __launch_bounds__(32 * GEMV_WARPS) k_gemv_multi(const double *__
     }
 }
 
+#ifndef BS_GEMVM_RPW
+#define BS_GEMVM_RPW 2
+#endif
+#ifndef BS_GEMVM_U
+#define BS_GEMVM_U 4
+#endif
+
 template <int NR>
 static void launch_gemv_multi(Context &c, const DMat &M, const double *X, size_t ldx, double *Y, size_t ldy) {
-  const size_t warps = (M.rows + GEMVM_RPW - 1) / GEMVM_RPW;
+  constexpr int RPW = BS_GEMVM_RPW, U = BS_GEMVM_U;
+  const size_t warps = (M.rows + RPW - 1) / RPW;
   const unsigned grid = (unsigned)((warps + GEMV_WARPS - 1) / GEMV_WARPS);
-  k_gemv_multi<NR><<<grid, 32 * GEMV_WARPS, 0, c.stream>>>(M.p, M.ld, M.rows, M.cols, X, ldx, Y, ldy);
+  k_gemv_multi<NR, RPW, U><<<grid, 32 * GEMV_WARPS, 0, c.stream>>>(M.p, M.ld, M.rows, M.cols, X, ldx, Y, ldy);
   BS_CUDA(cudaGetLastError());
   count_launch(c);
 }

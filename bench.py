@@ -209,6 +209,24 @@ def run_ours(args):
     # ---- matvec bandwidth: device-resident GEMV loop on the monolithic matrix (L2 flushed by its own 43 GB) ----
     ms_mv = C.c_double()
     check(lib.bs_bench_vmult(p._ctx, _lib.MAT_A, 10, C.byref(ms_mv)))
+    # ---- optional: BASELINE config-2 style batched solve (6 rigid-body right-hand sides in lockstep) ----
+    res6 = None
+    if args.resistance and world == 1:
+        torch.cuda.synchronize()
+        t6 = time.perf_counter()
+        Rm = p.resistance_matrix()
+        torch.cuda.synchronize()
+        t_batched = time.perf_counter() - t6
+        t6 = time.perf_counter()
+        for r in range(6):
+            p.monolithic_rhs[:] = 0
+            p.monolithic_rhs[n + r] = 1
+            p.monolithic_solution[:] = 0
+            p.solve_system(True)
+        torch.cuda.synchronize()
+        t_seq = time.perf_counter() - t6
+        res6 = {"batched_s": t_batched, "sequential_s": t_seq, "iterations": p.last_steps,
+                "R_diag_over_6pi_8pi": [float(Rm[i, i] / (6 * math.pi if i < 3 else 8 * math.pi)) for i in range(6)]}
     # ---- e2e through host buffers ----
     e2e_asm, e2e_tts = [], []
     for _ in range(max(1, min(args.steps, 2))):
@@ -266,6 +284,7 @@ def run_ours(args):
                           "gmres": solve_ms},
             "tiling": {"cell_blocks": int(st["n_cell_blocks"]), "colours": int(st["n_colours"]),
                        "node_touch_ratio": st["node_touch_ratio"]},
+            "resistance_6rhs": res6,
             "drag_over_6pi": (drag / (6 * math.pi)) if drag is not None else None,
             "clocks": clocks,
             "e2e": {"value": entries / e2e_asm_s / 1e9, "unit": "Gentries/s", "time_to_solution_s": e2e_tts_s,
@@ -354,6 +373,7 @@ def main():
     ap.add_argument("--subdiv", dest="m", type=int, default=0, help="cube-sphere subdivisions per face edge (default 64*N^(1/4))")
     ap.add_argument("--refine", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--resistance", action="store_true", help="also time the 6-RHS batched resistance solve")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -179,6 +179,7 @@ int bs_reset_stats(bs_context *ctx);
 
 /* ---- benchmarking helpers: device-resident repeat loops timed with CUDA events on the context stream ---- */
 int bs_bench_vmult(bs_context *ctx, int which, int repeats, double *ms_per_call);
+int bs_bench_vmult_multi(bs_context *ctx, int which, int nrhs, int repeats, double *ms_per_call);
 int bs_bench_fp64_peak(int device, double *tflops);                              /* burst, best of 3 */
 int bs_bench_fp64_sustained(int device, double seconds, double *tflops);         /* back-to-back under the power cap */
 
