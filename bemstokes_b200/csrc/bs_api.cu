@@ -817,6 +817,26 @@ int bs_kernel_eval(int device, int type, double eps, int o, int npts, const doub
   BS_API_END
 }
 
+int bs_evaluate_bie(bs_context *h, int npts, const double *points, const double *vel, const double *forces, double *out,
+                    int on_boundary) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(npts > 0 && points && vel && forces && out, "bad arguments");
+  DBuf<double> dp, dv, df, dout;
+  dp.upload(points, (size_t)3 * npts, c.stream);
+  dv.alloc(c.n3() + 2);
+  df.alloc(c.n3() + 2);
+  dout.alloc((size_t)3 * npts);
+  to_internal(c, vel, 0, dv.p, true);
+  to_internal(c, forces, 0, df.p, true);
+  if (on_boundary)  // the reference's on-boundary routine accumulates into val_velocities (bem_stokes.cc:5543-5550)
+    BS_CUDA(cudaMemcpyAsync(dout.p, out, sizeof(double) * 3 * npts, cudaMemcpyHostToDevice, c.stream));
+  evaluate_bie(c, npts, dp.p, dv.p, df.p, dout.p, on_boundary != 0, on_boundary != 0);
+  BS_CUDA(cudaMemcpyAsync(out, dout.p, sizeof(double) * 3 * npts, cudaMemcpyDeviceToHost, c.stream));
+  BS_CUDA(cudaStreamSynchronize(c.stream));
+  BS_API_END
+}
+
 int bs_set_comm(bs_context *h, bs_allgatherv_fn ag, bs_allreduce_sum_fn ar, void *user) {
   BS_API_BEGIN
   Context &c = ctx_of(h);

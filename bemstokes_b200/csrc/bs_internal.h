@@ -264,6 +264,8 @@ int gmres(Context &c, int which, const double *d_b_loc, double *d_x_loc, double 
           int *iters, double *final_res);
 int gmres_batched(Context &c, int which, int nrhs, const double *d_B, double *d_X, size_t ldv, double tol, int max_steps,
                   int max_tmp, int *iters, double *final_res);
+void evaluate_bie(Context &c, int npts, const double *d_pts, const double *d_vel, const double *d_forces, double *d_out,
+                  bool on_boundary, bool accumulate);
 void count_launch(Context &c, int n = 1);
 
 }  // namespace bs

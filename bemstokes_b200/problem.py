@@ -464,6 +464,40 @@ class BEMProblem:
         self.rigid_velocities = U
         self.stokes_forces = sum(U[r] * DN[r] for r in range(nr)) + self.dirichlet_to_neumann_operator(self.shape_velocities)
 
+    # ---- field evaluation ---------------------------------------------------------------------------------
+    def evaluate_stokes_bie(self, val_points, vel, forces, val_velocities=None):
+        """ref: BEMProblem::evaluate_stokes_bie (bem_stokes.cc:5366-5451); output component-major (i + P*idim)."""
+        pts = np.ascontiguousarray(val_points, dtype=np.float64).reshape(-1, 3)
+        out = np.zeros(3 * len(pts)) if val_velocities is None else val_velocities
+        out[:] = 0.0
+        self._set_kernel()
+        check(lib.bs_evaluate_bie(self._ctx, len(pts), _dp(pts), _dp(np.ascontiguousarray(vel, dtype=np.float64)),
+                                  _dp(np.ascontiguousarray(forces, dtype=np.float64)), _dp(out), 0))
+        return out
+
+    def evaluate_stokes_bie_on_boundary(self, val_points, vel, forces, val_velocities):
+        """ref: evaluate_stokes_bie_on_boundary (bem_stokes.cc:5454-5560): accumulates into val_velocities."""
+        pts = np.ascontiguousarray(val_points, dtype=np.float64).reshape(-1, 3)
+        check(lib.bs_evaluate_bie(self._ctx, len(pts), _dp(pts), _dp(np.ascontiguousarray(vel, dtype=np.float64)),
+                                  _dp(np.ascontiguousarray(forces, dtype=np.float64)), _dp(val_velocities), 1))
+        return val_velocities
+
+    def approximate_velocity_gradient(self, val_points, vel, forces, h):
+        """ref: approximate_velocity_gradient (bem_stokes.cc:5332-5364), including its one-sided '/h' scaling:
+        grad[i][j][k] = (u_j(x_i + h e_k) - u_j(x_i - h e_k)) / h.  All 6*P stencil points go in one device call."""
+        pts = np.ascontiguousarray(val_points, dtype=np.float64).reshape(-1, 3)
+        P = len(pts)
+        sten = np.repeat(pts, 6, axis=0).reshape(P, 6, 3)
+        for k in range(3):
+            sten[:, 2 * k, k] += h
+            sten[:, 2 * k + 1, k] -= h
+        u = self.evaluate_stokes_bie(sten.reshape(-1, 3), vel, forces).reshape(3, P, 6)
+        grad = np.zeros((P, 3, 3))
+        for j in range(3):
+            for k in range(3):
+                grad[:, j, k] = (u[j, :, 2 * k] - u[j, :, 2 * k + 1]) / h
+        return grad
+
     # ---- stats ------------------------------------------------------------------------------------------------
     def stats(self):
         s = _lib.BsStats()

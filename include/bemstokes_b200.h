@@ -143,6 +143,15 @@ int bs_gmres_multi(bs_context *ctx, int which, int nrhs, const double *B, double
 /* ref: TrilinosWrappers::SolverDirect (4261-4267): dense LU with partial pivoting on the device. */
 int bs_direct_solve(bs_context *ctx, int which, const double *b, double *x);
 
+/* ---- field evaluation (ref: BEMProblem::evaluate_stokes_bie bem_stokes.cc:5366-5451 and
+ *      evaluate_stokes_bie_on_boundary 5454-5560) ---------------------------------------------------------------
+ * u_a(x_i) = sum_cells sum_q [G_ab f_b - (W n)_ab u_b] JxW with the kernel of bs_set_kernel.  points: npts x 3
+ * (x,y,z per point); vel, forces: 3N reference ordering; out: 3*npts component-major (i + a*npts).  on_boundary=1:
+ * free-space kernel, cells with a support point within 1e-3 of x_i use the singular rule, result ACCUMULATED into
+ * out like the reference. */
+int bs_evaluate_bie(bs_context *ctx, int npts, const double *points, const double *vel, const double *forces, double *out,
+                    int on_boundary);
+
 /* ---- kernel point evaluation (ref: StokesKernel::value_tens / value_tens2 kernel.cc:61-104,
  *      FreeSurfaceStokesKernel::value_tens_image(2), NoSlipWallStokesKernel::value_tens_image(2)) -------
  * Evaluated by the same device functions the assembly kernels use.  p, p_image: npts x 3.

@@ -710,3 +710,47 @@ def lu_solve_factory(A):
     import scipy.linalg as sla
     lu = sla.lu_factor(A)
     return lambda v: sla.lu_solve(lu, v)
+
+
+# --------------------------------------------------------------------------------------------------------
+# Field evaluation (ref: bem_stokes.cc:5366-5451 evaluate_stokes_bie, 5454-5560 _on_boundary)
+# --------------------------------------------------------------------------------------------------------
+
+
+def evaluate_bie(geo, kernel, pts, vel, forces, quad_order=8, on_boundary=False, sing_kind="Mixed", sing_order=5, out=None):
+    """u_a(x_i) = sum_cells sum_q [G_ab f_b - S_ab u_b] JxW; vel/forces component-major (i + c*N); result
+    component-major over the points (i + P*a).  on_boundary: free kernel, singular rule for cells with a support
+    point within 1e-3 of x_i, accumulated into `out`."""
+    pts = np.asarray(pts, dtype=float).reshape(-1, 3)
+    P, N = len(pts), geo.N
+    res = np.zeros(3 * P) if (out is None or not on_boundary) else out
+    xi, w = gauss2(quad_order)
+    phi, _ = shape(geo.degree, xi)
+    F = np.asarray(forces).reshape(3, N).T
+    U = np.asarray(vel).reshape(3, N).T
+    ker = KernelSpec(FREE, kernel.eps) if on_boundary else kernel
+    srules = [singular_rule(sing_kind, sing_order, geo.degree, a) for a in range(geo.na)] if on_boundary else None
+    for c in range(geo.ncell):
+        Xc = geo.map_nodes[geo.map_conn[c]]
+        y, n, jxw = fe_cell(Xc, geo.map_degree, xi, w)
+        fq, uq = phi @ F[geo.conn[c]], phi @ U[geo.conn[c]]
+        near = np.zeros(P, dtype=int) - 1
+        if on_boundary:
+            d = np.linalg.norm(pts[:, None, :] - geo.support[geo.conn[c]][None, :, :], axis=2)  # [P, na]
+            hit = d <= 1e-3
+            near = np.where(hit.any(1), hit.argmax(1), -1)
+        reg = np.nonzero(near < 0)[0]
+        if len(reg):
+            G, S = ker.GS(y[None, :, :], n[None, :, :], pts[reg][:, None, :])
+            val = np.einsum("iqab,qb,q->ia", G, fq, jxw) - np.einsum("iqab,qb,q->ia", S, uq, jxw)
+            for a in range(3):
+                res[reg + a * P] += val[:, a]
+        for i in np.nonzero(near >= 0)[0]:
+            sx, sw = srules[near[i]]
+            ys, ns, js = fe_cell(Xc, geo.map_degree, sx, sw)
+            ph = shape(geo.degree, sx)[0]
+            G, S = ker.GS(ys, ns, pts[i][None, :])
+            val = np.einsum("qab,qb,q->a", G, ph @ F[geo.conn[c]], js) - np.einsum("qab,qb,q->a", S, ph @ U[geo.conn[c]], js)
+            for a in range(3):
+                res[i + a * P] += val[a]
+    return res

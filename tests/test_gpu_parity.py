@@ -386,3 +386,59 @@ def test_config_C2_prolate_six_batched_rhs():
     assert p.solver_control.last_step() == p.last_steps[2]
     assert np.abs(p.monolithic_solution - p.batched_solutions[2]).max() <= 1e-12 * np.abs(p.monolithic_solution).max()
     p.close()
+
+
+def test_field_evaluation_bie(half):
+    """evaluate_stokes_bie / _on_boundary / approximate_velocity_gradient (bem_stokes.cc:5332-5560) vs the oracle,
+    plus the physics: the flow around a translating sphere is Stokes' solution."""
+    m = bb.read_mesh(os.path.join(MESHES, "sphere_very_refined_0.inp"))  # 426 nodes
+    p = make_problem(m, grid_type="ImposedVelocity", imposed_component=0, solve_directly=True)
+    p.assemble_stokes_system(True)
+    p.solve_system(True)
+    n = p.n_dofs
+    t = p.stokes_forces
+    u = p.N_rigid[0] * p.rigid_velocities[0]
+    rng = np.random.default_rng(5)
+    pts = rng.normal(size=(257, 3))
+    pts *= (rng.uniform(1.3, 4.0, 257) / np.linalg.norm(pts, axis=1))[:, None]
+    geo = bo.Geometry(m.nodes, m.conn.astype(np.int64), 1)
+    for kern_kw, okern in [({}, bo.KernelSpec()),
+                           ({"reflect_kernel": True, "wall_spans_0": (80, 0, 80), "wall_position_0": (0, 5.4, 0)},
+                            bo.KernelSpec(bo.FREE_SURFACE, 0.0, 1, (0, 5.4, 0))),
+                           ({"reflect_kernel": False, "no_slip_kernel": True, "wall_spans_0": (80, 0, 80), "wall_position_0": (0, 5.4, 0)},
+                            bo.KernelSpec(bo.NO_SLIP, 0.0, 1, (0, 5.4, 0)))]:
+        for k, v in kern_kw.items():
+            setattr(p, k, v)
+        got = p.evaluate_stokes_bie(pts, u, t)
+        want = bo.evaluate_bie(geo, okern, pts, u, t, 8)
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+    p.reflect_kernel = p.no_slip_kernel = False
+    # Stokes' solution around a sphere of radius a=1 moving with U e_x; traction sign convention of the reference:
+    # forces act on the body, so the exterior velocity is -(G f) + double layer (which vanishes for rigid motion)
+    got = p.evaluate_stokes_bie(pts, u, t).reshape(3, -1).T
+    r = np.linalg.norm(pts, axis=1)
+    rh = pts / r[:, None]
+    e = np.array([1.0, 0, 0])
+    exact = (0.75 / r)[:, None] * (e[None, :] + (rh @ e)[:, None] * rh) + (0.25 / r ** 3)[:, None] * (e[None, :] - 3 * (rh @ e)[:, None] * rh)
+    err_plus, err_minus = np.abs(got - exact).max(), np.abs(got + exact).max()
+    assert min(err_plus, err_minus) < 5e-3, (err_plus, err_minus)
+    # velocity gradient helper (one-sided '/h' of the reference reproduced)
+    g = p.approximate_velocity_gradient(pts[:5], u, t, 1e-4)
+    go = np.zeros((5, 3, 3))
+    for i in range(5):
+        sten = np.repeat(pts[i][None, :], 6, 0)
+        for k in range(3):
+            sten[2 * k, k] += 1e-4
+            sten[2 * k + 1, k] -= 1e-4
+        uu = bo.evaluate_bie(geo, bo.KernelSpec(), sten, u, t, 8)
+        for j in range(3):
+            for k in range(3):
+                go[i, j, k] = (uu[j * 6 + 2 * k] - uu[j * 6 + 2 * k + 1]) / 1e-4
+    assert np.abs(g - go).max() <= 1e-7 * max(1.0, np.abs(go).max())
+    # on the boundary: collocation points themselves, singular rule for the adjacent cells, accumulating semantics
+    bpts = p.support_points[:40]
+    acc0 = rng.uniform(-1, 1, 3 * 40)
+    got_b = p.evaluate_stokes_bie_on_boundary(bpts, u, t, acc0.copy())
+    want_b = bo.evaluate_bie(geo, bo.KernelSpec(), bpts, u, t, 8, on_boundary=True, sing_kind="Mixed", sing_order=10, out=acc0.copy())
+    assert np.abs(got_b - want_b).max() <= 1e-11 * np.abs(want_b).max()
+    p.close()
