@@ -837,6 +837,17 @@ int bs_evaluate_bie(bs_context *h, int npts, const double *points, const double 
   BS_API_END
 }
 
+int bs_host_prepass(int fe_degree, int map_degree, int n_map_nodes, const double *euler_vec, int ncell, const int *conn_map,
+                    int n_nodes, const int *conn_stokes, int quad_order, const double *pole, double *nhat, double *Mnhat,
+                    double *l2gamma, double *N_rigid, double *N_rigid_dual, double *area, double *support_points) {
+  BS_API_BEGIN
+  BS_REQUIRE(euler_vec && conn_map && conn_stokes && nhat && Mnhat, "bad arguments");
+  const double origin[3] = {0, 0, 0};
+  host_prepass(fe_degree, map_degree, n_map_nodes, euler_vec, ncell, conn_map, n_nodes, conn_stokes, quad_order,
+               pole ? pole : origin, nhat, Mnhat, l2gamma, N_rigid, N_rigid_dual, area, support_points);
+  BS_API_END
+}
+
 int bs_set_comm(bs_context *h, bs_allgatherv_fn ag, bs_allreduce_sum_fn ar, void *user) {
   BS_API_BEGIN
   Context &c = ctx_of(h);

@@ -569,3 +569,170 @@ void build_tables(Context &c) {
 }
 
 }  // namespace bs
+
+// ---------------------------------------------------------------------------------------------------------
+// Host pre-pass (inputs of the hot path, O(N) sparse work the reference also does on the host):
+// scalar mass matrix M_ab = sum_q phi_a phi_b JxW (ref: bem_stokes.cc:2499-2517), L2-projected unit normals
+// M n = int phi n (3945-3998), M n_hat, l2 = n_hat^T M n_hat (4002-4005), rigid modes about `pole` and their duals
+// M N_r (2626-2641, 2773).  The mass solve uses Jacobi-preconditioned CG to 1e-15 (the reference: Trilinos CG + AMG).
+// ---------------------------------------------------------------------------------------------------------
+namespace bs {
+
+struct CsrMass {
+  int n = 0;
+  std::vector<int> ptr, col;
+  std::vector<double> val;
+  void mult(const double *x, double *y) const {
+    for (int i = 0; i < n; ++i) {
+      double s = 0;
+      for (int e = ptr[i]; e < ptr[i + 1]; ++e) s += val[e] * x[col[e]];
+      y[i] = s;
+    }
+  }
+};
+
+void host_prepass(int fe_degree, int map_degree, int n_map_nodes, const double *euler_vec, int ncell, const int *conn_map,
+                  int n_nodes, const int *conn, int quad_order, const double *pole, double *nhat, double *Mnhat, double *l2,
+                  double *N_rigid, double *N_rigid_dual, double *area_out, double *support_out) {
+  BS_REQUIRE((fe_degree == 1 || fe_degree == 2) && (map_degree == 1 || map_degree == 2), "FE degrees must be 1 or 2");
+  const int na = n_shape(fe_degree), nam = n_shape(map_degree), N = n_nodes;
+  std::vector<double> x1, w1;
+  gauss_legendre_01(quad_order, x1, w1);
+  Rule2D rule = tensor_rule(x1, w1);
+  const int nq = rule.size();
+  std::vector<double> phi((size_t)nq * na), pm((size_t)nq * nam), dpm((size_t)nq * nam * 2);
+  for (int q = 0; q < nq; ++q) {
+    shape_eval(fe_degree, rule.xi[2 * q], rule.xi[2 * q + 1], &phi[(size_t)q * na], nullptr);
+    shape_eval(map_degree, rule.xi[2 * q], rule.xi[2 * q + 1], &pm[(size_t)q * nam], &dpm[(size_t)q * nam * 2]);
+  }
+  // sparsity: node -> neighbour nodes through cells
+  std::vector<std::vector<int>> adj(N);
+  for (int c = 0; c < ncell; ++c)
+    for (int a = 0; a < na; ++a)
+      for (int b = 0; b < na; ++b) adj[conn[(size_t)c * na + a]].push_back(conn[(size_t)c * na + b]);
+  CsrMass M;
+  M.n = N;
+  M.ptr.assign(N + 1, 0);
+  for (int i = 0; i < N; ++i) {
+    std::sort(adj[i].begin(), adj[i].end());
+    adj[i].erase(std::unique(adj[i].begin(), adj[i].end()), adj[i].end());
+    M.ptr[i + 1] = M.ptr[i] + (int)adj[i].size();
+  }
+  M.col.resize(M.ptr[N]);
+  M.val.assign(M.ptr[N], 0.0);
+  for (int i = 0; i < N; ++i) std::copy(adj[i].begin(), adj[i].end(), M.col.begin() + M.ptr[i]);
+  auto entry = [&](int i, int j) -> double & {
+    const int *b = &M.col[M.ptr[i]], *e = &M.col[M.ptr[i + 1]];
+    return M.val[M.ptr[i] + (int)(std::lower_bound(b, e, j) - b)];
+  };
+  std::vector<double> rhs((size_t)3 * N, 0.0);  // [c][i]
+  double area = 0;
+  std::vector<double> X((size_t)nam * 3);
+  for (int c = 0; c < ncell; ++c) {
+    for (int a = 0; a < nam; ++a) {
+      const int m = conn_map[(size_t)c * nam + a];
+      for (int d = 0; d < 3; ++d) X[(size_t)3 * a + d] = euler_vec[(size_t)m + (size_t)d * n_map_nodes];
+    }
+    for (int q = 0; q < nq; ++q) {
+      double t1[3] = {0, 0, 0}, t2[3] = {0, 0, 0};
+      for (int a = 0; a < nam; ++a)
+        for (int d = 0; d < 3; ++d) {
+          t1[d] += dpm[((size_t)q * nam + a) * 2] * X[(size_t)3 * a + d];
+          t2[d] += dpm[((size_t)q * nam + a) * 2 + 1] * X[(size_t)3 * a + d];
+        }
+      const double nn[3] = {t1[1] * t2[2] - t1[2] * t2[1], t1[2] * t2[0] - t1[0] * t2[2], t1[0] * t2[1] - t1[1] * t2[0]};
+      const double J = std::sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
+      const double jxw = rule.w[q] * J;
+      area += jxw;
+      for (int a = 0; a < na; ++a) {
+        const int i = conn[(size_t)c * na + a];
+        const double pa = phi[(size_t)q * na + a];
+        for (int d = 0; d < 3; ++d) rhs[(size_t)d * N + i] += pa * (nn[d] / J) * jxw;
+        for (int b = 0; b < na; ++b) entry(i, conn[(size_t)c * na + b]) += pa * phi[(size_t)q * na + b] * jxw;
+      }
+    }
+  }
+  // CG with Jacobi preconditioning, one solve per component
+  std::vector<double> sol((size_t)3 * N, 0.0), r(N), z(N), p(N), Ap(N), dinv(N);
+  for (int i = 0; i < N; ++i) dinv[i] = 1.0 / entry(i, i);
+  for (int d = 0; d < 3; ++d) {
+    double *x = &sol[(size_t)d * N];
+    const double *b = &rhs[(size_t)d * N];
+    double bn = 0;
+    for (int i = 0; i < N; ++i) {
+      r[i] = b[i];
+      z[i] = dinv[i] * r[i];
+      p[i] = z[i];
+      bn += b[i] * b[i];
+    }
+    double rz = 0;
+    for (int i = 0; i < N; ++i) rz += r[i] * z[i];
+    for (int it = 0; it < 10 * N + 100 && bn > 0; ++it) {
+      M.mult(p.data(), Ap.data());
+      double pAp = 0;
+      for (int i = 0; i < N; ++i) pAp += p[i] * Ap[i];
+      const double alpha = rz / pAp;
+      double rn = 0;
+      for (int i = 0; i < N; ++i) {
+        x[i] += alpha * p[i];
+        r[i] -= alpha * Ap[i];
+        rn += r[i] * r[i];
+      }
+      if (rn <= 1e-30 * bn) break;
+      double rz2 = 0;
+      for (int i = 0; i < N; ++i) {
+        z[i] = dinv[i] * r[i];
+        rz2 += r[i] * z[i];
+      }
+      const double beta = rz2 / rz;
+      rz = rz2;
+      for (int i = 0; i < N; ++i) p[i] = z[i] + beta * p[i];
+    }
+  }
+  for (int i = 0; i < N; ++i) {
+    const double nrm = std::sqrt(sol[i] * sol[i] + sol[(size_t)N + i] * sol[(size_t)N + i] + sol[(size_t)2 * N + i] * sol[(size_t)2 * N + i]);
+    for (int d = 0; d < 3; ++d) nhat[(size_t)d * N + i] = sol[(size_t)d * N + i] / nrm;
+  }
+  double l2v = 0;
+  for (int d = 0; d < 3; ++d) {
+    M.mult(&nhat[(size_t)d * N], &Mnhat[(size_t)d * N]);
+    for (int i = 0; i < N; ++i) l2v += nhat[(size_t)d * N + i] * Mnhat[(size_t)d * N + i];
+  }
+  if (l2) *l2 = l2v;
+  if (area_out) *area_out = area;
+  // support points of the unknown space and rigid modes about the pole
+  std::vector<double> sup((size_t)3 * N, 0.0), pu((size_t)na * nam);
+  for (int a = 0; a < na; ++a) {
+    double sx, sy;
+    unit_support_point(fe_degree, a, sx, sy);
+    shape_eval(map_degree, sx, sy, &pu[(size_t)a * nam], nullptr);
+  }
+  for (int c = 0; c < ncell; ++c)
+    for (int a = 0; a < na; ++a) {
+      const int i = conn[(size_t)c * na + a];
+      for (int d = 0; d < 3; ++d) {
+        double s = 0;
+        for (int b = 0; b < nam; ++b) s += pu[(size_t)a * nam + b] * euler_vec[(size_t)conn_map[(size_t)c * nam + b] + (size_t)d * n_map_nodes];
+        sup[(size_t)3 * i + d] = s;
+      }
+    }
+  if (support_out) std::copy(sup.begin(), sup.end(), support_out);
+  if (N_rigid && N_rigid_dual) {
+    const size_t n3 = (size_t)3 * N;
+    std::fill(N_rigid, N_rigid + 6 * n3, 0.0);
+    for (int i = 0; i < N; ++i) {
+      const double x = sup[(size_t)3 * i] - pole[0], y = sup[(size_t)3 * i + 1] - pole[1], zc = sup[(size_t)3 * i + 2] - pole[2];
+      for (int d = 0; d < 3; ++d) N_rigid[(size_t)d * n3 + (size_t)d * N + i] = 1.0;
+      N_rigid[3 * n3 + (size_t)1 * N + i] = -zc;
+      N_rigid[3 * n3 + (size_t)2 * N + i] = y;
+      N_rigid[4 * n3 + (size_t)0 * N + i] = zc;
+      N_rigid[4 * n3 + (size_t)2 * N + i] = -x;
+      N_rigid[5 * n3 + (size_t)0 * N + i] = -y;
+      N_rigid[5 * n3 + (size_t)1 * N + i] = x;
+    }
+    for (int rr = 0; rr < 6; ++rr)
+      for (int d = 0; d < 3; ++d) M.mult(&N_rigid[rr * n3 + (size_t)d * N], &N_rigid_dual[rr * n3 + (size_t)d * N]);
+  }
+}
+
+}  // namespace bs

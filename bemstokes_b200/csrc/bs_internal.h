@@ -222,6 +222,9 @@ struct Context {
 };
 
 // ---- geometry / tables (bs_host.cu) ---------------------------------------------------------------------
+void host_prepass(int fe_degree, int map_degree, int n_map_nodes, const double *euler_vec, int ncell, const int *conn_map,
+                  int n_nodes, const int *conn, int quad_order, const double *pole, double *nhat, double *Mnhat, double *l2,
+                  double *N_rigid, double *N_rigid_dual, double *area_out, double *support_out);
 void build_geometry(Context &c);
 void update_coordinates(Context &c);    // same mesh, new map_nodes
 void build_tables(Context &c);          // after geometry + quadrature known

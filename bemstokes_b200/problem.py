@@ -300,7 +300,6 @@ class BEMProblem:
     def compute_center_of_mass_and_rigid_modes(self, frame=0):
         self._pre = Prepass(self.map_mesh.nodes, self.map_mesh.conn.astype(np.int64), self.map_degree, self.N,
                             self.mesh.conn.astype(np.int64), self.fe_degree, self.quadrature_order, self.force_pole)
-        self.Mass_Matrix = self._pre.M
         self.N_rigid = self._pre.N_rigid
         self.N_rigid_dual = self._pre.N_rigid_dual
         self.support_points = self._pre.support_points

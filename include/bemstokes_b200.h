@@ -95,6 +95,15 @@ int bs_set_kernel(bs_context *ctx, int type, double epsilon, int wall_orientatio
 int bs_make_gauss_1d(int n, double *x, double *w);
 int bs_make_singular_rule(int kind, int order, int fe_degree, int local_index, int capacity, double *xi, double *w);
 
+/* Host pre-pass with the reference's semantics (compute_center_of_mass_and_rigid_modes bem_stokes.cc:2440-2788,
+ * compute_normal_vector 3922-4011) for hosts without deal.II: scalar mass matrix, L2-projected unit normals nhat
+ * (= normal_vector_pure for a body-only mesh), Mnhat = M nhat, l2gamma = nhat^T M nhat, the six rigid modes about
+ * `pole` (NULL = origin) and their duals M N_r (each 6 x 3N row-major, may be NULL), surface area, support points
+ * [N][3] (may be NULL).  Pure host code, O(N); every vector component-major. */
+int bs_host_prepass(int fe_degree, int map_degree, int n_map_nodes, const double *euler_vec, int ncell, const int *conn_map,
+                    int n_nodes, const int *conn_stokes, int quad_order, const double *pole, double *nhat, double *Mnhat,
+                    double *l2gamma, double *N_rigid, double *N_rigid_dual, double *area, double *support_points);
+
 /* ---- assembly (ref: BEMProblem::assemble_stokes_system, bem_stokes.cc:2840-3435) ----------------------- */
 /* K1 (regular Gauss pass) + K2 (singular pass) -> row-block of V and K on the device (2871-3000). */
 int bs_assemble_VK(bs_context *ctx);

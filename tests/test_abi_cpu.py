@@ -47,12 +47,17 @@ def test_mesh_and_prepass_match_oracle():
     m = bb.read_mesh(path)
     v, q = bo.read_inp(path)
     assert np.array_equal(m.conn, q) and np.allclose(m.nodes, v)
-    p = Prepass(m.nodes, m.conn.astype(np.int64), 1, m.n_nodes, m.conn.astype(np.int64), 1, 8)
+    p = Prepass(m.nodes, m.conn, 1, m.n_nodes, m.conn, 1, 8)
     po = bo.Prepass(bo.Geometry(v, q, 1), 8)
     assert abs(p.area - po.area) < 1e-12
     assert np.abs(p.normal_vector_pure - po.nhat).max() < 1e-13
     assert np.abs(p.M_normal_vector_pure - po.Mnhat).max() < 1e-14
-    assert np.abs(p.N_rigid_dual - po.N_rigid_dual).max() < 1e-14
+    assert np.abs(p.N_rigid_dual - po.N_rigid_dual).max() < 1e-14 and np.abs(p.N_rigid - po.N_rigid).max() < 1e-15
+    assert abs(p.l2normGamma_pure - po.l2) < 1e-13
+    q2 = bb.cubesphere(2, 2)
+    p2 = Prepass(q2.nodes, q2.conn, 2, q2.n_nodes, q2.conn, 2, 8)
+    po2 = bo.Prepass(bo.Geometry(q2.nodes, q2.conn.astype(np.int64), 2), 8)
+    assert np.abs(p2.normal_vector_pure - po2.nhat).max() < 1e-13 and np.abs(p2.M_normal_vector_pure - po2.Mnhat).max() < 1e-14
     msh = bb.read_mesh(os.path.join(MESHES, "sphere_mesh_3d_0.msh"))
     v2, q2 = bo.read_msh(os.path.join(MESHES, "sphere_mesh_3d_0.msh"))
     assert msh.n_nodes == 386 and msh.n_cells == 384 and np.array_equal(msh.conn, q2)

@@ -1,0 +1,49 @@
+"""The C++ host mirror (include/bemstokes_b200.hpp): compiles and links against the C-ABI library on the CPU box;
+on the GPU the program — written like the reference's tests/minimum_preconditioner_test_no_box.cc — is run and
+its stdout fingerprints are compared with the reference's golden outputs."""
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import MESHES, ROOT
+
+SRC = os.path.join(ROOT, "tests", "cpp", "minimum_preconditioner_test_no_box.cpp")
+LIBDIR = os.path.join(ROOT, "bemstokes_b200")
+
+
+def build_exe(tmp):
+    exe = os.path.join(tmp, "minimum_preconditioner_test_no_box")
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), SRC, "-o", exe, "-L", LIBDIR,
+           "-lbemstokes_b200", "-Wl,-rpath," + LIBDIR, "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64", "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_cpp_host_compiles_and_links(tmp_path):
+    import bemstokes_b200  # noqa: F401  (makes sure the library is built)
+    exe = build_exe(str(tmp_path))
+    assert os.path.exists(exe)
+
+
+@pytest.mark.gpu
+def test_cpp_host_reference_style_test(tmp_path, goldens):
+    import bemstokes_b200  # noqa: F401
+    exe = build_exe(str(tmp_path))
+    r = subprocess.run([exe, os.path.join(MESHES, "sphere_half_refined_0.inp")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = r.stdout
+    assert "We have a tria of 106 cells." in out and "There are 324 degrees of freedom" in out
+    assert "The Mass (Surface) of the entire system is : 12.1766" in out          # tests/rigidity_sphere.output:8
+    assert "Check on the V operator Norm (should be zero) pure: 0.00245963" in out  # tests/rigidity_sphere.output:15
+    assert "Check on the V operator Norm post (should be one) pure: 1" in out
+    for k in range(3):
+        assert "check with versor vector : %d l_infty : 1" % k in out
+    its = [int(x) for x in re.findall(r"Iterations needed to solve monolithic:\s+(\d+)", out)]
+    assert its == [1, goldens["gmres_iterations_no_box"]["Jacobi"], 40]
+    assert "ERROR" not in out
+    assert out.count("OK") == 3 * (3 + 9)
+    fc = [float(x) for x in re.findall(r"FINAL CHECK 0 ([-0-9.e+]+)", out)]
+    assert len(fc) == 4 and max(fc) < 1e-9
