@@ -126,14 +126,17 @@ struct RegParams {
 };
 
 constexpr int ACC_LD = TI + 1;  // padded row-node stride of the shared accumulators (bank-conflict free both ways)
+// stride between consecutive values of the shared tile [value][slot][row]; the +5 spreads the three values a
+// write-out lane group reads for one node over different banks
+__host__ __device__ inline int acc_vstride(int tj) { return tj * ACC_LD + 5; }
 
 size_t assembly_smem_bytes(int na, int nv, int tj, int nq_pad) {
-  return (size_t)2 * nv * tj * ACC_LD * 8 + (size_t)2 * 7 * nq_pad * 8 + (size_t)nq_pad * na * 8 + 64;  // dynamic part
+  return (size_t)2 * nv * acc_vstride(tj) * 8 + (size_t)2 * 7 * nq_pad * 8 + (size_t)nq_pad * na * 8 + 64;  // dynamic part
 }
 
 int choose_tj(int na, int kernel_type, int nq_pad) {
   const int nv = (kernel_type == BS_KERNEL_FREE) ? 6 : 9;
-  const size_t budget = 227 * 1024 - 2048;  // minus the static block-metadata arrays
+  const size_t budget = (227 * 1024) / CTAS_PER_SM - 2048 - (CTAS_PER_SM > 1 ? 1024 : 0);  // minus static arrays / per-CTA reserve
   int tj = 2;
   for (int t = 2; t <= 32; t += 2)
     if (assembly_smem_bytes(na, nv, t, nq_pad) <= budget) tj = t;
@@ -223,9 +226,10 @@ __device__ __forceinline__ void cell_pass(const double *__restrict__ cq, const d
       for (int m = 1; m < QS; m <<= 1) acc[a][v] += __shfl_xor_sync(0xffffffffu, acc[a][v], m);
     }
     if ((a % QS) == part) {
-      double *dst = acc_s + ((size_t)VOFF * tj + slot[a]) * ACC_LD + rl;
+      const int vs = acc_vstride(tj);
+      double *dst = acc_s + (size_t)VOFF * vs + (size_t)slot[a] * ACC_LD + rl;
 #pragma unroll
-      for (int v = 0; v < NACC; ++v) dst[(size_t)v * tj * ACC_LD] += acc[a][v];
+      for (int v = 0; v < NACC; ++v) dst[(size_t)v * vs] += acc[a][v];
     }
   }
 }
@@ -236,7 +240,7 @@ __device__ __forceinline__ void cell_pass(const double *__restrict__ cq, const d
 constexpr int MAXC = 32;  // cells per block (a block touches at most tj <= 32 nodes)
 
 template <int NA, int KT, bool SPLIT, int QS, int VS, bool HAS_EPS>
-__global__ void __launch_bounds__(TI *QS *VS, 1) k_assemble_regular(const RegParams P) {
+__global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(const RegParams P) {
   constexpr int NV = GreenTraits<KT>::NV;
   constexpr int NV2 = 2 * NV;
   constexpr int NB1 = (NA == 4) ? 2 : 3;
@@ -246,7 +250,7 @@ __global__ void __launch_bounds__(TI *QS *VS, 1) k_assemble_regular(const RegPar
   double *cellbuf = reinterpret_cast<double *>(smem_raw);                   // [2][7][nqp]
   double *l1d_s = cellbuf + (size_t)2 * 7 * nqp;                            // [n1][NB1] 1-D shape values
   double *acc_s = l1d_s + (size_t)nqp * NA;                                 // [NV2][tj][ACC_LD]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(acc_s + (size_t)tj * NV2 * ACC_LD);  // [2]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(acc_s + (size_t)NV2 * acc_vstride(tj));  // [2]
   __shared__ int s_cells[MAXC];          // block metadata staged once: no dependent global loads per cell
   __shared__ int s_conn[MAXC * NA];
   __shared__ signed char s_slots[MAXC * NA];
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(TI *QS *VS, 1) k_assemble_regular(const RegPar
     s_conn[i] = P.conn_pos[(size_t)cell * NA + i % NA];
     s_slots[i] = P.blk_slots[(size_t)cs * NA + i];
   }
-  for (int i = t; i < tj * NV2 * ACC_LD; i += NT) acc_s[i] = 0.0;
+  for (int i = t; i < NV2 * acc_vstride(tj); i += NT) acc_s[i] = 0.0;
   __syncthreads();
   if (t == 0 && cs < ce) {
     mbar_expect_tx(&bars[0], cell_bytes);
@@ -326,36 +330,46 @@ __global__ void __launch_bounds__(TI *QS *VS, 1) k_assemble_regular(const RegPar
 
   // ---- combine the tile with global memory: rows 3*(p-p0)+i, columns 3*node(slot)+j.  The first colour that
   // touches a node column stores, later colours (launched after this one) add: fixed summation order.
+  // Each warp takes whole matrix rows; its lanes walk the 3*tj tile columns of the row in (slot, component) order,
+  // so runs of consecutive node positions become contiguous 8-byte stores / reductions (node positions ascend
+  // within a block).  Per-lane column metadata lives in registers: no division or metadata load in the loop.
   const int rows_tile = min(TI, P.p1 - (P.p0 + (int)blockIdx.y * TI));
   const int *nodes = P.blk_nodes + (size_t)blk * tj;
   const unsigned char *first = P.blk_first + (size_t)blk * tj;
-  const int total = rows_tile * 3 * tj;
-  for (int e = t; e < total; e += NT) {
-    const int rr = e / tj, sl = e - rr * tj;   // rr = 3*rowlocal + i
-    const int node = nodes[sl];
-    if (node < 0) continue;
+  const int lane = t & 31, warp = t >> 5;
+  constexpr int NWARP = NT / 32;
+  constexpr int MAXSTEP = 3;  // 3*tj <= 96 columns
+  const int vs = acc_vstride(tj);
+  int col_node[MAXSTEP], col_j[MAXSTEP], col_sl[MAXSTEP];
+  bool col_first[MAXSTEP];
+#pragma unroll
+  for (int sidx = 0; sidx < MAXSTEP; ++sidx) {
+    const int e = lane + 32 * sidx;
+    const int sl = e / 3;
+    col_sl[sidx] = sl;
+    col_j[sidx] = e - 3 * sl;
+    const bool valid = e < 3 * tj;
+    col_node[sidx] = valid ? nodes[sl] : -1;
+    col_first[sidx] = valid ? (first[sl] != 0) : false;
+  }
+  for (int rr = warp; rr < rows_tile * 3; rr += NWARP) {  // rr = 3*rowlocal + i
     const int r_ = rr / 3, i = rr - 3 * r_;
-    const size_t off = ((size_t)3 * (blockIdx.y * TI + r_) + i) * P.ld + (size_t)3 * node;
-    const double *as = acc_s + (size_t)sl * ACC_LD + r_;
-    double v[3], k[3];
+    const size_t rowoff = ((size_t)3 * (blockIdx.y * TI + r_) + i) * P.ld;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      v[j] = as[(size_t)vidx<NV>(i, j) * tj * ACC_LD];
-      k[j] = as[(size_t)(NV + vidx<NV>(i, j)) * tj * ACC_LD];
-    }
-    if (first[sl]) {
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        P.V[off + j] = v[j];
-        P.K[off + j] = k[j];
-      }
-    } else {
-      // fire-and-forget L2 reductions: no load latency on the critical path.  Blocks of one colour never share a
-      // node and colours are separate launches, so each address receives its addends in a fixed order.
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(P.V + off + j), "d"(v[j]) : "memory");
-        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(P.K + off + j), "d"(k[j]) : "memory");
+    for (int sidx = 0; sidx < MAXSTEP; ++sidx) {
+      if (col_node[sidx] < 0) continue;
+      const int vi = vidx<NV>(i, col_j[sidx]);
+      const double *as = acc_s + (size_t)vi * vs + (size_t)col_sl[sidx] * ACC_LD + r_;
+      const double v = as[0], k = as[(size_t)NV * vs];
+      const size_t off = rowoff + (size_t)3 * col_node[sidx] + col_j[sidx];
+      if (col_first[sidx]) {
+        P.V[off] = v;
+        P.K[off] = k;
+      } else {
+        // fire-and-forget L2 reductions: no load latency on the critical path.  Blocks of one colour never share a
+        // node and colours are separate launches, so each address receives its addends in a fixed order.
+        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(P.V + off), "d"(v) : "memory");
+        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(P.K + off), "d"(k) : "memory");
       }
     }
   }

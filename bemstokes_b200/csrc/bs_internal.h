@@ -104,7 +104,14 @@ struct KernelParams {
 // ---------------------------------------------------------------------------------------------------------
 // assembly tiling constants
 // ---------------------------------------------------------------------------------------------------------
-constexpr int TI = 128;       // row nodes per CTA (one per thread)
+#ifndef BS_TI
+#define BS_TI 64
+#endif
+#ifndef BS_CTAS_PER_SM
+#define BS_CTAS_PER_SM 2
+#endif
+constexpr int TI = BS_TI;                    // collocation (row) nodes per CTA of the regular assembly pass
+constexpr int CTAS_PER_SM = BS_CTAS_PER_SM;  // resident CTAs per SM the shared-memory tile is sized for
 constexpr int MAX_NA = 9;     // Q2
 constexpr int MAX_RIGID = 7;
 
