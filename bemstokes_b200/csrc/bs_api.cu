@@ -2,7 +2,9 @@
 // reference file:line each one replaces).  Exceptions never cross the ABI.
 #include "bs_internal.h"
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <numeric>
 
 namespace bs {
@@ -27,13 +29,30 @@ static void drop_extra(Context &c) {
 struct Timer {
   Context &c;
   double &acc;
-  Timer(Context &c_, double &a) : c(c_), acc(a) { cudaEventRecord(c.ev0, c.stream); }
+  const char *name;
+  double t0;
+  static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+  Timer(Context &c_, double &a, const char *n = "") : c(c_), acc(a), name(n), t0(now()) { cudaEventRecord(c.ev0, c.stream); }
   ~Timer() {
     cudaEventRecord(c.ev1, c.stream);
     cudaEventSynchronize(c.ev1);
     float ms = 0;
     cudaEventElapsedTime(&ms, c.ev0, c.ev1);
     acc += ms;
+    if (std::getenv("BS_TRACE")) fprintf(stderr, "[bs trace rank %d] %s: device-span %.2f ms, host wall %.2f ms\n", c.rank, name, ms, 1e3 * (now() - t0));
+  }
+};
+struct Mark {  // BS_TRACE sub-step marks
+  Context &c;
+  double t;
+  bool on;
+  Mark(Context &c_) : c(c_), t(Timer::now()), on(std::getenv("BS_TRACE") != nullptr) {}
+  void operator()(const char *what) {
+    if (!on) return;
+    cudaStreamSynchronize(c.stream);
+    const double n = Timer::now();
+    fprintf(stderr, "[bs trace rank %d]    %-28s %.2f ms\n", c.rank, what, 1e3 * (n - t));
+    t = n;
   }
 };
 
@@ -371,18 +390,23 @@ int bs_correct_V(bs_context *h, const double *nhat, const double *Mnhat, double 
   BS_API_BEGIN
   Context &c = ctx_of(h);
   BS_REQUIRE(c.V.valid(), "V not assembled");
-  Timer t(c, c.stats.correct_ms);
+  Timer t(c, c.stats.correct_ms, "bs_correct_V");
+  Mark mark(c);
   set_projector(c, nhat, Mnhat, l2gamma);
+  mark("set_projector");
   Extra &e = extra(c);
   e.vout.alloc(std::max(e.vout.n, c.n3() + MAX_RIGID + 2));
   double *vn_loc = e.vout.p + 3 * (size_t)c.p0;
   gemv(c, c.V, c.d_nhat.p, vn_loc);
+  mark("gemv V*nhat");
   if (Vn_out) from_internal(c, e.vout.p, 0, Vn_out, 3 * (size_t)c.p0, 3 * (size_t)c.p1, true);
+  mark("Vn to host");
   // u = nhat - V nhat on the owned rows
   e.vin.alloc(std::max(e.vin.n, c.n3() + MAX_RIGID + 2));
   sub(c, c.d_nhat.p + 3 * (size_t)c.p0, vn_loc, e.vin.p, c.rows_loc);
   rank1_update(c, c.V, e.vin.p, c.d_Mnhat.p, 1.0 / l2gamma);
   BS_CUDA(cudaStreamSynchronize(c.stream));
+  mark("rank-1 update");
   BS_API_END
 }
 
@@ -390,7 +414,8 @@ int bs_correct_K(bs_context *h, int use_internal_alpha) {
   BS_API_BEGIN
   Context &c = ctx_of(h);
   BS_REQUIRE(c.K.valid(), "K not assembled");
-  Timer t(c, c.stats.correct_ms);
+  Timer t(c, c.stats.correct_ms, "bs_correct_K");
+  Mark mark(c);
   const size_t n = c.n3();
   const size_t ldx = (n + 2) & ~(size_t)1;
   std::vector<double> E(3 * ldx, 0.0);
@@ -399,9 +424,12 @@ int bs_correct_K(bs_context *h, int use_internal_alpha) {
   Extra &e = extra(c);
   e.vin2.upload(E, c.stream);
   e.vout.alloc(std::max(e.vout.n, 3 * c.rows_loc + 2));
+  mark("versor upload");
   gemv_multi(c, c.K, 3, e.vin2.p, ldx, e.vout.p, c.rows_loc);
+  mark("K * versors");
   k_correct_diag(c, c.K, e.vout.p, use_internal_alpha);
   BS_CUDA(cudaStreamSynchronize(c.stream));
+  mark("diag correction");
   BS_API_END
 }
 
@@ -413,7 +441,7 @@ int bs_build_monolithic(bs_context *h, const unsigned char *col_is_K, int num_ri
   BS_REQUIRE(c.V.valid() && c.K.valid(), "V and K must be assembled (and corrected) first");
   BS_REQUIRE(num_rigid >= 0 && num_rigid <= MAX_RIGID, "num_rigid out of range");
   BS_REQUIRE(num_rigid == 0 || (N_rigid && N_rigid_dual), "rigid modes missing");
-  Timer t(c, c.stats.monolithic_ms);
+  Timer t(c, c.stats.monolithic_ms, "bs_build_monolithic");
   set_projector(c, nhat, Mnhat, l2gamma);
   Extra &e = extra(c);
   const size_t n = c.n3();
@@ -444,8 +472,8 @@ int bs_build_monolithic(bs_context *h, const unsigned char *col_is_K, int num_ri
   // second projection needs the full vectors: gather slices
   std::vector<double> Y((size_t)nvec * n, 0.0);
   {
-    DBuf<double> full;
-    full.alloc(n + 2);
+    struct P_ { double *p; } full;
+    full.p = c.wsd("mono.full", n + 2);
     std::vector<double> tmp(n);
     for (int v = 0; v < nvec; ++v) {
       exchange(c, BS_MAT_K, e.vout.p + (size_t)v * c.rows_loc, full.p + (c.nranks == 1 ? 0 : 0));
@@ -493,8 +521,8 @@ int bs_build_monolithic(bs_context *h, const unsigned char *col_is_K, int num_ri
     select_columns(c, c.A, Vv, c.K, d_flag, c.A_aliases_V);
   }
   // rigid columns A(i, 3N+r) = -scaling * tmpN[r][i]  (ref: bem_stokes.cc:3247-3251)
-  DBuf<double> colbuf;
-  colbuf.alloc(c.rows_loc + 2);
+  struct P2_ { double *p; } colbuf;
+  colbuf.p = c.wsd("mono.col", c.rows_loc + 2);
   DMat Arows = c.A;
   Arows.rows = c.rows_loc;
   for (int r = 0; r < nr; ++r) {
@@ -703,13 +731,13 @@ int bs_gmres(bs_context *h, int which, const double *b, double *x, double tol_ab
   Context &c = ctx_of(h);
   BS_REQUIRE(b && x, "null vectors");
   BS_REQUIRE(c.prec_kind == BS_PREC_NONE || c.prec_which == which, "preconditioner was set up for another matrix");
-  Timer t(c, c.stats.solve_ms);
+  Timer t(c, c.stats.solve_ms, "bs_gmres");
   Extra &e = extra(c);
   const int nx = nextra_of(c, which);
   const size_t m = c.full_vec_len(which), mloc = c.local_vec_len(which), off = c.slice_offset(which);
-  DBuf<double> db, dx;
-  db.alloc(m + 2);
-  dx.alloc(m + 2);
+  struct P_ { double *p; } db, dx;
+  db.p = c.wsd("api.b", m + 2);
+  dx.p = c.wsd("api.x", m + 2);
   to_internal(c, b, nx, db.p);
   to_internal(c, x, nx, dx.p);
   (void)e;
@@ -748,9 +776,9 @@ int bs_gmres_multi(bs_context *h, int which, int nrhs, const double *B, double *
   const int nx = nextra_of(c, which);
   const size_t m = c.full_vec_len(which), mloc = c.local_vec_len(which), off = c.slice_offset(which);
   const size_t ldv = (m + 3) & ~(size_t)1;
-  DBuf<double> db, dx;
-  db.alloc((size_t)nrhs * ldv);
-  dx.alloc((size_t)nrhs * ldv);
+  struct P_ { double *p; } db, dx;
+  db.p = c.wsd("api.b", (size_t)nrhs * ldv);
+  dx.p = c.wsd("api.x", (size_t)nrhs * ldv);
   for (int k = 0; k < nrhs; ++k) {
     to_internal(c, B + (size_t)k * m, nx, db.p + (size_t)k * ldv);
     to_internal(c, X + (size_t)k * m, nx, dx.p + (size_t)k * ldv);
@@ -781,11 +809,11 @@ int bs_direct_solve(bs_context *h, int which, const double *b, double *x) {
   Timer t(c, c.stats.solve_ms);
   const int nx = nextra_of(c, which);
   const size_t m = c.full_vec_len(which);
-  DBuf<double> lu, dx;
-  DBuf<int> piv;
-  lu.alloc(m * m + 2);
-  piv.alloc(m + 2);
-  dx.alloc(m + 2);
+  struct P_ { double *p; } lu, dx;
+  struct PI_ { int *p; } piv;
+  lu.p = c.wsd("direct.lu", m * m + 2);
+  piv.p = c.wsi("direct.piv", m + 2);
+  dx.p = c.wsd("api.x", m + 2);
   BS_CUDA(cudaMemcpy2DAsync(lu.p, m * sizeof(double), M.p, M.ld * sizeof(double), m * sizeof(double), m,
                             cudaMemcpyDeviceToDevice, c.stream));
   lu_factor(c, lu.p, m, m, piv.p);
@@ -822,11 +850,12 @@ int bs_evaluate_bie(bs_context *h, int npts, const double *points, const double 
   BS_API_BEGIN
   Context &c = ctx_of(h);
   BS_REQUIRE(npts > 0 && points && vel && forces && out, "bad arguments");
-  DBuf<double> dp, dv, df, dout;
-  dp.upload(points, (size_t)3 * npts, c.stream);
-  dv.alloc(c.n3() + 2);
-  df.alloc(c.n3() + 2);
-  dout.alloc((size_t)3 * npts);
+  struct P_ { double *p; } dp, dv, df, dout;
+  dp.p = c.wsd("eval.pts", (size_t)3 * npts);
+  BS_CUDA(cudaMemcpyAsync(dp.p, points, sizeof(double) * 3 * npts, cudaMemcpyHostToDevice, c.stream));
+  dv.p = c.wsd("eval.vel", c.n3() + 2);
+  df.p = c.wsd("eval.frc", c.n3() + 2);
+  dout.p = c.wsd("eval.out", (size_t)3 * npts);
   to_internal(c, vel, 0, dv.p, true);
   to_internal(c, forces, 0, df.p, true);
   if (on_boundary)  // the reference's on-boundary routine accumulates into val_velocities (bem_stokes.cc:5543-5550)

@@ -92,8 +92,9 @@ __global__ void k_cell_geometry(int ncell, int nq, int nq_pad, int nam, const in
 void launch_cell_geometry(Context &c) {
   c.d_cellq.alloc((size_t)c.ncell * 7 * c.nq_pad);
   c.d_cellq.zero(c.stream);
-  DBuf<double> dw;
-  dw.upload(c.reg.w, c.stream);
+  struct P_ { double *p; } dw;
+  dw.p = c.wsd("geom.w", c.reg.w.size());
+  BS_CUDA(cudaMemcpyAsync(dw.p, c.reg.w.data(), sizeof(double) * c.reg.w.size(), cudaMemcpyHostToDevice, c.stream));
   const long long total = (long long)c.ncell * c.nq;
   const int bs_ = 256;
   k_cell_geometry<<<(unsigned)((total + bs_ - 1) / bs_), bs_, 0, c.stream>>>(c.ncell, c.nq, c.nq_pad, c.na_map, c.d_conn_map.p,
@@ -101,7 +102,7 @@ void launch_cell_geometry(Context &c) {
                                                                             c.d_cellq.p);
   BS_CUDA(cudaGetLastError());
   count_launch(c);
-  BS_CUDA(cudaStreamSynchronize(c.stream));  // dw goes out of scope
+  BS_CUDA(cudaStreamSynchronize(c.stream));
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -218,9 +218,9 @@ void evaluate_bie(Context &c, int npts, const double *d_pts, const double *d_vel
   BS_REQUIRE(c.have_geometry && c.have_quadrature, "geometry and quadrature must be set");
   if (npts <= 0) return;
   launch_cell_geometry(c);
-  DBuf<double> dens, partial;
-  dens.alloc((size_t)c.ncell * 6 * c.nq_pad);
-  dens.zero(c.stream);
+  struct P_ { double *p; } dens, partial;
+  dens.p = c.wsd("eval.dens", (size_t)c.ncell * 6 * c.nq_pad);
+  BS_CUDA(cudaMemsetAsync(dens.p, 0, sizeof(double) * (size_t)c.ncell * 6 * c.nq_pad, c.stream));
   const long long total = (long long)c.ncell * c.nq;
   k_eval_density<<<(unsigned)((total + 255) / 256), 256, 0, c.stream>>>(c.ncell, c.nq, c.nq_pad, c.na, c.d_conn_pos.p, c.d_phi_reg.p,
                                                                        d_forces, d_vel, dens.p);
@@ -232,7 +232,7 @@ void evaluate_bie(Context &c, int npts, const double *d_pts, const double *d_vel
   chunks = std::min(chunks, 65535);
   const int cpc = (c.ncell + chunks - 1) / chunks;
   chunks = (c.ncell + cpc - 1) / cpc;
-  partial.alloc((size_t)chunks * 3 * npts);
+  partial.p = c.wsd("eval.partial", (size_t)chunks * 3 * npts);
   KernelParams kp = c.kp;
   if (on_boundary) kp.type = BS_KERNEL_FREE;  // the reference's on-boundary formula uses the free-space kernel only
   switch (kp.type) {

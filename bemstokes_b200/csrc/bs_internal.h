@@ -6,6 +6,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <map>
 #include <stdexcept>
 #include "../../include/bemstokes_b200.h"
 
@@ -35,10 +36,13 @@ void set_last_error(const std::string &m);
 // ---------------------------------------------------------------------------------------------------------
 // device buffer
 // ---------------------------------------------------------------------------------------------------------
+// Grow-only: cudaMalloc / cudaFree are expensive (hundreds of ms once NCCL has mapped peers), so a buffer is
+// reallocated only when it has to grow and nothing on a hot path allocates.
 template <class T>
 struct DBuf {
   T *p = nullptr;
-  size_t n = 0;
+  size_t n = 0;    // logical size
+  size_t cap = 0;  // allocated size
   DBuf() = default;
   DBuf(const DBuf &) = delete;
   DBuf &operator=(const DBuf &) = delete;
@@ -46,13 +50,16 @@ struct DBuf {
   void release() {
     if (p) cudaFree(p);
     p = nullptr;
-    n = 0;
+    n = cap = 0;
   }
   void alloc(size_t count) {
-    if (count == n && p) return;
+    if (count <= cap && p) {
+      n = count;
+      return;
+    }
     release();
     if (count) BS_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
-    n = count;
+    n = cap = count;
   }
   void upload(const std::vector<T> &h, cudaStream_t s) {
     alloc(h.size());
@@ -212,7 +219,19 @@ struct Context {
   DBuf<double> d_xchg;              // replicated vector buffer (exchange target)
   DBuf<unsigned long long> d_flags;
 
-  // scratch
+  // scratch: named, context-owned, grow-only workspaces for what used to be function-local buffers
+  std::map<std::string, DBuf<double>> ws_d;
+  std::map<std::string, DBuf<int>> ws_i;
+  double *wsd(const char *key, size_t count) {
+    DBuf<double> &b = ws_d[key];
+    if (b.cap < count) b.alloc(count);
+    return b.p;
+  }
+  int *wsi(const char *key, size_t count) {
+    DBuf<int> &b = ws_i[key];
+    if (b.cap < count) b.alloc(count);
+    return b.p;
+  }
   DBuf<double> d_tmp0, d_tmp1, d_tmp2, d_tmp3;
   DBuf<double> d_small;             // small reductions
   double *h_pinned = nullptr;       // pinned host scratch

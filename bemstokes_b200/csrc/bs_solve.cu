@@ -4,6 +4,8 @@
 #include "bs_internal.h"
 #include <cmath>
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 
 namespace bs {
 
@@ -374,12 +376,12 @@ int gmres_batched(Context &c, int which, int nrhs, const double *d_B, double *d_
   const size_t ldw = (mloc + 3) & ~(size_t)1, ldx = (mfull + 3) & ~(size_t)1;
   const size_t CS = (size_t)2 * (m + 2) + 2;
   const DMat &M = mat_of(c, which);
-  DBuf<double> basis, w, z, coef, xfull;
-  basis.alloc((size_t)nrhs * (m + 1) * mloc + 2);
-  w.alloc((size_t)nrhs * ldw);
-  z.alloc((size_t)nrhs * ldw);
-  coef.alloc((size_t)nrhs * CS);
-  xfull.alloc((size_t)nrhs * ldx);
+  struct P_ { double *p; } basis, w, z, coef, xfull;  // context-owned, grow-only (no cudaMalloc per solve)
+  basis.p = c.wsd("gmres.basis", (size_t)nrhs * (m + 1) * mloc + 2);
+  w.p = c.wsd("gmres.w", (size_t)nrhs * ldw);
+  z.p = c.wsd("gmres.z", (size_t)nrhs * ldw);
+  coef.p = c.wsd("gmres.coef", (size_t)nrhs * CS);
+  xfull.p = c.wsd("gmres.xfull", (size_t)nrhs * ldx);
   struct Sys {
     std::vector<double> H, gamma, ci, si, h, yk;
     int its = 0, dim = 0;
@@ -420,6 +422,15 @@ int gmres_batched(Context &c, int which, int nrhs, const double *d_B, double *d_
     sy.dim = 0;
   };
   const unsigned sgrid = (unsigned)std::min<size_t>((mloc + 255) / 256, 1184);
+  const bool trace = std::getenv("BS_TRACE") != nullptr;
+  double t_exch = 0, t_mv = 0, t_orth = 0, t_sync = 0;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  auto tsync = [&](double &acc) {  // trace mode: attribute device time to the phase that queued it
+    if (!trace) return;
+    const double t0 = now();
+    cudaStreamSynchronize(c.stream);
+    acc += now() - t0;
+  };
 
   while (true) {
     std::vector<int> act;
@@ -466,7 +477,20 @@ int gmres_batched(Context &c, int which, int nrhs, const double *d_B, double *d_
       if (act.empty()) break;
       src.clear();
       for (int s : act) src.push_back(Bs(s) + (size_t)inner * mloc);
-      matvec_all(act, src);
+      double tt0 = trace ? now() : 0;
+      if (trace) {
+        for (size_t k = 0; k < act.size(); ++k) exchange(c, which, src[k], xfull.p + k * ldx);
+        cudaStreamSynchronize(c.stream);
+        t_exch += now() - tt0;
+        tt0 = now();
+        if (act.size() == 1) gemv(c, M, xfull.p, w.p);
+        else gemv_multi(c, M, (int)act.size(), xfull.p, ldx, w.p, ldw);
+        cudaStreamSynchronize(c.stream);
+        t_mv += now() - tt0;
+        tt0 = now();
+      } else {
+        matvec_all(act, src);
+      }
       const int dim = inner + 1;
       for (size_t k = 0; k < act.size(); ++k) {
         const int s = act[k];
@@ -474,8 +498,14 @@ int gmres_batched(Context &c, int which, int nrhs, const double *d_B, double *d_
         apply_precond(c, w.p + k * ldw, z.p + k * ldw);
         orthogonalize(c, Bs(s), mloc, dim, z.p + k * ldw, Cf(s), m, S[s].its, Cf(s) + CS - 2);
       }
+      if (trace) {
+        cudaStreamSynchronize(c.stream);
+        t_orth += now() - tt0;
+        tt0 = now();
+      }
       BS_CUDA(cudaMemcpyAsync(hbuf.data(), coef.p, sizeof(double) * nrhs * CS, cudaMemcpyDeviceToHost, c.stream));
       BS_CUDA(cudaStreamSynchronize(c.stream));
+      if (trace) t_sync += now() - tt0;
       for (size_t k = 0; k < act.size(); ++k) {
         const int s = act[k];
         Sys &sy = S[s];
@@ -516,6 +546,10 @@ int gmres_batched(Context &c, int which, int nrhs, const double *d_B, double *d_
     for (int s = 0; s < nrhs; ++s)
       if (S[s].active) finish(s);
   }
+  (void)tsync;
+  if (trace)
+    fprintf(stderr, "[bs trace rank %d] gmres: exchange %.1f ms, matvec %.1f ms, precond+orthogonalisation %.1f ms, d2h+sync %.1f ms (%d its)\n",
+            c.rank, 1e3 * t_exch, 1e3 * t_mv, 1e3 * t_orth, 1e3 * t_sync, S[0].its);
   int rc = BS_OK;
   for (int s = 0; s < nrhs; ++s) {
     if (iters) iters[s] = S[s].its;
