@@ -53,6 +53,7 @@ SIGNATURES = {
     "bs_host_prepass": (C.c_int, [C.c_int, C.c_int, C.c_int, c_double_p, C.c_int, c_int_p, C.c_int, c_int_p, C.c_int, c_double_p,
                                   c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "bs_assemble_VK": (C.c_int, [ctx_p]),
+    "bs_assemble_fused": (C.c_int, [ctx_p, C.c_int, c_double_p, c_double_p, c_double_p, C.c_double, c_double_p]),
     "bs_correct_V": (C.c_int, [ctx_p, c_double_p, c_double_p, C.c_double, c_double_p]),
     "bs_correct_K": (C.c_int, [ctx_p, C.c_int]),
     "bs_build_monolithic": (C.c_int, [ctx_p, c_ubyte_p, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, C.c_double,

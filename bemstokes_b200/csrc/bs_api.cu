@@ -352,12 +352,17 @@ int bs_set_kernel(bs_context *h, int type, double eps, int wall_orientation, con
   BS_API_END
 }
 
-int bs_assemble_VK(bs_context *h) {
-  BS_API_BEGIN
-  Context &c = ctx_of(h);
+static void assemble_common(Context &c, bool fused) {
   BS_REQUIRE(c.have_geometry && c.have_quadrature && c.have_singular, "geometry, quadrature and singular quadrature must be set");
+  c.fused = fused;
   alloc_matrix(c, c.storeV, c.V, c.rows_loc, c.n3());
-  alloc_matrix(c, c.storeK, c.K, c.rows_loc, c.n3());
+  if (!fused) alloc_matrix(c, c.storeK, c.K, c.rows_loc, c.n3());
+  else {
+    c.K = DMat();
+    c.storeK.release();  // the point of the fused mode: the double-layer matrix is never materialised
+    c.d_KX.alloc(c.rows_loc * c.panel_p + 2);
+    c.d_KX.zero(c.stream);
+  }
   c.A = DMat();
   c.A_aliases_V = false;
   {
@@ -373,6 +378,47 @@ int bs_assemble_VK(bs_context *h) {
     launch_assembly_singular(c);
   }
   BS_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+int bs_assemble_VK(bs_context *h) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  assemble_common(c, false);
+  BS_API_END
+}
+
+// internal vector (3N) from a reference-ordered host vector after the tangential projection P v
+static void project_to_internal(Context &c, const double *v, const double *nhat, const double *Mnhat, double l2, double *dst,
+                                size_t stride) {
+  const size_t n = c.n3();
+  double d = 0;
+  for (size_t i = 0; i < n; ++i) d += Mnhat[i] * v[i];
+  d /= l2;
+  for (size_t p = 0; p < (size_t)c.N; ++p)
+    for (int k = 0; k < 3; ++k) {
+      const size_t ref = (size_t)c.node_of_pos[p] + (size_t)k * c.N;
+      dst[(3 * p + k) * stride] = v[ref] - d * nhat[ref];
+    }
+}
+
+int bs_assemble_fused(bs_context *h, int num_rigid, const double *N_rigid, const double *nhat, const double *Mnhat,
+                      double l2gamma, const double *shape_vel) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(num_rigid >= 0 && num_rigid <= MAX_RIGID && (num_rigid == 0 || N_rigid), "bad rigid modes");
+  BS_REQUIRE(nhat && Mnhat && l2gamma > 0, "projector data missing");
+  const size_t n = c.n3();
+  const int pp = 3 + num_rigid + 1;
+  BS_REQUIRE(pp <= MAX_PANEL, "panel too wide");
+  c.panel_p = pp;
+  c.panel_nr = num_rigid;
+  c.h_panel.assign(n * pp, 0.0);
+  for (size_t p = 0; p < (size_t)c.N; ++p)
+    for (int k = 0; k < 3; ++k) c.h_panel[(3 * p + k) * pp + k] = 1.0;  // versors e_k (K correction, bem_stokes.cc:3044-3072)
+  for (int r = 0; r < num_rigid; ++r) project_to_internal(c, N_rigid + (size_t)r * n, nhat, Mnhat, l2gamma, &c.h_panel[3 + r], pp);
+  if (shape_vel) project_to_internal(c, shape_vel, nhat, Mnhat, l2gamma, &c.h_panel[3 + num_rigid], pp);
+  c.d_panel.upload(c.h_panel, c.stream);
+  assemble_common(c, true);
   BS_API_END
 }
 
@@ -413,6 +459,18 @@ int bs_correct_V(bs_context *h, const double *nhat, const double *Mnhat, double 
 int bs_correct_K(bs_context *h, int use_internal_alpha) {
   BS_API_BEGIN
   Context &c = ctx_of(h);
+  if (c.fused) {
+    // C_k = K e_k are the first three panel products; they enter the monolithic build (no K to correct in place)
+    BS_REQUIRE(c.d_KX.p != nullptr, "fused assembly not run");
+    std::vector<double> kx(c.rows_loc * c.panel_p);
+    BS_CUDA(cudaMemcpyAsync(kx.data(), c.d_KX.p, kx.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    BS_CUDA(cudaStreamSynchronize(c.stream));
+    c.h_C.assign(3 * c.rows_loc, 0.0);
+    for (size_t r = 0; r < c.rows_loc; ++r)
+      for (int k = 0; k < 3; ++k) c.h_C[(size_t)k * c.rows_loc + r] = kx[r * c.panel_p + k];
+    c.fused_alpha = use_internal_alpha;
+    return BS_OK;
+  }
   BS_REQUIRE(c.K.valid(), "K not assembled");
   Timer t(c, c.stats.correct_ms, "bs_correct_K");
   Mark mark(c);
@@ -438,8 +496,13 @@ int bs_build_monolithic(bs_context *h, const unsigned char *col_is_K, int num_ri
                         int imposed_component, double scaling, const double *shape_vel, int keep_VK, double *rhs_out) {
   BS_API_BEGIN
   Context &c = ctx_of(h);
-  BS_REQUIRE(c.V.valid() && c.K.valid(), "V and K must be assembled (and corrected) first");
+  BS_REQUIRE(c.V.valid() && (c.K.valid() || c.fused), "V and K must be assembled (and corrected) first");
   BS_REQUIRE(num_rigid >= 0 && num_rigid <= MAX_RIGID, "num_rigid out of range");
+  if (c.fused) {
+    BS_REQUIRE(col_is_K == nullptr, "fused (no-K) assembly supports body-only systems: every column of A is a V column");
+    BS_REQUIRE(num_rigid == c.panel_nr && c.h_C.size() == 3 * c.rows_loc, "fused mode: call bs_assemble_fused and bs_correct_K first");
+    keep_VK = 0;
+  }
   BS_REQUIRE(num_rigid == 0 || (N_rigid && N_rigid_dual), "rigid modes missing");
   Timer t(c, c.stats.monolithic_ms, "bs_build_monolithic");
   set_projector(c, nhat, Mnhat, l2gamma);
@@ -466,9 +529,29 @@ int bs_build_monolithic(bs_context *h, const unsigned char *col_is_K, int num_ri
   for (int r = 0; r < nr; ++r) project_into(N_rigid + (size_t)r * n, &X[(size_t)r * ldx]);
   const bool use_shape = (grid_type == BS_GRID_REAL && shape_vel != nullptr);
   if (use_shape) project_into(shape_vel, &X[(size_t)nr * ldx]);
-  e.vin2.upload(X, c.stream);
   e.vout.alloc(std::max(e.vout.n, (size_t)nvec * c.rows_loc + 2));
-  gemv_multi(c, c.K, nvec, e.vin2.p, ldx, e.vout.p, c.rows_loc);
+  if (!c.fused) {
+    e.vin2.upload(X, c.stream);
+    gemv_multi(c, c.K, nvec, e.vin2.p, ldx, e.vout.p, c.rows_loc);
+  } else {
+    // K_corr x = K x - D x + x with the uncorrected products of the assembly epilogue, (D x)_(i,j) = sum_k C_k[i,j] x_(i,k)
+    std::vector<double> kx(c.rows_loc * c.panel_p), out((size_t)nvec * c.rows_loc, 0.0);
+    BS_CUDA(cudaMemcpyAsync(kx.data(), c.d_KX.p, kx.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    BS_CUDA(cudaStreamSynchronize(c.stream));
+    const int pp = c.panel_p;
+    for (int v = 0; v < nvec; ++v) {
+      if (v == nr && !use_shape) continue;
+      for (size_t r = 0; r < c.rows_loc; ++r) {
+        const size_t node_pos = (size_t)c.p0 + r / 3;
+        double val = kx[r * pp + 3 + v];
+        for (int k = 0; k < 3; ++k) val -= c.h_C[(size_t)k * c.rows_loc + r] * c.h_panel[(3 * node_pos + k) * pp + 3 + v];
+        if (!c.fused_alpha) val += c.h_panel[((size_t)3 * c.p0 + r) * pp + 3 + v];
+        out[(size_t)v * c.rows_loc + r] = val;
+      }
+    }
+    BS_CUDA(cudaMemcpyAsync(e.vout.p, out.data(), out.size() * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    BS_CUDA(cudaStreamSynchronize(c.stream));
+  }
   // second projection needs the full vectors: gather slices
   std::vector<double> Y((size_t)nvec * n, 0.0);
   {

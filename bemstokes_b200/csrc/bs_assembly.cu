@@ -124,6 +124,10 @@ struct RegParams {
   double *V, *K;
   size_t ld;
   KernelParams kp;
+  // fused mode: K is not stored; KX[row][pp] += K_tile * X  (X = panel [3N][pp])
+  const double *panel;
+  double *KX;
+  int pp;
 };
 
 constexpr int ACC_LD = TI + 1;  // padded row-node stride of the shared accumulators (bank-conflict free both ways)
@@ -240,7 +244,7 @@ __device__ __forceinline__ void cell_pass(const double *__restrict__ cq, const d
 // (half the accumulator registers per thread -> twice the resident warps).  A CTA has TI*QS*VS threads.
 constexpr int MAXC = 32;  // cells per block (a block touches at most tj <= 32 nodes)
 
-template <int NA, int KT, bool SPLIT, int QS, int VS, bool HAS_EPS>
+template <int NA, int KT, bool SPLIT, int QS, int VS, bool HAS_EPS, bool FUSED>
 __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(const RegParams P) {
   constexpr int NV = GreenTraits<KT>::NV;
   constexpr int NV2 = 2 * NV;
@@ -365,13 +369,42 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
       const size_t off = rowoff + (size_t)3 * col_node[sidx] + col_j[sidx];
       if (col_first[sidx]) {
         P.V[off] = v;
-        P.K[off] = k;
+        if (!FUSED) P.K[off] = k;
       } else {
         // fire-and-forget L2 reductions: no load latency on the critical path.  Blocks of one colour never share a
         // node and colours are separate launches, so each address receives its addends in a fixed order.
         asm volatile("red.global.add.f64 [%0], %1;" ::"l"(P.V + off), "d"(v) : "memory");
-        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(P.K + off), "d"(k) : "memory");
+        if (!FUSED) asm volatile("red.global.add.f64 [%0], %1;" ::"l"(P.K + off), "d"(k) : "memory");
       }
+    }
+  }
+  if (FUSED) {
+    // K tile (rows x 3*tj) times the panel rows of this block's nodes; the single-layer part of the shared tile is
+    // free after its write-out and stages the panel rows.  Products go to KX with L2 reductions (every block adds to
+    // the same rows: summation order of these few panel columns is not fixed; the stored matrix stays deterministic).
+    __syncthreads();
+    const int pp = P.pp;
+    double *xs = acc_s;  // [3*tj][pp]
+    for (int idx = t; idx < 3 * tj * pp; idx += NT) {
+      const int col = idx / pp, q = idx - col * pp;
+      const int sl = col / 3, j = col - 3 * sl;
+      const int node = nodes[sl];
+      xs[idx] = node >= 0 ? P.panel[((size_t)3 * node + j) * pp + q] : 0.0;
+    }
+    __syncthreads();
+    const int rows3 = rows_tile * 3;
+    const double *kacc = acc_s + (size_t)NV * vs;
+    for (int idx = t; idx < rows3 * pp; idx += NT) {
+      const int q = idx / rows3, rr = idx - q * rows3;
+      const int r_ = rr / 3, i = rr - 3 * r_;
+      double y = 0.0;
+      for (int sl = 0; sl < tj; ++sl) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          y = fma(kacc[(size_t)vidx<NV>(i, j) * vs + (size_t)sl * ACC_LD + r_], xs[(3 * sl + j) * pp + q], y);
+      }
+      double *dst = P.KX + ((size_t)3 * (blockIdx.y * TI + r_) + i) * pp + q;
+      asm volatile("red.global.add.f64 [%0], %1;" ::"l"(dst), "d"(y) : "memory");
     }
   }
 }
@@ -379,7 +412,10 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
 template <int NA, int KT, bool SPLIT, int QS, int VS>
 static void launch_reg(Context &c, RegParams P, int nrow_tiles, size_t smem) {
   BS_REQUIRE(c.blocks.max_cells <= MAXC, "cell block larger than MAXC");
-  auto kern = (c.kp.eps == 0.0) ? k_assemble_regular<NA, KT, SPLIT, QS, VS, false> : k_assemble_regular<NA, KT, SPLIT, QS, VS, true>;
+  auto kern = c.fused ? ((c.kp.eps == 0.0) ? k_assemble_regular<NA, KT, SPLIT, QS, VS, false, true>
+                                           : k_assemble_regular<NA, KT, SPLIT, QS, VS, true, true>)
+                      : ((c.kp.eps == 0.0) ? k_assemble_regular<NA, KT, SPLIT, QS, VS, false, false>
+                                           : k_assemble_regular<NA, KT, SPLIT, QS, VS, true, false>);
   BS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const std::vector<int> &cs = c.blocks.colour_start;
   for (size_t k = 0; k + 1 < cs.size(); ++k) {  // one launch per colour, stream order = summation order
@@ -415,6 +451,9 @@ void launch_assembly_regular(Context &c) {
   P.K = c.K.p;
   P.ld = c.ld;
   P.kp = c.kp;
+  P.panel = c.fused ? c.d_panel.p : nullptr;
+  P.KX = c.fused ? c.d_KX.p : nullptr;
+  P.pp = c.panel_p;
   const int nrow_tiles = (c.p1 - c.p0 + TI - 1) / TI;
   if (nrow_tiles == 0) return;
   BS_REQUIRE(nrow_tiles <= 65535, "too many row tiles per rank");
@@ -455,11 +494,14 @@ struct SingParams {
   double *V, *K;
   size_t ld;
   KernelParams kp;
+  const double *panel;  // fused mode (K not stored)
+  double *KX;
+  int pp;
 };
 
 constexpr int SING_WARPS = 4;
 
-template <int NA, int NAM, int KT>
+template <int NA, int NAM, int KT, bool FUSED>
 __global__ void __launch_bounds__(32 * SING_WARPS) k_assemble_singular(const SingParams P) {
   constexpr int NV = GreenTraits<KT>::NV;
   constexpr int NV2 = 2 * NV;
@@ -544,11 +586,25 @@ __global__ void __launch_bounds__(32 * SING_WARPS) k_assemble_singular(const Sin
       for (int idx = lane; idx < CH * 18; idx += 32) {
         const int a = idx / 18, r = idx - a * 18;
         const int mat = r / 9, ij = r - mat * 9, i = ij / 3, j = ij - 3 * i;
-        if (a0 + a < NA) {
+        if (a0 + a < NA && !(FUSED && mat == 1)) {
           const int cpos = P.conn_pos[(size_t)cell * NA + a0 + a];
           const double val = red[wid][a * NV2 + mat * NV + vidx<NV>(i, j)];
           double *M = mat == 0 ? P.V : P.K;
           M[(row0 + i) * P.ld + (size_t)3 * cpos + j] += val;
+        }
+      }
+      if (FUSED) {
+        // K block of this (node, cell) pair times the panel rows of the cell's nodes; this warp owns the rows
+        for (int idx = lane; idx < 3 * P.pp; idx += 32) {
+          const int i = idx / P.pp, q = idx - i * P.pp;
+          double y = 0.0;
+          for (int a = 0; a < CH; ++a) {
+            if (a0 + a >= NA) break;
+            const int cpos = P.conn_pos[(size_t)cell * NA + a0 + a];
+            for (int j = 0; j < 3; ++j)
+              y = fma(red[wid][a * NV2 + NV + vidx<NV>(i, j)], P.panel[((size_t)3 * cpos + j) * P.pp + q], y);
+          }
+          P.KX[(row0 + i) * P.pp + q] += y;
         }
       }
       __syncwarp();
@@ -560,7 +616,8 @@ template <int NA, int NAM, int KT>
 static void launch_sing(Context &c, const SingParams &P) {
   const int n = c.p1 - c.p0;
   if (n <= 0) return;
-  k_assemble_singular<NA, NAM, KT><<<(n + SING_WARPS - 1) / SING_WARPS, 32 * SING_WARPS, 0, c.stream>>>(P);
+  if (c.fused) k_assemble_singular<NA, NAM, KT, true><<<(n + SING_WARPS - 1) / SING_WARPS, 32 * SING_WARPS, 0, c.stream>>>(P);
+  else k_assemble_singular<NA, NAM, KT, false><<<(n + SING_WARPS - 1) / SING_WARPS, 32 * SING_WARPS, 0, c.stream>>>(P);
   BS_CUDA(cudaGetLastError());
 }
 
@@ -594,6 +651,9 @@ void launch_assembly_singular(Context &c) {
   P.K = c.K.p;
   P.ld = c.ld;
   P.kp = c.kp;
+  P.panel = c.fused ? c.d_panel.p : nullptr;
+  P.KX = c.fused ? c.d_KX.p : nullptr;
+  P.pp = c.panel_p;
   switch (c.kp.type) {
     case BS_KERNEL_FREE: launch_sing_kt<BS_KERNEL_FREE>(c, P); break;
     case BS_KERNEL_FREE_SURFACE: launch_sing_kt<BS_KERNEL_FREE_SURFACE>(c, P); break;

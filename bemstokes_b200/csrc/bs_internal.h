@@ -197,6 +197,15 @@ struct Context {
   bool has_rigid_rows = false;      // this rank stores the rigid rows (last rank)
   size_t mono_size = 0;             // 3N + num_rigid
 
+  // fused "no-K" assembly: K is never stored; K * panel products are accumulated in the tile epilogue.
+  // panel X[3N][panel_p] (internal rows, p fastest): columns 0..2 = versors e_k, 3..3+nr-1 = P N_r, last = P u_shape
+  bool fused = false;
+  int panel_p = 0, panel_nr = 0;
+  DBuf<double> d_panel;             // [3N][panel_p]
+  DBuf<double> d_KX;                // [rows_loc][panel_p] = K_loc * X (uncorrected K)
+  std::vector<double> h_panel;      // host copy of X
+  std::vector<double> h_C;          // [3][rows_loc] K e_k on the owned rows (after bs_correct_K in fused mode)
+  int fused_alpha = 0;
   // projector data (internal ordering, full length 3N)
   DBuf<double> d_nhat, d_Mnhat;
   double l2gamma = 0.0;
@@ -258,6 +267,7 @@ void build_tables(Context &c);          // after geometry + quadrature known
 void launch_cell_geometry(Context &c);
 void launch_assembly_regular(Context &c);
 void launch_assembly_singular(Context &c);
+constexpr int MAX_PANEL = 12;
 size_t assembly_smem_bytes(int na, int nv, int tj, int nq_pad);
 int choose_tj(int na, int kernel_type, int nq_pad);
 void kernel_eval_device(int type, double eps, int o, int npts, const double *d_p, const double *d_pim, double *d_G,

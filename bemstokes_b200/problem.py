@@ -197,6 +197,7 @@ class BEMProblem:
         self.solver_control = SolverControl(1000, 1e-10)
         self.force_pole = (0.0, 0.0, 0.0)
         self.keep_VK = True
+        self.fused_assembly = False    # True: never store K (bs_assemble_fused); body-only monolithic systems
         self.num_rigid = 6
         self._ctx = None
         self.mesh = None
@@ -319,9 +320,15 @@ class BEMProblem:
         """ref: BEMProblem::assemble_stokes_system (bem_stokes.cc:2840-3435)."""
         ctx = self._ctx
         self._set_kernel()
-        check(lib.bs_assemble_VK(ctx))
         nh = np.ascontiguousarray(self.normal_vector_pure)
         mn = np.ascontiguousarray(self.M_normal_vector_pure)
+        if self.fused_assembly:
+            Nr0 = np.ascontiguousarray(self.N_rigid[:self.num_rigid])
+            sv0 = np.ascontiguousarray(self.shape_velocities, dtype=np.float64)
+            check(lib.bs_assemble_fused(ctx, self.num_rigid, _dp(Nr0), _dp(nh), _dp(mn), self.l2normGamma_pure,
+                                        _dp(sv0) if self.grid_type == "Real" else None))
+        else:
+            check(lib.bs_assemble_VK(ctx))
         self.V_x_normals_body = np.zeros(self.n_dofs)
         if correction_on_V:
             check(lib.bs_correct_V(ctx, _dp(nh), _dp(mn), self.l2normGamma_pure, _dp(self.V_x_normals_body)))

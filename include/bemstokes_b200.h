@@ -107,6 +107,14 @@ int bs_host_prepass(int fe_degree, int map_degree, int n_map_nodes, const double
 /* ---- assembly (ref: BEMProblem::assemble_stokes_system, bem_stokes.cc:2840-3435) ----------------------- */
 /* K1 (regular Gauss pass) + K2 (singular pass) -> row-block of V and K on the device (2871-3000). */
 int bs_assemble_VK(bs_context *ctx);
+/* Fused "no-K" assembly for sizes where V and K do not fit together (BASELINE config 4: 294 918 DoF, 696 GB per
+ * matrix): same K1/K2 passes, but the double-layer tile is multiplied in the tile epilogue with the panel
+ * [e_0 e_1 e_2 | P N_r | P u_shape] instead of being stored, which is all the monolithic system of a body-only
+ * problem needs from K (K correction 3044-3098, projected rigid columns 3120-3148, rhs 3127-3132).  Afterwards
+ * call bs_correct_V, bs_correct_K and bs_build_monolithic as usual (col_is_K must be NULL, A aliases V);
+ * BS_MAT_K is not available. */
+int bs_assemble_fused(bs_context *ctx, int num_rigid, const double *N_rigid, const double *nhat, const double *Mnhat,
+                      double l2gamma, const double *shape_vel);
 /* V <- V + (nhat - V nhat)(M nhat)^T / l2 on owned rows (3004-3036). nhat = normal_vector_pure,
  * Mnhat = M_normal_vector_pure, l2 = l2normGamma_pure.  Vn_out (3N, may be NULL) receives V*nhat
  * computed BEFORE the correction ("Check on the V operator Norm"). */

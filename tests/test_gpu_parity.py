@@ -442,3 +442,37 @@ def test_field_evaluation_bie(half):
     want_b = bo.evaluate_bie(geo, bo.KernelSpec(), bpts, u, t, 8, on_boundary=True, sing_kind="Mixed", sing_order=10, out=acc0.copy())
     assert np.abs(got_b - want_b).max() <= 1e-11 * np.abs(want_b).max()
     p.close()
+
+
+@pytest.mark.parametrize("grid_type", ["ImposedVelocity", "ImposedForce", "Real"])
+def test_fused_no_K_assembly(half, grid_type):
+    """bs_assemble_fused (K never stored, K*panel accumulated in the tile epilogue) gives the same monolithic matrix,
+    right-hand side and solution as the stored-K path and the oracle."""
+    rng = np.random.default_rng(11)
+    sv = rng.uniform(-1, 1, 3 * half.n_nodes) if grid_type == "Real" else None
+    sols = {}
+    for fused in (False, True):
+        p = make_problem(half, grid_type=grid_type, imposed_component=2, solve_directly=True, fused_assembly=fused,
+                         keep_VK=not fused)
+        if sv is not None:
+            p.shape_velocities = sv.copy()
+        p.assemble_stokes_system(True)
+        A = p.monolithic_system_matrix.to_dense()
+        p.solve_system(True)
+        sols[fused] = (A, p.monolithic_rhs.copy(), p.monolithic_solution.copy())
+        if fused:
+            with pytest.raises(bb.BemStokesError):
+                p.K_matrix @ np.zeros(p.n_dofs)
+        p.close()
+    A0, b0, x0 = sols[False]
+    A1, b1, x1 = sols[True]
+    assert rel_rows(A1, A0) < ENTRY_TOL
+    assert np.abs(b1 - b0).max() <= 1e-13 * max(1.0, np.abs(b0).max())
+    assert np.abs(x1 - x0).max() <= 1e-10 * np.abs(x0).max()
+    geo = bo.Geometry(half.nodes, half.conn.astype(np.int64), 1)
+    Vo, Ko = bo.assemble_VK(geo, bo.KernelSpec(), 8, "Mixed", 10)
+    pre = bo.Prepass(geo, 8)
+    Vc, _ = bo.correct_V(Vo, pre)
+    Ao, bvec = bo.monolithic(Vc, bo.correct_K(Ko, geo.N), pre, grid_type, 2, 1.0, sv)
+    assert rel_rows(A1, Ao) < ENTRY_TOL
+    assert np.abs(b1 - bvec).max() <= 1e-12 * max(1.0, np.abs(bvec).max())
