@@ -384,27 +384,39 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
     // the same rows: summation order of these few panel columns is not fixed; the stored matrix stays deterministic).
     __syncthreads();
     const int pp = P.pp;
-    double *xs = acc_s;  // [3*tj][pp]
-    for (int idx = t; idx < 3 * tj * pp; idx += NT) {
-      const int col = idx / pp, q = idx - col * pp;
+    constexpr int PS = MAX_PANEL;  // padded panel stride in shared memory (zero filled): fixed-trip inner loops
+    double *xs = acc_s;            // [3*tj][PS]
+    for (int idx = t; idx < 3 * tj * PS; idx += NT) {
+      const int col = idx / PS, q = idx - col * PS;
       const int sl = col / 3, j = col - 3 * sl;
       const int node = nodes[sl];
-      xs[idx] = node >= 0 ? P.panel[((size_t)3 * node + j) * pp + q] : 0.0;
+      xs[idx] = (node >= 0 && q < pp) ? P.panel[((size_t)3 * node + j) * pp + q] : 0.0;
     }
     __syncthreads();
     const int rows3 = rows_tile * 3;
     const double *kacc = acc_s + (size_t)NV * vs;
-    for (int idx = t; idx < rows3 * pp; idx += NT) {
-      const int q = idx / rows3, rr = idx - q * rows3;
+    for (int rr = t; rr < rows3; rr += NT) {  // one matrix row per thread, all panel columns in registers
       const int r_ = rr / 3, i = rr - 3 * r_;
-      double y = 0.0;
+      double y[PS];
+#pragma unroll
+      for (int q = 0; q < PS; ++q) y[q] = 0.0;
       for (int sl = 0; sl < tj; ++sl) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j)
-          y = fma(kacc[(size_t)vidx<NV>(i, j) * vs + (size_t)sl * ACC_LD + r_], xs[(3 * sl + j) * pp + q], y);
+        for (int j = 0; j < 3; ++j) {
+          const double kv = kacc[(size_t)vidx<NV>(i, j) * vs + (size_t)sl * ACC_LD + r_];
+          const double2 *xr = reinterpret_cast<const double2 *>(xs + (3 * sl + j) * PS);  // broadcast reads
+#pragma unroll
+          for (int q2 = 0; q2 < PS / 2; ++q2) {
+            const double2 xv = xr[q2];
+            y[2 * q2] = fma(kv, xv.x, y[2 * q2]);
+            y[2 * q2 + 1] = fma(kv, xv.y, y[2 * q2 + 1]);
+          }
+        }
       }
-      double *dst = P.KX + ((size_t)3 * (blockIdx.y * TI + r_) + i) * pp + q;
-      asm volatile("red.global.add.f64 [%0], %1;" ::"l"(dst), "d"(y) : "memory");
+      double *dst = P.KX + ((size_t)3 * (blockIdx.y * TI + r_) + i) * pp;
+#pragma unroll
+      for (int q = 0; q < PS; ++q)
+        if (q < pp) asm volatile("red.global.add.f64 [%0], %1;" ::"l"(dst + q), "d"(y[q]) : "memory");
     }
   }
 }

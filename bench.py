@@ -9,10 +9,14 @@ in HBM); the line also carries the GMRES matvec HBM GB/s and the time-to-solutio
 of BASELINE.json's metric.  `e2e` = the same assembly metric through the public BEMProblem / C-ABI call with
 HOST buffers (geometry H2D inside the timed region, V*n check vector D2H), plus the host-to-host time to solution.
 
-Workloads (config.workload): N GPUs run cubesphere(m = round(64 * N^(1/4))) Q1, i.e. the same matrix memory per
-GPU at every N (weak scaling, rows sharded, no data-path collective in assembly); at N=1 that is 24 578 nodes /
-73 734 DoF / 43.5 GB per FP64 matrix — the same DoF count as BASELINE config "refined sphere" at refinement 5 and
-the largest V+K pair one 180 GB B200 holds.  --workload q2 runs BASELINE config 3 (Q2, Gauss 15 / singular 20).
+Workloads (config.workload): the default is the BASELINE config-4 family — synthetic cube-sphere, Q1, Gauss 8 /
+Lachat-Watson 10, translating sphere — with m = round(128 * (N/8)^(1/4)) subdivisions per face edge, i.e. the same
+matrix bytes per GPU (87 GB of FP64 A) at every N (weak scaling, rows sharded, no data-path collective in
+assembly).  At N=8 this is BASELINE config 4 exactly (98 306 nodes, 294 918 DoF, 696 GB matrix); at N=1 it is the
+largest member one 180 GB B200 holds (34 658 nodes, 103 974 DoF).  These sizes use the fused no-K assembly
+(bs_assemble_fused: the double-layer tile is consumed in the tile epilogue, V and K would not fit together).
+--workload vk keeps both matrices (m = 64 * N^(1/4), 43.5 GB each per GPU); --workload q2 runs BASELINE config 3
+(Q2, Gauss 15 / singular 20).
 
 `--impl reference` times the reference's CPU path (the C/OpenMP restatement under oracle/, all host threads)
 on a bounded row sample of the same workload.
@@ -44,12 +48,17 @@ def load_peaks():
 def workload(args, nranks):
     if args.workload == "q2":
         r = args.refine if args.refine is not None else 4
-        return dict(kind="cubesphere", m=2 ** r, degree=2, quad=15, sing=20,
+        return dict(kind="cubesphere", m=2 ** r, degree=2, quad=15, sing=20, fused=False,
                     name="BASELINE config 3: cube-sphere (sphere_2.inp topology) refined %dx, Q2, Gauss 15 / Mixed 20" % r)
-    m = args.m if args.m else int(round(64 * nranks ** 0.25))
-    return dict(kind="cubesphere", m=m, degree=1, quad=8, sing=10,
-                name="synthetic cube-sphere m=%d (6*m^2 quads), Q1 collocation, Gauss 8 / Lachat-Watson 10, translating "
-                     "sphere ImposedVelocity e_x" % m)
+    if args.workload == "vk":
+        m = args.m if args.m else int(round(64 * nranks ** 0.25))
+        return dict(kind="cubesphere", m=m, degree=1, quad=8, sing=10, fused=False,
+                    name="synthetic cube-sphere m=%d (6*m^2 quads), Q1 collocation, Gauss 8 / Lachat-Watson 10, translating "
+                         "sphere ImposedVelocity e_x, V and K both stored" % m)
+    m = args.m if args.m else int(round(128 * (nranks / 8.0) ** 0.25))
+    return dict(kind="cubesphere", m=m, degree=1, quad=8, sing=10, fused=not args.no_fused,
+                name="BASELINE config 4 family: synthetic cube-sphere m=%d (6*m^2 quads; m=128 at 8 GPUs = 98 306 nodes), Q1 "
+                     "collocation, Gauss 8 / Lachat-Watson 10, translating sphere ImposedVelocity e_x, fused no-K assembly" % m)
 
 
 class ClockSampler:
@@ -137,7 +146,8 @@ def run_ours(args):
     p.quadrature_order, p.singular_quadrature_order = wl["quad"], wl["sing"]
     p.grid_type, p.imposed_component = "ImposedVelocity", 0
     p.solve_directly, p.preconditioner_type = False, "None"
-    p.keep_VK = False  # A aliases V: V + K of 73 734 DoF already fill half of the 180 GB
+    p.keep_VK = False  # A aliases V's storage
+    p.fused_assembly = bool(wl.get("fused"))
     p.solver_control.tolerance, p.solver_control.max_steps = 1e-10, 1000
     p.gmres_restart = 200
     p.reinit()
@@ -161,10 +171,15 @@ def run_ours(args):
         """host buffers in (geometry, quadrature, normals, rigid modes), host result out"""
         t0 = time.perf_counter()
         p.update_geometry()              # bs_set_geometry: host euler vector -> device (per-frame flow of the reference)
-        check(lib.bs_assemble_VK(p._ctx))
         vn = np.zeros(n)
         nh = np.ascontiguousarray(p.normal_vector_pure)
         mn = np.ascontiguousarray(p.M_normal_vector_pure)
+        if p.fused_assembly:
+            Nr0 = np.ascontiguousarray(p.N_rigid[:p.num_rigid])
+            check(lib.bs_assemble_fused(p._ctx, p.num_rigid, Nr0.ctypes.data_as(_lib.c_double_p), nh.ctypes.data_as(_lib.c_double_p),
+                                        mn.ctypes.data_as(_lib.c_double_p), p.l2normGamma_pure, None))
+        else:
+            check(lib.bs_assemble_VK(p._ctx))
         check(lib.bs_correct_V(p._ctx, nh.ctypes.data_as(_lib.c_double_p), mn.ctypes.data_as(_lib.c_double_p),
                                p.l2normGamma_pure, vn.ctypes.data_as(_lib.c_double_p)))  # D2H of V*n
         torch.cuda.synchronize()
@@ -274,10 +289,11 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["name"], "nodes": N, "cells": ncell, "dofs": n, "matrix_gb_each": 8.0 * n * n / 1e9,
                        "sharding": "rows (collocation nodes) over %d GPU(s), contiguous ranges of the locality order" % world,
-                       "timing": "CUDA events on the launching stream inside the library; working set (>=2 x %.1f GB) "
+                       "timing": "CUDA events on the launching stream inside the library; working set (%.1f GB matrix per GPU) "
                                  "far larger than the 126 MB L2, no explicit flush needed" % (8.0 * n * n / 1e9 / world),
-                       "value_definition": "2*(3N)^2 entries / (K0+K1+K2 device time); ms_per_step is the whole step "
-                                           "(assembly + corrections + monolithic build + GMRES)"},
+                       "value_definition": "2*(3N)^2 entries of V and K evaluated / (K0+K1+K2 device time); ms_per_step is the "
+                                           "whole step (assembly + corrections + monolithic build + GMRES)"
+                                           + ("; fused mode stores V only and consumes the K tile in the epilogue" if wl.get("fused") else "")},
             "phases_ms": {"assembly": asm_ms, "assemble_regular": st["assemble_regular_ms"] / args.steps,
                           "assemble_singular": st["assemble_singular_ms"] / args.steps, "cell_geometry": st["geometry_ms"] / args.steps,
                           "corrections": st["correct_ms"] / args.steps, "monolithic": st["monolithic_ms"] / args.steps,
@@ -369,8 +385,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="q1", choices=["q1", "q2"])
-    ap.add_argument("--subdiv", dest="m", type=int, default=0, help="cube-sphere subdivisions per face edge (default 64*N^(1/4))")
+    ap.add_argument("--workload", default="c4", choices=["c4", "vk", "q2"])
+    ap.add_argument("--no-fused", action="store_true", help="c4 family with V and K both stored (needs 2x the memory)")
+    ap.add_argument("--subdiv", dest="m", type=int, default=0, help="cube-sphere subdivisions per face edge (default 128*(N/8)^(1/4); 64*N^(1/4) for --workload vk)")
     ap.add_argument("--refine", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--resistance", action="store_true", help="also time the 6-RHS batched resistance solve")
