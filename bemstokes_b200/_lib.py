@@ -74,8 +74,8 @@ SIGNATURES = {
     "bs_kernel_eval": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p,
                                  c_double_p]),
     "bs_set_comm": (C.c_int, [ctx_p, ALLGATHERV_FN, ALLREDUCE_FN, C.c_void_p]),
-    "bs_get_exchange_buffer": (C.c_int, [ctx_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
-    "bs_set_peer_buffers": (C.c_int, [ctx_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "bs_exchange_export": (C.c_int, [ctx_p, C.c_size_t, C.c_void_p]),
+    "bs_exchange_import": (C.c_int, [ctx_p, C.c_int, C.c_void_p]),
     "bs_get_stats": (C.c_int, [ctx_p, C.POINTER(BsStats)]),
     "bs_reset_stats": (C.c_int, [ctx_p]),
     "bs_bench_vmult": (C.c_int, [ctx_p, C.c_int, C.c_int, c_double_p]),

@@ -175,6 +175,11 @@ int bs_destroy(bs_context *h) {
   Context &c = h->c;
   cudaSetDevice(c.device);
   cudaStreamSynchronize(c.stream);
+  for (int r = 0; r < (int)c.peer_xbuf.size(); ++r)
+    if (r != c.rank) {
+      if (c.peer_xbuf[r]) cudaIpcCloseMemHandle(c.peer_xbuf[r]);
+      if (c.peer_flags[r]) cudaIpcCloseMemHandle(c.peer_flags[r]);
+    }
   drop_extra(c);
   if (c.ev0) cudaEventDestroy(c.ev0);
   if (c.ev1) cudaEventDestroy(c.ev1);
@@ -969,23 +974,55 @@ int bs_set_comm(bs_context *h, bs_allgatherv_fn ag, bs_allreduce_sum_fn ar, void
   BS_API_END
 }
 
-int bs_get_exchange_buffer(bs_context *h, void **dev_ptr, size_t *bytes) {
+int bs_exchange_export(bs_context *h, size_t max_vec_len, unsigned char *handles_out) {
   BS_API_BEGIN
   Context &c = ctx_of(h);
-  const size_t n = c.n3() + MAX_RIGID + 2;
-  c.d_xchg.alloc(std::max(c.d_xchg.n, n));
-  if (dev_ptr) *dev_ptr = c.d_xchg.p;
-  if (bytes) *bytes = c.d_xchg.n * sizeof(double);
+  BS_REQUIRE(handles_out != nullptr && max_vec_len > 0, "bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  c.xchg_ld = (max_vec_len + 17) & ~(size_t)15;
+  c.d_xchg.alloc(Context::XCHG_SLOTS * c.xchg_ld);
+  c.d_xchg.zero(c.stream);
+  c.d_flags.alloc(64);
+  c.d_flags.zero(c.stream);
+  BS_CUDA(cudaStreamSynchronize(c.stream));
+  cudaIpcMemHandle_t hx, hf;
+  BS_CUDA(cudaIpcGetMemHandle(&hx, c.d_xchg.p));
+  BS_CUDA(cudaIpcGetMemHandle(&hf, c.d_flags.p));
+  std::memcpy(handles_out, &hx, 64);
+  std::memcpy(handles_out + 64, &hf, 64);
   BS_API_END
 }
 
-int bs_set_peer_buffers(bs_context *h, int nranks, void *const *peer_xbuf, void *const *peer_flags) {
+int bs_exchange_import(bs_context *h, int nranks, const unsigned char *all) {
   BS_API_BEGIN
   Context &c = ctx_of(h);
-  BS_REQUIRE(nranks == c.nranks, "nranks mismatch");
-  c.peer_xbuf.assign(peer_xbuf, peer_xbuf + nranks);
-  c.peer_flags.clear();
-  if (peer_flags) c.peer_flags.assign(peer_flags, peer_flags + nranks);
+  BS_REQUIRE(nranks == c.nranks && all != nullptr, "nranks mismatch");
+  BS_REQUIRE(c.d_xchg.p != nullptr, "call bs_exchange_export first");
+  c.peer_xbuf.assign(nranks, nullptr);
+  c.peer_flags.assign(nranks, nullptr);
+  for (int r = 0; r < nranks; ++r) {
+    if (r == c.rank) {
+      c.peer_xbuf[r] = c.d_xchg.p;
+      c.peer_flags[r] = c.d_flags.p;
+      continue;
+    }
+    cudaIpcMemHandle_t hx, hf;
+    std::memcpy(&hx, all + (size_t)r * BS_IPC_EXPORT_BYTES, 64);
+    std::memcpy(&hf, all + (size_t)r * BS_IPC_EXPORT_BYTES + 64, 64);
+    BS_CUDA(cudaIpcOpenMemHandle(&c.peer_xbuf[r], hx, cudaIpcMemLazyEnablePeerAccess));
+    BS_CUDA(cudaIpcOpenMemHandle(&c.peer_flags[r], hf, cudaIpcMemLazyEnablePeerAccess));
+  }
+  std::vector<double *> px(nranks);
+  std::vector<unsigned long long *> pf(nranks);
+  for (int r = 0; r < nranks; ++r) {
+    px[r] = (double *)c.peer_xbuf[r];
+    pf[r] = (unsigned long long *)c.peer_flags[r];
+  }
+  c.d_peer_xbuf.upload(px, c.stream);
+  c.d_peer_flags.upload(pf, c.stream);
+  BS_CUDA(cudaStreamSynchronize(c.stream));
+  c.epoch = 0;
+  c.p2p = true;
   BS_API_END
 }
 

@@ -224,9 +224,16 @@ struct Context {
   bs_allgatherv_fn cb_allgatherv = nullptr;
   bs_allreduce_sum_fn cb_allreduce = nullptr;
   void *cb_user = nullptr;
-  std::vector<void *> peer_xbuf, peer_flags;
-  DBuf<double> d_xchg;              // replicated vector buffer (exchange target)
-  DBuf<unsigned long long> d_flags;
+  // peer-memory exchange (NVLink P2P through CUDA IPC)
+  static constexpr int XCHG_SLOTS = 8;   // replicated vectors in flight (multi-RHS lockstep solves)
+  bool p2p = false;
+  size_t xchg_ld = 0;               // doubles per slot
+  DBuf<double> d_xchg;              // [XCHG_SLOTS][xchg_ld] replicated vector buffer written by all ranks
+  DBuf<unsigned long long> d_flags; // [nranks] arrival epoch per source rank (+1 error word)
+  std::vector<void *> peer_xbuf, peer_flags;   // mapped pointers, rank order (own entry = local pointer)
+  DBuf<double *> d_peer_xbuf;
+  DBuf<unsigned long long *> d_peer_flags;
+  unsigned long long epoch = 0;
 
   // scratch: named, context-owned, grow-only workspaces for what used to be function-local buffers
   std::map<std::string, DBuf<double>> ws_d;
@@ -298,6 +305,8 @@ void lu_factor(Context &c, double *A, size_t n, size_t ld, int *piv);
 void lu_solve(Context &c, const double *LU, size_t n, size_t ld, const int *piv, double *x /* in/out */);
 void apply_operator(Context &c, int which, const double *x_full, double *y_loc);
 void exchange(Context &c, int which, const double *y_loc, double *x_full);
+void p2p_scatter(Context &c, int which, const double *src_loc, int slot, const double *inv_norm2, double *basis_dst);
+void p2p_wait(Context &c);
 void apply_precond(Context &c, const double *in_loc, double *out_loc);
 int gmres(Context &c, int which, const double *d_b_loc, double *d_x_loc, double tol, int max_steps, int max_tmp,
           int *iters, double *final_res);

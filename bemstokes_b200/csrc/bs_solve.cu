@@ -48,6 +48,60 @@ static void allreduce(Context &c, double *d_buf, int count) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Peer-memory exchange over NVLink (CUDA-IPC mapped buffers): the kernel that produces a Krylov vector stores this
+// rank's slice into the replicated buffer of EVERY rank; a release store per peer publishes it; the consumer
+// acquire-waits on its own flag array before the matvec.  No collective call, no staging copy.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void k_p2p_scatter(const double *__restrict__ src, size_t n, const double *inv_norm2, double *basis_dst,
+                              double *const *peer_bufs, int nranks, size_t dst_off) {
+  const double a = inv_norm2 ? rsqrt(*inv_norm2) : 1.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double v = src[i] * a;
+    if (basis_dst) basis_dst[i] = v;
+    for (int r = 0; r < nranks; ++r) peer_bufs[r][dst_off + i] = v;  // own buffer included; peers over NVLink
+  }
+}
+__global__ void k_p2p_signal(unsigned long long *const *peer_flags, int nranks, int myrank, unsigned long long epoch) {
+  const int r = threadIdx.x;
+  if (r >= nranks) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flags[r] + myrank), "l"(epoch) : "memory");
+}
+__global__ void k_p2p_wait(const unsigned long long *flags, int nranks, unsigned long long epoch, unsigned long long *err) {
+  const int r = threadIdx.x;
+  if (r >= nranks) return;
+  unsigned long long t0, t1, v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + r) : "memory");
+    if (v >= epoch) return;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+  } while (t1 - t0 < 20000000000ull);  // 20 s: a rank died; report instead of hanging the GPU
+  *err = epoch;
+}
+
+// store my slice (optionally normalised by 1/sqrt(*inv_norm2), optionally also into the local basis) into slot
+// `slot` of every rank's replicated buffer
+void p2p_scatter(Context &c, int which, const double *src_loc, int slot, const double *inv_norm2, double *basis_dst) {
+  BS_REQUIRE(slot < Context::XCHG_SLOTS, "too many vectors in flight for the peer exchange buffer");
+  BS_REQUIRE(c.full_vec_len(which) <= c.xchg_ld, "exchange buffer too small (bs_exchange_export max_vec_len)");
+  const size_t mloc = c.local_vec_len(which);
+  const size_t off = (size_t)slot * c.xchg_ld + c.slice_offset(which);
+  const unsigned grid = (unsigned)std::min<size_t>(std::max<size_t>((mloc + 255) / 256, 1), 592);
+  k_p2p_scatter<<<grid, 256, 0, c.stream>>>(src_loc, mloc, inv_norm2, basis_dst, c.d_peer_xbuf.p, c.nranks, off);
+  BS_CUDA(cudaGetLastError());
+  count_launch(c);
+}
+// publish everything scattered so far and wait until every rank has published the same epoch
+void p2p_wait(Context &c) {
+  ++c.epoch;
+  k_p2p_signal<<<1, 32, 0, c.stream>>>(c.d_peer_flags.p, c.nranks, c.rank, c.epoch);
+  k_p2p_wait<<<1, 32, 0, c.stream>>>(c.d_flags.p, c.nranks, c.epoch, c.d_flags.p + 48);
+  BS_CUDA(cudaGetLastError());
+  count_launch(c, 2);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // LU with partial pivoting, blocked right-looking, everything on the device
 // ---------------------------------------------------------------------------------------------------------
 constexpr int LU_NB = 32;
@@ -400,11 +454,31 @@ int gmres_batched(Context &c, int which, int nrhs, const double *d_B, double *d_
   std::vector<double> hbuf((size_t)nrhs * CS);
   auto Bs = [&](int s) { return basis.p + (size_t)s * (m + 1) * mloc; };
   auto Cf = [&](int s) { return coef.p + (size_t)s * CS; };
-  auto matvec_all = [&](const std::vector<int> &act, const std::vector<const double *> &src) {
-    // replicated copies of the sources, then one sweep over the matrix for all of them
-    for (size_t k = 0; k < act.size(); ++k) exchange(c, which, src[k], xfull.p + k * ldx);
-    if (act.size() == 1) gemv(c, M, xfull.p, w.p);
-    else gemv_multi(c, M, (int)act.size(), xfull.p, ldx, w.p, ldw);
+  const bool p2p = c.p2p && c.nranks > 1;
+  BS_REQUIRE(!p2p || nrhs <= Context::XCHG_SLOTS, "peer exchange supports at most 8 right-hand sides in lockstep");
+  double *const xbuf = p2p ? c.d_xchg.p : xfull.p;
+  const size_t xld = p2p ? c.xchg_ld : ldx;
+  // `published`: the sources already sit in the replicated buffers of all ranks (stored there by the kernel that
+  // produced them); otherwise gather them now
+  auto matvec_all = [&](const std::vector<int> &act, const std::vector<const double *> &src, bool published) {
+    if (p2p) {
+      if (!published)
+        for (size_t k = 0; k < act.size(); ++k) p2p_scatter(c, which, src[k], (int)k, nullptr, nullptr);
+      p2p_wait(c);
+    } else {
+      for (size_t k = 0; k < act.size(); ++k) exchange(c, which, src[k], xbuf + k * xld);
+    }
+    if (act.size() == 1) gemv(c, M, xbuf, w.p);
+    else gemv_multi(c, M, (int)act.size(), xbuf, xld, w.p, ldw);
+  };
+  // normalise z by 1/sqrt(*s2) into the local basis vector and (peer mode) into slot `slot` of every rank
+  auto normalize_publish = [&](const double *s2, const double *zsrc, double *basis_dst, int slot) {
+    if (p2p) {
+      p2p_scatter(c, which, zsrc, slot, s2, basis_dst);
+    } else {
+      k_scale_inv_norm<<<(unsigned)std::min<size_t>((mloc + 255) / 256, 1184), 256, 0, c.stream>>>(s2, zsrc, basis_dst, mloc);
+      count_launch(c);
+    }
   };
   auto finish = [&](int s) {  // back substitution H y = gamma, x += sum y_i v_i
     Sys &sy = S[s];
@@ -440,7 +514,7 @@ int gmres_batched(Context &c, int which, int nrhs, const double *d_B, double *d_
     // ---- r0 = M^{-1} (b - A x) for every active system
     std::vector<const double *> src;
     for (int s : act) src.push_back(d_X + (size_t)s * ldv);
-    matvec_all(act, src);
+    matvec_all(act, src, false);
     for (size_t k = 0; k < act.size(); ++k) {
       const int s = act[k];
       sub(c, d_B + (size_t)s * ldv, w.p + k * ldw, w.p + k * ldw, mloc);
@@ -463,11 +537,14 @@ int gmres_batched(Context &c, int which, int nrhs, const double *d_B, double *d_
         sy.active = false;
         continue;
       }
-      k_scale_inv_norm<<<sgrid, 256, 0, c.stream>>>(Cf(s) + CS - 1, z.p + k * ldw, Bs(s), mloc);
-      count_launch(c);
       std::fill(sy.gamma.begin(), sy.gamma.end(), 0.0);
       sy.gamma[0] = sy.rho;
       sy.dim = 0;
+    }
+    {  // first basis vectors, published into the slots of the systems that stay active
+      int slot = 0;
+      for (size_t k = 0; k < act.size(); ++k)
+        if (S[act[k]].active) normalize_publish(Cf(act[k]) + CS - 1, z.p + k * ldw, Bs(act[k]), slot++);
     }
     // ---- Arnoldi, all still-active systems share the inner index
     for (int inner = 0; inner < m; ++inner) {
@@ -479,17 +556,19 @@ int gmres_batched(Context &c, int which, int nrhs, const double *d_B, double *d_
       for (int s : act) src.push_back(Bs(s) + (size_t)inner * mloc);
       double tt0 = trace ? now() : 0;
       if (trace) {
-        for (size_t k = 0; k < act.size(); ++k) exchange(c, which, src[k], xfull.p + k * ldx);
+        if (p2p) p2p_wait(c);
+        else
+          for (size_t k = 0; k < act.size(); ++k) exchange(c, which, src[k], xbuf + k * xld);
         cudaStreamSynchronize(c.stream);
         t_exch += now() - tt0;
         tt0 = now();
-        if (act.size() == 1) gemv(c, M, xfull.p, w.p);
-        else gemv_multi(c, M, (int)act.size(), xfull.p, ldx, w.p, ldw);
+        if (act.size() == 1) gemv(c, M, xbuf, w.p);
+        else gemv_multi(c, M, (int)act.size(), xbuf, xld, w.p, ldw);
         cudaStreamSynchronize(c.stream);
         t_mv += now() - tt0;
         tt0 = now();
       } else {
-        matvec_all(act, src);
+        matvec_all(act, src, true);
       }
       const int dim = inner + 1;
       for (size_t k = 0; k < act.size(); ++k) {
@@ -513,8 +592,6 @@ int gmres_batched(Context &c, int which, int nrhs, const double *d_B, double *d_
         std::vector<double> &h = sy.h;
         for (int i = 0; i < dim; ++i) h[i] = hb[i] + hb[m + 2 + i];
         h[dim] = std::sqrt(hb[dim]);
-        k_scale_inv_norm<<<sgrid, 256, 0, c.stream>>>(Cf(s) + dim, z.p + k * ldw, Bs(s) + (size_t)(inner + 1) * mloc, mloc);
-        count_launch(c);
         // Givens rotations (deal.II SolverGMRES::givens_rotation)
         for (int i = 0; i < inner; ++i) {
           const double t = h[i];
@@ -537,8 +614,15 @@ int gmres_batched(Context &c, int which, int nrhs, const double *d_B, double *d_
           sy.active = false;
         }
       }
-      // the scale kernels above read coef: make sure they ran before the next iteration overwrites it (stream order
-      // guarantees it), then finalise the systems that just stopped
+      {  // next basis vectors of the systems that continue: normalise and publish (fused with the peer exchange)
+        int slot = 0;
+        for (size_t k = 0; k < act.size(); ++k) {
+          const int s = act[k];
+          if (S[s].active && inner + 1 < m)
+            normalize_publish(Cf(s) + dim, z.p + k * ldw, Bs(s) + (size_t)(inner + 1) * mloc, slot++);
+        }
+      }
+      // finalise the systems that just stopped (stream order keeps the kernels above ahead of the coefficient upload)
       for (int s : act)
         if (!S[s].active) finish(s);
     }
@@ -547,6 +631,13 @@ int gmres_batched(Context &c, int which, int nrhs, const double *d_B, double *d_
       if (S[s].active) finish(s);
   }
   (void)tsync;
+  (void)sgrid;
+  if (p2p) {  // a rank that timed out in the flag wait reports instead of hanging
+    unsigned long long err = 0;
+    BS_CUDA(cudaMemcpyAsync(&err, c.d_flags.p + 48, sizeof(err), cudaMemcpyDeviceToHost, c.stream));
+    BS_CUDA(cudaStreamSynchronize(c.stream));
+    if (err != 0) throw Error(BS_ERR_COMM, "peer exchange timed out waiting for epoch " + std::to_string(err));
+  }
   if (trace)
     fprintf(stderr, "[bs trace rank %d] gmres: exchange %.1f ms, matvec %.1f ms, precond+orthogonalisation %.1f ms, d2h+sync %.1f ms (%d its)\n",
             c.rank, 1e3 * t_exch, 1e3 * t_mv, 1e3 * t_orth, 1e3 * t_sync, S[0].its);

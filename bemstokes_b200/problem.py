@@ -198,6 +198,7 @@ class BEMProblem:
         self.force_pole = (0.0, 0.0, 0.0)
         self.keep_VK = True
         self.fused_assembly = False    # True: never store K (bs_assemble_fused); body-only monolithic systems
+        self.use_peer_exchange = True  # multi-GPU: NVLink peer stores fused into the Krylov-vector kernel (else NCCL allgather)
         self.num_rigid = 6
         self._ctx = None
         self.mesh = None
@@ -228,6 +229,8 @@ class BEMProblem:
             if self.comm is None:
                 raise ValueError("nranks > 1 needs a communicator (bemstokes_b200.comm.TorchComm)")
             self.comm.attach(ctx)
+            if self.use_peer_exchange:
+                self._enable_peer_exchange(ctx)
         mm = self.map_mesh
         euler = np.ascontiguousarray(mm.nodes.T.reshape(-1))  # component-major euler_vec
         check(lib.bs_set_geometry(ctx, mm.n_nodes, _dp(euler), self.mesh.n_cells, _ip(mm.conn), self.mesh.n_nodes,
@@ -270,6 +273,18 @@ class BEMProblem:
             ktype = _lib.KERNEL_NO_SLIP
         wp = np.asarray(self.wall_position_0, dtype=np.float64)
         check(lib.bs_set_kernel(self._ctx, ktype, self.epsilon, o, _dp(wp)))
+
+    def _enable_peer_exchange(self, ctx):
+        """Exchange CUDA-IPC handles of every rank's replicated Krylov buffer / arrival flags (host plumbing over
+        torch.distributed) and hand them to the library: from then on the solve makes no allgather call."""
+        import torch.distributed as dist
+        buf = (C.c_ubyte * 128)()
+        check(lib.bs_exchange_export(ctx, 3 * self.mesh.n_nodes + 8, buf))
+        allh = [None] * self.n_mpi_processes
+        dist.all_gather_object(allh, bytes(buf), group=getattr(self.comm, "group", None))
+        cat = b"".join(allh)
+        arr = (C.c_ubyte * len(cat)).from_buffer_copy(cat)
+        check(lib.bs_exchange_import(ctx, self.n_mpi_processes, arr))
 
     def _allsum(self, arr):
         """Sum host arrays over ranks (replicated host vectors out of rank-owned slices); no-op on one rank."""

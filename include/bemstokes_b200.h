@@ -185,10 +185,16 @@ typedef int (*bs_allgatherv_fn)(void *user, const double *send, int sendcount, d
                                 const int *displs, void *stream);
 typedef int (*bs_allreduce_sum_fn)(void *user, double *buf, int count, void *stream);
 int bs_set_comm(bs_context *ctx, bs_allgatherv_fn allgatherv, bs_allreduce_sum_fn allreduce, void *user);
-/* Peer-memory exchange: peer_xbuf[r] = device pointer (mapped in this process) of rank r's replicated
- * Krylov-vector buffer; the GEMV epilogue stores its slice straight into every peer (NVLink P2P). */
-int bs_get_exchange_buffer(bs_context *ctx, void **dev_ptr, size_t *bytes);
-int bs_set_peer_buffers(bs_context *ctx, int nranks, void *const *peer_xbuf, void *const *peer_flags);
+/* Peer-memory exchange (NVLink P2P), replacing the allgatherv callback: every rank exports CUDA-IPC handles of
+ * its replicated Krylov-vector buffer and of its arrival flags (bs_exchange_export, 2 x 64 bytes), the host
+ * all-gathers the handles of all ranks (rank order) and hands them to bs_exchange_import.  From then on the kernel
+ * that normalises a new Krylov vector stores its slice straight into every peer's buffer, a release store raises the
+ * per-source flag on each peer, and the next matvec starts after an acquire-wait on its own flags: the exchange is
+ * fused with the producing kernel and no collective call is made.  The dot-product reductions keep using the
+ * allreduce callback.  max_vec_len = 3N + num_rigid of the largest system that will be solved. */
+#define BS_IPC_EXPORT_BYTES 128
+int bs_exchange_export(bs_context *ctx, size_t max_vec_len, unsigned char *handles_out /* BS_IPC_EXPORT_BYTES */);
+int bs_exchange_import(bs_context *ctx, int nranks, const unsigned char *all_handles /* nranks x BS_IPC_EXPORT_BYTES */);
 
 /* ---- timers / counters (ref: Teuchos timers bem_stokes.cc:19-23) ---------------------------------------- */
 typedef struct {
