@@ -104,6 +104,20 @@ class ClockSampler:
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def load_traffic(wl, world):
+    """ncu-measured DRAM traffic of the two dominant kernels for exactly this workload (profiles/r01_traffic.json)."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    key = "c4:m=%d:%s:n_gpus=%d" % (wl["m"], "fused" if wl.get("fused") else "vk", world)
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        if t.get("workload_key") == key:
+            return t["k_gemv<4>"]["dram_bytes_per_launch"], t["k_assemble_regular"]["dram_bytes_per_assembly"]
+    except Exception:
+        pass
+    return None, None
+
+
 def pairs_count(n_rows_nodes, ncell, nq, sing_pts_per_cell):
     """(node, q-point) pairs: every (row node, cell) pair uses nq points, except the na singular pairs of each
     cell, which use their singular rule."""
@@ -148,6 +162,7 @@ def run_ours(args):
     p.solve_directly, p.preconditioner_type = False, "None"
     p.keep_VK = False  # A aliases V's storage
     p.fused_assembly = bool(wl.get("fused"))
+    p.use_peer_exchange = not args.no_peer_exchange
     p.solver_control.tolerance, p.solver_control.max_steps = 1e-10, 1000
     p.gmres_restart = 200
     p.reinit()
@@ -208,6 +223,8 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     p.reset_stats()
+    if comm is not None:
+        comm.n_allgather = comm.n_allreduce = 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
     t0 = time.perf_counter()
@@ -271,11 +288,13 @@ def run_ours(args):
         mv_gbs_job = mv_bytes / (mv_ms * 1e-3) / 1e9
         mv_gbs_gpu = mv_gbs_job / world
         solve_ms = st["solve_ms"] / args.steps
+        traffic_mv, traffic_asm = load_traffic(wl, world)
         roof_mv = {"kernel": "k_gemv<4>", "bound": "hbm", "achieved": mv_gbs_gpu, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                   "frac": mv_gbs_gpu / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
+                   "frac": mv_gbs_gpu / peaks["hbm_gbs"], "traffic": traffic_mv, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
                    "algorithmic_bytes_per_launch": 8.0 * rows_loc * (n + 6), "launch_ms": mv_ms}
         roof_asm = {"kernel": "k_assemble_regular", "bound": "fp64", "achieved": asm_tflops / world, "peak": fp64.value,
-                    "unit": "TFLOP/s", "frac": asm_tflops / world / fp64.value, "traffic": None,
+                    "unit": "TFLOP/s", "frac": asm_tflops / world / fp64.value, "traffic": traffic_asm,
+                    "traffic_note": "DRAM bytes of one assembly (all colour launches); see profiles/r01_traffic.json",
                     "peak_source": "measured in this run: 8-chain DFMA microbenchmark sustained for 1 s under the power cap "
                                    "(bs_bench_fp64_sustained); burst figure in fp64_peak_tflops_burst",
                     "algorithmic_flops_per_pair": f_pair, "pairs_regular": pr, "pairs_singular": ps, "launch_ms": asm_ms}
@@ -289,6 +308,9 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl["name"], "nodes": N, "cells": ncell, "dofs": n, "matrix_gb_each": 8.0 * n * n / 1e9,
                        "sharding": "rows (collocation nodes) over %d GPU(s), contiguous ranges of the locality order" % world,
+                       "exchange": ("none (1 GPU)" if world == 1 else ("NVLink peer stores fused into the Krylov-vector kernel + "
+                                    "NCCL allreduce of the dots" if p.use_peer_exchange else "NCCL allgather + allreduce")),
+                       "collective_calls_in_timed_region": ({"allgather": comm.n_allgather, "allreduce": comm.n_allreduce} if comm else None),
                        "timing": "CUDA events on the launching stream inside the library; working set (%.1f GB matrix per GPU) "
                                  "far larger than the 126 MB L2, no explicit flush needed" % (8.0 * n * n / 1e9 / world),
                        "value_definition": "2*(3N)^2 entries of V and K evaluated / (K0+K1+K2 device time); ms_per_step is the "
@@ -386,6 +408,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=["c4", "vk", "q2"])
+    ap.add_argument("--no-peer-exchange", action="store_true", help="multi-GPU: NCCL allgather callbacks instead of NVLink peer stores")
     ap.add_argument("--no-fused", action="store_true", help="c4 family with V and K both stored (needs 2x the memory)")
     ap.add_argument("--subdiv", dest="m", type=int, default=0, help="cube-sphere subdivisions per face edge (default 128*(N/8)^(1/4); 64*N^(1/4) for --workload vk)")
     ap.add_argument("--refine", type=int, default=None)
