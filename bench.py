@@ -346,9 +346,8 @@ def run_ours(args):
 def cpu_baseline(wl, sample_seconds=15.0, nthreads=0):
     """The reference's CPU path (oracle/bem_port.c) on a bounded row sample of the same workload."""
     from oracle import bem_oracle as bo, port
-    import bemstokes_b200 as bb
-    mesh = bb.cubesphere(degree=wl["degree"], m=wl["m"])
-    geo = bo.Geometry(mesh.nodes, mesh.conn.astype(np.int64), wl["degree"])
+    nodes, conn = bo.cubesphere(degree=wl["degree"], m=wl["m"])   # the oracle's own mesh generator: no product code here
+    geo = bo.Geometry(nodes, conn, wl["degree"])
     cores = port.max_threads() if nthreads == 0 else nthreads
     N = geo.N
     # calibrate on one row per thread, then size the sample
@@ -391,7 +390,6 @@ def run_reference(args):
         if i >= args.warmup:
             vals.append((cb["value"], time.perf_counter() - t0))
     v = float(np.mean([a for a, _ in vals]))
-    import bemstokes_b200.mesh as bm
     line = {"impl": "reference", "metric": "assembly Gentries/s + GMRES matvec HBM GB/s; time-to-solution at 3N DoF",
             "value": v, "unit": "Gentries/s", "matvec_hbm_gbs": cb["matvec_gbs"], "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean([b for _, b in vals])), "higher_is_better": True,

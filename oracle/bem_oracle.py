@@ -84,10 +84,10 @@ UNIT_SUPPORT = {
 }
 
 
-def cubesphere(r, degree=1, scale=(1.0, 1.0, 1.0)):
-    """Synthetic quad sphere: each face of [-1,1]^3 split into 2^r x 2^r quads, outward
-    orientation, every Q1/Q2 node projected radially to the unit sphere (then scaled per axis)."""
-    m = 2 ** r
+def cubesphere(r=None, degree=1, scale=(1.0, 1.0, 1.0), m=None):
+    """Synthetic quad sphere: each face of [-1,1]^3 split into m x m quads (m = 2^r unless given),
+    outward orientation, every Q1/Q2 node projected radially to the unit sphere (then scaled per axis)."""
+    m = 2 ** r if m is None else int(m)
     sub = m * degree  # node lattice intervals per face edge
     key2id, pts = {}, []
 

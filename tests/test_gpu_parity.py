@@ -476,3 +476,72 @@ def test_fused_no_K_assembly(half, grid_type):
     Ao, bvec = bo.monolithic(Vc, bo.correct_K(Ko, geo.N), pre, grid_type, 2, 1.0, sv)
     assert rel_rows(A1, Ao) < ENTRY_TOL
     assert np.abs(b1 - bvec).max() <= 1e-12 * max(1.0, np.abs(bvec).max())
+
+
+def test_row_partition_explicit_owners_and_user_rules(half):
+    """this_cpu_set given by the host (bs_set_partition with owner_of_node) and singular rules handed over point by
+    point (bs_set_singular_rule): every rank's row block equals the oracle's rows; together they cover the matrix."""
+    N = half.n_nodes
+    rng = np.random.default_rng(2)
+    owner = rng.integers(0, 3, N).astype(np.int32)
+    geo = bo.Geometry(half.nodes, half.conn.astype(np.int64), 1)
+    Vo, Ko = bo.assemble_VK(geo, bo.KernelSpec(), 8, "Telles", 7)
+    covered = np.zeros(N, dtype=int)
+    euler = np.ascontiguousarray(half.nodes.T.reshape(-1))
+    for rank in range(3):
+        ctx = _lib.ctx_p()
+        check(lib.bs_create(C.byref(ctx), 0, 1, 1))
+        check(lib.bs_set_partition(ctx, rank, 3, owner.ctypes.data_as(_lib.c_int_p), N))
+        check(lib.bs_set_geometry(ctx, N, euler.ctypes.data_as(_lib.c_double_p), half.n_cells, half.conn.ctypes.data_as(_lib.c_int_p),
+                                  N, half.conn.ctypes.data_as(_lib.c_int_p), None))
+        check(lib.bs_set_quadrature(ctx, 8, None, None))
+        for a in range(4):
+            X, W = bo.singular_rule("Telles", 7, 1, a)
+            X, W = np.ascontiguousarray(X), np.ascontiguousarray(W)
+            check(lib.bs_set_singular_rule(ctx, a, len(W), X.ctypes.data_as(_lib.c_double_p), W.ctypes.data_as(_lib.c_double_p)))
+        check(lib.bs_set_kernel(ctx, _lib.KERNEL_FREE, 0.0, 1, None))
+        n_own = C.c_int()
+        own = np.zeros(N, dtype=np.int32)
+        check(lib.bs_get_owned_nodes(ctx, C.byref(n_own), own.ctypes.data_as(_lib.c_int_p)))
+        own = own[:n_own.value]
+        assert sorted(own.tolist()) == sorted(np.nonzero(owner == rank)[0].tolist())
+        covered[own] += 1
+        check(lib.bs_assemble_VK(ctx))
+        rows = np.concatenate([own + c * N for c in range(3)]).astype(np.int32)
+        rr, cc = np.meshgrid(rows, np.arange(3 * N, dtype=np.int32), indexing="ij")
+        for which, ref in ((_lib.MAT_V, Vo), (_lib.MAT_K, Ko)):
+            out = np.zeros(rr.size)
+            check(lib.bs_get_entries(ctx, which, rr.size, np.ascontiguousarray(rr.reshape(-1)).ctypes.data_as(_lib.c_int_p),
+                                     np.ascontiguousarray(cc.reshape(-1)).ctypes.data_as(_lib.c_int_p),
+                                     out.ctypes.data_as(_lib.c_double_p)))
+            assert rel_rows(out.reshape(rr.shape), ref[rows]) < ENTRY_TOL
+        # a row this rank does not own is refused
+        foreign = int(np.nonzero(owner != rank)[0][0])
+        r1 = np.array([foreign], dtype=np.int32)
+        o1 = np.zeros(1)
+        assert lib.bs_get_entries(ctx, _lib.MAT_V, 1, r1.ctypes.data_as(_lib.c_int_p), r1.ctypes.data_as(_lib.c_int_p),
+                                  o1.ctypes.data_as(_lib.c_double_p)) != 0
+        check(lib.bs_destroy(ctx))
+    assert (covered == 1).all()
+
+
+def test_error_paths():
+    """Call-order and argument errors come back as status codes with a message, never as a crash."""
+    ctx = _lib.ctx_p()
+    assert lib.bs_create(C.byref(ctx), 0, 3, 1) != 0 and b"degree" in lib.bs_last_error()
+    check(lib.bs_create(C.byref(ctx), 0, 1, 1))
+    assert lib.bs_assemble_VK(ctx) != 0 and b"must be set" in lib.bs_last_error()
+    x = np.zeros(10)
+    assert lib.bs_vmult(ctx, _lib.MAT_V, x.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p)) != 0
+    assert lib.bs_set_kernel(ctx, 7, 0.0, 1, None) != 0
+    assert lib.bs_set_quadrature(ctx, 0, None, None) != 0
+    check(lib.bs_destroy(ctx))
+    # GMRES that cannot converge within max_steps reports it like SolverControl::NoConvergence
+    p = make_problem(bb.cubesphere(1, 1), quadrature_order=4, singular_quadrature_order=4, solve_directly=False,
+                     preconditioner_type="None")
+    p.assemble_stokes_system(True)
+    p.solver_control.max_steps = 3
+    with pytest.raises(bb.BemStokesError) as ei:
+        p.solve_system(True)
+    assert ei.value.code == _lib.ERR_NOT_CONVERGED and p.solver_control.last_step() == 3
+    p.close()
