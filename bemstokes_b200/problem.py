@@ -198,6 +198,7 @@ class BEMProblem:
         self.force_pole = (0.0, 0.0, 0.0)
         self.keep_VK = True
         self.fused_assembly = False    # True: never store K (bs_assemble_fused); body-only monolithic systems
+        self.col_is_K = None           # per dof: True -> the unknown is a wall velocity, column -K (index-set logic 3194-3245)
         self.use_peer_exchange = True  # multi-GPU: NVLink peer stores fused into the Krylov-vector kernel (else NCCL allgather)
         self.num_rigid = 6
         self._ctx = None
@@ -356,7 +357,11 @@ class BEMProblem:
             Nr = np.ascontiguousarray(self.N_rigid[:nr])
             Nd = np.ascontiguousarray(self.N_rigid_dual[:nr])
             sv = np.ascontiguousarray(self.shape_velocities, dtype=np.float64)
-            check(lib.bs_build_monolithic(ctx, None, nr, _dp(Nr), _dp(Nd), _dp(nh), _dp(mn), self.l2normGamma_pure,
+            flags = None
+            if self.col_is_K is not None:
+                flags = np.ascontiguousarray(self.col_is_K, dtype=np.uint8)
+            check(lib.bs_build_monolithic(ctx, flags.ctypes.data_as(_lib.c_ubyte_p) if flags is not None else None,
+                                          nr, _dp(Nr), _dp(Nd), _dp(nh), _dp(mn), self.l2normGamma_pure,
                                           _GRID[self.grid_type], self.imposed_component, self.assemble_scaling, _dp(sv),
                                           1 if self.keep_VK else 0, _dp(self.monolithic_rhs)))
             if getattr(self, "monolithic_solution", None) is None or len(self.monolithic_solution) != self.n_dofs + nr:
@@ -448,7 +453,11 @@ class BEMProblem:
                     self.reassemble_preconditoner = True
             r = self.monolithic_system_matrix @ x - b
             self.final_check_0 = (float(np.abs(r).max()), float(np.linalg.norm(r)))
-            self.stokes_forces = x[:n].copy()
+            # split the solution into tractions and wall velocities (the reference compares A(i,i) with -K(i,i) /
+            # V(i,i), bem_stokes.cc:4351-4368; here the column flags say it directly)
+            isK = np.zeros(n, dtype=bool) if self.col_is_K is None else np.asarray(self.col_is_K, dtype=bool)
+            self.stokes_forces = np.where(isK, 0.0, x[:n])
+            self.wall_velocities = np.where(isK, x[:n], 0.0)
             self.rigid_velocities = x[n:n + nr].copy() * self.assemble_scaling
         else:
             self.solve_dn()

@@ -612,12 +612,17 @@ def correct_K(K, N, use_internal_alpha=False):
     return K
 
 
-def monolithic(V, K, pre, grid_type="ImposedForce", imposed_component=1, scaling=1.0, shape_vel=None):
-    """Body-only monolithic matrix / rhs (no walls, no constraints)."""
+def monolithic(V, K, pre, grid_type="ImposedForce", imposed_component=1, scaling=1.0, shape_vel=None, col_is_K=None):
+    """Monolithic matrix / rhs without constraints.  col_is_K[j] set: column j belongs to a wall unknown whose
+    velocity is solved for, A(:,j) = -K(:,j) (neumann / free-surface tangential sets, bem_stokes.cc:3194-3245);
+    otherwise A(:,j) = V(:,j) (body, no-slip, dirichlet sets)."""
     n = V.shape[0]
     A = np.zeros((n + 6, n + 6))
     b = np.zeros(n + 6)
     A[:n, :n] = V
+    if col_is_K is not None:
+        f = np.asarray(col_is_K, dtype=bool)
+        A[:n, :n][:, f] = -K[:, f]
     for r in range(6):
         A[:n, n + r] = -scaling * pre.P(K @ pre.P(pre.N_rigid[r]))
     if grid_type == "Real" and shape_vel is not None:

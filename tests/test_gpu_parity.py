@@ -545,3 +545,44 @@ def test_error_paths():
         p.solve_system(True)
     assert ei.value.code == _lib.ERR_NOT_CONVERGED and p.solver_control.last_step() == 3
     p.close()
+
+
+def test_config_C5_free_surface_kernel_mixed_columns(half):
+    """BASELINE config 5 code path: image-system (free-surface) kernel with mixed velocity / traction unknowns — the
+    flagged columns of the monolithic matrix are -K columns (bem_stokes.cc:3194-3245).  Matrix, rhs, GMRES iterate and
+    the traction / wall-velocity split against the oracle."""
+    N = half.n_nodes
+    flags = np.zeros(3 * N, dtype=bool)
+    top = half.nodes[:, 1] > 0.6                      # nodes facing the symmetry plane: velocity unknowns
+    for c in (0, 2):                                  # tangential components only (free-surface set logic)
+        flags[c * N:(c + 1) * N] = top
+    kw = dict(reflect_kernel=True, wall_spans_0=(80, 0, 80), wall_position_0=(0, 1.4, 0))
+    p = make_problem(half, grid_type="ImposedForce", imposed_component=0, solve_directly=False, preconditioner_type="Jacobi",
+                     col_is_K=flags, **kw)
+    p.assemble_stokes_system(True)
+    geo, (Vo, Ko) = oracle_VK(p)
+    pre = bo.Prepass(geo, 8)
+    Vc, _ = bo.correct_V(Vo, pre)
+    Kc = bo.correct_K(Ko, geo.N)
+    Ao, bvec = bo.monolithic(Vc, Kc, pre, "ImposedForce", 0, 1.0, None, flags)
+    assert rel_rows(p.monolithic_system_matrix.to_dense(), Ao) < ENTRY_TOL
+    assert np.abs(p.monolithic_rhs - bvec).max() == 0
+    p.solve_system(True)
+    n = 3 * N
+    D = np.diag(Ao).copy()
+    D[n:] = 1.0
+    D[D == 0] = 1.0
+    xg, its, _, ok = bo.gmres(lambda v: Ao @ v, bvec, prec=lambda v: v / D, tol=1e-10)
+    assert ok and abs(p.solver_control.last_step() - its) <= 1
+    xo = np.linalg.solve(Ao, bvec)
+    assert np.abs(p.monolithic_solution - xo).max() <= 1e-6 * np.abs(xo).max()
+    assert np.abs(p.wall_velocities[~flags]).max() == 0 and np.abs(p.stokes_forces[flags]).max() == 0
+    assert np.abs(p.wall_velocities[flags] - xo[:n][flags]).max() <= 1e-6 * np.abs(xo).max()
+    # keep_VK: V and K are still intact next to A
+    assert rel_rows(p.V_matrix.to_dense(), Vc) < ENTRY_TOL and rel_rows(p.K_matrix.to_dense(), Kc) < ENTRY_TOL
+    p.close()
+    # aliasing mode (A shares V's storage): the same matrix
+    q = make_problem(half, grid_type="ImposedForce", imposed_component=0, col_is_K=flags, keep_VK=False, **kw)
+    q.assemble_stokes_system(True)
+    assert rel_rows(q.monolithic_system_matrix.to_dense(), Ao) < ENTRY_TOL
+    q.close()
