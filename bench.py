@@ -236,7 +236,7 @@ def run_ours(args):
     wall = time.perf_counter() - t0
     st = p.stats()
     clocks = sampler.stop() if rank == 0 else None
-    drag = float(p.rigid_total_forces[0]) if world == 1 else None
+    drag = float(p.rigid_total_forces[0])  # every rank holds the gathered solution
     asm_ms = (st["geometry_ms"] + st["assemble_regular_ms"] + st["assemble_singular_ms"]) / args.steps
     # ---- matvec bandwidth: device-resident GEMV loop on the monolithic matrix (L2 flushed by its own 43 GB) ----
     ms_mv = C.c_double()

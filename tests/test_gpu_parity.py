@@ -586,3 +586,60 @@ def test_config_C5_free_surface_kernel_mixed_columns(half):
     q.assemble_stokes_system(True)
     assert rel_rows(q.monolithic_system_matrix.to_dense(), Ao) < ENTRY_TOL
     q.close()
+
+
+def test_config_C3_Q2_reference_quadrature():
+    """BASELINE config 3 settings (Q2, Gauss 15 / singular order 20 = tests/parameters_test_alpha_box_ref_quadrature.prm)
+    on a small cube-sphere: 225-point regular rule, 1 600-point QIterated singular rule."""
+    m = bb.cubesphere(1, 2)
+    p = make_problem(m, quadrature_order=15, singular_quadrature_order=20)
+    V, K = raw_VK(p)
+    geo, (Vo, Ko) = oracle_VK(p)
+    assert rel_rows(V, Vo) < ENTRY_TOL
+    # The 1 600-point QIterated rule puts points within 1e-3 cell sizes of the collocation point, where the double-layer
+    # integrand (R.n)/r^5 is a difference of nearly equal numbers (R is almost tangent): float64 itself only carries
+    # ~1e-12 of the row scale there, for the oracle as much as for the device.  Regular (non node-in-cell) entries
+    # still agree to 1e-12; the singular ones to 1e-11.
+    N = m.n_nodes
+    sing = np.zeros((3 * N, 3 * N), dtype=bool)
+    for cell in m.conn:
+        for i in cell:
+            for j in cell:
+                for a in range(3):
+                    for b in range(3):
+                        sing[i + a * N, j + b * N] = True
+    scale = np.abs(Ko).max(axis=1, keepdims=True)
+    err = np.abs(K - Ko) / scale
+    assert err[~sing].max() < ENTRY_TOL and err[sing].max() < 1e-11
+    p.close()
+
+
+def test_large_size_properties():
+    """Size-independent properties at a size the oracle cannot assemble in seconds (6 146 nodes, 18 438 DoF):
+    corrected V maps the normal to itself, corrected K has unit row sums per component block, the fused no-K path
+    builds the same monolithic matrix as the stored path, drag within 1e-3 of 6 pi mu a U, GMRES residual honest."""
+    m = bb.cubesphere(m=32)
+    res = {}
+    for fused in (False, True):
+        p = make_problem(m, grid_type="ImposedVelocity", imposed_component=0, solve_directly=False, preconditioner_type="None",
+                         fused_assembly=fused, keep_VK=not fused)
+        p.assemble_stokes_system(True)
+        n, N = p.n_dofs, p.N
+        vn = p.V_matrix @ p.normal_vector_pure if not fused else (p.monolithic_system_matrix @ np.concatenate([p.normal_vector_pure, np.zeros(6)]))[:n]
+        assert abs(vn @ p.normal_vector_pure / N - 1) < 1e-11     # "Check on the V operator Norm post (should be one)"
+        if not fused:
+            for k in range(3):
+                e = np.zeros(n)
+                e[k * N:(k + 1) * N] = 1
+                assert abs(np.abs(p.K_matrix @ e).max() - 1) < 1e-11   # "check with versor vector ... l_infty : 1"
+        rows = np.arange(0, n + 6, 211, dtype=np.int32)
+        rr, cc = np.meshgrid(rows, np.arange(n + 6, dtype=np.int32), indexing="ij")
+        res[fused] = p.monolithic_system_matrix.entries(rr.reshape(-1), cc.reshape(-1)).reshape(rr.shape)
+        p.solve_system(True)
+        assert p.final_check_0[0] < 1e-9                        # "FINAL CHECK 0"
+        assert abs(p.rigid_total_forces[0] / (6 * math.pi) - 1) < 1e-3
+        assert np.abs(p.rigid_total_forces[1:]).max() < 1e-6 * abs(p.rigid_total_forces[0]) * 1e3
+        res[("x", fused)] = p.monolithic_solution.copy()
+        p.close()
+    assert rel_rows(res[True], res[False]) < ENTRY_TOL
+    assert np.abs(res[("x", True)] - res[("x", False)]).max() <= 1e-8 * np.abs(res[("x", False)]).max()
