@@ -176,6 +176,154 @@ __global__ void __launch_bounds__(1024) k_lu_panel(double *A, size_t ld, int n, 
   }
 }
 
+// Multi-CTA panel factorisation (cooperative launch: all CTAs resident, software grid barrier on a monotonic
+// counter).  Rows col..n of the panel are split into contiguous chunks, one per CTA; per column: local pivot
+// candidates -> barrier -> every CTA reduces the candidates (same winner everywhere), CTA 0 swaps the two rows inside
+// the panel -> barrier -> all CTAs scale their part of the column and apply the rank-1 update to the rest of the panel.
+__device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (*((volatile unsigned int *)counter) < target) {}
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Register-resident variant: every thread keeps its (at most RPT) panel rows of 32 columns in registers for the
+// whole panel; global memory is touched only for the pivot candidates, the two rows exchanged per column (published
+// through a scratch buffer that also broadcasts the pivot row) and the final write-back.  Rows are assigned once
+// per panel: row r -> CTA (r-k0)/chunk, thread ((r-k0)%chunk)%256.  Two grid barriers per column.
+constexpr int LU_RPT = 2;
+__global__ void __launch_bounds__(256) k_lu_panel_coop(double *A, size_t ld, int n, int k0, int nb, int *piv, double *cand_val,
+                                                        int *cand_idx, double *xrow /*[2][32]*/, unsigned int *counter,
+                                                        int chunk) {
+  __shared__ double s_val[8];
+  __shared__ int s_idx[8];
+  __shared__ int s_piv;
+  __shared__ double s_prow[LU_NB];
+  const int G = gridDim.x, g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int row[LU_RPT];
+  double a[LU_RPT][LU_NB];
+#pragma unroll
+  for (int rr = 0; rr < LU_RPT; ++rr) {
+    const int local = rr * 256 + tid;
+    row[rr] = (local < chunk && k0 + g * chunk + local < n) ? k0 + g * chunk + local : -1;
+#pragma unroll
+    for (int j = 0; j < LU_NB; ++j) a[rr][j] = (row[rr] >= 0 && j < nb) ? A[(size_t)row[rr] * ld + k0 + j] : 0.0;
+  }
+  unsigned int nbar = 0;
+#pragma unroll
+  for (int j = 0; j < LU_NB; ++j) {
+    if (j < nb) {  // nb is uniform over the grid
+      const int col = k0 + j;
+      // ---- pivot candidates from registers
+      double best = -1.0;
+      int bi = 0x7fffffff;
+#pragma unroll
+      for (int rr = 0; rr < LU_RPT; ++rr)
+        if (row[rr] >= col) {
+          const double v = fabs(a[rr][j]);
+          if (v > best || (v == best && row[rr] < bi)) {
+            best = v;
+            bi = row[rr];
+          }
+        }
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, m);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
+        if (ov > best || (ov == best && oi < bi)) {
+          best = ov;
+          bi = oi;
+        }
+      }
+      if (lane == 0) {
+        s_val[wid] = best;
+        s_idx[wid] = bi;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        for (int w = 1; w < 8; ++w)
+          if (s_val[w] > best || (s_val[w] == best && s_idx[w] < bi)) {
+            best = s_val[w];
+            bi = s_idx[w];
+          }
+        cand_val[g] = best;
+        cand_idx[g] = bi;
+      }
+      grid_barrier(counter, (++nbar) * G);
+      if (wid == 0) {  // every CTA reduces the G candidates: identical winner (largest value, lowest row on ties)
+        best = -1.0;
+        bi = 0x7fffffff;
+        for (int q = lane; q < G; q += 32) {
+          const double v = ((volatile double *)cand_val)[q];
+          const int ix = ((volatile int *)cand_idx)[q];
+          if (v > best || (v == best && ix < bi)) {
+            best = v;
+            bi = ix;
+          }
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+          const double ov = __shfl_xor_sync(0xffffffffu, best, m);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, m);
+          if (ov > best || (ov == best && oi < bi)) {
+            best = ov;
+            bi = oi;
+          }
+        }
+        if (lane == 0) s_piv = bi;
+      }
+      __syncthreads();
+      const int pr = s_piv;
+      if (g == 0 && tid == 0) piv[col] = pr;
+      // ---- publish the two rows: xrow[0] = old row `col`, xrow[1] = old row `pr` (= the new pivot row)
+#pragma unroll
+      for (int rr = 0; rr < LU_RPT; ++rr) {
+        if (row[rr] == col) {
+#pragma unroll
+          for (int jj = 0; jj < LU_NB; ++jj) xrow[jj] = a[rr][jj];
+        }
+        if (row[rr] == pr) {
+#pragma unroll
+          for (int jj = 0; jj < LU_NB; ++jj) xrow[LU_NB + jj] = a[rr][jj];
+        }
+      }
+      grid_barrier(counter, (++nbar) * G);
+      if (tid < LU_NB) s_prow[tid] = ((volatile double *)xrow)[LU_NB + tid];
+      __syncthreads();
+#pragma unroll
+      for (int rr = 0; rr < LU_RPT; ++rr) {
+        if (row[rr] == col) {  // receives the pivot row
+#pragma unroll
+          for (int jj = 0; jj < LU_NB; ++jj) a[rr][jj] = s_prow[jj];
+        } else if (row[rr] == pr) {  // receives the old row `col` and is eliminated like every other row below
+#pragma unroll
+          for (int jj = 0; jj < LU_NB; ++jj) a[rr][jj] = ((volatile double *)xrow)[jj];
+        }
+      }
+      const double dinv = 1.0 / s_prow[j];
+#pragma unroll
+      for (int rr = 0; rr < LU_RPT; ++rr)
+        if (row[rr] > col) {
+          const double l = a[rr][j] * dinv;
+          a[rr][j] = l;
+#pragma unroll
+          for (int jj = j + 1; jj < LU_NB; ++jj) a[rr][jj] = fma(-l, s_prow[jj], a[rr][jj]);
+        }
+      __syncthreads();  // s_prow is rewritten in the next column
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < LU_RPT; ++rr)
+    if (row[rr] >= 0)
+#pragma unroll
+      for (int j = 0; j < LU_NB; ++j)
+        if (j < nb) A[(size_t)row[rr] * ld + k0 + j] = a[rr][j];
+}
+
 // apply the panel's row swaps to columns outside the panel
 __global__ void k_lu_swap(double *A, size_t ld, int n, int k0, int nb, const int *piv) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -190,82 +338,166 @@ __global__ void k_lu_swap(double *A, size_t ld, int n, int k0, int nb, const int
   }
 }
 
-// U12 = L11^{-1} A12 : one thread per column of A12
-__global__ void k_lu_trsm(double *A, size_t ld, int n, int k0, int nb) {
-  __shared__ double L[LU_NB][LU_NB + 1];
-  for (int i = threadIdx.x; i < nb * nb; i += blockDim.x) L[i / nb][i % nb] = A[(size_t)(k0 + i / nb) * ld + k0 + i % nb];
+constexpr int LU_OUT = 128;  // outer block: trailing update of the columns right of it is one k=128 GEMM
+
+// Rows [j0, j0+nb) of U for every column c >= j0+nb:  u = L_jj^{-1} (A[j-rows][c] - L[j-rows][K0:j0) * U[K0:j0)[c]).
+// Columns inside the current outer block [K0, K0+Bw) already carry the rank-32 updates of the earlier inner panels
+// (left term empty); columns right of it are updated lazily here (left-looking inside the outer block).
+// One thread per column; the L rows of this step are staged in shared memory.
+__global__ void __launch_bounds__(128) k_lu_u12_step(double *A, size_t ld, int n, int K0, int Bw, int j0, int nb) {
+  extern __shared__ double Ls[];  // [LU_NB][LU_OUT + 1]: L[j0+r][K0 + k], k < j0 + nb - K0
+  const int kw = j0 + nb - K0;
+  for (int i = threadIdx.x; i < nb * kw; i += blockDim.x) {
+    const int r = i / kw, k = i - r * kw;
+    Ls[r * (LU_OUT + 1) + k] = A[(size_t)(j0 + r) * ld + K0 + k];
+  }
   __syncthreads();
-  const int c = k0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = j0 + nb + blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n) return;
   double u[LU_NB];
 #pragma unroll
-  for (int i = 0; i < LU_NB; ++i) u[i] = (i < nb) ? A[(size_t)(k0 + i) * ld + c] : 0.0;
+  for (int r = 0; r < LU_NB; ++r) u[r] = (r < nb) ? A[(size_t)(j0 + r) * ld + c] : 0.0;
+  if (c >= K0 + Bw) {  // lazy part: subtract L[j-rows][K0:j0) * U[K0:j0)[c]
+    for (int k = 0; k < j0 - K0; ++k) {
+      const double uk = A[(size_t)(K0 + k) * ld + c];
 #pragma unroll
-  for (int i = 0; i < LU_NB; ++i) {
-#pragma unroll
-    for (int j = 0; j < i; ++j) u[i] = fma(-L[i][j], u[j], u[i]);
-  }
-#pragma unroll
-  for (int i = 0; i < LU_NB; ++i)
-    if (i < nb) A[(size_t)(k0 + i) * ld + c] = u[i];
-}
-
-// A22 -= L21 * U12 ; 64x64 tile per CTA, 256 threads, 4x4 per thread, k = nb <= 32
-__global__ void __launch_bounds__(256) k_lu_gemm(double *A, size_t ld, int n, int k0, int nb) {
-  __shared__ double Ls[64][LU_NB + 1];
-  __shared__ double Us[LU_NB][64 + 2];
-  const int r0 = k0 + nb + blockIdx.y * 64, c0 = k0 + nb + blockIdx.x * 64;
-  const int tid = threadIdx.x;
-  for (int i = tid; i < 64 * nb; i += 256) {
-    const int r = i / nb, k = i % nb;
-    Ls[r][k] = (r0 + r < n) ? A[(size_t)(r0 + r) * ld + k0 + k] : 0.0;
-  }
-  for (int i = tid; i < nb * 64; i += 256) {
-    const int k = i / 64, cc = i % 64;
-    Us[k][cc] = (c0 + cc < n) ? A[(size_t)(k0 + k) * ld + c0 + cc] : 0.0;
-  }
-  __syncthreads();
-  const int tr = (tid / 16) * 4, tc = (tid % 16) * 4;
-  double acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  for (int k = 0; k < nb; ++k) {
-    double l[4], u[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) l[i] = Ls[tr + i][k];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) u[j] = Us[k][tc + j];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fma(l[i], u[j], acc[i][j]);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int r = r0 + tr + i, cc = c0 + tc + j;
-      if (r < n && cc < n) A[(size_t)r * ld + cc] -= acc[i][j];
+      for (int r = 0; r < LU_NB; ++r) u[r] = fma(-Ls[r * (LU_OUT + 1) + k], uk, u[r]);
     }
+  }
+  const int d0 = j0 - K0;  // unit-lower triangular solve with L_jj
+#pragma unroll
+  for (int r = 0; r < LU_NB; ++r) {
+#pragma unroll
+    for (int k = 0; k < r; ++k) u[r] = fma(-Ls[r * (LU_OUT + 1) + d0 + k], u[k], u[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < LU_NB; ++r)
+    if (r < nb) A[(size_t)(j0 + r) * ld + c] = u[r];
 }
 
+// C[r0.., c0..] -= L[r.., k0:k0+kw) * U[k0:k0+kw)[c..]  for rows >= row_begin, columns in [col_begin, col_end).
+// 128 x 128 tile per CTA, 256 threads, 8 x 8 register tile per thread, k in chunks of 16 through shared memory.
+constexpr int GM_T = 128, GM_K = 16;
+__global__ void __launch_bounds__(256) k_lu_gemm(double *A, size_t ld, int n, int k0, int kw, int row_begin, int col_begin,
+                                                 int col_end) {
+  __shared__ double Ls[GM_K][GM_T + 2];
+  __shared__ double Us[GM_K][GM_T + 2];
+  const int r0 = row_begin + blockIdx.y * GM_T, c0 = col_begin + blockIdx.x * GM_T;
+  const int tid = threadIdx.x;
+  // interleaved register tile: thread (ty, tx) owns rows ty + 16 i and columns tx + 16 j, so that the shared-memory
+  // reads of a warp are either broadcasts (rows) or 16 consecutive doubles (columns): no bank conflicts
+  const int ty = tid / 16, tx = tid % 16;
+  double acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+  for (int kk = 0; kk < kw; kk += GM_K) {
+    __syncthreads();
+    for (int i = tid; i < GM_T * GM_K; i += 256) {  // L tile: rows r0.., columns k0+kk.. (16 contiguous doubles per row)
+      const int r = i / GM_K, k = i % GM_K;
+      Ls[k][r] = (r0 + r < n && kk + k < kw) ? A[(size_t)(r0 + r) * ld + k0 + kk + k] : 0.0;
+    }
+    for (int i = tid; i < GM_K * GM_T; i += 256) {  // U tile: rows k0+kk.., columns c0.. (contiguous)
+      const int k = i / GM_T, cc = i % GM_T;
+      Us[k][cc] = (c0 + cc < col_end && kk + k < kw) ? A[(size_t)(k0 + kk + k) * ld + c0 + cc] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GM_K; ++k) {
+      double l[8], u[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) l[i] = Ls[k][ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u[j] = Us[k][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fma(l[i], u[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + ty + 16 * i;
+    if (r >= n) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int cc = c0 + tx + 16 * j;
+      if (cc < col_end) A[(size_t)r * ld + cc] -= acc[i][j];
+    }
+  }
+}
+
+// Right-looking blocked LU with partial pivoting: inner panels of 32 columns (one CTA each), immediate rank-32
+// updates only inside the current 128-column outer block, lazy U rows for the columns right of it, then one k=128
+// GEMM for the trailing matrix.
 void lu_factor(Context &c, double *A, size_t n_, size_t ld, int *piv) {
   const int n = (int)n_;
-  for (int k0 = 0; k0 < n; k0 += LU_NB) {
-    const int nb = std::min(LU_NB, n - k0);
-    k_lu_panel<<<1, 1024, 0, c.stream>>>(A, ld, n, k0, nb, piv);
-    k_lu_swap<<<(n + 255) / 256, 256, 0, c.stream>>>(A, ld, n, k0, nb, piv);
-    count_launch(c, 2);
-    const int rem = n - k0 - nb;
-    if (rem > 0) {
-      k_lu_trsm<<<(rem + 127) / 128, 128, 0, c.stream>>>(A, ld, n, k0, nb);
-      const int tiles = (rem + 63) / 64;
-      k_lu_gemm<<<dim3(tiles, tiles), 256, 0, c.stream>>>(A, ld, n, k0, nb);
-      count_launch(c, 2);
-    }
+  const size_t sm_u12 = (size_t)LU_NB * (LU_OUT + 1) * sizeof(double);
+  const bool trace = std::getenv("BS_TRACE") != nullptr;
+  double tacc[5] = {0, 0, 0, 0, 0};
+  auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double tlast = 0;
+  if (trace) {
+    cudaStreamSynchronize(c.stream);
+    tlast = tnow();
   }
+  auto tick = [&](int k) {
+    if (!trace) return;
+    cudaStreamSynchronize(c.stream);
+    const double t = tnow();
+    tacc[k] += t - tlast;
+    tlast = t;
+  };
+  for (int K0 = 0; K0 < n; K0 += LU_OUT) {
+    const int Bw = std::min(LU_OUT, n - K0);
+    for (int j0 = K0; j0 < K0 + Bw; j0 += LU_NB) {
+      const int nb = std::min(LU_NB, K0 + Bw - j0);
+      const int rows_left = n - j0;
+      // rows per CTA: at most 256*LU_RPT (register-resident rows), at least 64 so that tiny panels use few CTAs
+      int chunk = std::max(64, (rows_left + c.sm_count - 1) / c.sm_count);
+      if (chunk > 256 * LU_RPT || rows_left <= 1024) {
+        k_lu_panel<<<1, 1024, 0, c.stream>>>(A, ld, n, j0, nb, piv);  // short panel, or taller than all SMs can hold
+      } else {
+        const int G = (rows_left + chunk - 1) / chunk;
+        double *cand_val = c.wsd("lu.cand", 256 + 2 * LU_NB);
+        double *xrow = cand_val + 256;
+        int *cand_idx = c.wsi("lu.cand_idx", 256 + 4);
+        unsigned int *counter = reinterpret_cast<unsigned int *>(cand_idx + 256);
+        BS_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), c.stream));
+        int n_ = n, j0_ = j0, nb_ = nb;
+        size_t ld_ = ld;
+        void *args[] = {&A, &ld_, &n_, &j0_, &nb_, &piv, &cand_val, &cand_idx, &xrow, &counter, &chunk};
+        BS_CUDA(cudaLaunchCooperativeKernel((void *)k_lu_panel_coop, dim3(G), dim3(256), args, 0, c.stream));
+      }
+      tick(0);
+      k_lu_swap<<<(n + 255) / 256, 256, 0, c.stream>>>(A, ld, n, j0, nb, piv);
+      count_launch(c, 2);
+      tick(1);
+      const int right = n - j0 - nb;
+      if (right > 0) {
+        k_lu_u12_step<<<(right + 127) / 128, 128, sm_u12, c.stream>>>(A, ld, n, K0, Bw, j0, nb);
+        count_launch(c);
+      }
+      tick(2);
+      const int inside = K0 + Bw - (j0 + nb), below = n - (j0 + nb);
+      if (inside > 0 && below > 0) {  // rank-32 update of the rest of the outer block
+        k_lu_gemm<<<dim3((inside + GM_T - 1) / GM_T, (below + GM_T - 1) / GM_T), 256, 0, c.stream>>>(A, ld, n, j0, nb, j0 + nb,
+                                                                                                   j0 + nb, K0 + Bw);
+        count_launch(c);
+      }
+      tick(3);
+    }
+    const int rem = n - K0 - Bw;
+    if (rem > 0) {  // trailing matrix: one GEMM with k = Bw
+      k_lu_gemm<<<dim3((rem + GM_T - 1) / GM_T, (rem + GM_T - 1) / GM_T), 256, 0, c.stream>>>(A, ld, n, K0, Bw, K0 + Bw, K0 + Bw, n);
+      count_launch(c);
+    }
+    tick(4);
+  }
+  if (trace)
+    fprintf(stderr, "[bs trace] lu_factor n=%d: panel %.1f ms, swaps %.1f ms, U rows %.1f ms, inner GEMM %.1f ms, trailing GEMM %.1f ms\n", n,
+            1e3 * tacc[0], 1e3 * tacc[1], 1e3 * tacc[2], 1e3 * tacc[3], 1e3 * tacc[4]);
   BS_CUDA(cudaGetLastError());
 }
 
