@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "libbemstokes_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
-        "libbemstokes_b200.so not found at %s - build it with `python -m bemstokes_b200.build` "
+        "libbemstokes_b200.so not found at %s - build it with `python bemstokes_b200/build.py` "
         "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
 
 lib = C.CDLL(LIB_PATH)
