@@ -71,6 +71,20 @@ def main():
     r = lines("tests/rigidity_sphere.output")
     fc = [l for l in r if l.startswith("FINAL CHECK 0")]
     g["rigidity_sphere_final_check0"] = {"source": "tests/rigidity_sphere.output", "linf": [float(l.split()[3]) for l in fc]}
+    st = lines("tests/sphere_translation.output")
+    err = [l for l in st if l.startswith("ERROR on rigid translation 0")][0]
+    nums = [float(x) for x in re.findall(r"[-0-9.e]+", err.split(":")[1])]
+    g["sphere_translation"] = {"source": "tests/sphere_translation.output (ERROR line = expected text) + tests/sphere_translation.cc:60-75",
+                               "setup": "grid_test/sphere_translation_{0,1}.msh, Q1, grid Real, shape velocity = (x_1 - x_0)/time_step, time_step 0.1",
+                               "rigid_velocity_0": nums[0], "exact": nums[1], "rel_error": nums[2],
+                               "Vn_linf": float([l for l in st if "Check on the V operator Norm (should be zero):" in l][0].split(":")[1]),
+                               "surface": float([l for l in st if "The Mass (Surface) of the entire system is" in l][0].split(":")[1])}
+    sr = lines("tests/sphere_rotation.output")
+    g["sphere_rotation"] = {"source": "tests/sphere_rotation.output + tests/sphere_rotation.cc:30,62,99-102",
+                            "setup": "grid_test/sphere_rotation_{0,1}.msh, grid Real, exact omega = 2 pi/120/time_step about x, tol 1e-2",
+                            "Vn_linf": float([l for l in sr if "Check on the V operator Norm (should be zero):" in l][0].split(":")[1]),
+                            "omega_exact": 2 * 3.141592653589793 / 120 / 0.1, "tol": 1e-2,
+                            "ok_lines": len([l for l in sr if l.startswith("OK rigid")])}
     g["imposed_rotation"] = {"source": "tests/imposed_rotation_test_on_sphere.cc:28-31", "omega": 1.0 / (8 * 3.141592653589793),
                              "tol": 1.2e-3}
     with open(os.path.join(HERE, "reference_goldens.json"), "w") as f:
@@ -109,10 +123,14 @@ def main():
     for rel in ["tests/grid_test/sphere_half_refined_0.inp", "tests/grid_test/sphere_0.inp",
                 "tests/grid_test/sphere_coarse_0.inp", "debug_grids/sphere_mesh_3d_0.msh",
                 "debug_grids/prolate_spheroid_lambda_2_ref_0.msh", "debug_grids/sphere_very_refined_0.inp",
-                "debug_grids/sphere_very_very_refined_0.inp", "debug_grids/sphere_2.inp"]:
+                "debug_grids/sphere_very_very_refined_0.inp", "debug_grids/sphere_2.inp",
+                "tests/grid_test/sphere_translation_0.msh", "tests/grid_test/sphere_translation_1.msh",
+                "tests/grid_test/sphere_rotation_0.msh", "tests/grid_test/sphere_rotation_1.msh"]:
         src = os.path.join(REF, rel)
         if os.path.exists(src):
-            shutil.copy(src, os.path.join(HERE, "meshes", os.path.basename(rel)))
+            dst = os.path.join(HERE, "meshes", os.path.basename(rel))
+            shutil.copy(src, dst)
+            os.chmod(dst, 0o644)
         else:
             print("missing", rel)
     print("wrote goldens:", len(table), "quadrature rows,", len(exact), "exact constants")

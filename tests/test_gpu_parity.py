@@ -643,3 +643,55 @@ def test_large_size_properties():
         p.close()
     assert rel_rows(res[True], res[False]) < ENTRY_TOL
     assert np.abs(res[("x", True)] - res[("x", False)]).max() <= 1e-8 * np.abs(res[("x", False)]).max()
+
+
+def test_sphere_translation_real_grid(goldens):
+    """tests/sphere_translation.cc on the device: Real grid (swimmer), shape velocities from frames 0 -> 1, GMRES with
+    the Direct preconditioner; the reference prints rigid_velocities[0] = 0.0840328 and 'Iterations needed ... 1'."""
+    m0 = bb.read_mesh(os.path.join(MESHES, "sphere_translation_0.msh"))
+    m1 = bb.read_mesh(os.path.join(MESHES, "sphere_translation_1.msh"))
+    p = make_problem(m0, grid_type="Real", solve_directly=False, preconditioner_type="Direct")
+    p.shape_velocities = ((m1.nodes - m0.nodes) / 0.1).T.reshape(-1).copy()
+    p.assemble_stokes_system(True)
+    G = goldens["sphere_translation"]
+    assert abs(p.surface - G["surface"]) < 6e-5
+    assert abs(np.abs(p.V_x_normals_body).max() - G["Vn_linf"]) < 6e-9
+    p.solve_system(True)
+    assert p.solver_control.last_step() == 1
+    assert abs(p.rigid_velocities[0] - G["rigid_velocity_0"]) < 6e-8
+    assert np.abs(p.rigid_velocities[1:]).max() < 1e-5
+    assert p.final_check_0[0] < 1e-11
+    # next frame on the same context (per-frame flow): geometry update, LU reused as preconditioner
+    p.update_geometry(m1)
+    p.compute_center_of_mass_and_rigid_modes()
+    p.compute_normal_vector()
+    p.assemble_stokes_system(True)
+    p.monolithic_solution[:] = 0
+    p.solve_system(True)
+    assert p.solver_control.last_step() <= 3     # frame-0 LU is still an excellent preconditioner
+    assert abs(p.rigid_velocities[0] - G["rigid_velocity_0"]) < 1e-4
+    p.close()
+
+
+def test_sphere_rotation_real_grid(goldens):
+    """tests/sphere_rotation.cc on the device (Real grid, rotation about x)."""
+    m0 = bb.read_mesh(os.path.join(MESHES, "sphere_rotation_0.msh"))
+    m1 = bb.read_mesh(os.path.join(MESHES, "sphere_rotation_1.msh"))
+    p = make_problem(m0, grid_type="Real", solve_directly=False, preconditioner_type="Jacobi")
+    p.shape_velocities = ((m1.nodes - m0.nodes) / 0.1).T.reshape(-1).copy()
+    p.assemble_stokes_system(True)
+    G = goldens["sphere_rotation"]
+    assert abs(np.abs(p.V_x_normals_body).max() - G["Vn_linf"]) < 6e-9
+    p.solve_system(True)
+    U = p.rigid_velocities
+    assert abs(U[3] - G["omega_exact"]) / G["omega_exact"] <= G["tol"]
+    assert np.abs(U[:3]).max() <= G["tol"] and np.abs(U[4:]).max() <= G["tol"]
+    geo = bo.Geometry(m0.nodes, m0.conn.astype(np.int64), 1)
+    Vo, Ko = bo.assemble_VK(geo, bo.KernelSpec(), 8, "Mixed", 10)
+    pre = bo.Prepass(geo, 8)
+    Vc, _ = bo.correct_V(Vo, pre)
+    A, b = bo.monolithic(Vc, bo.correct_K(Ko, geo.N), pre, "Real", 1, 1.0, p.shape_velocities)
+    assert np.abs(p.monolithic_rhs - b).max() <= 1e-13 * np.abs(b).max()
+    xo = np.linalg.solve(A, b)
+    assert np.abs(p.monolithic_solution - xo).max() <= 1e-7 * np.abs(xo).max()
+    p.close()

@@ -210,3 +210,42 @@ def test_c_port_gmres_counts(goldens, half_refined, VK_free):
     assert ok and its == goldens["gmres_iterations_no_box"]["Jacobi"]
     x, its, res, ok = port.gmres(A, b)
     assert ok and its == 40
+
+
+def test_sphere_translation_real_grid(goldens):
+    """tests/sphere_translation.output: swimming ('Real') system — shape velocities from two frames, force-free rigid
+    rows; the reference prints rigid_velocities[0] = 0.0840328 (its 'ERROR' line is the expected text)."""
+    v0, q0 = bo.read_msh(os.path.join(MESHES, "sphere_translation_0.msh"))
+    v1, q1 = bo.read_msh(os.path.join(MESHES, "sphere_translation_1.msh"))
+    assert np.array_equal(q0, q1)
+    geo = bo.Geometry(v0, q0, 1)
+    pre = bo.Prepass(geo, 8)
+    G = goldens["sphere_translation"]
+    assert sig6(pre.area, G["surface"])
+    V, K = bo.assemble_VK(geo, bo.KernelSpec(), 8, "Mixed", 10)
+    assert sig6(np.abs(V @ pre.nhat).max(), G["Vn_linf"])
+    Vc, _ = bo.correct_V(V, pre)
+    sv = ((v1 - v0) / 0.1).T.reshape(-1)
+    A, b = bo.monolithic(Vc, bo.correct_K(K, geo.N), pre, "Real", 1, 1.0, sv)
+    x = np.linalg.solve(A, b)
+    U = x[3 * geo.N:]
+    assert sig6(U[0], G["rigid_velocity_0"])
+    assert abs(abs(U[0] - G["exact"]) / G["exact"] - G["rel_error"]) < 1e-6
+    assert np.abs(U[1:]).max() < 1e-5     # "OK rigid translation 1,2 / rotation 3,4,5" (tol 1e-5)
+
+
+def test_sphere_rotation_real_grid(goldens):
+    """tests/sphere_rotation.output: all six 'OK rigid ...' lines — omega_x within 1e-2 of 2 pi/120/time_step."""
+    v0, q0 = bo.read_msh(os.path.join(MESHES, "sphere_rotation_0.msh"))
+    v1, _ = bo.read_msh(os.path.join(MESHES, "sphere_rotation_1.msh"))
+    geo = bo.Geometry(v0, q0, 1)
+    pre = bo.Prepass(geo, 8)
+    G = goldens["sphere_rotation"]
+    V, K = bo.assemble_VK(geo, bo.KernelSpec(), 8, "Mixed", 10)
+    assert sig6(np.abs(V @ pre.nhat).max(), G["Vn_linf"])
+    Vc, _ = bo.correct_V(V, pre)
+    A, b = bo.monolithic(Vc, bo.correct_K(K, geo.N), pre, "Real", 1, 1.0, ((v1 - v0) / 0.1).T.reshape(-1))
+    U = np.linalg.solve(A, b)[3 * geo.N:]
+    assert G["ok_lines"] == 6
+    assert abs(U[3] - G["omega_exact"]) / G["omega_exact"] <= G["tol"]
+    assert np.abs(U[:3]).max() <= G["tol"] and np.abs(U[4:]).max() <= G["tol"]
