@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbemstokes_b200.so")
+LIB_PATH = os.environ.get("BEMSTOKES_B200_LIB") or os.path.join(HERE, "libbemstokes_b200.so")  # override: kernel-variant A/B runs
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

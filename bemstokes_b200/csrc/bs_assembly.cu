@@ -34,6 +34,9 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   uint32_t done;
   do {
@@ -55,12 +58,29 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                : "memory");
 }
 
+// Tile write-out primitive: what == 1 plain store (first colour to touch the column), what == 2 fire-and-forget L2
+// reduction (later colours; no load latency on the critical path), what == 0 nothing.  Predicated, no branch: the
+// lanes of a warp mix all three.  Blocks of one colour never share a node and colours are separate launches, so
+// every address receives its addends in a fixed order.
+__device__ __forceinline__ void store_or_reduce(double *p, double v, int what) {
+  asm volatile(
+      "{\n"
+      ".reg .pred ps, pr;\n"
+      "setp.eq.s32 ps, %2, 1;\n"
+      "setp.eq.s32 pr, %2, 2;\n"
+      "@ps st.global.f64 [%0], %1;\n"
+      "@pr red.global.add.f64 [%0], %1;\n"
+      "}\n" ::"l"(p),
+      "d"(v), "r"(what)
+      : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // K0: per-cell quadrature data with the regular rule.  cellq[cell][7][nq_pad] = y(3), n*JxW(3), JxW
 // ---------------------------------------------------------------------------------------------------------
 __global__ void k_cell_geometry(int ncell, int nq, int nq_pad, int nam, const int *__restrict__ conn_map,
                                 const double *__restrict__ map_nodes, const double *__restrict__ tab /*[nq][nam][3]*/,
-                                const double *__restrict__ w, double *__restrict__ cellq) {
+                                const double *__restrict__ w, double *__restrict__ cellq, double *__restrict__ cellq8) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (long long)ncell * nq) return;
   const int cell = (int)(gid / nq), q = (int)(gid % nq);
@@ -87,11 +107,25 @@ __global__ void k_cell_geometry(int ncell, int nq, int nq_pad, int nam, const in
   o[4 * nq_pad + q] = w[q] * ny;
   o[5 * nq_pad + q] = w[q] * nz;
   o[6 * nq_pad + q] = w[q] * J;
+  // point-major copy for the free-space fast path of K1, constants folded in:
+  //   y(3), JxW/(8 pi), 6*n(3), 0      (k = 3/(4 pi) (R.n JxW) r^-5 R(x)R = (R.6n) r^-2 * [JxW/(8 pi) r^-3] R(x)R)
+  double *o8 = cellq8 + ((size_t)cell * nq_pad + q) * 8;
+  const double s6 = 6.0 / J;
+  o8[0] = y[0];
+  o8[1] = y[1];
+  o8[2] = y[2];
+  o8[3] = (w[q] * J) * BS_INV_8PI;
+  o8[4] = s6 * nx;
+  o8[5] = s6 * ny;
+  o8[6] = s6 * nz;
+  o8[7] = 0.0;
 }
 
 void launch_cell_geometry(Context &c) {
   c.d_cellq.alloc((size_t)c.ncell * 7 * c.nq_pad);
   c.d_cellq.zero(c.stream);
+  c.d_cellq8.alloc((size_t)c.ncell * 8 * c.nq_pad);
+  c.d_cellq8.zero(c.stream);
   struct P_ { double *p; } dw;
   dw.p = c.wsd("geom.w", c.reg.w.size());
   BS_CUDA(cudaMemcpyAsync(dw.p, c.reg.w.data(), sizeof(double) * c.reg.w.size(), cudaMemcpyHostToDevice, c.stream));
@@ -99,7 +133,7 @@ void launch_cell_geometry(Context &c) {
   const int bs_ = 256;
   k_cell_geometry<<<(unsigned)((total + bs_ - 1) / bs_), bs_, 0, c.stream>>>(c.ncell, c.nq, c.nq_pad, c.na_map, c.d_conn_map.p,
                                                                             c.d_map_nodes.p, c.d_map_tab_reg.p, dw.p,
-                                                                            c.d_cellq.p);
+                                                                            c.d_cellq.p, c.d_cellq8.p);
   BS_CUDA(cudaGetLastError());
   count_launch(c);
   BS_CUDA(cudaStreamSynchronize(c.stream));
@@ -114,6 +148,7 @@ struct RegParams {
   const double *support;    // [N][3]
   const int *conn_pos;      // [ncell][NA]
   const double *cellq;      // [ncell][7][nq_pad]
+  const double *cellq8;     // [ncell][nq_pad][8] point-major, prescaled (free-space fast path)
   const double *l1d;        // [n1d][NB1] 1-D Lagrange values at the 1-D rule points (NB1 = degree+1)
   int n1d;
   const int *blk_cell_ptr, *blk_cells;
@@ -135,13 +170,20 @@ constexpr int ACC_LD = TI + 1;  // padded row-node stride of the shared accumula
 // write-out lane group reads for one node over different banks
 __host__ __device__ inline int acc_vstride(int tj) { return tj * ACC_LD + 5; }
 
+// cell records in flight per CTA (bulk-copy ring): 3 when a record is small, else 2
+__host__ __device__ inline int cell_stages(int nq_pad) { return nq_pad <= 64 ? 3 : 2; }
+// doubles reserved for the 1-D shape table and its x-flipped copy (2 * (degree+1) * n1d <= max(nq_pad, 96))
+__host__ __device__ inline int l1d_doubles(int nq_pad) { return nq_pad > 96 ? nq_pad : 96; }
+
 size_t assembly_smem_bytes(int na, int nv, int tj, int nq_pad) {
-  return (size_t)2 * nv * acc_vstride(tj) * 8 + (size_t)2 * 7 * nq_pad * 8 + (size_t)nq_pad * na * 8 + 64;  // dynamic part
+  (void)na;
+  return (size_t)2 * nv * acc_vstride(tj) * 8 + (size_t)cell_stages(nq_pad) * 8 * nq_pad * 8 +
+         (size_t)l1d_doubles(nq_pad) * 8 + 64;  // dynamic part: tile, cell ring, shape table, mbarriers
 }
 
 int choose_tj(int na, int kernel_type, int nq_pad) {
   const int nv = (kernel_type == BS_KERNEL_FREE) ? 6 : 9;
-  const size_t budget = (227 * 1024) / CTAS_PER_SM - 2048 - (CTAS_PER_SM > 1 ? 1024 : 0);  // minus static arrays / per-CTA reserve
+  const size_t budget = (227 * 1024) / CTAS_PER_SM - 1024 - 1024;  // minus static arrays (768 B) / per-CTA reserve
   int tj = 2;
   for (int t = 2; t <= 32; t += 2)
     if (assembly_smem_bytes(na, nv, t, nq_pad) <= budget) tj = t;
@@ -166,11 +208,141 @@ __device__ __forceinline__ constexpr int shape_iy(int a) {
   return NA == 4 ? (a >> 1) : (a == 0 ? 0 : a == 1 ? 0 : a == 2 ? 2 : a == 3 ? 2 : a == 4 ? 1 : a == 5 ? 1 : a == 6 ? 0 : a == 7 ? 2 : 1);
 }
 
+// Free-space fast path: one quadrature point of the point-major prescaled cell record (see K0).
+//   G JxW = c3 R(x)R + c1 I,  -S.n JxW = ck R(x)R   with c1 = J' / r, c3 = c1 / r^2, ck = (R.6n) c3 / r^2.
+// The x-direction sums are taken over the six products P = R(x)R with the weights l_b*c3 and l_b*ck (and the
+// isotropic part l_b*c1 as a 13th scalar): 55 FP64 instructions per point for Q1 instead of 64.
+template <int NB1, int MODE>
+struct FreePoint {
+  double P[6], sg[NB1], sk[NB1], c1;
+};
+
+template <int NB1, int MODE>
+__device__ __forceinline__ void free_point(const double *__restrict__ c8, const double *__restrict__ lrow,
+                                           const double (&x)[3], FreePoint<NB1, MODE> &pt) {
+  const double2 a = *reinterpret_cast<const double2 *>(c8);
+  const double2 b = *reinterpret_cast<const double2 *>(c8 + 2);
+  const double Rx = a.x - x[0], Ry = a.y - x[1], Rz = b.x - x[2];
+  const double r2 = fma(Rx, Rx, fma(Ry, Ry, Rz * Rz));
+  const double ri = rsqrt_normal(r2);
+  const double ri2 = ri * ri;
+  const double c1 = b.y * ri;
+  const double c3 = c1 * ri2;
+  pt.c1 = c1;
+  pt.P[0] = Rx * Rx;
+  pt.P[1] = Rx * Ry;
+  pt.P[2] = Rx * Rz;
+  pt.P[3] = Ry * Ry;
+  pt.P[4] = Ry * Rz;
+  pt.P[5] = Rz * Rz;
+  if (MODE != 1) {
+#pragma unroll
+    for (int bb = 0; bb < NB1; ++bb) pt.sg[bb] = lrow[bb] * c3;
+  }
+  if (MODE != 0) {
+    const double2 n01 = *reinterpret_cast<const double2 *>(c8 + 4);
+    const double n2 = c8[6];
+    const double Rn = fma(Rx, n01.x, fma(Ry, n01.y, Rz * n2));
+    const double ck = (Rn * ri2) * c3;
+#pragma unroll
+    for (int bb = 0; bb < NB1; ++bb) pt.sk[bb] = lrow[bb] * ck;
+  }
+}
+
+template <int NB1, int MODE, int NACC>
+__device__ __forceinline__ void free_accumulate(const FreePoint<NB1, MODE> &pt, const double *__restrict__ lrow,
+                                                double (&tmp)[NB1][NACC], double (&tmpI)[NB1]) {
+#pragma unroll
+  for (int bb = 0; bb < NB1; ++bb) {
+#pragma unroll
+    for (int v = 0; v < 6; ++v) {
+      if (MODE == 2) {
+        tmp[bb][v] = fma(pt.sg[bb], pt.P[v], tmp[bb][v]);
+        tmp[bb][6 + v] = fma(pt.sk[bb], pt.P[v], tmp[bb][6 + v]);
+      } else {
+        tmp[bb][v] = fma(MODE == 0 ? pt.sg[bb] : pt.sk[bb], pt.P[v], tmp[bb][v]);
+      }
+    }
+    if (MODE != 1) tmpI[bb] = fma(lrow[bb], pt.c1, tmpI[bb]);
+  }
+}
+
+// Software-pipelined integration of one (row, cell) pair with the free-space kernel: the dependent chain of
+// point q+1 (load, r^2, rsqrt, coefficients) is issued together with the independent accumulation FMAs of point
+// q, across the rows of the rule as well.  N1C > 0: compile-time 1-D rule size (fully unrolled rows).
+//
+// `lx_s` is the 1-D shape table used in the x direction.  For Q1 with two threads per row the odd thread gets the
+// table with its two columns swapped: its accumulator slot s then holds shape function s^1, so that the pair
+// exchanges only the slots the partner finalises (half the shuffles, see cell_pass).
+template <int NA, int MODE, int QS, int N1C, int NACC>
+__device__ __forceinline__ void integrate_free(const double *__restrict__ c8, const double *__restrict__ lx_s,
+                                               const double *__restrict__ ly_s, int n1rt, const double (&x)[3], int part,
+                                               double (&acc)[NA][NACC]) {
+  constexpr int NB1 = (NA == 4) ? 2 : 3;
+  const int n1 = N1C > 0 ? N1C : n1rt;
+  const double *l1d_s = lx_s;
+  double accI[NA];
+#pragma unroll
+  for (int a = 0; a < NA; ++a) accI[a] = 0.0;
+  FreePoint<NB1, MODE> cur;
+  if (part < n1) free_point<NB1, MODE>(c8 + (size_t)8 * part * n1, l1d_s, x, cur);
+  for (int qy = part; qy < n1; qy += QS) {
+    double tmp[NB1][NACC], tmpI[NB1];
+#pragma unroll
+    for (int bb = 0; bb < NB1; ++bb) {
+      tmpI[bb] = 0.0;
+#pragma unroll
+      for (int v = 0; v < NACC; ++v) tmp[bb][v] = 0.0;
+    }
+    const double *crow = c8 + (size_t)8 * qy * n1;
+    if (N1C > 0) {
+#pragma unroll
+      for (int qx = 0; qx + 1 < N1C; ++qx) {
+        FreePoint<NB1, MODE> nxt;
+        free_point<NB1, MODE>(crow + 8 * (qx + 1), l1d_s + (qx + 1) * NB1, x, nxt);
+        free_accumulate<NB1, MODE, NACC>(cur, l1d_s + qx * NB1, tmp, tmpI);
+        cur = nxt;
+      }
+    } else {
+#pragma unroll 2
+      for (int qx = 0; qx + 1 < n1; ++qx) {
+        FreePoint<NB1, MODE> nxt;
+        free_point<NB1, MODE>(crow + 8 * (qx + 1), l1d_s + (qx + 1) * NB1, x, nxt);
+        free_accumulate<NB1, MODE, NACC>(cur, l1d_s + qx * NB1, tmp, tmpI);
+        cur = nxt;
+      }
+    }
+    {  // last point of the row; the chain of the first point of this thread's next row rides along
+      const int qyn = (qy + QS < n1) ? qy + QS : qy;
+      FreePoint<NB1, MODE> nxt;
+      free_point<NB1, MODE>(c8 + (size_t)8 * qyn * n1, l1d_s, x, nxt);
+      free_accumulate<NB1, MODE, NACC>(cur, l1d_s + (n1 - 1) * NB1, tmp, tmpI);
+      cur = nxt;
+    }
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      const double l = ly_s[qy * NB1 + shape_iy<NA>(a)];
+#pragma unroll
+      for (int v = 0; v < NACC; ++v) acc[a][v] = fma(tmp[shape_ix<NA>(a)][v], l, acc[a][v]);
+      if (MODE != 1) accI[a] = fma(tmpI[shape_ix<NA>(a)], l, accI[a]);
+    }
+  }
+  if (MODE != 1) {
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      acc[a][0] += accI[a];
+      acc[a][3] += accI[a];
+      acc[a][5] += accI[a];
+    }
+  }
+}
+
 // One (row, cell) integration over this thread's share of the tensor rule.  MODE 0: single layer only, 1: double
 // layer only, 2: both.  Sum-factorised: x-direction into NB1 temporaries per value, y-direction once per row of
 // the rule; then the QS partial sums of a row (adjacent lanes) are combined by shuffles and lane `part` adds its
 // share of the shape functions into the shared tile [value][slot][row].
-template <int NA, int KT, int MODE, int QS, bool HAS_EPS>
+// FAST: free-space kernel without regularisation, `cq` is the point-major prescaled record.
+template <int NA, int KT, int MODE, int QS, bool HAS_EPS, bool FAST, int N1C>
 __device__ __forceinline__ void cell_pass(const double *__restrict__ cq, const double *__restrict__ l1d_s, int n1, int nqp,
                                           const double (&x)[3], const double (&xim)[3], double eps, int o, bool ok,
                                           int part, const int (&slot)[NA], double *__restrict__ acc_s, int tj, int rl) {
@@ -183,6 +355,11 @@ __device__ __forceinline__ void cell_pass(const double *__restrict__ cq, const d
   for (int a = 0; a < NA; ++a)
 #pragma unroll
     for (int v = 0; v < NACC; ++v) acc[a][v] = 0.0;
+  constexpr bool FLIP = FAST && QS == 2 && NA == 4;
+  if (FAST) {
+    const double *lx_s = FLIP ? l1d_s + part * (n1 * NB1) : l1d_s;  // odd partner: x-flipped copy of the table
+    if (ok) integrate_free<NA, MODE, QS, N1C, NACC>(cq, lx_s, l1d_s, n1, x, part, acc);
+  } else {
   for (int qy = part; ok && qy < n1; qy += QS) {
     double tmp[NB1][NACC];
 #pragma unroll
@@ -223,6 +400,21 @@ __device__ __forceinline__ void cell_pass(const double *__restrict__ cq, const d
       for (int v = 0; v < NACC; ++v) acc[a][v] = fma(tmp[shape_ix<NA>(a)][v], l, acc[a][v]);
     }
   }
+  }
+  if (FLIP) {
+    // slots 1 and 3 hold the partner's shape functions (0^1, 2^1 in its numbering): send them, finalise 0 and 2
+    const int vs = acc_vstride(tj);
+#pragma unroll
+    for (int a = 0; a < NA; a += 2) {
+      double *dst = acc_s + (size_t)VOFF * vs + (size_t)slot[a] * ACC_LD + rl;  // slot[] arrives flipped for part 1
+#pragma unroll
+      for (int v = 0; v < NACC; ++v) {
+        acc[a][v] += __shfl_xor_sync(0xffffffffu, acc[a + 1][v], 1);
+        dst[(size_t)v * vs] += acc[a][v];
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int a = 0; a < NA; ++a) {
 #pragma unroll
@@ -244,21 +436,26 @@ __device__ __forceinline__ void cell_pass(const double *__restrict__ cq, const d
 // (half the accumulator registers per thread -> twice the resident warps).  A CTA has TI*QS*VS threads.
 constexpr int MAXC = 32;  // cells per block (a block touches at most tj <= 32 nodes)
 
-template <int NA, int KT, bool SPLIT, int QS, int VS, bool HAS_EPS, bool FUSED>
+template <int NA, int KT, bool SPLIT, int QS, int VS, bool HAS_EPS, bool FUSED, int N1C>
 __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(const RegParams P) {
+  constexpr bool FAST = (KT == BS_KERNEL_FREE) && !HAS_EPS;  // point-major prescaled cell records, pipelined points
+  constexpr int CQ = FAST ? 8 : 7;                           // doubles per quadrature point in a cell record
   constexpr int NV = GreenTraits<KT>::NV;
   constexpr int NV2 = 2 * NV;
   constexpr int NB1 = (NA == 4) ? 2 : 3;
   constexpr int NT = TI * QS * VS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tj = P.tj, nqp = P.nq_pad, n1 = P.n1d;
-  double *cellbuf = reinterpret_cast<double *>(smem_raw);                   // [2][7][nqp]
-  double *l1d_s = cellbuf + (size_t)2 * 7 * nqp;                            // [n1][NB1] 1-D shape values
-  double *acc_s = l1d_s + (size_t)nqp * NA;                                 // [NV2][tj][ACC_LD]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(acc_s + (size_t)NV2 * acc_vstride(tj));  // [2]
+  const int ns = cell_stages(nqp);
+  double *cellbuf = reinterpret_cast<double *>(smem_raw);                   // [ns][7][nqp] or [ns][nqp][8]
+  double *l1d_s = cellbuf + (size_t)ns * 8 * nqp;                           // [n1][NB1] 1-D shape values (+ x-flipped copy)
+  double *acc_s = l1d_s + l1d_doubles(nqp);                                 // [NV2][tj][ACC_LD]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(acc_s + (size_t)NV2 * acc_vstride(tj));  // full[3], empty[3]
+  uint64_t *full = bars, *empty = bars + 3;
   __shared__ int s_cells[MAXC];          // block metadata staged once: no dependent global loads per cell
   __shared__ int s_conn[MAXC * NA];
   __shared__ signed char s_slots[MAXC * NA];
+  constexpr bool FLIP = FAST && QS == 2 && NA == 4;  // see cell_pass
 
   const int t = threadIdx.x;
   const int vpart = (VS == 2) ? t / (TI * QS) : 0;   // warp-uniform role: 0 single layer, 1 double layer
@@ -268,14 +465,22 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
   const int p = P.p0 + blockIdx.y * TI + rl;
   const bool row_ok = p < P.p1;
   const int cs = P.blk_cell_ptr[blk], ce = P.blk_cell_ptr[blk + 1];
-  const uint32_t cell_bytes = (uint32_t)(7 * nqp * sizeof(double));
+  const uint32_t cell_bytes = (uint32_t)(CQ * nqp * sizeof(double));
+  const double *cell_src = FAST ? P.cellq8 : P.cellq;
 
   if (t == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], NT / 32);  // one arrival per warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = t; i < n1 * NB1; i += NT) l1d_s[i] = P.l1d[i];
+  for (int i = t; i < n1 * NB1; i += NT) {
+    const double l = P.l1d[i];
+    l1d_s[i] = l;
+    if (FLIP) l1d_s[n1 * NB1 + (i ^ 1)] = l;  // columns swapped (NB1 == 2)
+  }
   for (int i = t; i < (ce - cs) * NA; i += NT) {
     const int cell = P.blk_cells[cs + i / NA];
     if (i % NA == 0) s_cells[i / NA] = cell;
@@ -284,9 +489,11 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
   }
   for (int i = t; i < NV2 * acc_vstride(tj); i += NT) acc_s[i] = 0.0;
   __syncthreads();
-  if (t == 0 && cs < ce) {
-    mbar_expect_tx(&bars[0], cell_bytes);
-    bulk_g2s(cellbuf, P.cellq + (size_t)s_cells[0] * 7 * nqp, cell_bytes, &bars[0]);
+  if (t == 0) {
+    for (int i = 0; i < ns - 1 && cs + i < ce; ++i) {
+      mbar_expect_tx(&full[i], cell_bytes);
+      bulk_g2s(cellbuf + (size_t)i * CQ * nqp, cell_src + (size_t)s_cells[i] * CQ * nqp, cell_bytes, &full[i]);
+    }
   }
   double x[3] = {0, 0, 0};
   if (row_ok) {
@@ -303,35 +510,47 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
   const double eps = HAS_EPS ? P.kp.eps : 0.0;
   const int o = P.kp.o;
 
+  // Cell ring: thread 0 keeps ns-1 records in flight ahead of the one being integrated.  A stage is refilled once
+  // every warp has released it (empty barrier) - warps are not held in lock step by a CTA barrier per cell.
+  int st = 0, st_fill = ns - 1;             // stage of cell `it`, stage of cell `it + ns - 1`
+  uint32_t ph_full = 0, ph_empty = 0;       // parity bits, one per stage
   for (int kc = cs; kc < ce; ++kc) {
     const int it = kc - cs;
-    const int buf = it & 1;
-    if (t == 0 && kc + 1 < ce) {
-      mbar_expect_tx(&bars[buf ^ 1], cell_bytes);
-      bulk_g2s(cellbuf + (size_t)(buf ^ 1) * 7 * nqp, P.cellq + (size_t)s_cells[it + 1] * 7 * nqp, cell_bytes,
-               &bars[buf ^ 1]);
+    if (t == 0 && kc + ns - 1 < ce) {
+      if (it >= 1) {  // the stage was last used by cell it-1
+        mbar_wait(&empty[st_fill], (ph_empty >> st_fill) & 1u);
+        ph_empty ^= 1u << st_fill;
+      }
+      mbar_expect_tx(&full[st_fill], cell_bytes);
+      bulk_g2s(cellbuf + (size_t)st_fill * CQ * nqp, cell_src + (size_t)s_cells[it + ns - 1] * CQ * nqp, cell_bytes,
+               &full[st_fill]);
     }
     int slot[NA];
     bool sing = false;
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
-      slot[a] = s_slots[it * NA + a];
+      slot[a] = s_slots[it * NA + (FLIP ? (a ^ part) : a)];
       sing |= (s_conn[it * NA + a] == p);
     }
-    mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
-    const double *cq = cellbuf + (size_t)buf * 7 * nqp;
+    mbar_wait(&full[st], (ph_full >> st) & 1u);
+    ph_full ^= 1u << st;
+    const double *cq = cellbuf + (size_t)st * CQ * nqp;
     const bool ok = row_ok && !sing;  // singular (node in cell) pairs are integrated by K2 (ref: 2885-2908)
     if (VS == 2) {
-      if (vpart == 0) cell_pass<NA, KT, 0, QS, HAS_EPS>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
-      else cell_pass<NA, KT, 1, QS, HAS_EPS>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
+      if (vpart == 0) cell_pass<NA, KT, 0, QS, HAS_EPS, FAST, N1C>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
+      else cell_pass<NA, KT, 1, QS, HAS_EPS, FAST, N1C>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
     } else if (SPLIT) {
-      cell_pass<NA, KT, 0, QS, HAS_EPS>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
-      cell_pass<NA, KT, 1, QS, HAS_EPS>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
+      cell_pass<NA, KT, 0, QS, HAS_EPS, FAST, N1C>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
+      cell_pass<NA, KT, 1, QS, HAS_EPS, FAST, N1C>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
     } else {
-      cell_pass<NA, KT, 2, QS, HAS_EPS>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
+      cell_pass<NA, KT, 2, QS, HAS_EPS, FAST, N1C>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
     }
-    __syncthreads();  // everyone is done with cellbuf[buf] before it is refilled two iterations later
+    __syncwarp();
+    if ((t & 31) == 0) mbar_arrive(&empty[st]);  // this warp is done with the record
+    st = (st + 1 == ns) ? 0 : st + 1;
+    st_fill = (st_fill + 1 == ns) ? 0 : st_fill + 1;
   }
+  __syncthreads();  // the tile is complete
 
   // ---- combine the tile with global memory: rows 3*(p-p0)+i, columns 3*node(slot)+j.  The first colour that
   // touches a node column stores, later colours (launched after this one) add: fixed summation order.
@@ -345,36 +564,31 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
   constexpr int NWARP = NT / 32;
   constexpr int MAXSTEP = 3;  // 3*tj <= 96 columns
   const int vs = acc_vstride(tj);
-  int col_node[MAXSTEP], col_j[MAXSTEP], col_sl[MAXSTEP];
-  bool col_first[MAXSTEP];
+  // per-lane column metadata, loop invariant: shared-tile offset of the value for each matrix-row component i,
+  // global column, and what to do with it (0 nothing, 1 store, 2 reduce) -- the row loop below is branch free
+  int soff[MAXSTEP][3], gcol[MAXSTEP], todo[MAXSTEP];
 #pragma unroll
   for (int sidx = 0; sidx < MAXSTEP; ++sidx) {
     const int e = lane + 32 * sidx;
-    const int sl = e / 3;
-    col_sl[sidx] = sl;
-    col_j[sidx] = e - 3 * sl;
-    const bool valid = e < 3 * tj;
-    col_node[sidx] = valid ? nodes[sl] : -1;
-    col_first[sidx] = valid ? (first[sl] != 0) : false;
-  }
-  for (int rr = warp; rr < rows_tile * 3; rr += NWARP) {  // rr = 3*rowlocal + i
-    const int r_ = rr / 3, i = rr - 3 * r_;
-    const size_t rowoff = ((size_t)3 * (blockIdx.y * TI + r_) + i) * P.ld;
+    const int sl = e / 3, j = e - 3 * sl;
+    const int node = (e < 3 * tj) ? nodes[sl] : -1;
+    const bool valid = node >= 0;
+    todo[sidx] = valid ? (first[sl] != 0 ? 1 : 2) : 0;
+    gcol[sidx] = valid ? 3 * node + j : 0;
 #pragma unroll
-    for (int sidx = 0; sidx < MAXSTEP; ++sidx) {
-      if (col_node[sidx] < 0) continue;
-      const int vi = vidx<NV>(i, col_j[sidx]);
-      const double *as = acc_s + (size_t)vi * vs + (size_t)col_sl[sidx] * ACC_LD + r_;
-      const double v = as[0], k = as[(size_t)NV * vs];
-      const size_t off = rowoff + (size_t)3 * col_node[sidx] + col_j[sidx];
-      if (col_first[sidx]) {
-        P.V[off] = v;
-        if (!FUSED) P.K[off] = k;
-      } else {
-        // fire-and-forget L2 reductions: no load latency on the critical path.  Blocks of one colour never share a
-        // node and colours are separate launches, so each address receives its addends in a fixed order.
-        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(P.V + off), "d"(v) : "memory");
-        if (!FUSED) asm volatile("red.global.add.f64 [%0], %1;" ::"l"(P.K + off), "d"(k) : "memory");
+    for (int i = 0; i < 3; ++i) soff[sidx][i] = valid ? vidx<NV>(i, j) * vs + sl * ACC_LD : 0;
+  }
+  for (int r_ = warp; r_ < rows_tile; r_ += NWARP) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const size_t rowoff = ((size_t)3 * (blockIdx.y * TI + r_) + i) * P.ld;
+      double *vrow = P.V + rowoff, *krow = FUSED ? nullptr : P.K + rowoff;
+#pragma unroll
+      for (int sidx = 0; sidx < MAXSTEP; ++sidx) {
+        if (32 * sidx >= 3 * tj) break;  // warp-uniform
+        const double *as = acc_s + soff[sidx][i] + r_;
+        store_or_reduce(vrow + gcol[sidx], as[0], todo[sidx]);
+        if (!FUSED) store_or_reduce(krow + gcol[sidx], as[(size_t)NV * vs], todo[sidx]);
       }
     }
   }
@@ -393,30 +607,43 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
       xs[idx] = (node >= 0 && q < pp) ? P.panel[((size_t)3 * node + j) * pp + q] : 0.0;
     }
     __syncthreads();
-    const int rows3 = rows_tile * 3;
+    // TPR threads per row node split the panel columns; each keeps the three matrix rows of its node in registers,
+    // so a K value is read from the tile once and every thread is busy (TI*TPR == NT).
+    constexpr int TPR = NT / TI, PSH = PS / TPR;
+    static_assert(TPR * TI == NT && PSH * TPR == PS && PSH % 2 == 0, "fused epilogue thread layout");
     const double *kacc = acc_s + (size_t)NV * vs;
-    for (int rr = t; rr < rows3; rr += NT) {  // one matrix row per thread, all panel columns in registers
-      const int r_ = rr / 3, i = rr - 3 * r_;
-      double y[PS];
+    const int r_ = t / TPR, h_ = t - r_ * TPR;
+    if (r_ < rows_tile) {
+      double y[3][PSH];
 #pragma unroll
-      for (int q = 0; q < PS; ++q) y[q] = 0.0;
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int q = 0; q < PSH; ++q) y[i][q] = 0.0;
       for (int sl = 0; sl < tj; ++sl) {
+        double kv[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) kv[v] = kacc[(size_t)v * vs + (size_t)sl * ACC_LD + r_];
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          const double kv = kacc[(size_t)vidx<NV>(i, j) * vs + (size_t)sl * ACC_LD + r_];
-          const double2 *xr = reinterpret_cast<const double2 *>(xs + (3 * sl + j) * PS);  // broadcast reads
+          const double2 *xr = reinterpret_cast<const double2 *>(xs + (3 * sl + j) * PS + h_ * PSH);  // broadcast reads
 #pragma unroll
-          for (int q2 = 0; q2 < PS / 2; ++q2) {
+          for (int q2 = 0; q2 < PSH / 2; ++q2) {
             const double2 xv = xr[q2];
-            y[2 * q2] = fma(kv, xv.x, y[2 * q2]);
-            y[2 * q2 + 1] = fma(kv, xv.y, y[2 * q2 + 1]);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+              y[i][2 * q2] = fma(kv[vidx<NV>(i, j)], xv.x, y[i][2 * q2]);
+              y[i][2 * q2 + 1] = fma(kv[vidx<NV>(i, j)], xv.y, y[i][2 * q2 + 1]);
+            }
           }
         }
       }
-      double *dst = P.KX + ((size_t)3 * (blockIdx.y * TI + r_) + i) * pp;
 #pragma unroll
-      for (int q = 0; q < PS; ++q)
-        if (q < pp) asm volatile("red.global.add.f64 [%0], %1;" ::"l"(dst + q), "d"(y[q]) : "memory");
+      for (int i = 0; i < 3; ++i) {
+        double *dst = P.KX + ((size_t)3 * (blockIdx.y * TI + r_) + i) * pp + h_ * PSH;
+#pragma unroll
+        for (int q = 0; q < PSH; ++q)
+          if (h_ * PSH + q < pp) asm volatile("red.global.add.f64 [%0], %1;" ::"l"(dst + q), "d"(y[i][q]) : "memory");
+      }
     }
   }
 }
@@ -424,10 +651,16 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
 template <int NA, int KT, bool SPLIT, int QS, int VS>
 static void launch_reg(Context &c, RegParams P, int nrow_tiles, size_t smem) {
   BS_REQUIRE(c.blocks.max_cells <= MAXC, "cell block larger than MAXC");
-  auto kern = c.fused ? ((c.kp.eps == 0.0) ? k_assemble_regular<NA, KT, SPLIT, QS, VS, false, true>
-                                           : k_assemble_regular<NA, KT, SPLIT, QS, VS, true, true>)
-                      : ((c.kp.eps == 0.0) ? k_assemble_regular<NA, KT, SPLIT, QS, VS, false, false>
-                                           : k_assemble_regular<NA, KT, SPLIT, QS, VS, true, false>);
+  // the free-space kernel has a variant with the 1-D rule size fixed at compile time (Gauss 8, the order of the
+  // reference's parameter files): fully unrolled, software-pipelined rows
+  const bool n8 = (KT == BS_KERNEL_FREE) && c.kp.eps == 0.0 && P.n1d == 8;
+  constexpr int N8 = (KT == BS_KERNEL_FREE) ? 8 : 0;
+  auto kern = c.fused ? ((c.kp.eps == 0.0) ? (n8 ? k_assemble_regular<NA, KT, SPLIT, QS, VS, false, true, N8>
+                                                 : k_assemble_regular<NA, KT, SPLIT, QS, VS, false, true, 0>)
+                                           : k_assemble_regular<NA, KT, SPLIT, QS, VS, true, true, 0>)
+                      : ((c.kp.eps == 0.0) ? (n8 ? k_assemble_regular<NA, KT, SPLIT, QS, VS, false, false, N8>
+                                                 : k_assemble_regular<NA, KT, SPLIT, QS, VS, false, false, 0>)
+                                           : k_assemble_regular<NA, KT, SPLIT, QS, VS, true, false, 0>);
   BS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const std::vector<int> &cs = c.blocks.colour_start;
   for (size_t k = 0; k + 1 < cs.size(); ++k) {  // one launch per colour, stream order = summation order
@@ -452,6 +685,7 @@ void launch_assembly_regular(Context &c) {
   P.support = c.d_support.p;
   P.conn_pos = c.d_conn_pos.p;
   P.cellq = c.d_cellq.p;
+  P.cellq8 = c.d_cellq8.p;
   P.l1d = c.d_l1d.p;
   P.blk_cell_ptr = c.d_blk_cell_ptr.p;
   P.blk_cells = c.d_blk_cells.p;

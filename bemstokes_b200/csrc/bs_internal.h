@@ -172,6 +172,7 @@ struct Context {
   DBuf<int> d_conn_pos;             // [ncell][na] internal positions
   DBuf<int> d_conn_map;             // [ncell][na_map]
   DBuf<double> d_cellq;             // [ncell][7][nq_pad]
+  DBuf<double> d_cellq8;            // [ncell][nq_pad][8] point-major prescaled copy (free-space fast path of K1)
   DBuf<double> d_phi_reg;           // [nq][na]
   DBuf<double> d_l1d;               // [n1d][degree+1] 1-D Lagrange values at the 1-D rule points
   DBuf<double> d_map_tab_reg;       // [nq][na_map][3]  (phi, dphi_x, dphi_y)
