@@ -267,6 +267,63 @@ __device__ __forceinline__ void free_accumulate(const FreePoint<NB1, MODE> &pt, 
   }
 }
 
+// Three-stage split of the same arithmetic for the fully unrolled rows: A = load, R, r^2, 1/r (and R.6n),
+// B = coefficients c1, c3, ck, C = products R(x)R, weights and the accumulation FMAs.  With A of point q+2 and B of
+// point q+1 in flight next to C of point q every dependent chain has two points' worth of independent work to
+// hide behind (one warp per scheduler cannot rely on its neighbour for that).
+struct FreeA {
+  double R[3], ri, Jp, Rn;
+};
+struct FreeB {
+  double R[3], c1, c3, ck;
+};
+template <int MODE>
+__device__ __forceinline__ void free_stage_a(const double *__restrict__ c8, const double (&x)[3], FreeA &a) {
+  const double2 u = *reinterpret_cast<const double2 *>(c8);
+  const double2 v = *reinterpret_cast<const double2 *>(c8 + 2);
+  a.R[0] = u.x - x[0];
+  a.R[1] = u.y - x[1];
+  a.R[2] = v.x - x[2];
+  a.Jp = v.y;
+  const double r2 = fma(a.R[0], a.R[0], fma(a.R[1], a.R[1], a.R[2] * a.R[2]));
+  a.ri = rsqrt_normal(r2);
+  a.Rn = 0.0;
+  if (MODE != 0) {
+    const double2 n01 = *reinterpret_cast<const double2 *>(c8 + 4);
+    a.Rn = fma(a.R[0], n01.x, fma(a.R[1], n01.y, a.R[2] * c8[6]));
+  }
+}
+template <int MODE>
+__device__ __forceinline__ void free_stage_b(const FreeA &a, FreeB &b) {
+  const double ri2 = a.ri * a.ri;
+  b.R[0] = a.R[0];
+  b.R[1] = a.R[1];
+  b.R[2] = a.R[2];
+  b.c1 = a.Jp * a.ri;
+  b.c3 = b.c1 * ri2;
+  b.ck = (MODE != 0) ? (a.Rn * ri2) * b.c3 : 0.0;
+}
+template <int NB1, int MODE, int NACC>
+__device__ __forceinline__ void free_stage_c(const FreeB &b, const double *__restrict__ lrow, double (&tmp)[NB1][NACC],
+                                             double (&tmpI)[NB1]) {
+  const double P[6] = {b.R[0] * b.R[0], b.R[0] * b.R[1], b.R[0] * b.R[2], b.R[1] * b.R[1], b.R[1] * b.R[2], b.R[2] * b.R[2]};
+#pragma unroll
+  for (int bb = 0; bb < NB1; ++bb) {
+    const double l = lrow[bb];
+    const double sg = l * b.c3, sk = l * b.ck;
+#pragma unroll
+    for (int v = 0; v < 6; ++v) {
+      if (MODE == 2) {
+        tmp[bb][v] = fma(sg, P[v], tmp[bb][v]);
+        tmp[bb][6 + v] = fma(sk, P[v], tmp[bb][6 + v]);
+      } else {
+        tmp[bb][v] = fma(MODE == 0 ? sg : sk, P[v], tmp[bb][v]);
+      }
+    }
+    if (MODE != 1) tmpI[bb] = fma(l, b.c1, tmpI[bb]);
+  }
+}
+
 // Software-pipelined integration of one (row, cell) pair with the free-space kernel: the dependent chain of
 // point q+1 (load, r^2, rsqrt, coefficients) is issued together with the independent accumulation FMAs of point
 // q, across the rows of the rule as well.  N1C > 0: compile-time 1-D rule size (fully unrolled rows).
@@ -284,8 +341,19 @@ __device__ __forceinline__ void integrate_free(const double *__restrict__ c8, co
   double accI[NA];
 #pragma unroll
   for (int a = 0; a < NA; ++a) accI[a] = 0.0;
-  FreePoint<NB1, MODE> cur;
-  if (part < n1) free_point<NB1, MODE>(c8 + (size_t)8 * part * n1, l1d_s, x, cur);
+  FreePoint<NB1, MODE> cur;  // two-stage pipeline state (run-time rule size)
+  FreeA sa;                  // three-stage pipeline state (compile-time rule size)
+  FreeB sb;
+  if (part < n1) {
+    if (N1C > 0) {
+      FreeA a0;
+      free_stage_a<MODE>(c8 + (size_t)8 * part * n1, x, a0);
+      free_stage_b<MODE>(a0, sb);
+      free_stage_a<MODE>(c8 + (size_t)8 * (part * n1 + 1), x, sa);
+    } else {
+      free_point<NB1, MODE>(c8 + (size_t)8 * part * n1, l1d_s, x, cur);
+    }
+  }
   for (int qy = part; qy < n1; qy += QS) {
     double tmp[NB1][NACC], tmpI[NB1];
 #pragma unroll
@@ -295,13 +363,18 @@ __device__ __forceinline__ void integrate_free(const double *__restrict__ c8, co
       for (int v = 0; v < NACC; ++v) tmp[bb][v] = 0.0;
     }
     const double *crow = c8 + (size_t)8 * qy * n1;
+    const int qyn = (qy + QS < n1) ? qy + QS : qy;  // this thread's next row (or a harmless re-read at the end)
     if (N1C > 0) {
+      const double *nrow = c8 + (size_t)8 * qyn * n1;
 #pragma unroll
-      for (int qx = 0; qx + 1 < N1C; ++qx) {
-        FreePoint<NB1, MODE> nxt;
-        free_point<NB1, MODE>(crow + 8 * (qx + 1), l1d_s + (qx + 1) * NB1, x, nxt);
-        free_accumulate<NB1, MODE, NACC>(cur, l1d_s + qx * NB1, tmp, tmpI);
-        cur = nxt;
+      for (int qx = 0; qx < N1C; ++qx) {
+        FreeB nb;
+        free_stage_b<MODE>(sa, nb);                                                         // point qx+1
+        FreeA na;
+        free_stage_a<MODE>(qx + 2 < N1C ? crow + 8 * (qx + 2) : nrow + 8 * (qx + 2 - N1C), x, na);  // point qx+2
+        free_stage_c<NB1, MODE, NACC>(sb, l1d_s + qx * NB1, tmp, tmpI);                     // point qx
+        sb = nb;
+        sa = na;
       }
     } else {
 #pragma unroll 2
@@ -311,9 +384,7 @@ __device__ __forceinline__ void integrate_free(const double *__restrict__ c8, co
         free_accumulate<NB1, MODE, NACC>(cur, l1d_s + qx * NB1, tmp, tmpI);
         cur = nxt;
       }
-    }
-    {  // last point of the row; the chain of the first point of this thread's next row rides along
-      const int qyn = (qy + QS < n1) ? qy + QS : qy;
+      // last point of the row; the chain of the first point of this thread's next row rides along
       FreePoint<NB1, MODE> nxt;
       free_point<NB1, MODE>(c8 + (size_t)8 * qyn * n1, l1d_s, x, nxt);
       free_accumulate<NB1, MODE, NACC>(cur, l1d_s + (n1 - 1) * NB1, tmp, tmpI);
