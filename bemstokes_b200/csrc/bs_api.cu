@@ -223,6 +223,29 @@ int bs_set_partition(bs_context *h, int rank, int nranks, const int *owner_of_no
   BS_API_END
 }
 
+int bs_prepass(bs_context *h, const double *pole, double *nhat, double *Mnhat, double *l2gamma, double *N_rigid,
+               double *N_rigid_dual, double *area, double *support_points, int *cg_iterations) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(nhat && Mnhat, "nhat / Mnhat output arrays are required");
+  BS_REQUIRE((N_rigid == nullptr) == (N_rigid_dual == nullptr), "N_rigid and N_rigid_dual go together");
+  const double origin[3] = {0, 0, 0};
+  const size_t n3 = c.n3();
+  double *d_nh = c.wsd("pre.nhat", n3), *d_mn = c.wsd("pre.Mnhat", n3);
+  double *d_nr = N_rigid ? c.wsd("pre.Nr", 6 * n3) : nullptr, *d_nrd = N_rigid ? c.wsd("pre.Nrd", 6 * n3) : nullptr;
+  device_prepass(c, pole ? pole : origin, d_nh, d_mn, d_nr, d_nrd, l2gamma, area, cg_iterations);
+  from_internal(c, d_nh, 0, nhat, 0, n3);
+  from_internal(c, d_mn, 0, Mnhat, 0, n3);
+  if (N_rigid)
+    for (int r = 0; r < 6; ++r) {
+      from_internal(c, d_nr + r * n3, 0, N_rigid + r * n3, 0, n3);
+      from_internal(c, d_nrd + r * n3, 0, N_rigid_dual + r * n3, 0, n3);
+    }
+  if (support_points) std::copy(c.support.begin(), c.support.end(), support_points);  // host copy, original node order
+  BS_CUDA(cudaStreamSynchronize(c.stream));
+  BS_API_END
+}
+
 int bs_get_owned_nodes(bs_context *h, int *n_owned, int *owned) {
   BS_API_BEGIN
   Context &c = ctx_of(h);

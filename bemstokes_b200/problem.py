@@ -15,7 +15,7 @@ import numpy as np
 from . import _lib
 from ._lib import lib, check
 from .mesh import QuadMesh
-from .prepass import Prepass, gauss_1d
+from .prepass import DevicePrepass, Prepass, gauss_1d
 
 
 def _dp(a):
@@ -196,6 +196,7 @@ class BEMProblem:
         self.gmres_orthogonalization = "CGS2"   # "MGS" = deal.II's modified Gram-Schmidt verbatim
         self.solver_control = SolverControl(1000, 1e-10)
         self.force_pole = (0.0, 0.0, 0.0)
+        self.host_prepass = False         # True: mass matrix / normals / rigid modes by the host code (bs_host_prepass)
         self.keep_VK = True
         self.fused_assembly = False    # True: never store K (bs_assemble_fused); body-only monolithic systems
         self.col_is_K = None           # per dof: True -> the unknown is a wall velocity, column -K (index-set logic 3194-3245)
@@ -315,8 +316,13 @@ class BEMProblem:
 
     # ---- pre-pass (host) --------------------------------------------------------------------------------
     def compute_center_of_mass_and_rigid_modes(self, frame=0):
-        self._pre = Prepass(self.map_mesh.nodes, self.map_mesh.conn.astype(np.int64), self.map_degree, self.N,
-                            self.mesh.conn.astype(np.int64), self.fe_degree, self.quadrature_order, self.force_pole)
+        """ref: bem_stokes.cc:2440-2788 (+ compute_normal_vector 3922-4011): on the device (bs_prepass); the host
+        restatement (bs_host_prepass) only when `host_prepass` is set."""
+        if self.host_prepass:
+            self._pre = Prepass(self.map_mesh.nodes, self.map_mesh.conn.astype(np.int64), self.map_degree, self.N,
+                                self.mesh.conn.astype(np.int64), self.fe_degree, self.quadrature_order, self.force_pole)
+        else:
+            self._pre = DevicePrepass(self._ctx, self.N, self.force_pole)
         self.N_rigid = self._pre.N_rigid
         self.N_rigid_dual = self._pre.N_rigid_dual
         self.support_points = self._pre.support_points

@@ -281,14 +281,13 @@ public:
     shape_velocities.assign(n_dofs, 0.);
   }
 
-  // host pre-pass (mass matrix, rigid modes, L2 normals): bem_stokes.cc:2440-2788, 3922-4011
+  // pre-pass (mass matrix, rigid modes, L2 normals) on the device: bem_stokes.cc:2440-2788, 3922-4011
   void compute_center_of_mass_and_rigid_modes(unsigned int /*frame*/ = 0) {
     normal_vector_pure.assign(n_dofs, 0.);
     M_normal_vector_pure.assign(n_dofs, 0.);
     std::vector<double> nr(6 * (size_t)n_dofs), nd(6 * (size_t)n_dofs);
-    check(bs_host_prepass(mesh.degree, mesh.degree, (int)N, euler_vec.data(), mesh.n_cells(), mesh.conn.data(), (int)N,
-                          mesh.conn.data(), (int)quadrature_order, nullptr, normal_vector_pure.data(), M_normal_vector_pure.data(),
-                          &l2normGamma_pure, nr.data(), nd.data(), &surface, nullptr));
+    check(bs_prepass(ctx, nullptr, normal_vector_pure.data(), M_normal_vector_pure.data(), &l2normGamma_pure, nr.data(),
+                     nd.data(), &surface, nullptr, nullptr));
     N_rigid.assign(6, Vector());
     N_rigid_dual.assign(6, Vector());
     for (int r = 0; r < 6; ++r) {

@@ -707,3 +707,43 @@ def test_sphere_rotation_real_grid(goldens):
     xo = np.linalg.solve(A, b)
     assert np.abs(p.monolithic_solution - xo).max() <= 1e-7 * np.abs(xo).max()
     p.close()
+
+
+@pytest.mark.parametrize("case", ["q1_half", "q2_cubesphere", "subparametric"])
+def test_device_prepass(half, case):
+    """bs_prepass (mass matrix, L2 normals, rigid modes on the device; bem_stokes.cc:2440-2788, 3922-4011) against
+    the oracle's dense solve and against the host restatement bs_host_prepass."""
+    pole = (0.1, -0.2, 0.3)
+    if case == "q1_half":
+        p = make_problem(half, force_pole=pole)
+        geo = bo.Geometry(half.nodes, half.conn.astype(np.int64), 1)
+    elif case == "q2_cubesphere":
+        m = bb.cubesphere(2, 2)
+        p = make_problem(m, force_pole=pole)
+        geo = bo.Geometry(m.nodes, m.conn.astype(np.int64), 2)
+    else:
+        q1 = bb.cubesphere(2, 1)
+        q2 = bb.to_q2(q1, 1.0)
+        p = bb.BEMProblem()
+        p.set_mesh(q1, q2)
+        p.quadrature_order, p.singular_quadrature_order, p.force_pole = 8, 10, pole
+        p.reinit()
+        p.compute_center_of_mass_and_rigid_modes()
+        p.compute_normal_vector()
+        geo = bo.Geometry(q1.nodes, q1.conn.astype(np.int64), 1, q2.nodes, q2.conn.astype(np.int64), 2)
+    dev = p._pre
+    assert isinstance(dev, bb.prepass.DevicePrepass) and 0 < dev.cg_iterations < 200
+    ora = bo.Prepass(geo, 8, pole)
+    host = bb.prepass.Prepass(p.map_mesh.nodes, p.map_mesh.conn.astype(np.int64), p.map_degree, p.N,
+                              p.mesh.conn.astype(np.int64), p.fe_degree, 8, pole)
+    for ref_nh, ref_mn, ref_l2, ref_area, ref_nr, ref_nd in [
+            (ora.nhat, ora.Mnhat, ora.l2, ora.area, ora.N_rigid, ora.N_rigid_dual),
+            (host.normal_vector_pure, host.M_normal_vector_pure, host.l2normGamma_pure, host.area, host.N_rigid, host.N_rigid_dual)]:
+        assert np.abs(dev.normal_vector_pure - ref_nh).max() <= 1e-12
+        assert np.abs(dev.M_normal_vector_pure - ref_mn).max() <= 1e-12 * np.abs(ref_mn).max() + 1e-15
+        assert abs(dev.l2normGamma_pure - ref_l2) <= 1e-12 * ref_l2
+        assert abs(dev.area - ref_area) <= 1e-12 * ref_area
+        assert np.abs(dev.N_rigid - ref_nr).max() <= 1e-13
+        assert np.abs(dev.N_rigid_dual - ref_nd).max() <= 1e-12 * np.abs(ref_nd).max()
+    assert np.abs(dev.support_points - geo.support).max() <= 1e-14
+    p.close()
