@@ -15,6 +15,7 @@ import numpy as np
 from . import _lib
 from ._lib import lib, check
 from .mesh import QuadMesh
+from .frontend import FrameLoop
 from .prepass import DevicePrepass, Prepass, gauss_1d
 
 
@@ -168,7 +169,7 @@ class SolverControl:
 
 
 # ---------------------------------------------------------------------------------------------------------------
-class BEMProblem:
+class BEMProblem(FrameLoop):
     def __init__(self, device=0, rank=0, nranks=1, comm=None, stream=None):
         self.device, self.this_mpi_process, self.n_mpi_processes = device, rank, nranks
         self.comm, self.stream = comm, stream
@@ -207,6 +208,7 @@ class BEMProblem:
         self.direct_trilinos_preconditioner = DirectPreconditioner()
         self.reassemble_preconditoner = False
         self.shape_velocities = None
+        self._init_frontend()   # frame loop / parameter file state (frontend.py)
 
     # ---- geometry ---------------------------------------------------------------------------------------
     def set_mesh(self, mesh: QuadMesh, map_mesh: QuadMesh = None):
@@ -468,6 +470,12 @@ class BEMProblem:
         else:
             self.solve_dn()
         self.rigid_total_forces = np.array([self.stokes_forces @ self.N_rigid_dual[r] for r in range(nr)])
+        # velocities are solved about the force pole; the reference reports them at the origin (4479-4492)
+        self.baricenter_rigid_velocities = self.rigid_velocities.copy()
+        pole = np.asarray(self.force_pole, dtype=float)
+        if nr >= 6 and np.any(pole != 0.0):
+            self.rigid_velocities = self.rigid_velocities.copy()
+            self.rigid_velocities[:3] += np.cross(self.baricenter_rigid_velocities[3:6], -pole)
         return self
 
     def dirichlet_to_neumann_operator(self, input_vel, output_force=None):

@@ -133,6 +133,15 @@ def main():
             os.chmod(dst, 0o644)
         else:
             print("missing", rel)
+    # ---- parameter files (input data of the front-end tests) ------------------------------------------
+    for rel in ["tests/parameters_test_alpha_box.prm", "tests/parameters_test_alpha_box_ref_quadrature.prm"]:
+        src = os.path.join(REF, rel)
+        if os.path.exists(src):
+            dst = os.path.join(HERE, os.path.basename(rel))
+            shutil.copy(src, dst)
+            os.chmod(dst, 0o644)
+        else:
+            print("missing", rel)
     print("wrote goldens:", len(table), "quadrature rows,", len(exact), "exact constants")
 
 

@@ -747,3 +747,41 @@ def test_device_prepass(half, case):
         assert np.abs(dev.N_rigid_dual - ref_nd).max() <= 1e-12 * np.abs(ref_nd).max()
     assert np.abs(dev.support_points - geo.support).max() <= 1e-14
     p.close()
+
+
+def test_frame_loop_run(tmp_path, goldens):
+    """BEMProblem::run (bem_stokes.cc:5636-5888) through the host front-end on the reference's two-frame swimmer
+    grids: frame 0 reproduces the golden of tests/sphere_translation.output, the state update integrates it, the
+    result files use deal.II's block_write format, and frame 1 (next frame = frame 0 again) swims back."""
+    from bemstokes_b200 import frontend as fe
+    p = bb.BEMProblem()
+    p.parse_parameters(os.path.join(os.path.dirname(MESHES), "parameters_test_alpha_box.prm"))
+    p.grid_type, p.use_internal_alpha = "Real", False
+    p.input_grid_path, p.input_grid_base_name, p.input_grid_format = MESHES, "sphere_translation_", "msh"
+    p.n_frames, p.time_step = 2, 0.1
+    p.solve_directly, p.preconditioner_type = False, "Direct"
+    p.output_dir = str(tmp_path)
+    p.log = lambda *_: None
+    res = p.run(0, 1)
+    G = goldens["sphere_translation"]
+    assert len(res) == 2 and res[0]["gmres_iterations"] == 1
+    U0, U1 = res[0]["rigid_velocities"], res[1]["rigid_velocities"]
+    assert abs(U0[0] - G["rigid_velocity_0"]) < 6e-8
+    assert np.abs(U0[1:]).max() < 1e-3
+    # frame 1: LU of frame 0 reused as preconditioner (a few iterations), shape velocity reversed
+    assert 1 <= res[1]["gmres_iterations"] <= 4
+    assert abs(U1[0] + U0[0]) < 2e-2 * abs(U0[0])
+    # rotation stays the identity up to the tiny angular velocities; displacement = dt * U
+    assert np.abs(res[1]["rotation_matrix"] - np.eye(3)).max() < 1e-3
+    d0 = fe.vector_block_read(os.path.join(p.output_dir, "stokes_rigid_displ_0.bin"))
+    N = p.N
+    assert np.abs(d0[:N] - 0.1 * U0[0]).max() < 1e-12 and np.abs(d0[N:]).max() < 1e-3
+    for name in ("stokes_forces_1.bin", "shape_velocities_1.bin", "total_velocities_1.bin", "rotation_matrix_1.bin",
+                 "4_6_rigid_velocities_1.bin", "4_6_overall_forces_1.bin", "stokes_rigid_vel_1.bin", "euler_vec_1.bin",
+                 "normal_vector1.bin", "point_0_on_proc_0_displacement_frame_1.txt"):
+        assert os.path.exists(os.path.join(p.output_dir, name)), name
+    assert np.array_equal(fe.vector_block_read(os.path.join(p.output_dir, "4_6_rigid_velocities_0.bin")), U0)
+    # swimmer force free: total force and torque vanish
+    assert np.abs(res[0]["rigid_total_forces"]).max() < 1e-8
+    assert np.abs(p.final_test).max() < 1e-8
+    p.close()
