@@ -503,7 +503,7 @@ int bs_correct_K(bs_context *h, int use_internal_alpha) {
   Timer t(c, c.stats.correct_ms, "bs_correct_K");
   Mark mark(c);
   const size_t n = c.n3();
-  const size_t ldx = (n + 2) & ~(size_t)1;
+  const size_t ldx = (n + 4) & ~(size_t)3;  // multiple of 4: 32-byte vector loads in the tensor-path sweep
   std::vector<double> E(3 * ldx, 0.0);
   for (size_t p = 0; p < (size_t)c.N; ++p)
     for (int k = 0; k < 3; ++k) E[k * ldx + 3 * p + k] = 1.0;
@@ -542,7 +542,7 @@ int bs_build_monolithic(bs_context *h, const unsigned char *col_is_K, int num_ri
   c.mono_size = n + nr;
   const bool last = (c.rank == c.nranks - 1);
   // ---- P N_r and P u_shape on the host (O(n) work, inputs of the boundary), then K * panel on the device
-  const size_t ldx = (n + 2) & ~(size_t)1;
+  const size_t ldx = (n + 4) & ~(size_t)3;  // multiple of 4: 32-byte vector loads in the tensor-path sweep
   std::vector<double> X((size_t)nvec * ldx, 0.0);
   auto project_into = [&](const double *v, double *dst_int) {
     double d = 0;
@@ -700,7 +700,7 @@ int bs_vmult_multi(bs_context *h, int which, int nrhs, const double *X, double *
   Extra &e = extra(c);
   const int nx = nextra_of(c, which);
   const size_t m = c.full_vec_len(which), mloc = c.local_vec_len(which);
-  const size_t ldx = (m + 2) & ~(size_t)1;
+  const size_t ldx = (m + 4) & ~(size_t)3;
   e.vin.alloc(std::max(e.vin.n, (size_t)nrhs * ldx));
   e.vout.alloc(std::max(e.vout.n, (size_t)nrhs * ldx));
   for (int k = 0; k < nrhs; ++k) to_internal(c, X + (size_t)k * m, nx, e.vin.p + (size_t)k * ldx);
@@ -1073,7 +1073,7 @@ int bs_bench_vmult_multi(bs_context *h, int which, int nrhs, int repeats, double
   BS_REQUIRE(M.valid() && repeats > 0 && nrhs >= 1, "matrix not available");
   Extra &e = extra(c);
   const size_t m = c.full_vec_len(which);
-  const size_t ldx = (m + 3) & ~(size_t)1;
+  const size_t ldx = (m + 4) & ~(size_t)3;
   e.vin.alloc(std::max(e.vin.n, (size_t)nrhs * ldx));
   e.vout.alloc(std::max(e.vout.n, (size_t)nrhs * ldx));
   fill(c, e.vin.p, 1.0, (size_t)nrhs * ldx);

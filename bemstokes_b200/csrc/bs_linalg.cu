@@ -11,7 +11,7 @@ namespace bs {
 // One warp owns RPW consecutive rows (x is re-used from registers across them), lanes stride the columns.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int GEMV_WARPS = 8;
-constexpr int GEMV_RPW = 4;
+constexpr int GEMV_RPW = 2;  // rows per warp: 2 streams 7.2 TB/s, 4 only 6.6 TB/s (measured, 87 GB matrix)
 
 __device__ __forceinline__ double2 ld_stream2(const double *p) {
   double2 v;
@@ -160,6 +160,117 @@ static void launch_gemv_multi(Context &c, const DMat &M, const double *X, size_t
   count_launch(c);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Multi-RHS sweep on the FP64 tensor path: Y[n][rows] = A[rows x cols] * X[n][cols]^T for 4 <= n <= 8 right-hand sides
+// (batched rigid-body resistance solves, projected rigid columns).  DMMA m8n8k4: a warp owns MB blocks of 8 matrix
+// rows (see k_gemm_dmma); the L1/LSU traffic for the vectors is 1/MB of the matrix stream instead of n times it
+// (k_gemv_multi).  The columns are split over gridDim.y for enough warps in flight; k_sum_ksplit adds the partial
+// results in fixed order.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+constexpr int DMMA_WARPS = 4;
+
+// Lane (g = lane/4, kk = lane%4) streams A[row g][k0 + 2kk, +1] with one 16-byte load per 8-row block and step and
+// feeds the two elements to two MMAs whose k-slot kk stands for column k0+2kk resp. k0+2kk+1 (the sum over k does not
+// care about the order); the B fragments X[g][k0 + 2kk, +1] are one 16-byte load per step shared by all MB blocks.
+// (Measured: 32-byte LDG.256 loads - a full line per row and instruction - are slower here, 15.9 vs 14.5 ms.)
+template <int MB, int U>
+__global__ void __launch_bounds__(32 * DMMA_WARPS) k_gemm_dmma(const double *__restrict__ A, size_t ld, size_t rows, size_t cols,
+                                                              const double *__restrict__ X, size_t ldx, int nrhs,
+                                                              double *__restrict__ P, size_t ldp, size_t kchunk) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, kk = lane & 3;
+  const size_t warp = (size_t)blockIdx.x * DMMA_WARPS + (threadIdx.x >> 5);
+  const size_t r0 = warp * (8 * MB);
+  if (r0 >= rows) return;
+  const size_t kbeg = (size_t)blockIdx.y * kchunk, kend = min(cols, kbeg + kchunk);  // kchunk is a multiple of 8
+  const double *a[MB];
+#pragma unroll
+  for (int mb = 0; mb < MB; ++mb) a[mb] = A + min(r0 + 8 * mb + g, rows - 1) * ld + 2 * kk;
+  const bool xon = g < nrhs;
+  const double *x = X + (size_t)(xon ? g : 0) * ldx + 2 * kk;
+  double c[MB][2][2];
+#pragma unroll
+  for (int mb = 0; mb < MB; ++mb) c[mb][0][0] = c[mb][0][1] = c[mb][1][0] = c[mb][1][1] = 0.0;
+  size_t k0 = kbeg;
+  for (; k0 + 8 * U <= kend; k0 += 8 * U) {  // full steps: no masking
+    double2 av[U][MB], xv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) av[u][mb] = ld_stream2(a[mb] + k0 + 8 * u);
+      xv[u] = xon ? *reinterpret_cast<const double2 *>(x + k0 + 8 * u) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) {
+        dmma_m8n8k4(c[mb][0][0], c[mb][0][1], av[u][mb].x, xv[u].x);
+        dmma_m8n8k4(c[mb][1][0], c[mb][1][1], av[u][mb].y, xv[u].y);
+      }
+  }
+  for (; k0 < kend; k0 += 8) {  // tail: the matrix is zero padded up to ld, the vectors are masked
+    const size_t col = k0 + 2 * kk;
+    double2 xv = make_double2(0.0, 0.0);
+    if (xon && col < kend) xv.x = x[k0];
+    if (xon && col + 1 < kend) xv.y = x[k0 + 1];
+#pragma unroll
+    for (int mb = 0; mb < MB; ++mb) {
+      const double2 av = ld_stream2(a[mb] + k0);
+      dmma_m8n8k4(c[mb][0][0], c[mb][0][1], av.x, xv.x);
+      dmma_m8n8k4(c[mb][1][0], c[mb][1][1], av.y, xv.y);
+    }
+  }
+  // C fragment: lane holds rows g, right-hand sides 2kk and 2kk+1
+  double *Pk = P + (size_t)blockIdx.y * 8 * ldp;
+#pragma unroll
+  for (int mb = 0; mb < MB; ++mb) {
+    const size_t row = r0 + 8 * mb + g;
+    if (row < rows) {
+      if (2 * kk < nrhs) Pk[(size_t)(2 * kk) * ldp + row] = c[mb][0][0] + c[mb][1][0];
+      if (2 * kk + 1 < nrhs) Pk[(size_t)(2 * kk + 1) * ldp + row] = c[mb][0][1] + c[mb][1][1];
+    }
+  }
+}
+
+__global__ void k_sum_ksplit(size_t rows, int nrhs, int ksplit, const double *__restrict__ P, size_t ldp, double *__restrict__ Y,
+                             size_t ldy) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (i >= rows || n >= nrhs) return;
+  double s = 0.0;
+  for (int k = 0; k < ksplit; ++k) s += P[((size_t)k * 8 + n) * ldp + i];
+  Y[(size_t)n * ldy + i] = s;
+}
+
+#ifndef BS_DMMA_MB
+#define BS_DMMA_MB 2
+#endif
+#ifndef BS_DMMA_U
+#define BS_DMMA_U 4
+#endif
+
+static void gemm_dmma(Context &c, const DMat &M, int nrhs, const double *X, size_t ldx, double *Y, size_t ldy) {
+  constexpr int MB = BS_DMMA_MB, U = BS_DMMA_U;
+  const size_t row_warps = (M.rows + 8 * MB - 1) / (8 * MB);
+  const unsigned gx = (unsigned)((row_warps + DMMA_WARPS - 1) / DMMA_WARPS);
+  // enough CTAs for ~8 waves of 16 per SM; at least 2048 columns per chunk
+  int ksplit = (int)std::min<size_t>(16, std::max<size_t>(1, ((size_t)c.sm_count * 16 * 8 + gx - 1) / gx));
+  ksplit = (int)std::min<size_t>(ksplit, std::max<size_t>(1, M.cols / 2048));
+  size_t kchunk = (M.cols + ksplit - 1) / ksplit;
+  kchunk = (kchunk + 7) & ~(size_t)7;
+  ksplit = (int)((M.cols + kchunk - 1) / kchunk);
+  const size_t ldp = (M.rows + 1) & ~(size_t)1;
+  double *P = c.wsd("gemm.partial", (size_t)ksplit * 8 * ldp);
+  k_gemm_dmma<MB, U><<<dim3(gx, ksplit), 32 * DMMA_WARPS, 0, c.stream>>>(M.p, M.ld, M.rows, M.cols, X, ldx, nrhs, P, ldp, kchunk);
+  BS_CUDA(cudaGetLastError());
+  k_sum_ksplit<<<dim3((unsigned)((M.rows + 255) / 256), nrhs), 256, 0, c.stream>>>(M.rows, nrhs, ksplit, P, ldp, Y, ldy);
+  BS_CUDA(cudaGetLastError());
+  count_launch(c, 2);
+}
+
 void gemv_multi(Context &c, const DMat &M, int nrhs, const double *X, size_t ldx, double *Y, size_t ldy) {
   if (M.rows == 0) return;
   BS_REQUIRE((ldx & 1) == 0, "multi-vector ld must be even");
@@ -168,6 +279,13 @@ void gemv_multi(Context &c, const DMat &M, int nrhs, const double *X, size_t ldx
     const int nr = std::min(8, nrhs - done);
     const double *Xp = X + (size_t)done * ldx;
     double *Yp = Y + (size_t)done * ldy;
+    const bool aligned16 = (ldx % 2 == 0) && (reinterpret_cast<uintptr_t>(Xp) % 16 == 0) && (M.ld % 8 == 0) &&
+                           (reinterpret_cast<uintptr_t>(M.p) % 16 == 0);
+    if (nr >= 4 && aligned16 && !std::getenv("BS_NO_DMMA")) {  // FP64 tensor path; up to 3 right-hand sides the FMA kernel is HBM bound
+      gemm_dmma(c, M, nr, Xp, ldx, Yp, ldy);
+      done += nr;
+      continue;
+    }
     switch (nr) {
       case 1: launch_gemv_multi<1>(c, M, Xp, ldx, Yp, ldy); break;
       case 2: launch_gemv_multi<2>(c, M, Xp, ldx, Yp, ldy); break;

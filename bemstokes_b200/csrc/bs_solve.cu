@@ -659,7 +659,7 @@ int gmres_batched(Context &c, int which, int nrhs, const double *d_B, double *d_
   BS_REQUIRE(nrhs >= 1, "nrhs must be positive");
   const int m = max_tmp - 2;  // restart length (deal.II: n_tmp_vectors - 2 inner iterations)
   const size_t mloc = c.local_vec_len(which), mfull = c.full_vec_len(which);
-  const size_t ldw = (mloc + 3) & ~(size_t)1, ldx = (mfull + 3) & ~(size_t)1;
+  const size_t ldw = (mloc + 3) & ~(size_t)1, ldx = (mfull + 4) & ~(size_t)3;
   const size_t CS = (size_t)2 * (m + 2) + 2;
   const DMat &M = mat_of(c, which);
   struct P_ { double *p; } basis, w, z, coef, xfull;  // context-owned, grow-only (no cudaMalloc per solve)
