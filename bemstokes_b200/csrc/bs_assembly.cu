@@ -171,7 +171,10 @@ constexpr int ACC_LD = TI + 1;  // padded row-node stride of the shared accumula
 __host__ __device__ inline int acc_vstride(int tj) { return tj * ACC_LD + 5; }
 
 // cell records in flight per CTA (bulk-copy ring): 3 when a record is small, else 2
-__host__ __device__ inline int cell_stages(int nq_pad) { return nq_pad <= 64 ? 3 : 2; }
+#ifndef BS_CELL_STAGES
+#define BS_CELL_STAGES 3
+#endif
+__host__ __device__ inline int cell_stages(int nq_pad) { return nq_pad <= 64 ? BS_CELL_STAGES : 2; }
 // doubles reserved for the 1-D shape table and its x-flipped copy (2 * (degree+1) * n1d <= max(nq_pad, 96))
 __host__ __device__ inline int l1d_doubles(int nq_pad) { return nq_pad > 96 ? nq_pad : 96; }
 
@@ -532,8 +535,11 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
   const int vpart = (VS == 2) ? t / (TI * QS) : 0;   // warp-uniform role: 0 single layer, 1 double layer
   const int tt = t - vpart * (TI * QS);
   const int rl = tt / QS, part = tt - rl * QS;
-  const int blk = P.blk_begin + blockIdx.x;
-  const int p = P.p0 + blockIdx.y * TI + rl;
+  // row tile fastest: co-resident CTAs integrate the same cell block for different rows, so its cell records and
+  // metadata stay in L1/L2 instead of being re-streamed from HBM per row tile
+  const unsigned bx = blockIdx.y, by = blockIdx.x;
+  const int blk = P.blk_begin + bx;
+  const int p = P.p0 + by * TI + rl;
   const bool row_ok = p < P.p1;
   const int cs = P.blk_cell_ptr[blk], ce = P.blk_cell_ptr[blk + 1];
   const uint32_t cell_bytes = (uint32_t)(CQ * nqp * sizeof(double));
@@ -628,7 +634,7 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
   // Each warp takes whole matrix rows; its lanes walk the 3*tj tile columns of the row in (slot, component) order,
   // so runs of consecutive node positions become contiguous 8-byte stores / reductions (node positions ascend
   // within a block).  Per-lane column metadata lives in registers: no division or metadata load in the loop.
-  const int rows_tile = min(TI, P.p1 - (P.p0 + (int)blockIdx.y * TI));
+  const int rows_tile = min(TI, P.p1 - (P.p0 + (int)by * TI));
   const int *nodes = P.blk_nodes + (size_t)blk * tj;
   const unsigned char *first = P.blk_first + (size_t)blk * tj;
   const int lane = t & 31, warp = t >> 5;
@@ -652,7 +658,7 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
   for (int r_ = warp; r_ < rows_tile; r_ += NWARP) {
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      const size_t rowoff = ((size_t)3 * (blockIdx.y * TI + r_) + i) * P.ld;
+      const size_t rowoff = ((size_t)3 * (by * TI + r_) + i) * P.ld;
       double *vrow = P.V + rowoff, *krow = FUSED ? nullptr : P.K + rowoff;
 #pragma unroll
       for (int sidx = 0; sidx < MAXSTEP; ++sidx) {
@@ -710,7 +716,7 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
       }
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        double *dst = P.KX + ((size_t)3 * (blockIdx.y * TI + r_) + i) * pp + h_ * PSH;
+        double *dst = P.KX + ((size_t)3 * (by * TI + r_) + i) * pp + h_ * PSH;
 #pragma unroll
         for (int q = 0; q < PSH; ++q)
           if (h_ * PSH + q < pp) asm volatile("red.global.add.f64 [%0], %1;" ::"l"(dst + q), "d"(y[i][q]) : "memory");
@@ -737,10 +743,12 @@ static void launch_reg(Context &c, RegParams P, int nrow_tiles, size_t smem) {
   for (size_t k = 0; k + 1 < cs.size(); ++k) {  // one launch per colour, stream order = summation order
     const int nb = cs[k + 1] - cs[k];
     if (nb <= 0) continue;
-    P.blk_begin = cs[k];
-    kern<<<dim3(nb, nrow_tiles), TI * QS * VS, smem, c.stream>>>(P);
-    BS_CUDA(cudaGetLastError());
-    count_launch(c);
+    for (int b0 = 0; b0 < nb; b0 += 65535) {  // gridDim.y limit
+      P.blk_begin = cs[k] + b0;
+      kern<<<dim3(nrow_tiles, std::min(nb - b0, 65535)), TI * QS * VS, smem, c.stream>>>(P);
+      BS_CUDA(cudaGetLastError());
+      count_launch(c);
+    }
   }
 }
 
@@ -773,7 +781,7 @@ void launch_assembly_regular(Context &c) {
   P.pp = c.panel_p;
   const int nrow_tiles = (c.p1 - c.p0 + TI - 1) / TI;
   if (nrow_tiles == 0) return;
-  BS_REQUIRE(nrow_tiles <= 65535, "too many row tiles per rank");
+  
   const int grid = nrow_tiles;
   const int nv = (c.kp.type == BS_KERNEL_FREE) ? 6 : 9;
   const size_t smem = assembly_smem_bytes(c.na, nv, c.blocks.tj, c.nq_pad);
