@@ -50,6 +50,11 @@ def workload(args, nranks):
         r = args.refine if args.refine is not None else 4
         return dict(kind="cubesphere", m=2 ** r, degree=2, quad=15, sing=20, fused=False,
                     name="BASELINE config 3: cube-sphere (sphere_2.inp topology) refined %dx, Q2, Gauss 15 / Mixed 20" % r)
+    if args.workload == "c5":
+        m = args.m if args.m else int(round(64 * nranks ** 0.25))
+        return dict(kind="cubesphere", m=m, degree=1, quad=8, sing=10, fused=False, kernel="free_surface",
+                    name="BASELINE config 5 kernel: synthetic cube-sphere m=%d, Q1, Gauss 8 / Lachat-Watson 10, "
+                         "FreeSurfaceStokesKernel (image system, wall y = 1.4), V and K both stored" % m)
     if args.workload == "vk":
         m = args.m if args.m else int(round(64 * nranks ** 0.25))
         return dict(kind="cubesphere", m=m, degree=1, quad=8, sing=10, fused=False,
@@ -158,6 +163,8 @@ def run_ours(args):
     p = bb.BEMProblem(device=local, rank=rank, nranks=world, comm=comm, stream=stream)
     p.set_mesh(mesh)
     p.quadrature_order, p.singular_quadrature_order = wl["quad"], wl["sing"]
+    if wl.get("kernel") == "free_surface":   # tests/parameters_test_alpha_box.prm: wall 0 spans 80,0,80 at y = 1.4
+        p.reflect_kernel, p.wall_spans_0, p.wall_position_0 = True, (80.0, 0.0, 80.0), (0.0, 1.4, 0.0)
     p.grid_type, p.imposed_component = "ImposedVelocity", 0
     p.solve_directly, p.preconditioner_type = False, "None"
     p.keep_VK = False  # A aliases V's storage
@@ -288,7 +295,7 @@ def run_ours(args):
         nq = wl["quad"] ** 2
         sing_pts = sum(lib.bs_make_singular_rule(_lib.SING_MIXED, wl["sing"], wl["degree"], a, 0, None, None) for a in range(na))
         pr, ps = pairs_count(N, ncell, nq, sing_pts)
-        f_pair = 50 + 24 * na
+        f_pair = (95 + 36 * na) if wl.get("kernel") == "free_surface" else (50 + 24 * na)
         asm_tflops = (pr + ps) * f_pair / (asm_ms * 1e-3) / 1e12   # whole job (all ranks assemble concurrently)
         mv_bytes = 8.0 * (n + 6) * (n + 6)                          # whole job: every rank streams its row block
         mv_gbs_job = mv_bytes / (mv_ms * 1e-3) / 1e9
@@ -415,7 +422,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c4", choices=["c4", "vk", "q2"])
+    ap.add_argument("--workload", default="c4", choices=["c4", "vk", "q2", "c5"])
     ap.add_argument("--no-peer-exchange", action="store_true", help="multi-GPU: NCCL allgather callbacks instead of NVLink peer stores")
     ap.add_argument("--no-fused", action="store_true", help="c4 family with V and K both stored (needs 2x the memory)")
     ap.add_argument("--subdiv", dest="m", type=int, default=0, help="cube-sphere subdivisions per face edge (default 128*(N/8)^(1/4); 64*N^(1/4) for --workload vk)")
