@@ -1,13 +1,16 @@
 // Collocation assembly of V (single layer) and K (double layer) on sm_100a — replaces the (cell, node, q)
 // loop nest of BEMProblem::assemble_stokes_system (ref: source/bem_stokes.cc:2871-3000).
 //
-//   K0  k_cell_geometry      FEValues::reinit for every cell with the regular rule: y_q, n_q*JxW_q, JxW_q
-//   K1  k_assemble_regular   CTA tile = 128 collocation nodes (one per thread) x one column block of TJ
-//                            nodes; the cells touching the block are streamed through shared memory by
-//                            bulk-async copies (TMA engine, mbarrier-tracked, double buffered); per-thread
-//                            register accumulators over q, per-CTA shared-memory accumulators over cells,
-//                            one coalesced vectorised write of the finished V/K tile (no atomics, no
-//                            read-modify-write of HBM, deterministic summation order).
+//   K0  k_cell_geometry      FEValues::reinit for every cell with the regular rule: y_q, n_q*JxW_q, JxW_q (and a
+//                            point-major copy with the constants folded in for the free-space fast path)
+//   K1  k_assemble_regular   CTA tile = TI (64) collocation nodes x one cell block (<= tj nodes, disjoint cells,
+//                            coloured); QS threads per node split the rows of the tensor rule; the block's cells are
+//                            streamed through shared memory by bulk-async copies (TMA engine) in a full/empty
+//                            mbarrier ring; per-thread sum-factorised register accumulators over q (free-space
+//                            kernel: software-pipelined 55-instruction formulation), per-CTA shared-memory tile over
+//                            cells, one coalesced write-out per CTA: plain stores where this colour is the first to
+//                            touch a node column, RED.ADD.F64 otherwise (colours are separate launches -> fixed
+//                            summation order); fused variant multiplies the K tile with the panel instead of storing it
 //   K2  k_assemble_singular  one warp per owned collocation node: the cells containing the node are
 //                            integrated with the singular rule of that local index (geometry evaluated on
 //                            the fly) and added to the node's three rows.

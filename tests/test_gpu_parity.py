@@ -788,3 +788,28 @@ def test_frame_loop_run(tmp_path, goldens):
     assert np.abs(res[0]["rigid_total_forces"]).max() < 1e-8
     assert np.abs(p.final_test).max() < 1e-8
     p.close()
+
+
+def test_frame_loop_heun(tmp_path):
+    """Heun predictor-corrector of BEMProblem::run (bem_stokes.cc:5780-5830): the corrector integrates the mean of the
+    velocities at frame i and i+1; on the two-frame translation grids the second is the reversed stroke, so the mean
+    nearly cancels."""
+    def make(strategy):
+        p = bb.BEMProblem()
+        p.parse_parameters(os.path.join(os.path.dirname(MESHES), "parameters_test_alpha_box.prm"))
+        p.grid_type, p.use_internal_alpha, p.res_strategy = "Real", False, strategy
+        p.input_grid_path, p.input_grid_base_name, p.input_grid_format = MESHES, "sphere_translation_", "msh"
+        p.n_frames, p.time_step, p.solve_directly = 2, 0.1, True
+        p.output_dir = str(tmp_path)
+        p.log = lambda *_: None
+        return p
+    pf = make("Forward")
+    U0 = pf.run(0, 0)[0]["rigid_velocities"]
+    pf.close()
+    ph = make("Heun")
+    res = ph.run(0, 0)
+    Um = res[0]["rigid_velocities"]
+    assert abs(U0[0]) > 0.08 and abs(Um[0]) < 2e-2 * abs(U0[0])
+    assert np.abs(ph.old_rigid_velocities - U0).max() < 1e-12          # predictor = the Forward solve
+    assert np.abs(res[0]["rotation_matrix"] - np.eye(3)).max() < 1e-3
+    ph.close()
