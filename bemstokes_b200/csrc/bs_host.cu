@@ -433,6 +433,12 @@ void build_tables(Context &c) {
     ckey[cell] = m;
   }
   std::stable_sort(corder.begin(), corder.end(), [&](int x, int y) { return ckey[x] < ckey[y]; });
+  // cell centroids: the growth prefers, among the cheapest candidates, the one closest to the block's centre, which
+  // turns 2x4 strips into 3x3 patches (more cells per tile, fewer shared node columns)
+  std::vector<double> ccen((size_t)3 * c.ncell, 0.0);
+  for (int cell = 0; cell < c.ncell; ++cell)
+    for (int a = 0; a < na; ++a)
+      for (int d = 0; d < 3; ++d) ccen[(size_t)3 * cell + d] += c.support[(size_t)3 * c.conn[(size_t)cell * na + a] + d] / na;
   std::vector<int> block_of(c.ncell, -1);
   std::vector<std::vector<int>> bcells, bnodes;
   std::vector<int> mark(c.N, -1);  // mark[node] == current block id when the node is in the block
@@ -441,9 +447,11 @@ void build_tables(Context &c) {
     const int b = (int)bcells.size();
     bcells.emplace_back();
     bnodes.emplace_back();
+    double bsum[3] = {0, 0, 0};  // sum of the centroids of the block's cells
     auto add_cell = [&](int cell) {
       block_of[cell] = b;
       bcells[b].push_back(cell);
+      for (int d = 0; d < 3; ++d) bsum[d] += ccen[(size_t)3 * cell + d];
       for (int a = 0; a < na; ++a) {
         const int p = cpos[(size_t)cell * na + a];
         if (mark[p] != b) {
@@ -454,8 +462,10 @@ void build_tables(Context &c) {
     };
     add_cell(seed);
     while (true) {
-      // candidate = unassigned neighbour cell adding the fewest new nodes (ties: most shared nodes, lowest key)
+      // candidate = unassigned neighbour cell adding the fewest new nodes (ties: closest to the block centre, lowest key)
       int best = -1, best_new = 1 << 30, best_key = 1 << 30;
+      double best_d2 = 1e300;
+      const double inv = 1.0 / (double)bcells[b].size();
       for (size_t in = 0; in < bnodes[b].size(); ++in) {
         const int p = bnodes[b][in];
         for (int e = nptr[p]; e < nptr[p + 1]; ++e) {
@@ -463,10 +473,17 @@ void build_tables(Context &c) {
           if (block_of[cell] >= 0) continue;
           int nn = 0;
           for (int a = 0; a < na; ++a) nn += (mark[cpos[(size_t)cell * na + a]] != b);
-          if (nn < best_new || (nn == best_new && ckey[cell] < best_key)) {
+          double d2 = 0;
+          for (int d = 0; d < 3; ++d) {
+            const double t = ccen[(size_t)3 * cell + d] - bsum[d] * inv;
+            d2 += t * t;
+          }
+          const bool closer = d2 < best_d2 * (1.0 - 1e-9), same = !closer && d2 <= best_d2 * (1.0 + 1e-9);
+          if (nn < best_new || (nn == best_new && (closer || (same && ckey[cell] < best_key)))) {
             best = cell;
             best_new = nn;
             best_key = ckey[cell];
+            best_d2 = d2;
           }
         }
       }
