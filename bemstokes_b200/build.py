@@ -33,7 +33,8 @@ def build(force=False, verbose=False):
     log = []
     for s, p in procs:
         out = p.communicate()[0]
-        log.append("== %s ==\n%s" % (s, out))
+        keep = [ln for ln in out.splitlines() if "Compile time" not in ln]  # stable report: no timing noise
+        log.append("== %s ==\n%s" % (s, "\n".join(keep)))
         if p.returncode != 0:
             sys.stderr.write(out)
             raise RuntimeError("nvcc failed on %s" % s)
