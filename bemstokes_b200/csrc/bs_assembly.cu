@@ -555,6 +555,11 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
       mbar_init(&empty[i], NT / 32);  // one arrival per warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // first records of the ring right away: their HBM latency hides behind the tile clear and the metadata staging
+    for (int i = 0; i < ns - 1 && cs + i < ce; ++i) {
+      mbar_expect_tx(&full[i], cell_bytes);
+      bulk_g2s(cellbuf + (size_t)i * CQ * nqp, cell_src + (size_t)P.blk_cells[cs + i] * CQ * nqp, cell_bytes, &full[i]);
+    }
   }
   for (int i = t; i < n1 * NB1; i += NT) {
     const double l = P.l1d[i];
@@ -569,12 +574,6 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
   }
   for (int i = t; i < NV2 * acc_vstride(tj); i += NT) acc_s[i] = 0.0;
   __syncthreads();
-  if (t == 0) {
-    for (int i = 0; i < ns - 1 && cs + i < ce; ++i) {
-      mbar_expect_tx(&full[i], cell_bytes);
-      bulk_g2s(cellbuf + (size_t)i * CQ * nqp, cell_src + (size_t)s_cells[i] * CQ * nqp, cell_bytes, &full[i]);
-    }
-  }
   double x[3] = {0, 0, 0};
   if (row_ok) {
     x[0] = P.support[(size_t)3 * p];
@@ -642,33 +641,41 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
   const unsigned char *first = P.blk_first + (size_t)blk * tj;
   const int lane = t & 31, warp = t >> 5;
   constexpr int NWARP = NT / 32;
-  constexpr int MAXSTEP = 3;  // 3*tj <= 96 columns
+  // A warp takes two consecutive row nodes at a time and its lanes walk the 2 * 3*tj tile columns of the pair, so
+  // that the 48 columns of a 16-node block fill three warp steps completely instead of 2 x (32 + 16) lanes.
+  constexpr int MAXSTEP = 6;  // 2 * 3*tj <= 192 columns
   const int vs = acc_vstride(tj);
-  // per-lane column metadata, loop invariant: shared-tile offset of the value for each matrix-row component i,
-  // global column, and what to do with it (0 nothing, 1 store, 2 reduce) -- the row loop below is branch free
+  const int E = 3 * tj;
+  // per-lane column metadata, loop invariant: shared-tile offset of the value for each matrix-row component i (+ row
+  // of the pair), global column, and what to do with it (0 nothing, 1 store, 2 reduce) -- the row loop is branch free
   int soff[MAXSTEP][3], gcol[MAXSTEP], todo[MAXSTEP];
+  bool second[MAXSTEP];
 #pragma unroll
   for (int sidx = 0; sidx < MAXSTEP; ++sidx) {
-    const int e = lane + 32 * sidx;
+    const int e2 = lane + 32 * sidx;
+    second[sidx] = e2 >= E;
+    const int e = e2 - (second[sidx] ? E : 0);
     const int sl = e / 3, j = e - 3 * sl;
-    const int node = (e < 3 * tj) ? nodes[sl] : -1;
+    const int node = (e2 < 2 * E) ? nodes[sl] : -1;
     const bool valid = node >= 0;
     todo[sidx] = valid ? (first[sl] != 0 ? 1 : 2) : 0;
     gcol[sidx] = valid ? 3 * node + j : 0;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) soff[sidx][i] = valid ? vidx<NV>(i, j) * vs + sl * ACC_LD : 0;
+    for (int i = 0; i < 3; ++i) soff[sidx][i] = valid ? vidx<NV>(i, j) * vs + sl * ACC_LD + (second[sidx] ? 1 : 0) : 0;
   }
-  for (int r_ = warp; r_ < rows_tile; r_ += NWARP) {
+  for (int r_ = 2 * warp; r_ < rows_tile; r_ += 2 * NWARP) {
+    const bool has2 = r_ + 1 < rows_tile;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const size_t rowoff = ((size_t)3 * (by * TI + r_) + i) * P.ld;
-      double *vrow = P.V + rowoff, *krow = FUSED ? nullptr : P.K + rowoff;
 #pragma unroll
       for (int sidx = 0; sidx < MAXSTEP; ++sidx) {
-        if (32 * sidx >= 3 * tj) break;  // warp-uniform
+        if (32 * sidx >= 2 * E) break;  // warp-uniform
+        const size_t off = rowoff + (second[sidx] ? (size_t)3 * P.ld : 0) + gcol[sidx];
+        const int what = (second[sidx] && !has2) ? 0 : todo[sidx];
         const double *as = acc_s + soff[sidx][i] + r_;
-        store_or_reduce(vrow + gcol[sidx], as[0], todo[sidx]);
-        if (!FUSED) store_or_reduce(krow + gcol[sidx], as[(size_t)NV * vs], todo[sidx]);
+        store_or_reduce(P.V + off, as[0], what);
+        if (!FUSED) store_or_reduce(P.K + off, as[(size_t)NV * vs], what);
       }
     }
   }
