@@ -181,18 +181,26 @@ __host__ __device__ inline int cell_stages(int nq_pad) { return nq_pad <= 64 ? B
 // doubles reserved for the 1-D shape table and its x-flipped copy (2 * (degree+1) * n1d <= max(nq_pad, 96))
 __host__ __device__ inline int l1d_doubles(int nq_pad) { return nq_pad > 96 ? nq_pad : 96; }
 
-size_t assembly_smem_bytes(int na, int nv, int tj, int nq_pad) {
+// Value planes of the shared tile: V and K together, except for the Q1 image kernels, which integrate the two layers
+// in two launches (LAYER 1, 2) so that a 9-value tile still covers a 16-node block.
+int tile_planes(int na, int kernel_type) {
+  const int nv = (kernel_type == BS_KERNEL_FREE) ? 6 : 9;
+  return (na == 4 && kernel_type != BS_KERNEL_FREE) ? nv : 2 * nv;
+}
+
+size_t assembly_smem_bytes(int na, int planes, int tj, int nq_pad) {
   (void)na;
-  return (size_t)2 * nv * acc_vstride(tj) * 8 + (size_t)cell_stages(nq_pad) * 8 * nq_pad * 8 +
-         (size_t)l1d_doubles(nq_pad) * 8 + 64;  // dynamic part: tile, cell ring, shape table, mbarriers
+  size_t ring = (size_t)cell_stages(nq_pad) * 8 * nq_pad * 8;
+  ring = std::max(ring, (size_t)3 * tj * MAX_PANEL * 8);  // K-only launches stage the fused panel rows in the ring
+  return (size_t)planes * acc_vstride(tj) * 8 + ring + (size_t)l1d_doubles(nq_pad) * 8 + 64;  // tile, ring, shape table, mbarriers
 }
 
 int choose_tj(int na, int kernel_type, int nq_pad) {
-  const int nv = (kernel_type == BS_KERNEL_FREE) ? 6 : 9;
+  const int planes = tile_planes(na, kernel_type);
   const size_t budget = (227 * 1024) / CTAS_PER_SM - 1024 - 1024;  // minus static arrays (768 B) / per-CTA reserve
   int tj = 2;
   for (int t = 2; t <= 32; t += 2)
-    if (assembly_smem_bytes(na, nv, t, nq_pad) <= budget) tj = t;
+    if (assembly_smem_bytes(na, planes, t, nq_pad) <= budget) tj = t;
   return tj;
 }
 
@@ -419,14 +427,14 @@ __device__ __forceinline__ void integrate_free(const double *__restrict__ c8, co
 // the rule; then the QS partial sums of a row (adjacent lanes) are combined by shuffles and lane `part` adds its
 // share of the shape functions into the shared tile [value][slot][row].
 // FAST: free-space kernel without regularisation, `cq` is the point-major prescaled record.
-template <int NA, int KT, int MODE, int QS, bool HAS_EPS, bool FAST, int N1C>
+template <int NA, int KT, int MODE, int QS, bool HAS_EPS, bool FAST, int N1C, bool KLOW = false>
 __device__ __forceinline__ void cell_pass(const double *__restrict__ cq, const double *__restrict__ l1d_s, int n1, int nqp,
                                           const double (&x)[3], const double (&xim)[3], double eps, int o, bool ok,
                                           int part, const int (&slot)[NA], double *__restrict__ acc_s, int tj, int rl) {
   constexpr int NV = GreenTraits<KT>::NV;
   constexpr int NB1 = (NA == 4) ? 2 : 3;
   constexpr int NACC = (MODE == 2) ? 2 * NV : NV;
-  constexpr int VOFF = (MODE == 1) ? NV : 0;
+  constexpr int VOFF = (MODE == 1 && !KLOW) ? NV : 0;  // KLOW: double-layer-only launch, K lives in planes 0..NV-1
   double acc[NA][NACC];
 #pragma unroll
   for (int a = 0; a < NA; ++a)
@@ -513,19 +521,23 @@ __device__ __forceinline__ void cell_pass(const double *__restrict__ cq, const d
 // (half the accumulator registers per thread -> twice the resident warps).  A CTA has TI*QS*VS threads.
 constexpr int MAXC = 32;  // cells per block (a block touches at most tj <= 32 nodes)
 
-template <int NA, int KT, bool SPLIT, int QS, int VS, bool HAS_EPS, bool FUSED, int N1C>
+// LAYER 0: both layers in one tile; 1: single layer only; 2: double layer only (two launches, half the tile per node).
+template <int NA, int KT, int LAYER, int QS, int VS, bool HAS_EPS, bool FUSED, int N1C>
 __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(const RegParams P) {
   constexpr bool FAST = (KT == BS_KERNEL_FREE) && !HAS_EPS;  // point-major prescaled cell records, pipelined points
   constexpr int CQ = FAST ? 8 : 7;                           // doubles per quadrature point in a cell record
   constexpr int NV = GreenTraits<KT>::NV;
-  constexpr int NV2 = 2 * NV;
+  constexpr int NV2 = (LAYER == 0) ? 2 * NV : NV;  // value planes of the tile
+  constexpr int KPL = (LAYER == 0) ? NV : 0;       // first plane of the double layer
+  static_assert(LAYER == 0 || VS == 1, "layer-split launches use one thread set");
   constexpr int NB1 = (NA == 4) ? 2 : 3;
   constexpr int NT = TI * QS * VS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tj = P.tj, nqp = P.nq_pad, n1 = P.n1d;
   const int ns = cell_stages(nqp);
   double *cellbuf = reinterpret_cast<double *>(smem_raw);                   // [ns][7][nqp] or [ns][nqp][8]
-  double *l1d_s = cellbuf + (size_t)ns * 8 * nqp;                           // [n1][NB1] 1-D shape values (+ x-flipped copy)
+  const size_t ring_doubles = max((size_t)ns * 8 * nqp, (size_t)3 * tj * MAX_PANEL);
+  double *l1d_s = cellbuf + ring_doubles;                                   // [n1][NB1] 1-D shape values (+ x-flipped copy)
   double *acc_s = l1d_s + l1d_doubles(nqp);                                 // [NV2][tj][ACC_LD]
   uint64_t *bars = reinterpret_cast<uint64_t *>(acc_s + (size_t)NV2 * acc_vstride(tj));  // full[3], empty[3]
   uint64_t *full = bars, *empty = bars + 3;
@@ -618,9 +630,10 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
     if (VS == 2) {
       if (vpart == 0) cell_pass<NA, KT, 0, QS, HAS_EPS, FAST, N1C>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
       else cell_pass<NA, KT, 1, QS, HAS_EPS, FAST, N1C>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
-    } else if (SPLIT) {
+    } else if (LAYER == 1) {
       cell_pass<NA, KT, 0, QS, HAS_EPS, FAST, N1C>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
-      cell_pass<NA, KT, 1, QS, HAS_EPS, FAST, N1C>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
+    } else if (LAYER == 2) {
+      cell_pass<NA, KT, 1, QS, HAS_EPS, FAST, N1C, true>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
     } else {
       cell_pass<NA, KT, 2, QS, HAS_EPS, FAST, N1C>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
     }
@@ -674,19 +687,19 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
         const size_t off = rowoff + (second[sidx] ? (size_t)3 * P.ld : 0) + gcol[sidx];
         const int what = (second[sidx] && !has2) ? 0 : todo[sidx];
         const double *as = acc_s + soff[sidx][i] + r_;
-        store_or_reduce(P.V + off, as[0], what);
-        if (!FUSED) store_or_reduce(P.K + off, as[(size_t)NV * vs], what);
+        if (LAYER != 2) store_or_reduce(P.V + off, as[0], what);
+        if (!FUSED && LAYER != 1) store_or_reduce(P.K + off, as[(size_t)KPL * vs], what);
       }
     }
   }
-  if (FUSED) {
+  if (FUSED && LAYER != 1) {
     // K tile (rows x 3*tj) times the panel rows of this block's nodes; the single-layer part of the shared tile is
-    // free after its write-out and stages the panel rows.  Products go to KX with L2 reductions (every block adds to
+    // free after its write-out and stages the panel rows (double-layer-only launches use the idle cell ring).  Products go to KX with L2 reductions (every block adds to
     // the same rows: summation order of these few panel columns is not fixed; the stored matrix stays deterministic).
     __syncthreads();
     const int pp = P.pp;
     constexpr int PS = MAX_PANEL;  // padded panel stride in shared memory (zero filled): fixed-trip inner loops
-    double *xs = acc_s;            // [3*tj][PS]
+    double *xs = (LAYER == 0) ? acc_s : cellbuf;  // [3*tj][PS]
     for (int idx = t; idx < 3 * tj * PS; idx += NT) {
       const int col = idx / PS, q = idx - col * PS;
       const int sl = col / 3, j = col - 3 * sl;
@@ -698,7 +711,7 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
     // so a K value is read from the tile once and every thread is busy (TI*TPR == NT).
     constexpr int TPR = NT / TI, PSH = PS / TPR;
     static_assert(TPR * TI == NT && PSH * TPR == PS && PSH % 2 == 0, "fused epilogue thread layout");
-    const double *kacc = acc_s + (size_t)NV * vs;
+    const double *kacc = acc_s + (size_t)KPL * vs;
     const int r_ = t / TPR, h_ = t - r_ * TPR;
     if (r_ < rows_tile) {
       double y[3][PSH];
@@ -735,29 +748,41 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
   }
 }
 
-template <int NA, int KT, bool SPLIT, int QS, int VS>
-static void launch_reg(Context &c, RegParams P, int nrow_tiles, size_t smem) {
-  BS_REQUIRE(c.blocks.max_cells <= MAXC, "cell block larger than MAXC");
+template <int NA, int KT, int LAYER, int QS, int VS>
+static void launch_reg_layer(Context &c, RegParams P, int nrow_tiles, size_t smem, int colour) {
   // the free-space kernel has a variant with the 1-D rule size fixed at compile time (Gauss 8, the order of the
   // reference's parameter files): fully unrolled, software-pipelined rows
   const bool n8 = (KT == BS_KERNEL_FREE) && c.kp.eps == 0.0 && P.n1d == 8;
   constexpr int N8 = (KT == BS_KERNEL_FREE) ? 8 : 0;
-  auto kern = c.fused ? ((c.kp.eps == 0.0) ? (n8 ? k_assemble_regular<NA, KT, SPLIT, QS, VS, false, true, N8>
-                                                 : k_assemble_regular<NA, KT, SPLIT, QS, VS, false, true, 0>)
-                                           : k_assemble_regular<NA, KT, SPLIT, QS, VS, true, true, 0>)
-                      : ((c.kp.eps == 0.0) ? (n8 ? k_assemble_regular<NA, KT, SPLIT, QS, VS, false, false, N8>
-                                                 : k_assemble_regular<NA, KT, SPLIT, QS, VS, false, false, 0>)
-                                           : k_assemble_regular<NA, KT, SPLIT, QS, VS, true, false, 0>);
+  auto kern = c.fused ? ((c.kp.eps == 0.0) ? (n8 ? k_assemble_regular<NA, KT, LAYER, QS, VS, false, true, N8>
+                                                 : k_assemble_regular<NA, KT, LAYER, QS, VS, false, true, 0>)
+                                           : k_assemble_regular<NA, KT, LAYER, QS, VS, true, true, 0>)
+                      : ((c.kp.eps == 0.0) ? (n8 ? k_assemble_regular<NA, KT, LAYER, QS, VS, false, false, N8>
+                                                 : k_assemble_regular<NA, KT, LAYER, QS, VS, false, false, 0>)
+                                           : k_assemble_regular<NA, KT, LAYER, QS, VS, true, false, 0>);
   BS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const std::vector<int> &cs = c.blocks.colour_start;
-  for (size_t k = 0; k + 1 < cs.size(); ++k) {  // one launch per colour, stream order = summation order
-    const int nb = cs[k + 1] - cs[k];
-    if (nb <= 0) continue;
-    for (int b0 = 0; b0 < nb; b0 += 65535) {  // gridDim.y limit
-      P.blk_begin = cs[k] + b0;
-      kern<<<dim3(nrow_tiles, std::min(nb - b0, 65535)), TI * QS * VS, smem, c.stream>>>(P);
-      BS_CUDA(cudaGetLastError());
-      count_launch(c);
+  const int nb = cs[colour + 1] - cs[colour];
+  for (int b0 = 0; b0 < nb; b0 += 65535) {  // gridDim.y limit
+    P.blk_begin = cs[colour] + b0;
+    kern<<<dim3(nrow_tiles, std::min(nb - b0, 65535)), TI * QS * VS, smem, c.stream>>>(P);
+    BS_CUDA(cudaGetLastError());
+    count_launch(c);
+  }
+}
+
+// SPLIT: the two layers in two launches per colour (single layer, then double layer)
+template <int NA, int KT, bool SPLIT, int QS, int VS>
+static void launch_reg(Context &c, RegParams P, int nrow_tiles, size_t smem) {
+  BS_REQUIRE(c.blocks.max_cells <= MAXC, "cell block larger than MAXC");
+  const std::vector<int> &cs = c.blocks.colour_start;
+  for (size_t k = 0; k + 1 < cs.size(); ++k) {  // one launch (pair) per colour, stream order = summation order
+    if (cs[k + 1] - cs[k] <= 0) continue;
+    if constexpr (SPLIT) {
+      launch_reg_layer<NA, KT, 1, QS, VS>(c, P, nrow_tiles, smem, (int)k);
+      launch_reg_layer<NA, KT, 2, QS, VS>(c, P, nrow_tiles, smem, (int)k);
+    } else {
+      launch_reg_layer<NA, KT, 0, QS, VS>(c, P, nrow_tiles, smem, (int)k);
     }
   }
 }
@@ -793,8 +818,7 @@ void launch_assembly_regular(Context &c) {
   if (nrow_tiles == 0) return;
   
   const int grid = nrow_tiles;
-  const int nv = (c.kp.type == BS_KERNEL_FREE) ? 6 : 9;
-  const size_t smem = assembly_smem_bytes(c.na, nv, c.blocks.tj, c.nq_pad);
+  const size_t smem = assembly_smem_bytes(c.na, tile_planes(c.na, c.kp.type), c.blocks.tj, c.nq_pad);
   const bool q2 = (c.na == 9);
   switch (c.kp.type) {
     // <NA, kernel, two sequential passes?, threads per row over q, thread sets over {V,K}>

@@ -279,7 +279,8 @@ void launch_cell_geometry(Context &c);
 void launch_assembly_regular(Context &c);
 void launch_assembly_singular(Context &c);
 constexpr int MAX_PANEL = 12;
-size_t assembly_smem_bytes(int na, int nv, int tj, int nq_pad);
+int tile_planes(int na, int kernel_type);
+size_t assembly_smem_bytes(int na, int planes, int tj, int nq_pad);
 int choose_tj(int na, int kernel_type, int nq_pad);
 void kernel_eval_device(int type, double eps, int o, int npts, const double *d_p, const double *d_pim, double *d_G,
                         double *d_W, cudaStream_t s);
