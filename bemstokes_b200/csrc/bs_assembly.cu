@@ -422,6 +422,80 @@ __device__ __forceinline__ void integrate_free(const double *__restrict__ c8, co
   }
 }
 
+// Free-surface image system on the same fast path: G_fs = G(R) + s_i G(R_im), K likewise, with s_i = -1 on the row of
+// the wall normal and +1 otherwise (ref: source/free_surface_kernel.cc:19-72, 135-209).  Both terms are free-space
+// kernels, so one layer at a time (MODE 0 or 1, the layer-split launches) is accumulated as two symmetric 6-vectors
+// (direct and image part) with the 55-instruction formulation; the sign is applied once per cell when the 2 x 6
+// sums are expanded to the 9 unsymmetric tile values.  Two-stage software pipeline over the points of a rule row.
+template <int NA, int MODE, int QS>
+__device__ __forceinline__ void integrate_free_surface(const double *__restrict__ c8, const double *__restrict__ lx_s,
+                                                       const double *__restrict__ ly_s, int n1, const double (&x)[3],
+                                                       const double (&xim)[3], int o, int part, double (&out)[NA][9]) {
+  constexpr int NB1 = (NA == 4) ? 2 : 3;
+  double acc[NA][12], accI[NA][2];
+#pragma unroll
+  for (int a = 0; a < NA; ++a) {
+    accI[a][0] = accI[a][1] = 0.0;
+#pragma unroll
+    for (int v = 0; v < 12; ++v) acc[a][v] = 0.0;
+  }
+  auto point = [&](const double *rec, FreeB &pa, FreeB &pb) {
+    FreeA a;
+    free_stage_a<MODE>(rec, x, a);
+    free_stage_b<MODE>(a, pa);
+    free_stage_a<MODE>(rec, xim, a);
+    free_stage_b<MODE>(a, pb);
+  };
+  FreeB ca, cb;
+  if (part < n1) point(c8 + (size_t)8 * part * n1, ca, cb);
+  for (int qy = part; qy < n1; qy += QS) {
+    double tA[NB1][6], tB[NB1][6], tIA[NB1], tIB[NB1];
+#pragma unroll
+    for (int bb = 0; bb < NB1; ++bb) {
+      tIA[bb] = tIB[bb] = 0.0;
+#pragma unroll
+      for (int v = 0; v < 6; ++v) tA[bb][v] = tB[bb][v] = 0.0;
+    }
+    const double *crow = c8 + (size_t)8 * qy * n1;
+    const int qyn = (qy + QS < n1) ? qy + QS : qy;
+    const double *nrow = c8 + (size_t)8 * qyn * n1;
+#pragma unroll 2
+    for (int qx = 0; qx < n1; ++qx) {
+      FreeB na_, nb_;
+      point(qx + 1 < n1 ? crow + 8 * (qx + 1) : nrow, na_, nb_);  // next point (first of this thread's next row at the end)
+      free_stage_c<NB1, MODE, 6>(ca, lx_s + qx * NB1, tA, tIA);
+      free_stage_c<NB1, MODE, 6>(cb, lx_s + qx * NB1, tB, tIB);
+      ca = na_;
+      cb = nb_;
+    }
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      const double l = ly_s[qy * NB1 + shape_iy<NA>(a)];
+#pragma unroll
+      for (int v = 0; v < 6; ++v) {
+        acc[a][v] = fma(tA[shape_ix<NA>(a)][v], l, acc[a][v]);
+        acc[a][6 + v] = fma(tB[shape_ix<NA>(a)][v], l, acc[a][6 + v]);
+      }
+      if (MODE == 0) {
+        accI[a][0] = fma(tIA[shape_ix<NA>(a)], l, accI[a][0]);
+        accI[a][1] = fma(tIB[shape_ix<NA>(a)], l, accI[a][1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < NA; ++a)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double sg = (i == o) ? -1.0 : 1.0;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        double v = fma(sg, acc[a][6 + vidx<6>(i, j)], acc[a][vidx<6>(i, j)]);
+        if (MODE == 0 && i == j) v += fma(sg, accI[a][1], accI[a][0]);
+        out[a][3 * i + j] = v;
+      }
+    }
+}
+
 // One (row, cell) integration over this thread's share of the tensor rule.  MODE 0: single layer only, 1: double
 // layer only, 2: both.  Sum-factorised: x-direction into NB1 temporaries per value, y-direction once per row of
 // the rule; then the QS partial sums of a row (adjacent lanes) are combined by shuffles and lane `part` adds its
@@ -443,7 +517,13 @@ __device__ __forceinline__ void cell_pass(const double *__restrict__ cq, const d
   constexpr bool FLIP = FAST && QS == 2 && NA == 4;
   if (FAST) {
     const double *lx_s = FLIP ? l1d_s + part * (n1 * NB1) : l1d_s;  // odd partner: x-flipped copy of the table
-    if (ok) integrate_free<NA, MODE, QS, N1C, NACC>(cq, lx_s, l1d_s, n1, x, part, acc);
+    if constexpr (KT == BS_KERNEL_FREE) {
+      if (ok) integrate_free<NA, MODE, QS, N1C, NACC>(cq, lx_s, l1d_s, n1, x, part, acc);
+    } else {
+      if constexpr (KT == BS_KERNEL_FREE_SURFACE && MODE != 2) {
+        if (ok) integrate_free_surface<NA, MODE, QS>(cq, lx_s, l1d_s, n1, x, xim, o, part, acc);
+      }
+    }
   } else {
   for (int qy = part; ok && qy < n1; qy += QS) {
     double tmp[NB1][NACC];
@@ -524,7 +604,9 @@ constexpr int MAXC = 32;  // cells per block (a block touches at most tj <= 32 n
 // LAYER 0: both layers in one tile; 1: single layer only; 2: double layer only (two launches, half the tile per node).
 template <int NA, int KT, int LAYER, int QS, int VS, bool HAS_EPS, bool FUSED, int N1C>
 __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(const RegParams P) {
-  constexpr bool FAST = (KT == BS_KERNEL_FREE) && !HAS_EPS;  // point-major prescaled cell records, pipelined points
+  // point-major prescaled cell records, pipelined points: free space, and the Q1 free-surface image system (its two
+  // layers are integrated by separate launches; with Q2 the 9 x 12 partial sums would not fit the register file)
+  constexpr bool FAST = !HAS_EPS && (KT == BS_KERNEL_FREE || (KT == BS_KERNEL_FREE_SURFACE && NA == 4 && LAYER != 0));
   constexpr int CQ = FAST ? 8 : 7;                           // doubles per quadrature point in a cell record
   constexpr int NV = GreenTraits<KT>::NV;
   constexpr int NV2 = (LAYER == 0) ? 2 * NV : NV;  // value planes of the tile
