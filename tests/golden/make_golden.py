@@ -85,6 +85,32 @@ def main():
                             "Vn_linf": float([l for l in sr if "Check on the V operator Norm (should be zero):" in l][0].split(":")[1]),
                             "omega_exact": 2 * 3.141592653589793 / 120 / 0.1, "tol": 1e-2,
                             "ok_lines": len([l for l in sr if l.startswith("OK rigid")])}
+    # field evaluation: tests/test_bie_4.output prints, for the rotation modes, the double-layer
+    # potential at the interior point (0.1, 0.1, 0.1) and the squared distance to the test's naive expectation (the
+    # mode's value at node 0); translations and all exterior points (4, 4, 4) print "OK".  The grid is refined twice
+    # there, but DL[rigid motion] = that motion inside a closed surface holds on any closed grid.
+    tb = lines("tests/test_bie_4.output")
+    modes = {}
+    for k, l in enumerate(tb):
+        if l.startswith("Test on the ") and "th rigid mode" in l:
+            i = int(l.split()[3][0])
+            blk = tb[k + 1:k + 8]
+            mode0 = [float(t) for t in blk[0].split("=")[1].split()]
+            e = {"mode_at_node0": mode0, "interior_ok": any(b.startswith("OK interior") for b in blk),
+                 "exterior_ok": any(b.startswith("OK exterior") for b in blk)}
+            ux = [b for b in blk if b.startswith("ux =")]
+            if ux:
+                uz = [b for b in blk if b.startswith("uz =")][0].split("=")[1].split()
+                e["interior"] = [float(ux[0].split("=")[1]), float([b for b in blk if b.startswith("uy =")][0].split("=")[1]), float(uz[0])]
+                e["interior_sq_dist_to_node0_value"] = float(uz[1])
+            modes[str(i)] = e
+    g["test_bie_4"] = {"source": "tests/test_bie_4.output + tests/test_bie_4.cc:18-20 (tol_int 6e-2, tol_ext 1e-5)",
+                       "setup": "sphere_half_refined_0.inp (refined twice in the reference), free-space kernel, u = N_rigid[i], f = 0, "
+                                "points (0.1,0.1,0.1) and (4,4,4)", "tol_int": 6e-2, "tol_ext": 1e-5, "modes": modes}
+    t2 = lines("tests/test_bie_2.output")
+    g["test_bie_2"] = {"source": "tests/test_bie_2.output + tests/test_bie_2.cc:19-20", "tol": 1e-3,
+                       "setup": "single layer of f = normal_vector at (0.1,0.1,0.1) and (4,4,4): both below tol",
+                       "interior_ok": any(l.startswith("OK interior") for l in t2), "exterior_ok": any(l.startswith("OK exterior") for l in t2)}
     g["imposed_rotation"] = {"source": "tests/imposed_rotation_test_on_sphere.cc:28-31", "omega": 1.0 / (8 * 3.141592653589793),
                              "tol": 1.2e-3}
     with open(os.path.join(HERE, "reference_goldens.json"), "w") as f:

@@ -813,3 +813,28 @@ def test_frame_loop_heun(tmp_path):
     assert np.abs(ph.old_rigid_velocities - U0).max() < 1e-12          # predictor = the Forward solve
     assert np.abs(res[0]["rotation_matrix"] - np.eye(3)).max() < 1e-3
     ph.close()
+
+
+def test_field_evaluation_reference_goldens(half, goldens):
+    """tests/test_bie_2.output / test_bie_4.output through the device path (bs_evaluate_bie)."""
+    p = make_problem(half)
+    pts = np.array([[0.1, 0.1, 0.1], [4.0, 4.0, 4.0]])
+    zero = np.zeros(p.n_dofs)
+    G2, G4 = goldens["test_bie_2"], goldens["test_bie_4"]
+    u = p.evaluate_stokes_bie(pts, zero, p.normal_vector).reshape(3, 2)
+    assert np.linalg.norm(u[:, 0]) < G2["tol"] and np.linalg.norm(u[:, 1]) < G2["tol"]
+    N = p.N
+    for i in range(6):
+        gm = G4["modes"][str(i)]
+        u = p.evaluate_stokes_bie(pts, p.N_rigid[i], zero).reshape(3, 2)
+        node0 = p.N_rigid[i][[0, N, 2 * N]]
+        assert np.linalg.norm(u[:, 1]) < G4["tol_ext"]
+        if gm["interior_ok"]:
+            assert np.linalg.norm(u[:, 0] - node0) < G4["tol_int"]
+        else:
+            for k in range(3):
+                ref = gm["interior"][k]
+                assert abs(u[k, 0] - ref) <= (5e-7 if abs(ref) > 1e-3 else 1e-13)
+            got = float(((u[:, 0] - node0) ** 2).sum())
+            assert abs(got - gm["interior_sq_dist_to_node0_value"]) <= 6e-6 * gm["interior_sq_dist_to_node0_value"]
+    p.close()

@@ -249,3 +249,30 @@ def test_sphere_rotation_real_grid(goldens):
     assert G["ok_lines"] == 6
     assert abs(U[3] - G["omega_exact"]) / G["omega_exact"] <= G["tol"]
     assert np.abs(U[:3]).max() <= G["tol"] and np.abs(U[4:]).max() <= G["tol"]
+
+
+def test_field_evaluation_bie_goldens(goldens):
+    """tests/test_bie_2.output, test_bie_4.output: potentials of the single layer of the normal and of the double layer
+    of the six rigid modes at an interior and an exterior point (evaluate_stokes_bie, bem_stokes.cc:5366-5451)."""
+    v, q = bo.read_inp(os.path.join(MESHES, "sphere_half_refined_0.inp"))
+    geo = bo.Geometry(v, q, 1)
+    pre = bo.Prepass(geo, 8)
+    pts = np.array([[0.1, 0.1, 0.1], [4.0, 4.0, 4.0]])
+    zero = np.zeros(3 * geo.N)
+    G2, G4 = goldens["test_bie_2"], goldens["test_bie_4"]
+    u = bo.evaluate_bie(geo, bo.KernelSpec(), pts, zero, pre.nhat, 8).reshape(3, 2)
+    assert G2["interior_ok"] and G2["exterior_ok"]
+    assert np.linalg.norm(u[:, 0]) < G2["tol"] and np.linalg.norm(u[:, 1]) < G2["tol"]
+    for i in range(6):
+        gm = G4["modes"][str(i)]
+        u = bo.evaluate_bie(geo, bo.KernelSpec(), pts, pre.N_rigid[i], zero, 8).reshape(3, 2)
+        node0 = pre.N_rigid[i][[0, geo.N, 2 * geo.N]]
+        assert np.abs(node0 - gm["mode_at_node0"]).max() < 5e-6          # same grid, same rigid modes
+        assert gm["exterior_ok"] and np.linalg.norm(u[:, 1]) < G4["tol_ext"]
+        if gm["interior_ok"]:
+            assert np.linalg.norm(u[:, 0] - node0) < G4["tol_int"]
+        else:   # the reference prints the values: the rotation mode itself at the interior point
+            for k in range(3):
+                ref = gm["interior"][k]
+                assert abs(u[k, 0] - ref) <= (5e-7 if abs(ref) > 1e-3 else 1e-13)
+            assert sig6(float(((u[:, 0] - node0) ** 2).sum()), gm["interior_sq_dist_to_node0_value"])
