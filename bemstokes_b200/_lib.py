@@ -50,8 +50,8 @@ SIGNATURES = {
     "bs_set_kernel": (C.c_int, [ctx_p, C.c_int, C.c_double, C.c_int, c_double_p]),
     "bs_make_gauss_1d": (C.c_int, [C.c_int, c_double_p, c_double_p]),
     "bs_make_singular_rule": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p]),
-    "bs_prepass": (C.c_int, [ctx_p, c_double_p, c_double_p, c_double_p, C.POINTER(C.c_double), c_double_p, c_double_p,
-                             C.POINTER(C.c_double), c_double_p, C.POINTER(C.c_int)]),
+    "bs_prepass": (C.c_int, [ctx_p, C.c_int, c_double_p, c_double_p, c_double_p, C.POINTER(C.c_double), c_double_p, c_double_p,
+                             C.POINTER(C.c_double), c_double_p, c_double_p, c_double_p, C.POINTER(C.c_int)]),
     "bs_host_prepass": (C.c_int, [C.c_int, C.c_int, C.c_int, c_double_p, C.c_int, c_int_p, C.c_int, c_int_p, C.c_int, c_double_p,
                                   c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "bs_assemble_VK": (C.c_int, [ctx_p]),

@@ -223,17 +223,19 @@ int bs_set_partition(bs_context *h, int rank, int nranks, const int *owner_of_no
   BS_API_END
 }
 
-int bs_prepass(bs_context *h, const double *pole, double *nhat, double *Mnhat, double *l2gamma, double *N_rigid,
-               double *N_rigid_dual, double *area, double *support_points, int *cg_iterations) {
+int bs_prepass(bs_context *h, int pole_kind, const double *pole, double *nhat, double *Mnhat, double *l2gamma, double *N_rigid,
+               double *N_rigid_dual, double *area, double *support_points, double *center_of_mass, double *pole_used,
+               int *cg_iterations) {
   BS_API_BEGIN
   Context &c = ctx_of(h);
   BS_REQUIRE(nhat && Mnhat, "nhat / Mnhat output arrays are required");
   BS_REQUIRE((N_rigid == nullptr) == (N_rigid_dual == nullptr), "N_rigid and N_rigid_dual go together");
-  const double origin[3] = {0, 0, 0};
+  BS_REQUIRE(pole_kind == BS_POLE_ORIGIN || pole_kind == BS_POLE_POINT || pole_kind == BS_POLE_BARICENTER, "unknown pole kind");
+  BS_REQUIRE(pole_kind != BS_POLE_POINT || pole, "BS_POLE_POINT needs the point");
   const size_t n3 = c.n3();
   double *d_nh = c.wsd("pre.nhat", n3), *d_mn = c.wsd("pre.Mnhat", n3);
   double *d_nr = N_rigid ? c.wsd("pre.Nr", 6 * n3) : nullptr, *d_nrd = N_rigid ? c.wsd("pre.Nrd", 6 * n3) : nullptr;
-  device_prepass(c, pole ? pole : origin, d_nh, d_mn, d_nr, d_nrd, l2gamma, area, cg_iterations);
+  device_prepass(c, pole_kind, pole, d_nh, d_mn, d_nr, d_nrd, l2gamma, area, center_of_mass, pole_used, cg_iterations);
   from_internal(c, d_nh, 0, nhat, 0, n3);
   from_internal(c, d_mn, 0, Mnhat, 0, n3);
   if (N_rigid)

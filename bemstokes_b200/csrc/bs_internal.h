@@ -269,8 +269,8 @@ void host_prepass(int fe_degree, int map_degree, int n_map_nodes, const double *
                   int n_nodes, const int *conn, int quad_order, const double *pole, double *nhat, double *Mnhat, double *l2,
                   double *N_rigid, double *N_rigid_dual, double *area_out, double *support_out);
 // same quantities on the device from the context's geometry (bs_prepass.cu); results in internal ordering
-void device_prepass(Context &c, const double pole[3], double *d_nhat, double *d_Mnhat, double *d_Nr, double *d_Nrd,
-                    double *h_l2, double *h_area, int *cg_iterations);
+void device_prepass(Context &c, int pole_kind, const double pole_in[3], double *d_nhat, double *d_Mnhat, double *d_Nr,
+                    double *d_Nrd, double *h_l2, double *h_area, double *h_center_of_mass, double *h_pole_used, int *cg_iterations);
 void build_geometry(Context &c);
 void update_coordinates(Context &c);    // same mesh, new map_nodes
 void build_tables(Context &c);          // after geometry + quadrature known

@@ -23,12 +23,12 @@ constexpr int PRE_T = 256;
 // local mass rows and normal moments: thread (cell, a)
 __global__ void k_pre_local(int ncell, int na, int nq, int nq_pad, const double *__restrict__ cellq,
                             const double *__restrict__ phi /*[nq][na]*/, double *__restrict__ mloc /*[ncell][na][na]*/,
-                            double *__restrict__ bloc /*[ncell][na][3]*/, double *__restrict__ cell_area) {
+                            double *__restrict__ bloc /*[ncell][na][3]*/, double *__restrict__ cell_area /*[4][ncell]: area, int y dS*/) {
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= ncell * na) return;
   const int cell = gid / na, a = gid - cell * na;
   const double *cq = cellq + (size_t)cell * 7 * nq_pad;
-  double m[MAX_NA], b[3] = {0, 0, 0}, area = 0;
+  double m[MAX_NA], b[3] = {0, 0, 0}, area = 0, cy[3] = {0, 0, 0};
   for (int k = 0; k < MAX_NA; ++k) m[k] = 0.0;
   for (int q = 0; q < nq; ++q) {
     const double pa = phi[(size_t)q * na + a], jxw = cq[6 * nq_pad + q];
@@ -39,11 +39,17 @@ __global__ void k_pre_local(int ncell, int na, int nq, int nq_pad, const double 
 #pragma unroll
     for (int d = 0; d < 3; ++d) b[d] = fma(pa, cq[(3 + d) * nq_pad + q], b[d]);  // phi_a * n_d * JxW
     area += jxw;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) cy[d] = fma(cq[d * nq_pad + q], jxw, cy[d]);  // first moment: centre of mass (ref: 2487-2493)
   }
   for (int k = 0; k < na; ++k) mloc[((size_t)cell * na + a) * na + k] = m[k];
 #pragma unroll
   for (int d = 0; d < 3; ++d) bloc[((size_t)cell * na + a) * 3 + d] = b[d];
-  if (a == 0) cell_area[cell] = area;
+  if (a == 0) {
+    cell_area[cell] = area;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) cell_area[(size_t)(1 + d) * ncell + cell] = cy[d];
+  }
 }
 
 // rhs[3p+d] = sum over the node's patch of bloc; dinv[p] = 1 / M_pp
@@ -206,15 +212,15 @@ __global__ void k_pre_sum1(int n, const double *__restrict__ v, double *__restri
 }  // namespace
 
 // Results stay on the device in internal ordering: nhat, Mnhat [3N]; Nr, Nrd [6][3N]; scalars[0] = l2, [1] = area.
-void device_prepass(Context &c, const double pole[3], double *d_nhat, double *d_Mnhat, double *d_Nr, double *d_Nrd,
-                    double *h_l2, double *h_area, int *cg_iterations) {
+void device_prepass(Context &c, int pole_kind, const double pole_in[3], double *d_nhat, double *d_Mnhat, double *d_Nr,
+                    double *d_Nrd, double *h_l2, double *h_area, double *h_center_of_mass, double *h_pole_used, int *cg_iterations) {
   BS_REQUIRE(c.have_geometry && c.have_quadrature, "geometry and quadrature must be set before the pre-pass");
   const int N = c.N, na = c.na, ncell = c.ncell;
   const size_t n3 = (size_t)3 * N;
   launch_cell_geometry(c);
   double *mloc = c.wsd("pre.mloc", (size_t)ncell * na * na);
   double *bloc = c.wsd("pre.bloc", (size_t)ncell * na * 3);
-  double *carea = c.wsd("pre.area", (size_t)ncell);
+  double *carea = c.wsd("pre.area", (size_t)4 * ncell);
   double *rhs = c.wsd("pre.rhs", n3), *dinv = c.wsd("pre.dinv", N);
   double *x = c.wsd("pre.x", n3), *r = c.wsd("pre.r", n3), *z = c.wsd("pre.z", n3), *pv = c.wsd("pre.p", n3), *Ap = c.wsd("pre.Ap", n3);
   const int nb_dot = std::min(4 * c.sm_count, (N + PRE_T - 1) / PRE_T);
@@ -267,19 +273,28 @@ void device_prepass(Context &c, const double pole[3], double *d_nhat, double *d_
   k_pre_normalise<<<gN, PRE_T, 0, s>>>(N, x, d_nhat);
   mult(1, d_nhat, d_Mnhat);
   dot3(d_nhat, d_Mnhat, sc + 16);
-  k_pre_sum1<<<1, PRE_T, 0, s>>>(ncell, carea, sc + 20);
-  // ---- rigid modes and duals
-  if (d_Nr && d_Nrd) {
-    k_pre_rigid<<<gN, PRE_T, 0, s>>>(N, c.d_support.p, pole[0], pole[1], pole[2], d_Nr);
-    mult(6, d_Nr, d_Nrd);
-  }
-  BS_CUDA(cudaGetLastError());
-  double hs[5];
-  BS_CUDA(cudaMemcpyAsync(hs, sc + 16, 5 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  for (int k = 0; k < 4; ++k) k_pre_sum1<<<1, PRE_T, 0, s>>>(ncell, carea + (size_t)k * ncell, sc + 20 + k);
+  double hs[8];
+  BS_CUDA(cudaMemcpyAsync(hs, sc + 16, 8 * sizeof(double), cudaMemcpyDeviceToHost, s));
   BS_CUDA(cudaStreamSynchronize(s));
   if (h_l2) *h_l2 = hs[0] + hs[1] + hs[2];
   if (h_area) *h_area = hs[4];
-  c.stats.kernel_launches += 8;
+  const double com[3] = {hs[5] / hs[4], hs[6] / hs[4], hs[7] / hs[4]};  // surface centroid (ref: 2540-2545)
+  double pole[3] = {0, 0, 0};                                          // BS_POLE_ORIGIN
+  for (int d = 0; d < 3; ++d) {
+    if (pole_kind == BS_POLE_POINT) pole[d] = pole_in ? pole_in[d] : 0.0;
+    if (pole_kind == BS_POLE_BARICENTER) pole[d] = com[d];
+    if (h_center_of_mass) h_center_of_mass[d] = com[d];
+    if (h_pole_used) h_pole_used[d] = pole[d];
+  }
+  // ---- rigid modes about the pole and duals
+  if (d_Nr && d_Nrd) {
+    k_pre_rigid<<<gN, PRE_T, 0, s>>>(N, c.d_support.p, pole[0], pole[1], pole[2], d_Nr);
+    mult(6, d_Nr, d_Nrd);
+    BS_CUDA(cudaGetLastError());
+    BS_CUDA(cudaStreamSynchronize(s));
+  }
+  c.stats.kernel_launches += 11;
 }
 
 }  // namespace bs

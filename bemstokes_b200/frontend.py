@@ -214,7 +214,7 @@ class FrameLoop:
         self.input_grid_path, self.input_grid_base_name, self.input_grid_format = "../debug_grids/", "sphere_mesh_3d_", "msh"
         self.res_strategy = "Forward"
         self.time_step = 0.1
-        self.force_pole_kind, self.force_arbitrary_point = "Origin", (1.0, 0.0, 0.0)
+        self.force_arbitrary_point = (1.0, 0.0, 0.0)
         self.use_previous_state = False
         self.extra_debug_info = False
         self.create_box_bool = False
@@ -270,8 +270,8 @@ class FrameLoop:
             self.force_pole = (0.0, 0.0, 0.0)
         elif self.force_pole_kind == "Point":
             self.force_pole = tuple(self.force_arbitrary_point)
-        else:
-            raise NotImplementedError("force pole 'Baricenter' is not supported by this front-end")
+        elif self.force_pole_kind not in (None, "Baricenter"):   # Baricenter: the pre-pass computes the surface centroid
+            raise ValueError("unknown force pole %r" % (self.force_pole_kind,))
         return self
 
     # ---- geometry per frame -------------------------------------------------------------------------------------

@@ -48,7 +48,9 @@ class Prepass:
 class DevicePrepass:
     """Same attributes as `Prepass`, computed on the GPU by bs_prepass from the context's geometry and quadrature."""
 
-    def __init__(self, ctx, n_nodes, pole=(0., 0., 0.)):
+    POLE_KINDS = {"Origin": 0, "Point": 1, "Baricenter": 2}
+
+    def __init__(self, ctx, n_nodes, pole=(0., 0., 0.), pole_kind="Point"):
         dp = _lib.c_double_p
         n3 = 3 * n_nodes
         self.normal_vector_pure = np.zeros(n3)
@@ -58,10 +60,14 @@ class DevicePrepass:
         self.support_points = np.zeros((n_nodes, 3))
         l2, area, its = C.c_double(), C.c_double(), C.c_int()
         pl = np.asarray(pole, dtype=np.float64)
-        _lib.check(_lib.lib.bs_prepass(ctx, pl.ctypes.data_as(dp), self.normal_vector_pure.ctypes.data_as(dp),
+        self.center_of_mass_body = np.zeros(3)
+        self.point_force_pole = np.zeros(3)
+        _lib.check(_lib.lib.bs_prepass(ctx, self.POLE_KINDS[pole_kind], pl.ctypes.data_as(dp),
+                                       self.normal_vector_pure.ctypes.data_as(dp),
                                        self.M_normal_vector_pure.ctypes.data_as(dp), C.byref(l2),
                                        self.N_rigid.ctypes.data_as(dp), self.N_rigid_dual.ctypes.data_as(dp), C.byref(area),
-                                       self.support_points.ctypes.data_as(dp), C.byref(its)))
+                                       self.support_points.ctypes.data_as(dp), self.center_of_mass_body.ctypes.data_as(dp),
+                                       self.point_force_pole.ctypes.data_as(dp), C.byref(its)))
         self.normal_vector = self.normal_vector_pure
         self.l2normGamma_pure = l2.value
         self.area = area.value

@@ -196,7 +196,8 @@ class BEMProblem(FrameLoop):
         self.gmres_restart = 100
         self.gmres_orthogonalization = "CGS2"   # "MGS" = deal.II's modified Gram-Schmidt verbatim
         self.solver_control = SolverControl(1000, 1e-10)
-        self.force_pole = (0.0, 0.0, 0.0)
+        self.force_pole = (0.0, 0.0, 0.0)   # explicit pole point ("Force Pole Point Setting"; the origin by default)
+        self.force_pole_kind = None          # None: use force_pole; "Origin" | "Point" | "Baricenter" as in the reference
         self.host_prepass = False         # True: mass matrix / normals / rigid modes by the host code (bs_host_prepass)
         self.keep_VK = True
         self.fused_assembly = False    # True: never store K (bs_assemble_fused); body-only monolithic systems
@@ -321,10 +322,16 @@ class BEMProblem(FrameLoop):
         """ref: bem_stokes.cc:2440-2788 (+ compute_normal_vector 3922-4011): on the device (bs_prepass); the host
         restatement (bs_host_prepass) only when `host_prepass` is set."""
         if self.host_prepass:
+            if self.force_pole_kind == "Baricenter":
+                raise NotImplementedError("the Baricenter pole needs the device pre-pass")
+            self.point_force_pole = np.asarray(self.force_pole, dtype=float)
             self._pre = Prepass(self.map_mesh.nodes, self.map_mesh.conn.astype(np.int64), self.map_degree, self.N,
                                 self.mesh.conn.astype(np.int64), self.fe_degree, self.quadrature_order, self.force_pole)
         else:
-            self._pre = DevicePrepass(self._ctx, self.N, self.force_pole)
+            kind = self.force_pole_kind or "Point"
+            self._pre = DevicePrepass(self._ctx, self.N, self.force_pole, kind)
+            self.center_of_mass_body = self._pre.center_of_mass_body
+            self.point_force_pole = self._pre.point_force_pole   # ref: 2546-2552
         self.N_rigid = self._pre.N_rigid
         self.N_rigid_dual = self._pre.N_rigid_dual
         self.support_points = self._pre.support_points
@@ -472,7 +479,7 @@ class BEMProblem(FrameLoop):
         self.rigid_total_forces = np.array([self.stokes_forces @ self.N_rigid_dual[r] for r in range(nr)])
         # velocities are solved about the force pole; the reference reports them at the origin (4479-4492)
         self.baricenter_rigid_velocities = self.rigid_velocities.copy()
-        pole = np.asarray(self.force_pole, dtype=float)
+        pole = np.asarray(getattr(self, "point_force_pole", self.force_pole), dtype=float)
         if nr >= 6 and np.any(pole != 0.0):
             self.rigid_velocities = self.rigid_velocities.copy()
             self.rigid_velocities[:3] += np.cross(self.baricenter_rigid_velocities[3:6], -pole)

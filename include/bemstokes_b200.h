@@ -108,11 +108,15 @@ int bs_host_prepass(int fe_degree, int map_degree, int n_map_nodes, const double
  * bs_set_quadrature): per-cell local mass matrices, matrix-free M x as a gather over node patches, the three normal
  * components solved together by Jacobi-preconditioned CG to 1e-15 (ref: compute_normal_vector bem_stokes.cc:3922-4011,
  * compute_center_of_mass_and_rigid_modes 2440-2788).  Outputs as bs_host_prepass, reference ordering (i + c*N),
- * host or device arrays per pointer mode (support_points is always a host array, [N][3]); pole NULL = origin;
- * N_rigid / N_rigid_dual ([6][3N]), l2gamma, area, support_points, cg_iterations may be NULL.  Every rank computes
+ * host or device arrays per pointer mode (support_points, center_of_mass[3], pole_used[3] are always host arrays).
+ * The rigid modes are taken about the origin, about `pole` (BS_POLE_POINT) or about the surface centroid
+ * int y dS / int dS (BS_POLE_BARICENTER, ref: 2487-2493, 2540-2550), which is also returned in center_of_mass.
+ * N_rigid / N_rigid_dual ([6][3N]), l2gamma, area, support_points, center_of_mass, pole_used, cg_iterations may be NULL.  Every rank computes
  * the full vectors (O(N) work, geometry is replicated).  Cells with repeated nodes are not supported here. */
-int bs_prepass(bs_context *ctx, const double *pole, double *nhat, double *Mnhat, double *l2gamma, double *N_rigid,
-               double *N_rigid_dual, double *area, double *support_points, int *cg_iterations);
+typedef enum { BS_POLE_ORIGIN = 0, BS_POLE_POINT = 1, BS_POLE_BARICENTER = 2 } bs_pole_kind; /* "Force Pole to be used" */
+int bs_prepass(bs_context *ctx, int pole_kind, const double *pole, double *nhat, double *Mnhat, double *l2gamma,
+               double *N_rigid, double *N_rigid_dual, double *area, double *support_points, double *center_of_mass,
+               double *pole_used, int *cg_iterations);
 
 /* ---- assembly (ref: BEMProblem::assemble_stokes_system, bem_stokes.cc:2840-3435) ----------------------- */
 /* K1 (regular Gauss pass) + K2 (singular pass) -> row-block of V and K on the device (2871-3000). */

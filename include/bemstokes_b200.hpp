@@ -286,8 +286,8 @@ public:
     normal_vector_pure.assign(n_dofs, 0.);
     M_normal_vector_pure.assign(n_dofs, 0.);
     std::vector<double> nr(6 * (size_t)n_dofs), nd(6 * (size_t)n_dofs);
-    check(bs_prepass(ctx, nullptr, normal_vector_pure.data(), M_normal_vector_pure.data(), &l2normGamma_pure, nr.data(),
-                     nd.data(), &surface, nullptr, nullptr));
+    check(bs_prepass(ctx, BS_POLE_ORIGIN, nullptr, normal_vector_pure.data(), M_normal_vector_pure.data(), &l2normGamma_pure,
+                     nr.data(), nd.data(), &surface, nullptr, nullptr, nullptr, nullptr));
     N_rigid.assign(6, Vector());
     N_rigid_dual.assign(6, Vector());
     for (int r = 0; r < 6; ++r) {

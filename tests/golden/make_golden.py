@@ -111,6 +111,14 @@ def main():
     g["test_bie_2"] = {"source": "tests/test_bie_2.output + tests/test_bie_2.cc:19-20", "tol": 1e-3,
                        "setup": "single layer of f = normal_vector at (0.1,0.1,0.1) and (4,4,4): both below tol",
                        "interior_ok": any(l.startswith("OK interior") for l in t2), "exterior_ok": any(l.startswith("OK exterior") for l in t2)}
+    dl = lines("tests/imposed_rotation_test_on_dilated_sphere.output")
+    g["dilated_sphere"] = {"source": "tests/imposed_rotation_test_on_dilated_sphere.output + .cc:28-34,56-67,84-90",
+                           "setup": "sphere_half_refined_0.inp scaled by L = 10 and shifted by 34.913639 per axis, force pole "
+                                    "Baricenter, ImposedForce unit torque i = 3..5, exact omega = 1/(8 pi L^3), tol 3e-2",
+                           "L": 10.0, "shift": 34.913639, "tol": 3e-2,
+                           "surface": float([l for l in dl if "The Mass (Surface) of the entire system is" in l][0].split(":")[1]),
+                           "Vn_linf": float([l for l in dl if "Check on the V operator Norm (should be zero):" in l][0].split(":")[1]),
+                           "ok_lines": len([l for l in dl if "OK OMEGA_" in l])}
     g["imposed_rotation"] = {"source": "tests/imposed_rotation_test_on_sphere.cc:28-31", "omega": 1.0 / (8 * 3.141592653589793),
                              "tol": 1.2e-3}
     with open(os.path.join(HERE, "reference_goldens.json"), "w") as f:

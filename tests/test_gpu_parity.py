@@ -838,3 +838,28 @@ def test_field_evaluation_reference_goldens(half, goldens):
             got = float(((u[:, 0] - node0) ** 2).sum())
             assert abs(got - gm["interior_sq_dist_to_node0_value"]) <= 6e-6 * gm["interior_sq_dist_to_node0_value"]
     p.close()
+
+
+def test_dilated_sphere_baricenter_pole(half, goldens):
+    """tests/imposed_rotation_test_on_dilated_sphere.cc on the device: force pole 'Baricenter' from bs_prepass."""
+    G = goldens["dilated_sphere"]
+    m = bb.QuadMesh(half.nodes * G["L"] + G["shift"], half.conn, 1)
+    p = make_problem(m, grid_type="ImposedForce", imposed_component=3, solve_directly=False, preconditioner_type="Direct",
+                     force_pole_kind="Baricenter")
+    assert np.abs(p.center_of_mass_body - G["shift"]).max() < 0.02
+    assert np.abs(p.point_force_pole - p.center_of_mass_body).max() == 0
+    assert abs(p.surface - G["surface"]) < 6e-6 * G["surface"]
+    p.assemble_stokes_system(True)
+    assert abs(np.abs(p.V_x_normals_body).max() - G["Vn_linf"]) < 6e-8
+    n = p.n_dofs
+    exact = 1.0 / (8 * np.pi * G["L"] ** 3)
+    for i in range(3, 6):
+        p.monolithic_rhs[:] = 0
+        p.monolithic_rhs[n + i] = 1.0
+        p.monolithic_solution[:] = 0
+        p.solve_system(True)
+        assert abs(p.rigid_velocities[i] - exact) / exact <= G["tol"]
+        # velocities are reported at the origin (bem_stokes.cc:4479-4492): U_O = U_pole + omega x (0 - pole)
+        w = p.baricenter_rigid_velocities
+        assert np.abs(p.rigid_velocities[:3] - (w[:3] + np.cross(w[3:6], -p.point_force_pole))).max() < 1e-15
+    p.close()

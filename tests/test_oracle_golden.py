@@ -276,3 +276,33 @@ def test_field_evaluation_bie_goldens(goldens):
                 ref = gm["interior"][k]
                 assert abs(u[k, 0] - ref) <= (5e-7 if abs(ref) > 1e-3 else 1e-13)
             assert sig6(float(((u[:, 0] - node0) ** 2).sum()), gm["interior_sq_dist_to_node0_value"])
+
+
+def test_dilated_sphere_baricenter_pole(goldens):
+    """tests/imposed_rotation_test_on_dilated_sphere.output: the rigid modes are taken about the surface centroid
+    ('Baricenter' force pole, bem_stokes.cc:2540-2552) of a sphere of radius 10 centred far from the origin."""
+    G = goldens["dilated_sphere"]
+    v, q = bo.read_inp(os.path.join(MESHES, "sphere_half_refined_0.inp"))
+    v = v * G["L"] + G["shift"]
+    geo = bo.Geometry(v, q, 1)
+    xi, w = bo.gauss2(8)
+    num, area = np.zeros(3), 0.0
+    for c in range(geo.ncell):
+        y, n, jxw = bo.fe_cell(geo.map_nodes[geo.map_conn[c]], 1, xi, w)
+        num += (y * jxw[:, None]).sum(0)
+        area += jxw.sum()
+    com = num / area
+    assert np.abs(com - G["shift"]).max() < 0.02 and sig6(area, G["surface"])
+    pre = bo.Prepass(geo, 8, com)
+    V, K = bo.assemble_VK(geo, bo.KernelSpec(), 8, "Mixed", 10)
+    assert sig6(np.abs(V @ pre.nhat).max(), G["Vn_linf"])
+    Vc, _ = bo.correct_V(V, pre)
+    A, b = bo.monolithic(Vc, bo.correct_K(K, geo.N), pre, "ImposedForce", 3)
+    n = 3 * geo.N
+    exact = 1.0 / (8 * np.pi * G["L"] ** 3)
+    assert G["ok_lines"] == 3
+    for i in range(3, 6):
+        rhs = np.zeros(n + 6)
+        rhs[n + i] = 1.0
+        U = np.linalg.solve(A, rhs)[n:]
+        assert abs(U[i] - exact) / exact <= G["tol"]
