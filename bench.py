@@ -367,13 +367,14 @@ def cpu_baseline(wl, sample_seconds=15.0, nthreads=0):
     geo = bo.Geometry(nodes, conn, wl["degree"])
     cores = port.max_threads() if nthreads == 0 else nthreads
     N = geo.N
+    kspec = bo.KernelSpec(bo.FREE_SURFACE, 0.0, 1, (0.0, 1.4, 0.0)) if wl.get("kernel") == "free_surface" else bo.KernelSpec()
     # calibrate on one row per thread, then size the sample
     t0 = time.perf_counter()
-    _, _, pairs = port.assemble_VK(geo, bo.KernelSpec(), wl["quad"], "Mixed", wl["sing"], 0, cores, nthreads)
+    _, _, pairs = port.assemble_VK(geo, kspec, wl["quad"], "Mixed", wl["sing"], 0, cores, nthreads)
     t_cal = time.perf_counter() - t0
     rows = int(max(cores, min(N, cores * max(1, int(sample_seconds / max(t_cal, 1e-3))))))
     t0 = time.perf_counter()
-    V, K, pairs = port.assemble_VK(geo, bo.KernelSpec(), wl["quad"], "Mixed", wl["sing"], 0, rows, nthreads)
+    V, K, pairs = port.assemble_VK(geo, kspec, wl["quad"], "Mixed", wl["sing"], 0, rows, nthreads)
     t = time.perf_counter() - t0
     entries = 2.0 * 3 * rows * 3 * N
     # matvec sample: the assembled row block itself
