@@ -86,3 +86,84 @@ def test_block_write_format(tmp_path):
     open(path, "wb").write(b"3\n(" + v.tobytes() + b"]")
     with pytest.raises(ValueError):
         fe.vector_block_read(path)
+
+
+class _StubProblem(fe.FrameLoop):
+    """State container for the host-only parts of the frame loop (no device context)."""
+
+    def __init__(self, N):
+        self._init_frontend()
+        self.n_dofs, self.num_rigid, self.assemble_scaling = 3 * N, 6, 1.0
+        rng = np.random.default_rng(3)
+        x = rng.uniform(-1, 1, (N, 3))
+        R = np.zeros((6, 3, N))
+        for c in range(3):
+            R[c, c] = 1.0
+        R[3, 1], R[3, 2] = -x[:, 2], x[:, 1]
+        R[4, 0], R[4, 2] = x[:, 2], -x[:, 0]
+        R[5, 0], R[5, 1] = -x[:, 1], x[:, 0]
+        self.N_rigid = R.reshape(6, 3 * N)
+        self.rigid_displacements_for_sim = np.zeros(3 * N)
+        self.log = lambda *_: None
+
+
+def test_update_system_state_forward_and_heun():
+    """ref: update_system_state (bem_stokes.cc:4725-4846)."""
+    N = 7
+    s = _StubProblem(N)
+    s.time_step, s.bool_dipl_x, s.bool_dipl_z = 0.1, True, True
+    U = np.array([0.3, -0.2, 0.5, 0.0, 0.0, 2.0])
+    s.rigid_velocities = U.copy()
+    s.baricenter_rigid_velocities = U.copy()
+    s.update_system_state(True, 0, True, True, "Forward")
+    assert np.allclose(s.rigid_puntual_velocities, U @ s.N_rigid)
+    assert np.allclose(s.rigid_puntual_translation_velocities, U[:3] @ s.N_rigid[:3])
+    assert np.allclose(s.next_rigid_puntual_displacements, 0.1 * (U[:3] @ s.N_rigid[:3]))
+    d = s.rigid_displacements_for_sim.reshape(3, N)
+    assert np.allclose(d[0], 0.03) and np.allclose(d[1], 0.0) and np.allclose(d[2], 0.05)   # y is switched off
+    ang = 2.0 * 0.1   # rotation about z by omega*dt (forward Euler on the quaternion: tan(half angle) = omega dt / 2)
+    Rz = s.rotation_matrix
+    assert abs(math.atan2(Rz[1, 0], Rz[0, 0]) - 2 * math.atan(ang / 2)) < 1e-14 and abs(Rz[2, 2] - 1) < 1e-14
+    # Heun: the predictor backs the state up, the corrector restores it and averages the velocities
+    h = _StubProblem(N)
+    h.res_strategy, h.time_step = "Heun", 0.1
+    h.rigid_velocities = U.copy()
+    h.baricenter_rigid_velocities = U.copy()
+    h.update_system_state(True, 0, True, False, "Forward")
+    R_pred = h.rotation_matrix.copy()
+    assert np.array_equal(h.old_rigid_velocities, U) and np.array_equal(h.old_rotation_matrix, np.eye(3))
+    U2 = np.array([0.1, 0.0, 0.1, 0.0, 0.0, 1.0])
+    h.rigid_velocities = U2.copy()
+    h.baricenter_rigid_velocities = U2.copy()
+    h.update_system_state(True, 0, True, False, "Heun")
+    assert np.allclose(h.rigid_velocities, 0.5 * (U + U2))
+    half = fe.update_rotation_matrix(np.eye(3), 0.5 * (U + U2)[3:], 0.1)
+    assert np.allclose(h.rotation_matrix, half) and not np.allclose(h.rotation_matrix, R_pred)
+
+
+def test_result_files_and_main_arguments(tmp_path):
+    N = 3
+    s = _StubProblem(N)
+    s.output_dir = str(tmp_path)
+    n = 3 * N
+    for name in ("stokes_forces", "shape_velocities", "total_velocities", "next_rigid_puntual_displacements",
+                 "rigid_puntual_velocities", "euler_vec", "normal_vector", "rigid_puntual_displacements"):
+        setattr(s, name, np.arange(n, dtype=float) + len(name))
+    s.rigid_velocities, s.rigid_total_forces = np.arange(6.0), -np.arange(6.0)
+    s.output_save_stokes_results(5)
+    assert np.array_equal(fe.vector_block_read(str(tmp_path / "stokes_forces_5.bin")), s.stokes_forces)
+    assert np.array_equal(fe.vector_block_read(str(tmp_path / "4_6_overall_forces_5.bin")), s.rigid_total_forces)
+    assert np.array_equal(s.read_rotation_matrix(5), np.eye(3))
+    assert (tmp_path / "point_0_on_proc_0_displacement_frame_5.txt").read_text().startswith("5 ")
+    from bemstokes_b200.__main__ import parse_args
+    a = parse_args([])
+    assert (a.start_frame, a.end_frame, a.prm) == (0, 139, "parameters_3.prm")      # main.cc:14-15, 33
+    a = parse_args(["3", "7", "--prm", "x.prm"])
+    assert (a.start_frame, a.end_frame, a.prm) == (3, 7, "x.prm")
+
+
+def test_main_reports_exceptions_like_the_reference(capsys):
+    from bemstokes_b200.__main__ import main
+    assert main(["--prm", "does_not_exist.prm"]) == 1          # main.cc:48-60: message on stderr, status 1
+    err = capsys.readouterr().err
+    assert "Exception on processing" in err and "Aborting!" in err
