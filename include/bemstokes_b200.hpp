@@ -37,6 +37,7 @@ inline void check(int rc) {
 }
 
 using Tensor1 = std::array<double, 3>;
+using Matrix3 = std::array<std::array<double, 3>, 3>;  // FullMatrix<double>(3,3) of the rotation code
 using Tensor2 = std::array<std::array<double, 3>, 3>;
 using Tensor3 = std::array<std::array<std::array<double, 3>, 3>, 3>;
 
@@ -243,6 +244,13 @@ public:
   unsigned int bandwith = 100, gmres_restart = 100, num_rigid = 6;
   SolverControl solver_control;
   bool keep_VK = true;
+  // frame loop (bem_stokes.cc:215-216, 222-229, 282-300, 327-329)
+  unsigned int n_frames = 120, delta_frame = 1;
+  bool bool_rot = true, bool_dipl = false, bool_dipl_x = false, bool_dipl_y = false, bool_dipl_z = false;
+  std::string input_grid_path = "../debug_grids/", input_grid_base_name = "sphere_mesh_3d_", input_grid_format = "msh";
+  std::string res_strategy = "Forward", output_dir = ".";
+  double time_step = 0.1;
+  std::array<double, 4> initial_quaternion{{1., 0., 0., 0.}};
 
   // ---- state ----
   int device;
@@ -253,6 +261,9 @@ public:
       shape_velocities;
   std::vector<Vector> N_rigid, N_rigid_dual;
   Vector rigid_velocities, rigid_total_forces;
+  Matrix3 rotation_matrix = identity3();
+  Vector next_euler_vec, rigid_puntual_velocities, rigid_puntual_translation_velocities, next_rigid_puntual_displacements,
+      rigid_puntual_displacements, rigid_displacements_for_sim, total_velocities;
   double l2normGamma_pure = 0, surface = 0;
   DeviceMatrix V_matrix, K_matrix, monolithic_system_matrix;
   DirectPreconditioner direct_trilinos_preconditioner;
@@ -404,6 +415,180 @@ public:
     val_velocities.assign(3 * val_points.size(), 0.);
     set_kernel();
     check(bs_evaluate_bie(ctx, (int)val_points.size(), val_points[0].data(), vel.data(), forces.data(), val_velocities.data(), 0));
+  }
+
+  // ---- multi-frame workflow (host logic; Forward strategy, body-only swimmer, one mesh file per frame) ----------
+  static Matrix3 identity3() {
+    Matrix3 I{};
+    for (int i = 0; i < 3; ++i) I[i][i] = 1.;
+    return I;
+  }
+  // ref: compute_rotation_matrix_from_quaternion bem_stokes.cc:4512-4525
+  static void compute_rotation_matrix_from_quaternion(Matrix3 &R, const std::array<double, 4> &q) {
+    R[0] = {{1. - 2 * (q[3] * q[3] + q[2] * q[2]), -2 * q[0] * q[3] + 2 * q[1] * q[2], 2 * q[0] * q[2] + 2 * q[1] * q[3]}};
+    R[1] = {{2 * q[0] * q[3] + 2 * q[1] * q[2], 1. - 2 * (q[3] * q[3] + q[1] * q[1]), -2 * q[0] * q[1] + 2 * q[3] * q[2]}};
+    R[2] = {{-2 * q[0] * q[2] + 2 * q[1] * q[3], 2 * q[0] * q[1] + 2 * q[3] * q[2], 1. - 2 * (q[1] * q[1] + q[2] * q[2])}};
+  }
+  // ref: update_rotation_matrix bem_stokes.cc:4527-4720 (forward Euler on the quaternion; the theta scheme's 4x4
+  // system, which the reference hands to GMRES, is solved by Gaussian elimination)
+  void update_rotation_matrix(Matrix3 &rotation, const std::array<double, 3> &omega, const double dt,
+                              const bool forward_euler = true, const double theta = 0.5) const {
+    std::array<double, 4> q;
+    q[0] = std::sqrt(1. + rotation[0][0] + rotation[1][1] + rotation[2][2]) / 2;
+    q[1] = 1 / q[0] * 0.25 * (rotation[2][1] - rotation[1][2]);
+    q[2] = 1 / q[0] * 0.25 * (rotation[0][2] - rotation[2][0]);
+    q[3] = 1 / q[0] * 0.25 * (rotation[1][0] - rotation[0][1]);
+    auto normalise = [](std::array<double, 4> &v) {
+      const double n = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3]);
+      for (double &x : v) x /= n;
+    };
+    normalise(q);
+    const double op[4] = {0., omega[0], omega[1], omega[2]};
+    const double S[4][4] = {{q[0], -q[1], -q[2], -q[3]}, {q[1], q[0], q[3], -q[2]}, {q[2], -q[3], q[0], q[1]}, {q[3], q[2], -q[1], q[0]}};
+    std::array<double, 4> qdot{{0, 0, 0, 0}};
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) qdot[i] += 0.5 * S[i][j] * op[j];
+    if (forward_euler) {
+      for (int i = 0; i < 4; ++i) q[i] += dt * qdot[i];
+    } else {
+      const double h = theta * dt * 0.5;
+      double A[4][5] = {{1. + h * op[0], h * op[1], h * op[2], h * op[3], 0}, {-h * op[1], 1. + h * op[0], -h * op[3], h * op[2], 0},
+                        {-h * op[2], h * op[3], 1. + h * op[0], -h * op[1], 0}, {-h * op[3], -h * op[2], h * op[1], 1. + h * op[0], 0}};
+      for (int i = 0; i < 4; ++i) A[i][4] = q[i] + (1 - theta) * dt * qdot[i];
+      for (int c = 0; c < 4; ++c) {  // partial pivoting
+        int piv = c;
+        for (int r = c + 1; r < 4; ++r)
+          if (std::fabs(A[r][c]) > std::fabs(A[piv][c])) piv = r;
+        for (int k = 0; k < 5; ++k) std::swap(A[c][k], A[piv][k]);
+        for (int r = c + 1; r < 4; ++r) {
+          const double f = A[r][c] / A[c][c];
+          for (int k = c; k < 5; ++k) A[r][k] -= f * A[c][k];
+        }
+      }
+      for (int r = 3; r >= 0; --r) {
+        double v = A[r][4];
+        for (int k = r + 1; k < 4; ++k) v -= A[r][k] * q[k];
+        q[r] = v / A[r][r];
+      }
+    }
+    normalise(q);
+    compute_rotation_matrix_from_quaternion(rotation, q);
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        double d = -(i == j ? 1. : 0.);
+        for (int k = 0; k < 3; ++k) d += rotation[k][i] * rotation[k][j];
+        if (std::fabs(d) >= 1e-7)
+          *pcout << "Something Wrong in Rotations, " << (i == j ? "on" : "out") << " the diagonal " << std::fabs(d) << std::endl;
+      }
+  }
+  // ref: apply_rotation_along_axis bem_stokes.cc:846-878 (Rodrigues)
+  static void apply_rotation_along_axis(Tensor1 &out, const Tensor1 &in, const Tensor1 &a, const double angle) {
+    const double c = std::cos(angle), s = std::sin(angle);
+    const double R[3][3] = {{c + a[0] * a[0] * (1 - c), a[0] * a[1] * (1 - c) - a[2] * s, a[0] * a[2] * (1 - c) + a[1] * s},
+                            {a[0] * a[1] * (1 - c) + a[2] * s, c + a[1] * a[1] * (1 - c), a[1] * a[2] * (1 - c) - a[0] * s},
+                            {a[0] * a[2] * (1 - c) - a[1] * s, a[1] * a[2] * (1 - c) + a[0] * s, c + a[2] * a[2] * (1 - c)}};
+    Tensor1 r{{0, 0, 0}};
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) r[i] += R[i][j] * in[j];
+    out = r;
+  }
+  QuadMesh read_input_mesh_file(unsigned int frame) const {  // bem_stokes.cc:496-523
+    return read_mesh(input_grid_path + input_grid_base_name + std::to_string(frame) + "." + input_grid_format);
+  }
+  // ref: compute_euler_vector bem_stokes.cc:2247-2431 (mesh-file branch): nodes of the frame, rotated, component-major
+  void compute_euler_vector(Vector &euler, unsigned int frame, bool consider_displacements = true) const {
+    const QuadMesh m = read_input_mesh_file(frame);
+    if (m.n_nodes() != (int)N) throw std::runtime_error("frame grid has a different topology");
+    euler.assign(n_dofs, 0.);
+    for (unsigned int i = 0; i < N; ++i)
+      for (int r = 0; r < 3; ++r) {
+        double v = 0;
+        for (int k = 0; k < 3; ++k) v += rotation_matrix[r][k] * m.nodes[3 * i + k];
+        euler[i + r * N] = v;
+      }
+    if (consider_displacements && bool_dipl)
+      for (unsigned int i = 0; i < n_dofs; ++i) euler[i] += rigid_displacements_for_sim[i];
+  }
+  void project_shape_velocities(unsigned int /*frame*/) {  // bem_stokes.cc:2120-2137, isoparametric
+    shape_velocities.assign(n_dofs, 0.);
+    for (unsigned int i = 0; i < n_dofs; ++i) shape_velocities[i] = (next_euler_vec[i] - euler_vec[i]) / time_step;
+  }
+  // ref: update_system_state bem_stokes.cc:4725-4846 (Forward)
+  void update_system_state(bool /*compute*/, unsigned int /*frame*/, bool consider_rotations, bool consider_displacements) {
+    rigid_puntual_velocities.assign(n_dofs, 0.);
+    for (unsigned int r = 0; r < 3; ++r)
+      for (unsigned int i = 0; i < n_dofs; ++i) rigid_puntual_velocities[i] += assemble_scaling * rigid_velocities[r] * N_rigid[r][i];
+    rigid_puntual_translation_velocities = rigid_puntual_velocities;
+    for (unsigned int r = 3; r < num_rigid; ++r)
+      for (unsigned int i = 0; i < n_dofs; ++i) rigid_puntual_velocities[i] += assemble_scaling * rigid_velocities[r] * N_rigid[r][i];
+    if (consider_rotations) update_rotation_matrix(rotation_matrix, {{rigid_velocities[3], rigid_velocities[4], rigid_velocities[5]}}, time_step);
+    next_rigid_puntual_displacements.assign(n_dofs, 0.);
+    for (unsigned int i = 0; i < n_dofs; ++i) next_rigid_puntual_displacements[i] = time_step * rigid_puntual_translation_velocities[i];
+    if (consider_displacements) {
+      const bool flag[3] = {bool_dipl_x, bool_dipl_y, bool_dipl_z};
+      for (int c = 0; c < 3; ++c)
+        if (flag[c])
+          for (unsigned int i = c * N; i < (c + 1) * N; ++i) rigid_displacements_for_sim[i] += next_rigid_puntual_displacements[i];
+    }
+  }
+  // deal.II Vector<double>::block_write: "<size>\n[" raw doubles "]"
+  static void block_write(const std::string &path, const Vector &v) {
+    std::ofstream f(path, std::ios::binary);
+    const std::string head = std::to_string(v.size()) + "\n[";
+    f.write(head.data(), (std::streamsize)head.size());
+    f.write(reinterpret_cast<const char *>(v.data()), (std::streamsize)(v.size() * sizeof(double)));
+    f.write("]", 1);
+  }
+  void output_save_stokes_results(unsigned int cycle) const {  // the .bin files of bem_stokes.cc:5264-5316
+    const std::string d = output_dir + "/", c = std::to_string(cycle);
+    block_write(d + "stokes_forces_" + c + ".bin", stokes_forces);
+    block_write(d + "shape_velocities_" + c + ".bin", shape_velocities);
+    block_write(d + "total_velocities_" + c + ".bin", total_velocities);
+    Vector rot;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) rot.push_back(rotation_matrix[i][j]);
+    block_write(d + "rotation_matrix_" + c + ".bin", rot);
+    block_write(d + "4_6_rigid_velocities_" + c + ".bin", rigid_velocities);
+    block_write(d + "4_6_overall_forces_" + c + ".bin", rigid_total_forces);
+    block_write(d + "stokes_rigid_displ_" + c + ".bin", next_rigid_puntual_displacements);
+    block_write(d + "stokes_rigid_vel_" + c + ".bin", rigid_puntual_velocities);
+    block_write(d + "euler_vec_" + c + ".bin", euler_vec);
+    block_write(d + "normal_vector" + c + ".bin", normal_vector_pure);
+  }
+  // ref: BEMProblem::run bem_stokes.cc:5636-5888 (Forward)
+  void run(unsigned int start_frame = 0, unsigned int end_frame = 0) {
+    if (res_strategy != "Forward") throw Error(BS_ERR_UNSUPPORTED, "the C++ mirror runs the Forward strategy only");
+    compute_rotation_matrix_from_quaternion(rotation_matrix, initial_quaternion);
+    read_domain(read_input_mesh_file(start_frame % n_frames));
+    reinit();
+    rigid_displacements_for_sim.assign(n_dofs, 0.);
+    rigid_puntual_displacements.assign(n_dofs, 0.);
+    Vector frame_euler;
+    compute_euler_vector(frame_euler, start_frame % n_frames, true);
+    reassemble_preconditoner = true;
+    for (unsigned int i = start_frame; i <= end_frame; i += delta_frame) {
+      *pcout << "Analyzing frame = " << i << " over " << n_frames << std::endl;
+      compute_euler_vector(next_euler_vec, (i + 1) % n_frames, true);
+      euler_vec = frame_euler;
+      check(bs_set_geometry(ctx, (int)N, euler_vec.data(), mesh.n_cells(), mesh.conn.data(), (int)N, mesh.conn.data(), nullptr));
+      compute_center_of_mass_and_rigid_modes(i);
+      compute_normal_vector();
+      if (grid_type != "Real") next_euler_vec = euler_vec;
+      project_shape_velocities(i);
+      if (grid_type != "Real") shape_velocities.assign(n_dofs, 0.);
+      *pcout << "Assembling" << std::endl;
+      assemble_stokes_system(true);
+      monolithic_solution.assign(n_dofs + num_rigid, 0.);
+      solve_system(monolithic_bool);
+      update_system_state(true, i, bool_rot, bool_dipl);
+      total_velocities = shape_velocities;
+      for (unsigned int k = 0; k < n_dofs; ++k) total_velocities[k] += rigid_puntual_velocities[k];
+      rigid_puntual_displacements = next_rigid_puntual_displacements;
+      output_save_stokes_results(i);
+      *pcout << "preparing for new time" << std::endl;
+      compute_euler_vector(frame_euler, (i + delta_frame) % n_frames, true);
+    }
+    *pcout << "THE END" << std::endl;
   }
 
   static double linfty(const Vector &v) {

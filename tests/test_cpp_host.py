@@ -13,9 +13,9 @@ SRC = os.path.join(ROOT, "tests", "cpp", "minimum_preconditioner_test_no_box.cpp
 LIBDIR = os.path.join(ROOT, "bemstokes_b200")
 
 
-def build_exe(tmp):
-    exe = os.path.join(tmp, "minimum_preconditioner_test_no_box")
-    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), SRC, "-o", exe, "-L", LIBDIR,
+def build_exe(tmp, src=SRC):
+    exe = os.path.join(tmp, os.path.splitext(os.path.basename(src))[0])
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), src, "-o", exe, "-L", LIBDIR,
            "-lbemstokes_b200", "-Wl,-rpath," + LIBDIR, "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64", "-lcudart"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
@@ -47,3 +47,18 @@ def test_cpp_host_reference_style_test(tmp_path, goldens):
     assert out.count("OK") == 3 * (3 + 9)
     fc = [float(x) for x in re.findall(r"FINAL CHECK 0 ([-0-9.e+]+)", out)]
     assert len(fc) == 4 and max(fc) < 1e-9
+
+
+@pytest.mark.parametrize("scheme", ["forward_euler", "cn"])
+def test_cpp_rotation_test(tmp_path, scheme):
+    """tests/cpp/rotation_test.cpp = the reference's tests/rotation_test.cc / rotation_test_cranck_nicholson.cc on the
+    C++ mirror's quaternion integrator (host code, no GPU): every check line reads 'OK : OK : OK : '."""
+    import bemstokes_b200  # noqa: F401
+    exe = build_exe(str(tmp_path), os.path.join(ROOT, "tests", "cpp", "rotation_test.cpp"))
+    r = subprocess.run([exe] + (["cn"] if scheme == "cn" else []), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    lines = r.stdout.splitlines()
+    assert lines[0] == "Minimum Test for the rotation with quaternions"       # tests/rotation_test.output:1
+    checks = [lines[k + 1] for k, l in enumerate(lines) if l.startswith("Testing j = ")]
+    assert len(checks) == 3 * 10 and all(c == "OK : OK : OK : " for c in checks)
+    assert "ERROR" not in r.stdout and "Something Wrong in Rotations" not in r.stdout
