@@ -62,3 +62,31 @@ def test_cpp_rotation_test(tmp_path, scheme):
     checks = [lines[k + 1] for k, l in enumerate(lines) if l.startswith("Testing j = ")]
     assert len(checks) == 3 * 10 and all(c == "OK : OK : OK : " for c in checks)
     assert "ERROR" not in r.stdout and "Something Wrong in Rotations" not in r.stdout
+
+
+@pytest.mark.gpu
+def test_cpp_sphere_translation_and_frame_loop(tmp_path, goldens):
+    """tests/cpp/sphere_translation.cpp = the reference's tests/sphere_translation.cc on the C++ mirror, then the same
+    grids through BEMProblem::run; the printed lines are those of tests/sphere_translation.output."""
+    import bemstokes_b200  # noqa: F401
+    import numpy as np
+    from bemstokes_b200 import frontend as fe
+    exe = build_exe(str(tmp_path), os.path.join(ROOT, "tests", "cpp", "sphere_translation.cpp"))
+    r = subprocess.run([exe, MESHES, str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = r.stdout
+    G = goldens["sphere_translation"]
+    m = re.search(r"ERROR on rigid translation 0 : ([-0-9.e+]+) , ([-0-9.e+]+) , ([-0-9.e+]+)", out)
+    assert m, out[-1500:]
+    assert abs(float(m.group(1)) - G["rigid_velocity_0"]) < 6e-7 and abs(float(m.group(3)) - G["rel_error"]) < 6e-8
+    assert "Check on the V operator Norm (should be zero) pure: 0.00218351" in out   # tests/sphere_translation.output
+    for i in (1, 2):
+        assert "OK rigid translation %d" % i in out
+    for i in (3, 4, 5):
+        assert "OK rigid rotation %d" % i in out
+    ratio = float(re.search(r"run frame 1 velocity ratio ([-0-9.e+]+)", out).group(1))
+    assert abs(ratio + 1.0) < 2e-2
+    d0 = fe.vector_block_read(os.path.join(str(tmp_path), "stokes_rigid_displ_0.bin"))
+    N = len(d0) // 3
+    assert np.abs(d0[:N] - 0.1 * G["rigid_velocity_0"]).max() < 1e-7
+    assert os.path.exists(os.path.join(str(tmp_path), "rotation_matrix_1.bin"))
