@@ -644,13 +644,15 @@ void host_prepass(int fe_degree, int map_degree, int n_map_nodes, const double *
   };
   std::vector<double> rhs((size_t)3 * N, 0.0);  // [c][i]
   double area = 0;
-  std::vector<double> X((size_t)nam * 3);
+  std::vector<double> X((size_t)nam * 3), mloc((size_t)na * na), bloc((size_t)na * 3);
   for (int c = 0; c < ncell; ++c) {
     for (int a = 0; a < nam; ++a) {
       const int m = conn_map[(size_t)c * nam + a];
       for (int d = 0; d < 3; ++d) X[(size_t)3 * a + d] = euler_vec[(size_t)m + (size_t)d * n_map_nodes];
     }
-    for (int q = 0; q < nq; ++q) {
+    std::fill(mloc.begin(), mloc.end(), 0.0);
+    std::fill(bloc.begin(), bloc.end(), 0.0);
+    for (int q = 0; q < nq; ++q) {  // local element matrix and normal moments first, one scatter per cell afterwards
       double t1[3] = {0, 0, 0}, t2[3] = {0, 0, 0};
       for (int a = 0; a < nam; ++a)
         for (int d = 0; d < 3; ++d) {
@@ -662,11 +664,15 @@ void host_prepass(int fe_degree, int map_degree, int n_map_nodes, const double *
       const double jxw = rule.w[q] * J;
       area += jxw;
       for (int a = 0; a < na; ++a) {
-        const int i = conn[(size_t)c * na + a];
         const double pa = phi[(size_t)q * na + a];
-        for (int d = 0; d < 3; ++d) rhs[(size_t)d * N + i] += pa * (nn[d] / J) * jxw;
-        for (int b = 0; b < na; ++b) entry(i, conn[(size_t)c * na + b]) += pa * phi[(size_t)q * na + b] * jxw;
+        for (int d = 0; d < 3; ++d) bloc[(size_t)3 * a + d] += pa * (nn[d] / J) * jxw;
+        for (int b = 0; b < na; ++b) mloc[(size_t)a * na + b] += pa * phi[(size_t)q * na + b] * jxw;
       }
+    }
+    for (int a = 0; a < na; ++a) {
+      const int i = conn[(size_t)c * na + a];
+      for (int d = 0; d < 3; ++d) rhs[(size_t)d * N + i] += bloc[(size_t)3 * a + d];
+      for (int b = 0; b < na; ++b) entry(i, conn[(size_t)c * na + b]) += mloc[(size_t)a * na + b];
     }
   }
   // CG with Jacobi preconditioning, one solve per component
