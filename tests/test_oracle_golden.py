@@ -93,6 +93,18 @@ def test_V_test_with_Green_cycle0(goldens):
     pytest.fail("||V n|| of the 6-cell sphere not reproduced")
 
 
+def test_V_test_with_Green_cycle1(goldens):
+    """Second cycle of tests/V_test_with_Green.cc: one global refinement on the SphericalManifold.  On this symmetric
+    grid deal.II's new points (arc mid-points, spherical quad centres) are the radial projections the cube-sphere
+    generator uses, so the 24-cell grid is cubesphere(m=2): surface 11.0403, ||V n||_inf 0.0125199 as printed."""
+    nodes, conn = bo.cubesphere(m=2)
+    geo = bo.Geometry(nodes, conn, 1)
+    pre = bo.Prepass(geo, 8)
+    assert geo.ncell == 24 and sig6(pre.area, 11.0403)
+    V, K = bo.assemble_VK(geo, bo.KernelSpec(), 8, "Mixed", 10)
+    assert sig6(np.abs(V @ pre.nhat).max(), goldens["V_test_with_Green"]["Vn_linf"][1])
+
+
 def test_corrections_and_gmres_counts(goldens, half_refined, VK_free):
     geo, pre = half_refined
     V, K = VK_free
