@@ -119,6 +119,11 @@ def main():
                            "surface": float([l for l in dl if "The Mass (Surface) of the entire system is" in l][0].split(":")[1]),
                            "Vn_linf": float([l for l in dl if "Check on the V operator Norm (should be zero):" in l][0].split(":")[1]),
                            "ok_lines": len([l for l in dl if "OK OMEGA_" in l])}
+    vq = lines("tests/V_test_with_Green_Q2.output")
+    g["V_test_with_Green_Q2"] = {"source": "tests/V_test_with_Green_Q2.output:13,20,38,45 (parameters_test_alpha_box_ref_quadrature.prm: "
+                                           "Gauss 15, singular order 20)",
+                                 "surface": [float(l.split(":")[1]) for l in vq if "The Mass (Surface) of the entire system is" in l],
+                                 "Vn_linf": [float(l.split(":")[1]) for l in vq if "Check on the V operator Norm (should be zero) pure:" in l]}
     g["imposed_rotation"] = {"source": "tests/imposed_rotation_test_on_sphere.cc:28-31", "omega": 1.0 / (8 * 3.141592653589793),
                              "tol": 1.2e-3}
     with open(os.path.join(HERE, "reference_goldens.json"), "w") as f:

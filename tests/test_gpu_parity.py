@@ -863,3 +863,14 @@ def test_dilated_sphere_baricenter_pole(half, goldens):
         w = p.baricenter_rigid_velocities
         assert np.abs(p.rigid_velocities[:3] - (w[:3] + np.cross(w[3:6], -p.point_force_pole))).max() < 1e-15
     p.close()
+
+
+def test_V_test_with_Green_Q2_golden(goldens):
+    """tests/V_test_with_Green_Q2.output, first cycle, on the device: 6-cell Q2 sphere, Gauss 15 / QIterated(20, 2)."""
+    G = goldens["V_test_with_Green_Q2"]
+    p = make_problem(bb.cubesphere(m=1, degree=2), quadrature_order=15, singular_quadrature_order=20)
+    assert p.N == 26 and abs(p.surface - G["surface"][0]) < 6e-6 * G["surface"][0]
+    V, K = raw_VK(p)
+    vn = V @ p.normal_vector_pure
+    assert abs(np.abs(vn).max() - G["Vn_linf"][0]) < 6e-10
+    p.close()
