@@ -124,6 +124,11 @@ def main():
                                            "Gauss 15, singular order 20)",
                                  "surface": [float(l.split(":")[1]) for l in vq if "The Mass (Surface) of the entire system is" in l],
                                  "Vn_linf": [float(l.split(":")[1]) for l in vq if "Check on the V operator Norm (should be zero) pure:" in l]}
+    for name in ("V_test_with_Green_cube", "V_test_with_Green_Q2_cube"):
+        vc = lines("tests/%s.output" % name)
+        g[name] = {"source": "tests/%s.output (grid_test/sphere_0.inp refined globally WITHOUT manifold: a cube of surface 8)" % name,
+                   "surface": [float(l.split(":")[1]) for l in vc if "The Mass (Surface) of the entire system is" in l],
+                   "Vn_linf": [float(l.split(":")[1]) for l in vc if "Check on the V operator Norm (should be zero) pure:" in l]}
     g["imposed_rotation"] = {"source": "tests/imposed_rotation_test_on_sphere.cc:28-31", "omega": 1.0 / (8 * 3.141592653589793),
                              "tol": 1.2e-3}
     with open(os.path.join(HERE, "reference_goldens.json"), "w") as f:

@@ -119,6 +119,29 @@ def test_V_test_with_Green_Q2_cycle0(goldens):
     assert sig6(np.abs(V @ pre.nhat).max(), G["Vn_linf"][0])
 
 
+def _cube(m, degree):
+    """grid_test/sphere_0.inp refined m-fold without a manifold: the cube with vertices of norm 1 (the cube-sphere
+    lattice before its radial projection)."""
+    nodes, conn = bo.cubesphere(m=m, degree=degree)
+    return nodes / np.abs(nodes).max(1, keepdims=True) / np.sqrt(3.0), conn
+
+
+@pytest.mark.parametrize("name,degree,quad,sing", [("V_test_with_Green_cube", 1, 8, 10), ("V_test_with_Green_Q2_cube", 2, 15, 20)])
+def test_V_test_with_Green_on_the_cube(goldens, name, degree, quad, sing):
+    """tests/V_test_with_Green_cube.output (Q1, 6 and 24 cells) and V_test_with_Green_Q2_cube.output (Q2 with the
+    reference quadrature, 6 / 24 / 96 cells): surface 8 and ||V n||_inf on every refinement cycle, all printed digits."""
+    G = goldens[name]
+    assert len(G["Vn_linf"]) == (2 if degree == 1 else 3)
+    for cycle, want in enumerate(G["Vn_linf"]):
+        nodes, conn = _cube(2 ** cycle, degree)
+        geo = bo.Geometry(nodes, conn, degree)
+        pre = bo.Prepass(geo, quad)
+        assert geo.ncell == 6 * 4 ** cycle and sig6(pre.area, G["surface"][cycle])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            V, K = bo.assemble_VK(geo, bo.KernelSpec(), quad, "Mixed", sing)
+        assert sig6(np.abs(V @ pre.nhat).max(), want)
+
+
 def test_corrections_and_gmres_counts(goldens, half_refined, VK_free):
     geo, pre = half_refined
     V, K = VK_free
