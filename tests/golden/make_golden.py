@@ -129,6 +129,30 @@ def main():
         g[name] = {"source": "tests/%s.output (grid_test/sphere_0.inp refined globally WITHOUT manifold: a cube of surface 8)" % name,
                    "surface": [float(l.split(":")[1]) for l in vc if "The Mass (Surface) of the entire system is" in l],
                    "Vn_linf": [float(l.split(":")[1]) for l in vc if "Check on the V operator Norm (should be zero) pure:" in l]}
+    # rigidity_spiral / rigidity_flagellum: ImposedForce unit loads i = 0..5 on a helical body; for every j != i the test
+    # prints "OK" (|U_j/U_i| < 6e-3) or "ratio U_j U_i": the 6x6 mobility matrix to six digits
+    import re as _re
+    for name, grid in (("rigidity_spiral", "spiral_0.msh"), ("rigidity_flagellum", "flagellum_0.msh")):
+        out = lines("tests/%s.output" % name)
+        marks = [l.strip() for l in out if l.strip() == "OK" or _re.fullmatch(r"[-0-9.e+]+ [-0-9.e+]+ [-0-9.e+]+", l.strip())]
+        assert len(marks) == 30, (name, len(marks))
+        cols = []
+        for i in range(6):
+            col = {}
+            js = [j for j in range(6) if j != i]
+            for j, mk in zip(js, marks[5 * i:5 * i + 5]):
+                if mk == "OK":
+                    col[str(j)] = "OK"
+                else:
+                    ratio, uj, ui = [float(t) for t in mk.split()]
+                    col[str(j)] = uj
+                    col[str(i)] = ui
+            cols.append(col)
+        g[name] = {"source": "tests/%s.output + tests/%s.cc (tol 6e-3, grid_test/%s, ImposedForce, pole Origin)" % (name, name, grid),
+                   "grid": grid, "tol": 6e-3,
+                   "surface": float([l for l in out if "The Mass (Surface) of the entire system is" in l][0].split(":")[1]),
+                   "Vn_linf": float([l for l in out if "Check on the V operator Norm (should be zero) pure:" in l][0].split(":")[1]),
+                   "mobility_columns": cols}
     g["imposed_rotation"] = {"source": "tests/imposed_rotation_test_on_sphere.cc:28-31", "omega": 1.0 / (8 * 3.141592653589793),
                              "tol": 1.2e-3}
     with open(os.path.join(HERE, "reference_goldens.json"), "w") as f:
@@ -169,7 +193,8 @@ def main():
                 "debug_grids/prolate_spheroid_lambda_2_ref_0.msh", "debug_grids/sphere_very_refined_0.inp",
                 "debug_grids/sphere_very_very_refined_0.inp", "debug_grids/sphere_2.inp",
                 "tests/grid_test/sphere_translation_0.msh", "tests/grid_test/sphere_translation_1.msh",
-                "tests/grid_test/sphere_rotation_0.msh", "tests/grid_test/sphere_rotation_1.msh"]:
+                "tests/grid_test/sphere_rotation_0.msh", "tests/grid_test/sphere_rotation_1.msh",
+                "tests/grid_test/spiral_0.msh", "tests/grid_test/flagellum_0.msh"]:
         src = os.path.join(REF, rel)
         if os.path.exists(src):
             dst = os.path.join(HERE, "meshes", os.path.basename(rel))

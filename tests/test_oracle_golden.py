@@ -142,6 +142,38 @@ def test_V_test_with_Green_on_the_cube(goldens, name, degree, quad, sing):
         assert sig6(np.abs(V @ pre.nhat).max(), want)
 
 
+@pytest.mark.parametrize("name", ["rigidity_spiral", "rigidity_flagellum"])
+def test_mobility_matrix_of_helical_bodies(goldens, name):
+    """tests/rigidity_spiral.output, rigidity_flagellum.output: unit force / torque i on a helical body (ImposedForce,
+    pole at the origin); for every j != i the reference prints U_j and U_i to six digits, or OK when |U_j/U_i| < 6e-3
+    - the full 6 x 6 mobility matrix of a non-convex swimmer.  Also surface and ||V n||_inf."""
+    G = goldens[name]
+    v, q = bo.read_msh(os.path.join(MESHES, G["grid"]))
+    geo = bo.Geometry(v, q, 1)
+    pre = bo.Prepass(geo, 8)
+    assert sig6(pre.area, G["surface"])
+    V, K = bo.assemble_VK(geo, bo.KernelSpec(), 8, "Mixed", 10)
+    assert sig6(np.abs(V @ pre.nhat).max(), G["Vn_linf"])
+    Vc, _ = bo.correct_V(V, pre)
+    A, b = bo.monolithic(Vc, bo.correct_K(K, geo.N), pre, "ImposedForce", 0)
+    n = 3 * geo.N
+    checked = 0
+    for i, col in enumerate(G["mobility_columns"]):
+        rhs = np.zeros(n + 6)
+        rhs[n + i] = 1.0
+        U = np.linalg.solve(A, rhs)[n:]
+        for j in range(6):
+            want = col.get(str(j))
+            if want is None:
+                continue
+            if want == "OK":
+                assert abs(U[j] / U[i]) < G["tol"]
+            else:
+                assert sig6(U[j], want), (i, j, U[j], want)
+                checked += 1
+    assert checked >= (25 if name == "rigidity_spiral" else 8)
+
+
 def test_corrections_and_gmres_counts(goldens, half_refined, VK_free):
     geo, pre = half_refined
     V, K = VK_free
