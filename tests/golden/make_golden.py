@@ -153,6 +153,16 @@ def main():
                    "surface": float([l for l in out if "The Mass (Surface) of the entire system is" in l][0].split(":")[1]),
                    "Vn_linf": float([l for l in out if "Check on the V operator Norm (should be zero) pure:" in l][0].split(":")[1]),
                    "mobility_columns": cols}
+    # motility_spiral / motility_flagellum: ImposedVelocity unit rigid velocity i; for every j != i "OK" or |F_j/F_i|
+    for name, grid in (("motility_spiral", "spiral_0.msh"), ("motility_flagellum", "flagellum_0.msh")):
+        out = lines("tests/%s.output" % name)
+        marks = [l.strip() for l in out if l.strip() == "OK" or _re.fullmatch(r"[-0-9.e+]+( [-0-9.e+]+ [-0-9.e+]+)?", l.strip())]
+        assert len(marks) == 30, (name, len(marks))
+        # an entry is "OK", the ratio |F_j/F_i|, or [ratio, F_j, F_i] (the two tests print differently)
+        conv = lambda m: m if m == "OK" else ([float(t) for t in m.split()] if " " in m else float(m))
+        g[name] = {"source": "tests/%s.output + tests/%s.cc (tol 6e-3, grid_test/%s, ImposedVelocity)" % (name, name, grid),
+                   "grid": grid, "tol": 6e-3,
+                   "force_ratio_columns": [[conv(m) for m in marks[5 * i:5 * i + 5]] for i in range(6)]}
     g["imposed_rotation"] = {"source": "tests/imposed_rotation_test_on_sphere.cc:28-31", "omega": 1.0 / (8 * 3.141592653589793),
                              "tol": 1.2e-3}
     with open(os.path.join(HERE, "reference_goldens.json"), "w") as f:

@@ -174,6 +174,38 @@ def test_mobility_matrix_of_helical_bodies(goldens, name):
     assert checked >= (25 if name == "rigidity_spiral" else 8)
 
 
+@pytest.mark.parametrize("name", ["motility_spiral", "motility_flagellum"])
+def test_resistance_ratios_of_helical_bodies(goldens, name):
+    """tests/motility_spiral.output, motility_flagellum.output: unit rigid velocity i (ImposedVelocity); for every
+    j != i the reference prints |F_j / F_i| to six digits or OK below 6e-3 - the resistance matrix up to column scales."""
+    G = goldens[name]
+    tol = G["tol"]
+    v, q = bo.read_msh(os.path.join(MESHES, G["grid"]))
+    geo = bo.Geometry(v, q, 1)
+    pre = bo.Prepass(geo, 8)
+    V, K = bo.assemble_VK(geo, bo.KernelSpec(), 8, "Mixed", 10)
+    Vc, _ = bo.correct_V(V, pre)
+    A, b = bo.monolithic(Vc, bo.correct_K(K, geo.N), pre, "ImposedVelocity", 0)
+    n = 3 * geo.N
+    checked = 0
+    for i, col in enumerate(G["force_ratio_columns"]):
+        rhs = np.zeros(n + 6)
+        rhs[n + i] = 1.0
+        x = np.linalg.solve(A, rhs)
+        F = np.array([x[:n] @ pre.N_rigid_dual[r] for r in range(6)])
+        for j, want in zip([j for j in range(6) if j != i], col):
+            ratio = abs(F[j] / F[i])
+            if want == "OK":
+                assert ratio < tol
+            elif isinstance(want, list):   # ratio, F_j, F_i
+                assert sig6(ratio, want[0]) and sig6(F[j], want[1]) and sig6(F[i], want[2]), (i, j, ratio, F[j], F[i], want)
+                checked += 1
+            else:
+                assert sig6(ratio, want), (i, j, ratio, want)
+                checked += 1
+    assert checked >= 6
+
+
 def test_corrections_and_gmres_counts(goldens, half_refined, VK_free):
     geo, pre = half_refined
     V, K = VK_free
