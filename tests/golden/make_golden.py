@@ -163,6 +163,10 @@ def main():
         g[name] = {"source": "tests/%s.output + tests/%s.cc (tol 6e-3, grid_test/%s, ImposedVelocity)" % (name, name, grid),
                    "grid": grid, "tol": 6e-3,
                    "force_ratio_columns": [[conv(m) for m in marks[5 * i:5 * i + 5]] for i in range(6)]}
+    bt = lines("tests/baricenter_torus.output")
+    g["baricenter_torus"] = {"source": "tests/baricenter_torus.output:9-11 (grid_test/torus_0.inp)",
+                             "surface": float([l for l in bt if "The Mass (Surface) of the entire system is" in l][0].split(":")[1]),
+                             "center_of_mass": [float(t) for t in [l for l in bt if l.startswith("Center of mass position")][0].split("=")[1].split()]}
     g["imposed_rotation"] = {"source": "tests/imposed_rotation_test_on_sphere.cc:28-31", "omega": 1.0 / (8 * 3.141592653589793),
                              "tol": 1.2e-3}
     with open(os.path.join(HERE, "reference_goldens.json"), "w") as f:
@@ -204,7 +208,7 @@ def main():
                 "debug_grids/sphere_very_very_refined_0.inp", "debug_grids/sphere_2.inp",
                 "tests/grid_test/sphere_translation_0.msh", "tests/grid_test/sphere_translation_1.msh",
                 "tests/grid_test/sphere_rotation_0.msh", "tests/grid_test/sphere_rotation_1.msh",
-                "tests/grid_test/spiral_0.msh", "tests/grid_test/flagellum_0.msh"]:
+                "tests/grid_test/spiral_0.msh", "tests/grid_test/flagellum_0.msh", "tests/grid_test/torus_0.inp"]:
         src = os.path.join(REF, rel)
         if os.path.exists(src):
             dst = os.path.join(HERE, "meshes", os.path.basename(rel))

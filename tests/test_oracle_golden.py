@@ -206,6 +206,25 @@ def test_resistance_ratios_of_helical_bodies(goldens, name):
     assert checked >= 6
 
 
+def test_center_of_mass_of_the_torus(goldens):
+    """tests/baricenter_torus.output: surface and centre of mass int y dS / int dS of grid_test/torus_0.inp
+    (compute_center_of_mass_and_rigid_modes, bem_stokes.cc:2487-2493, 2540-2545) - the quantity behind the
+    'Baricenter' force pole."""
+    G = goldens["baricenter_torus"]
+    v, q = bo.read_inp(os.path.join(MESHES, "torus_0.inp"))
+    geo = bo.Geometry(v, q, 1)
+    xi, w = bo.gauss2(8)
+    num, area = np.zeros(3), 0.0
+    for c in range(geo.ncell):
+        y, n, jxw = bo.fe_cell(geo.map_nodes[geo.map_conn[c]], 1, xi, w)
+        num += (y * jxw[:, None]).sum(0)
+        area += jxw.sum()
+    com = num / area
+    assert sig6(area, G["surface"])
+    assert abs(com[0]) < 1e-11 and abs(G["center_of_mass"][0]) < 1e-11            # rounding-level component
+    assert sig6(com[1], G["center_of_mass"][1]) and sig6(com[2], G["center_of_mass"][2])
+
+
 def test_corrections_and_gmres_counts(goldens, half_refined, VK_free):
     geo, pre = half_refined
     V, K = VK_free
