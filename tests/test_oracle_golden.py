@@ -225,6 +225,22 @@ def test_center_of_mass_of_the_torus(goldens):
     assert sig6(com[1], G["center_of_mass"][1]) and sig6(com[2], G["center_of_mass"][2])
 
 
+def test_origin_rigid_modes():
+    """tests/origin_rigid_modes.cc (1 116 'OK' lines): the six rigid modes about the origin are 1;0;0  0;1;0  0;0;1
+    0;-z;y  z;0;-x  -y;x;0 at the support points of grid_test/spiral_0.msh, to 1e-13 - oracle and host pre-pass."""
+    from bemstokes_b200.prepass import Prepass
+    v, q = bo.read_msh(os.path.join(MESHES, "spiral_0.msh"))
+    geo = bo.Geometry(v, q, 1)
+    x, y, z = geo.support.T
+    o, e = np.zeros_like(x), np.ones_like(x)
+    exact = [np.concatenate(t) for t in ((e, o, o), (o, e, o), (o, o, e), (o, -z, y), (z, o, -x), (-y, x, o))]
+    host = Prepass(v, q, 1, geo.N, q, 1, 8)
+    ora = bo.Prepass(geo, 8)
+    for k in range(6):
+        assert np.abs(host.N_rigid[k] - exact[k]).max() <= 1e-13
+        assert np.abs(ora.N_rigid[k] - exact[k]).max() <= 1e-13
+
+
 def test_corrections_and_gmres_counts(goldens, half_refined, VK_free):
     geo, pre = half_refined
     V, K = VK_free
