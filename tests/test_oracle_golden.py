@@ -454,3 +454,49 @@ def test_dilated_sphere_baricenter_pole(goldens):
         rhs[n + i] = 1.0
         U = np.linalg.solve(A, rhs)[n:]
         assert abs(U[i] - exact) / exact <= G["tol"]
+
+
+def _G_fs_old(p, pim, o):
+    """FreeSurfaceStokesKernel<3>::value_tens_image_old (source/free_surface_kernel.cc:82-127): the image point is the
+    mirrored SOURCE, the sign sits on column j == wall_orientation."""
+    R, Ri = np.linalg.norm(p), np.linalg.norm(pim)
+    G = np.zeros((3, 3))
+    for i in range(3):
+        for j in range(3):
+            d = 1.0 * (i == j)
+            a, b = p[i] * p[j] / R ** 3 + d / R, pim[i] * pim[j] / Ri ** 3 + d / Ri
+            G[i, j] = ((a - b) if j == o else (a + b)) / (8 * np.pi)
+    return G
+
+
+def _W_fs_old(p, pim, o):
+    """value_tens_image2_old (source/free_surface_kernel.cc:331-400): signs by (j, k) against the wall orientation."""
+    R, Ri = np.linalg.norm(p), np.linalg.norm(pim)
+    W = np.zeros((3, 3, 3))
+    for i in range(3):
+        for j in range(3):
+            for k in range(3):
+                a = -3 * p[i] * p[j] * p[k] / R ** 5 / (4 * np.pi)
+                b = -3 * pim[i] * pim[j] * pim[k] / Ri ** 5 / (4 * np.pi)
+                W[i, j, k] = a + b if (j == o) == (k == o) else a - b
+    return W
+
+
+def test_reflected_kernel_comparison_tests():
+    """tests/reflected_kernel_test_G_comparison.cc / _W_comparison.cc (all lines 'OK', tol 1e-6): the free-surface
+    kernels evaluated with the mirrored valuation point agree with the older formulation that mirrors the source - an
+    independent pin of the image double-layer kernel W (SURVEY App. B lists it as otherwise unpinned)."""
+    rng = np.random.default_rng(5)
+    for o in range(3):
+        position = 1.0
+        cases = [(np.zeros(3), np.eye(3)[o] * (position + 3.0) + np.eye(3)[(o + 1) % 3] * 3.0)]       # the reference's point
+        cases += [(rng.uniform(-2, 0.5, 3), rng.uniform(-2, 0.5, 3)) for _ in range(20)]              # and random ones
+        for source, val in cases:
+            val_image, source_image = val.copy(), source.copy()
+            val_image[o] -= 2 * (val[o] - position)
+            source_image[o] -= 2 * (source[o] - position)
+            R, R_image, R_image_old = val - source, val_image - source, val - source_image
+            G = bo.G_fs(R[None], R_image[None], o)[0]
+            W = bo.W_fs(R[None], R_image[None], o)[0]
+            assert np.abs(G - _G_fs_old(R, R_image_old, o)).max() < 1e-13 * max(1.0, np.abs(G).max())
+            assert np.abs(W - _W_fs_old(R, R_image_old, o)).max() < 1e-13 * max(1.0, np.abs(W).max())
