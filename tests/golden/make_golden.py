@@ -167,6 +167,17 @@ def main():
     g["baricenter_torus"] = {"source": "tests/baricenter_torus.output:9-11 (grid_test/torus_0.inp)",
                              "surface": float([l for l in bt if "The Mass (Surface) of the entire system is" in l][0].split(":")[1]),
                              "center_of_mass": [float(t) for t in [l for l in bt if l.startswith("Center of mass position")][0].split("=")[1].split()]}
+    mr = lines("tests/motility_rotation_spiral.output")
+    pairs = [l for l in mr if " --- " in l]
+    assert len(pairs) == 6
+    g["motility_rotation_spiral"] = {
+        "source": "tests/motility_rotation_spiral.output (last 6 lines: F_j(frame 30) : R F_j(frame 0) --- U_j : U_j) + .cc",
+        "setup": "grid_test/spiral_0.msh and spiral_30.msh, ImposedVelocity unit omega_x (i = 3), solved directly; the frame-0 "
+                 "forces are rotated by the quaternion (cos(a/2), sin(a/2), 0, 0), a = -2 pi 30/120",
+        "forces_frame30": [float(l.split(":")[0]) for l in pairs],
+        "forces_frame0_rotated": [float(l.split(":")[1].split("---")[0]) for l in pairs],
+        "surface": [float(l.split(":")[1]) for l in mr if "The Mass (Surface) of the entire system is" in l],
+        "Vn_linf": [float(l.split(":")[1]) for l in mr if "Check on the V operator Norm (should be zero) pure:" in l]}
     g["imposed_rotation"] = {"source": "tests/imposed_rotation_test_on_sphere.cc:28-31", "omega": 1.0 / (8 * 3.141592653589793),
                              "tol": 1.2e-3}
     with open(os.path.join(HERE, "reference_goldens.json"), "w") as f:
@@ -208,7 +219,8 @@ def main():
                 "debug_grids/sphere_very_very_refined_0.inp", "debug_grids/sphere_2.inp",
                 "tests/grid_test/sphere_translation_0.msh", "tests/grid_test/sphere_translation_1.msh",
                 "tests/grid_test/sphere_rotation_0.msh", "tests/grid_test/sphere_rotation_1.msh",
-                "tests/grid_test/spiral_0.msh", "tests/grid_test/flagellum_0.msh", "tests/grid_test/torus_0.inp"]:
+                "tests/grid_test/spiral_0.msh", "tests/grid_test/flagellum_0.msh", "tests/grid_test/torus_0.inp",
+                "tests/grid_test/spiral_30.msh"]:
         src = os.path.join(REF, rel)
         if os.path.exists(src):
             dst = os.path.join(HERE, "meshes", os.path.basename(rel))

@@ -500,3 +500,32 @@ def test_reflected_kernel_comparison_tests():
             W = bo.W_fs(R[None], R_image[None], o)[0]
             assert np.abs(G - _G_fs_old(R, R_image_old, o)).max() < 1e-13 * max(1.0, np.abs(G).max())
             assert np.abs(W - _W_fs_old(R, R_image_old, o)).max() < 1e-13 * max(1.0, np.abs(W).max())
+
+
+def test_motility_rotation_spiral(goldens):
+    """tests/motility_rotation_spiral.output: resistance column of a unit omega_x on the helix at frame 0 and at frame 30
+    (a quarter turn later), every printed force / torque to six digits; the frame-0 values are rotated with
+    compute_rotation_matrix_from_quaternion exactly as the reference test does."""
+    from bemstokes_b200 import frontend as fe
+    G = goldens["motility_rotation_spiral"]
+    F = []
+    for k, grid in enumerate(("spiral_0.msh", "spiral_30.msh")):
+        v, q = bo.read_msh(os.path.join(MESHES, grid))
+        geo = bo.Geometry(v, q, 1)
+        pre = bo.Prepass(geo, 8)
+        assert sig6(pre.area, G["surface"][k])
+        V, K = bo.assemble_VK(geo, bo.KernelSpec(), 8, "Mixed", 10)
+        assert sig6(np.abs(V @ pre.nhat).max(), G["Vn_linf"][k])
+        Vc, _ = bo.correct_V(V, pre)
+        A, b = bo.monolithic(Vc, bo.correct_K(K, geo.N), pre, "ImposedVelocity", 0)
+        n = 3 * geo.N
+        rhs = np.zeros(n + 6)
+        rhs[n + 3] = 1.0
+        x = np.linalg.solve(A, rhs)
+        F.append(np.array([x[:n] @ pre.N_rigid_dual[r] for r in range(6)]))
+    angle = -2 * np.pi * 30 / 120
+    Rm = fe.compute_rotation_matrix_from_quaternion([np.cos(angle / 2), np.sin(angle / 2), 0.0, 0.0])
+    rotated = np.concatenate([Rm @ F[0][:3], Rm @ F[0][3:]])
+    for j in range(6):
+        assert sig6(F[1][j], G["forces_frame30"][j]), (j, F[1][j])
+        assert sig6(rotated[j], G["forces_frame0_rotated"][j]), (j, rotated[j])
