@@ -529,3 +529,21 @@ def test_motility_rotation_spiral(goldens):
     for j in range(6):
         assert sig6(F[1][j], G["forces_frame30"][j]), (j, F[1][j])
         assert sig6(rotated[j], G["forces_frame0_rotated"][j]), (j, rotated[j])
+
+
+def test_motility_sphere(half_refined, VK_free):
+    """tests/motility_sphere.output: 30 'OK' lines - for a sphere every off-diagonal entry of the resistance matrix
+    (ImposedVelocity, unit rigid velocity i) is below 6e-3 of the diagonal one."""
+    geo, pre = half_refined
+    V, K = VK_free
+    Vc, _ = bo.correct_V(V, pre)
+    A, b = bo.monolithic(Vc, bo.correct_K(K, geo.N), pre, "ImposedVelocity", 0)
+    n = 3 * geo.N
+    for i in range(6):
+        rhs = np.zeros(n + 6)
+        rhs[n + i] = 1.0
+        x = np.linalg.solve(A, rhs)
+        F = np.array([x[:n] @ pre.N_rigid_dual[r] for r in range(6)])
+        for j in range(6):
+            if j != i:
+                assert abs(F[j] / F[i]) < 6e-3
