@@ -261,7 +261,8 @@ public:
       shape_velocities;
   std::vector<Vector> N_rigid, N_rigid_dual;
   Vector rigid_velocities, rigid_total_forces;
-  Matrix3 rotation_matrix = identity3();
+  Matrix3 rotation_matrix = identity3(), old_rotation_matrix = identity3();
+  Vector old_rigid_velocities, old_rigid_displacements_for_sim;
   Vector next_euler_vec, rigid_puntual_velocities, rigid_puntual_translation_velocities, next_rigid_puntual_displacements,
       rigid_puntual_displacements, rigid_displacements_for_sim, total_velocities;
   double l2normGamma_pure = 0, surface = 0;
@@ -513,8 +514,19 @@ public:
     shape_velocities.assign(n_dofs, 0.);
     for (unsigned int i = 0; i < n_dofs; ++i) shape_velocities[i] = (next_euler_vec[i] - euler_vec[i]) / time_step;
   }
-  // ref: update_system_state bem_stokes.cc:4725-4846 (Forward)
-  void update_system_state(bool /*compute*/, unsigned int /*frame*/, bool consider_rotations, bool consider_displacements) {
+  // ref: update_system_state bem_stokes.cc:4725-4846 ("Forward"; Heun's corrector restores the backed-up state and
+  // integrates the mean of the two velocities)
+  void update_system_state(bool /*compute*/, unsigned int /*frame*/, bool consider_rotations, bool consider_displacements,
+                           const std::string &res_system = "Forward") {
+    if (res_system == "Heun" && res_strategy == "Heun") {
+      rotation_matrix = old_rotation_matrix;
+      rigid_displacements_for_sim = old_rigid_displacements_for_sim;
+      for (unsigned int r = 0; r < num_rigid; ++r) rigid_velocities[r] = 0.5 * rigid_velocities[r] + 0.5 * old_rigid_velocities[r];
+    } else if (res_system == "Forward" && res_strategy == "Heun") {
+      old_rigid_velocities = rigid_velocities;
+      old_rotation_matrix = rotation_matrix;
+      old_rigid_displacements_for_sim = rigid_displacements_for_sim;
+    }
     rigid_puntual_velocities.assign(n_dofs, 0.);
     for (unsigned int r = 0; r < 3; ++r)
       for (unsigned int i = 0; i < n_dofs; ++i) rigid_puntual_velocities[i] += assemble_scaling * rigid_velocities[r] * N_rigid[r][i];
@@ -555,9 +567,9 @@ public:
     block_write(d + "euler_vec_" + c + ".bin", euler_vec);
     block_write(d + "normal_vector" + c + ".bin", normal_vector_pure);
   }
-  // ref: BEMProblem::run bem_stokes.cc:5636-5888 (Forward)
+  // ref: BEMProblem::run bem_stokes.cc:5636-5888 (Forward and Heun)
   void run(unsigned int start_frame = 0, unsigned int end_frame = 0) {
-    if (res_strategy != "Forward") throw Error(BS_ERR_UNSUPPORTED, "the C++ mirror runs the Forward strategy only");
+    if (res_strategy != "Forward" && res_strategy != "Heun") throw Error(BS_ERR_UNSUPPORTED, "unknown time integration " + res_strategy);
     compute_rotation_matrix_from_quaternion(rotation_matrix, initial_quaternion);
     read_domain(read_input_mesh_file(start_frame % n_frames));
     reinit();
@@ -566,9 +578,7 @@ public:
     Vector frame_euler;
     compute_euler_vector(frame_euler, start_frame % n_frames, true);
     reassemble_preconditoner = true;
-    for (unsigned int i = start_frame; i <= end_frame; i += delta_frame) {
-      *pcout << "Analyzing frame = " << i << " over " << n_frames << std::endl;
-      compute_euler_vector(next_euler_vec, (i + 1) % n_frames, true);
+    auto solve_frame = [&](unsigned int i) {  // geometry of frame_euler -> pre-pass -> shape velocities -> assemble -> solve
       euler_vec = frame_euler;
       check(bs_set_geometry(ctx, (int)N, euler_vec.data(), mesh.n_cells(), mesh.conn.data(), (int)N, mesh.conn.data(), nullptr));
       compute_center_of_mass_and_rigid_modes(i);
@@ -580,7 +590,20 @@ public:
       assemble_stokes_system(true);
       monolithic_solution.assign(n_dofs + num_rigid, 0.);
       solve_system(monolithic_bool);
-      update_system_state(true, i, bool_rot, bool_dipl);
+    };
+    for (unsigned int i = start_frame; i <= end_frame; i += delta_frame) {
+      *pcout << "Analyzing frame = " << i << " over " << n_frames << std::endl;
+      compute_euler_vector(next_euler_vec, (i + 1) % n_frames, true);
+      solve_frame(i);
+      if (res_strategy == "Forward") {
+        update_system_state(true, i, bool_rot, bool_dipl, "Forward");
+      } else {  // Heun: predictor state, geometry and solve at the next frame, corrector with the mean velocity
+        update_system_state(true, i, bool_rot, bool_dipl, "Forward");
+        compute_euler_vector(frame_euler, (i + 1) % n_frames, true);
+        compute_euler_vector(next_euler_vec, (i + 2) % n_frames, true);
+        solve_frame(i);
+        update_system_state(true, i, bool_rot, bool_dipl, "Heun");
+      }
       total_velocities = shape_velocities;
       for (unsigned int k = 0; k < n_dofs; ++k) total_velocities[k] += rigid_puntual_velocities[k];
       rigid_puntual_displacements = next_rigid_puntual_displacements;

@@ -51,7 +51,7 @@ int main(int argc, char **argv) {
     if (std::fabs(U[i]) <= tol) std::cout << "OK rigid rotation " << i << std::endl;
     else std::cout << "ERROR on rigid rotation " << i << " : " << U[i] << std::endl;
   }
-  bem_problem_3d.update_system_state(true, 0, false, false);
+  bem_problem_3d.update_system_state(true, 0, false, false, "Forward");
   bem_problem_3d.total_velocities = bem_problem_3d.shape_velocities;
   bem_problem_3d.output_save_stokes_results(0);
   const double u0 = U[0];
