@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbemstokes_b200.so")
-SOURCES = ["bs_host.cu", "bs_assembly.cu", "bs_linalg.cu", "bs_solve.cu", "bs_eval.cu", "bs_prepass.cu", "bs_api.cu"]
+SOURCES = ["bs_host.cu", "bs_assembly.cu", "bs_linalg.cu", "bs_solve.cu", "bs_gmres.cu", "bs_eval.cu", "bs_prepass.cu", "bs_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("BS_NVCC_EXTRA", "").split()
 

@@ -2,6 +2,7 @@
 box, gloo in the CPU tests).  The reference gets these from Epetra: Import in vmult = allgather of the Krylov
 vector, Allreduce in Dot/Norm.  PyTorch is plumbing here: device pointers are wrapped without
 copies and the collectives are ordered on the context's stream."""
+import contextlib
 import ctypes as C
 
 import numpy as np
@@ -41,22 +42,30 @@ class TorchComm:
     def attach(self, ctx):
         _lib.check(_lib.lib.bs_set_comm(ctx, self.allgatherv_cb, self.allreduce_cb, None))
 
+    def _on_stream(self, stream):
+        """Order torch's work on the stream the library launches on (the `stream` argument of the callback): the
+        collectives read and write the same device buffers as the library's kernels."""
+        if stream and self.device is not None and torch.device(self.device).type == "cuda":
+            return torch.cuda.stream(torch.cuda.ExternalStream(int(stream), device=self.device))
+        return contextlib.nullcontext()
+
     def _allgatherv(self, user, send, sendcount, recv, counts, displs, stream):
         try:
-            P = dist.get_world_size(self.group)
-            cnt = [counts[r] for r in range(P)]
-            dsp = [displs[r] for r in range(P)]
-            mx = max(cnt)
-            total = max(d + c for d, c in zip(dsp, cnt))
-            if self._scratch is None or self._scratch.numel() < (P + 1) * mx:
-                self._scratch = torch.zeros((P + 1) * mx, dtype=torch.float64, device=self.device)
-            pad = self._scratch[P * mx:(P + 1) * mx]
-            pad[:sendcount].copy_(dev_tensor(send, sendcount, self.device))
-            out = self._scratch[:P * mx]
-            dist.all_gather_into_tensor(out, pad, group=self.group)
-            dst = dev_tensor(recv, total, self.device)
-            for r in range(P):
-                dst[dsp[r]:dsp[r] + cnt[r]].copy_(out[r * mx:r * mx + cnt[r]])
+            with self._on_stream(stream):
+                P = dist.get_world_size(self.group)
+                cnt = [counts[r] for r in range(P)]
+                dsp = [displs[r] for r in range(P)]
+                mx = max(cnt)
+                total = max(d + c for d, c in zip(dsp, cnt))
+                if self._scratch is None or self._scratch.numel() < (P + 1) * mx:
+                    self._scratch = torch.zeros((P + 1) * mx, dtype=torch.float64, device=self.device)
+                pad = self._scratch[P * mx:(P + 1) * mx]
+                pad[:sendcount].copy_(dev_tensor(send, sendcount, self.device))
+                out = self._scratch[:P * mx]
+                dist.all_gather_into_tensor(out, pad, group=self.group)
+                dst = dev_tensor(recv, total, self.device)
+                for r in range(P):
+                    dst[dsp[r]:dsp[r] + cnt[r]].copy_(out[r * mx:r * mx + cnt[r]])
             self.n_allgather += 1
             return 0
         except Exception as e:  # never let an exception cross the C boundary
@@ -65,8 +74,9 @@ class TorchComm:
 
     def _allreduce(self, user, buf, count, stream):
         try:
-            t = dev_tensor(buf, count, self.device)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            with self._on_stream(stream):
+                t = dev_tensor(buf, count, self.device)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
             self.n_allreduce += 1
             return 0
         except Exception as e:

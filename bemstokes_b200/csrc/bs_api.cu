@@ -181,6 +181,7 @@ int bs_destroy(bs_context *h) {
       if (c.peer_flags[r]) cudaIpcCloseMemHandle(c.peer_flags[r]);
     }
   drop_extra(c);
+  gm_host_release(c);
   if (c.ev0) cudaEventDestroy(c.ev0);
   if (c.ev1) cudaEventDestroy(c.ev1);
   if (c.own_stream && c.stream) cudaStreamDestroy(c.stream);
@@ -1004,10 +1005,12 @@ int bs_exchange_export(bs_context *h, size_t max_vec_len, unsigned char *handles
   Context &c = ctx_of(h);
   BS_REQUIRE(handles_out != nullptr && max_vec_len > 0, "bad arguments");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  BS_REQUIRE(c.nranks <= BS_MAX_RANKS, "the peer exchange supports at most 32 ranks");
   c.xchg_ld = (max_vec_len + 17) & ~(size_t)15;
-  c.d_xchg.alloc(Context::XCHG_SLOTS * c.xchg_ld);
+  c.red_off = Context::XCHG_SLOTS * c.xchg_ld;  // then [2 parities][nranks][BS_RED_CAP] partial sums of the peers
+  c.d_xchg.alloc(c.red_off + 2 * (size_t)c.nranks * BS_RED_CAP);
   c.d_xchg.zero(c.stream);
-  c.d_flags.alloc(64);
+  c.d_flags.alloc(BS_FLAG_WORDS);
   c.d_flags.zero(c.stream);
   BS_CUDA(cudaStreamSynchronize(c.stream));
   cudaIpcMemHandle_t hx, hf;
@@ -1022,6 +1025,7 @@ int bs_exchange_import(bs_context *h, int nranks, const unsigned char *all) {
   BS_API_BEGIN
   Context &c = ctx_of(h);
   BS_REQUIRE(nranks == c.nranks && all != nullptr, "nranks mismatch");
+  BS_REQUIRE(nranks <= BS_MAX_RANKS, "the peer exchange supports at most 32 ranks");
   BS_REQUIRE(c.d_xchg.p != nullptr, "call bs_exchange_export first");
   c.peer_xbuf.assign(nranks, nullptr);
   c.peer_flags.assign(nranks, nullptr);

@@ -122,6 +122,16 @@ constexpr int CTAS_PER_SM = BS_CTAS_PER_SM;  // resident CTAs per SM the shared-
 constexpr int MAX_NA = 9;     // Q2
 constexpr int MAX_RIGID = 7;
 
+// flag words of the peer exchange (own copy in d_flags, written by the peers through the IPC mapping)
+constexpr int BS_MAX_RANKS = 32;
+constexpr int BS_FLAG_XCHG = 0;    // [32] arrival epoch of every source rank's Krylov slice
+constexpr int BS_FLAG_RED = 32;    // [32] arrival sequence number of every source rank's partial sums
+constexpr int BS_FLAG_ERR = 64;    // non-zero: a wait timed out (a rank stopped answering)
+constexpr int BS_FLAG_EPOCH = 65;  // this rank's exchange epoch (device-resident counter)
+constexpr int BS_FLAG_SEQ = 66;    // this rank's reduction sequence number
+constexpr int BS_FLAG_WORDS = 128;
+constexpr size_t BS_RED_CAP = 8192;  // doubles per (parity, source rank) of the cross-rank reduction area
+
 struct ColumnBlocks {
   int tj = 0;                       // column nodes per block
   int nblocks = 0;
@@ -229,8 +239,10 @@ struct Context {
   static constexpr int XCHG_SLOTS = 8;   // replicated vectors in flight (multi-RHS lockstep solves)
   bool p2p = false;
   size_t xchg_ld = 0;               // doubles per slot
-  DBuf<double> d_xchg;              // [XCHG_SLOTS][xchg_ld] replicated vector buffer written by all ranks
-  DBuf<unsigned long long> d_flags; // [nranks] arrival epoch per source rank (+1 error word)
+  size_t red_off = 0;               // offset of the reduction area [2][nranks][BS_RED_CAP] inside d_xchg
+  DBuf<double> d_xchg;              // [XCHG_SLOTS][xchg_ld] replicated vector buffer written by all ranks, then the reduction area
+  DBuf<unsigned long long> d_flags; // BS_FLAG_WORDS words, see the BS_FLAG_* layout below
+  void *gm_host = nullptr;          // bs_gmres.cu: pinned status mirror of the device-resident GMRES
   std::vector<void *> peer_xbuf, peer_flags;   // mapped pointers, rank order (own entry = local pointer)
   DBuf<double *> d_peer_xbuf;
   DBuf<unsigned long long *> d_peer_flags;
@@ -285,8 +297,9 @@ int choose_tj(int na, int kernel_type, int nq_pad);
 void kernel_eval_device(int type, double eps, int o, int npts, const double *d_p, const double *d_pim, double *d_G,
                         double *d_W, cudaStream_t s);
 // ---- linear algebra (bs_linalg.cu) ------------------------------------------------------------------------
-void gemv(Context &c, const DMat &M, const double *x, double *y);                  // y[rows] = M x
-void gemv_multi(Context &c, const DMat &M, int nrhs, const double *X, size_t ldx, double *Y, size_t ldy);
+// y[rows] = M x; skip != nullptr: device flag, the sweep returns at once when it is set (device-resident GMRES)
+void gemv(Context &c, const DMat &M, const double *x, double *y, const int *skip = nullptr);
+void gemv_multi(Context &c, const DMat &M, int nrhs, const double *X, size_t ldx, double *Y, size_t ldy, const int *skip = nullptr);
 void rank1_update(Context &c, DMat &M, const double *u, const double *w, double scale);  // M += scale u w^T
 void perm_in(Context &c, const double *src_dev, double *dst_int, const int *d_node_of_pos, int nextra);
 void perm_out(Context &c, const double *src_int, double *dst_dev, const int *d_node_of_pos, int nextra, size_t lo, size_t hi);
@@ -312,7 +325,13 @@ void apply_operator(Context &c, int which, const double *x_full, double *y_loc);
 void exchange(Context &c, int which, const double *y_loc, double *x_full);
 void p2p_scatter(Context &c, int which, const double *src_loc, int slot, const double *inv_norm2, double *basis_dst);
 void p2p_wait(Context &c);
-void apply_precond(Context &c, const double *in_loc, double *out_loc);
+void p2p_signal(Context &c);                                         // bs_gmres.cu: device-resident epoch
+void p2p_wait_only(Context &c, const int *skip, void *gm_status);
+void apply_precond(Context &c, const double *in_loc, double *out_loc, const int *skip = nullptr);
+bool gmres_device_eligible(Context &c, int nrhs, int max_tmp);
+int gmres_device(Context &c, int which, int nrhs, const double *d_B, double *d_X, size_t ldv, double tol, int max_steps,
+                 int max_tmp, int *iters, double *final_res);
+void gm_host_release(Context &c);
 int gmres(Context &c, int which, const double *d_b_loc, double *d_x_loc, double tol, int max_steps, int max_tmp,
           int *iters, double *final_res);
 int gmres_batched(Context &c, int which, int nrhs, const double *d_B, double *d_X, size_t ldv, double tol, int max_steps,

@@ -21,7 +21,9 @@ __device__ __forceinline__ double2 ld_stream2(const double *p) {
 
 template <int RPW>
 __global__ void __launch_bounds__(32 * GEMV_WARPS) k_gemv(const double *__restrict__ A, size_t ld, size_t rows, size_t cols,
-                                                          const double *__restrict__ x, double *__restrict__ y) {
+                                                          const double *__restrict__ x, double *__restrict__ y,
+                                                          const int *skip) {
+  if (skip && *skip) return;
   const int lane = threadIdx.x & 31;
   const size_t warp = (size_t)blockIdx.x * GEMV_WARPS + (threadIdx.x >> 5);
   const size_t r0 = warp * RPW;
@@ -69,12 +71,12 @@ __global__ void __launch_bounds__(32 * GEMV_WARPS) k_gemv(const double *__restri
   }
 }
 
-void gemv(Context &c, const DMat &M, const double *x, double *y) {
+void gemv(Context &c, const DMat &M, const double *x, double *y, const int *skip) {
   if (M.rows == 0) return;
   BS_REQUIRE((M.ld & 1) == 0, "matrix ld must be even");
   const size_t warps = (M.rows + GEMV_RPW - 1) / GEMV_RPW;
   const unsigned grid = (unsigned)((warps + GEMV_WARPS - 1) / GEMV_WARPS);
-  k_gemv<GEMV_RPW><<<grid, 32 * GEMV_WARPS, 0, c.stream>>>(M.p, M.ld, M.rows, M.cols, x, y);
+  k_gemv<GEMV_RPW><<<grid, 32 * GEMV_WARPS, 0, c.stream>>>(M.p, M.ld, M.rows, M.cols, x, y, skip);
   BS_CUDA(cudaGetLastError());
   count_launch(c);
 }
@@ -85,7 +87,8 @@ void gemv(Context &c, const DMat &M, const double *x, double *y) {
 template <int NR, int RPW, int U>
 __global__ void __launch_bounds__(32 * GEMV_WARPS) k_gemv_multi(const double *__restrict__ A, size_t ld, size_t rows,
                                                                 size_t cols, const double *__restrict__ X, size_t ldx,
-                                                                double *__restrict__ Y, size_t ldy) {
+                                                                double *__restrict__ Y, size_t ldy, const int *skip) {
+  if (skip && *skip) return;
   const int lane = threadIdx.x & 31;
   const size_t warp = (size_t)blockIdx.x * GEMV_WARPS + (threadIdx.x >> 5);
   const size_t r0 = warp * RPW;
@@ -151,11 +154,11 @@ __global__ void __launch_bounds__(32 * GEMV_WARPS) k_gemv_multi(const double *__
 #endif
 
 template <int NR>
-static void launch_gemv_multi(Context &c, const DMat &M, const double *X, size_t ldx, double *Y, size_t ldy) {
+static void launch_gemv_multi(Context &c, const DMat &M, const double *X, size_t ldx, double *Y, size_t ldy, const int *skip) {
   constexpr int RPW = BS_GEMVM_RPW, U = BS_GEMVM_U;
   const size_t warps = (M.rows + RPW - 1) / RPW;
   const unsigned grid = (unsigned)((warps + GEMV_WARPS - 1) / GEMV_WARPS);
-  k_gemv_multi<NR, RPW, U><<<grid, 32 * GEMV_WARPS, 0, c.stream>>>(M.p, M.ld, M.rows, M.cols, X, ldx, Y, ldy);
+  k_gemv_multi<NR, RPW, U><<<grid, 32 * GEMV_WARPS, 0, c.stream>>>(M.p, M.ld, M.rows, M.cols, X, ldx, Y, ldy, skip);
   BS_CUDA(cudaGetLastError());
   count_launch(c);
 }
@@ -180,7 +183,8 @@ constexpr int DMMA_WARPS = 4;
 template <int MB, int U>
 __global__ void __launch_bounds__(32 * DMMA_WARPS) k_gemm_dmma(const double *__restrict__ A, size_t ld, size_t rows, size_t cols,
                                                               const double *__restrict__ X, size_t ldx, int nrhs,
-                                                              double *__restrict__ P, size_t ldp, size_t kchunk) {
+                                                              double *__restrict__ P, size_t ldp, size_t kchunk, const int *skip) {
+  if (skip && *skip) return;
   const int lane = threadIdx.x & 31, g = lane >> 2, kk = lane & 3;
   const size_t warp = (size_t)blockIdx.x * DMMA_WARPS + (threadIdx.x >> 5);
   const size_t r0 = warp * (8 * MB);
@@ -236,7 +240,8 @@ __global__ void __launch_bounds__(32 * DMMA_WARPS) k_gemm_dmma(const double *__r
 }
 
 __global__ void k_sum_ksplit(size_t rows, int nrhs, int ksplit, const double *__restrict__ P, size_t ldp, double *__restrict__ Y,
-                             size_t ldy) {
+                             size_t ldy, const int *skip) {
+  if (skip && *skip) return;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y;
   if (i >= rows || n >= nrhs) return;
@@ -252,7 +257,7 @@ __global__ void k_sum_ksplit(size_t rows, int nrhs, int ksplit, const double *__
 #define BS_DMMA_U 4
 #endif
 
-static void gemm_dmma(Context &c, const DMat &M, int nrhs, const double *X, size_t ldx, double *Y, size_t ldy) {
+static void gemm_dmma(Context &c, const DMat &M, int nrhs, const double *X, size_t ldx, double *Y, size_t ldy, const int *skip) {
   constexpr int MB = BS_DMMA_MB, U = BS_DMMA_U;
   const size_t row_warps = (M.rows + 8 * MB - 1) / (8 * MB);
   const unsigned gx = (unsigned)((row_warps + DMMA_WARPS - 1) / DMMA_WARPS);
@@ -264,14 +269,14 @@ static void gemm_dmma(Context &c, const DMat &M, int nrhs, const double *X, size
   ksplit = (int)((M.cols + kchunk - 1) / kchunk);
   const size_t ldp = (M.rows + 1) & ~(size_t)1;
   double *P = c.wsd("gemm.partial", (size_t)ksplit * 8 * ldp);
-  k_gemm_dmma<MB, U><<<dim3(gx, ksplit), 32 * DMMA_WARPS, 0, c.stream>>>(M.p, M.ld, M.rows, M.cols, X, ldx, nrhs, P, ldp, kchunk);
+  k_gemm_dmma<MB, U><<<dim3(gx, ksplit), 32 * DMMA_WARPS, 0, c.stream>>>(M.p, M.ld, M.rows, M.cols, X, ldx, nrhs, P, ldp, kchunk, skip);
   BS_CUDA(cudaGetLastError());
-  k_sum_ksplit<<<dim3((unsigned)((M.rows + 255) / 256), nrhs), 256, 0, c.stream>>>(M.rows, nrhs, ksplit, P, ldp, Y, ldy);
+  k_sum_ksplit<<<dim3((unsigned)((M.rows + 255) / 256), nrhs), 256, 0, c.stream>>>(M.rows, nrhs, ksplit, P, ldp, Y, ldy, skip);
   BS_CUDA(cudaGetLastError());
   count_launch(c, 2);
 }
 
-void gemv_multi(Context &c, const DMat &M, int nrhs, const double *X, size_t ldx, double *Y, size_t ldy) {
+void gemv_multi(Context &c, const DMat &M, int nrhs, const double *X, size_t ldx, double *Y, size_t ldy, const int *skip) {
   if (M.rows == 0) return;
   BS_REQUIRE((ldx & 1) == 0, "multi-vector ld must be even");
   int done = 0;
@@ -282,19 +287,19 @@ void gemv_multi(Context &c, const DMat &M, int nrhs, const double *X, size_t ldx
     const bool aligned16 = (ldx % 2 == 0) && (reinterpret_cast<uintptr_t>(Xp) % 16 == 0) && (M.ld % 8 == 0) &&
                            (reinterpret_cast<uintptr_t>(M.p) % 16 == 0);
     if (nr >= 4 && aligned16 && !std::getenv("BS_NO_DMMA")) {  // FP64 tensor path; up to 3 right-hand sides the FMA kernel is HBM bound
-      gemm_dmma(c, M, nr, Xp, ldx, Yp, ldy);
+      gemm_dmma(c, M, nr, Xp, ldx, Yp, ldy, skip);
       done += nr;
       continue;
     }
     switch (nr) {
-      case 1: launch_gemv_multi<1>(c, M, Xp, ldx, Yp, ldy); break;
-      case 2: launch_gemv_multi<2>(c, M, Xp, ldx, Yp, ldy); break;
-      case 3: launch_gemv_multi<3>(c, M, Xp, ldx, Yp, ldy); break;
-      case 4: launch_gemv_multi<4>(c, M, Xp, ldx, Yp, ldy); break;
-      case 5: launch_gemv_multi<5>(c, M, Xp, ldx, Yp, ldy); break;
-      case 6: launch_gemv_multi<6>(c, M, Xp, ldx, Yp, ldy); break;
-      case 7: launch_gemv_multi<7>(c, M, Xp, ldx, Yp, ldy); break;
-      default: launch_gemv_multi<8>(c, M, Xp, ldx, Yp, ldy); break;
+      case 1: launch_gemv_multi<1>(c, M, Xp, ldx, Yp, ldy, skip); break;
+      case 2: launch_gemv_multi<2>(c, M, Xp, ldx, Yp, ldy, skip); break;
+      case 3: launch_gemv_multi<3>(c, M, Xp, ldx, Yp, ldy, skip); break;
+      case 4: launch_gemv_multi<4>(c, M, Xp, ldx, Yp, ldy, skip); break;
+      case 5: launch_gemv_multi<5>(c, M, Xp, ldx, Yp, ldy, skip); break;
+      case 6: launch_gemv_multi<6>(c, M, Xp, ldx, Yp, ldy, skip); break;
+      case 7: launch_gemv_multi<7>(c, M, Xp, ldx, Yp, ldy, skip); break;
+      default: launch_gemv_multi<8>(c, M, Xp, ldx, Yp, ldy, skip); break;
     }
     done += nr;
   }

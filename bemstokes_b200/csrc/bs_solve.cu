@@ -61,25 +61,6 @@ __global__ void k_p2p_scatter(const double *__restrict__ src, size_t n, const do
     for (int r = 0; r < nranks; ++r) peer_bufs[r][dst_off + i] = v;  // own buffer included; peers over NVLink
   }
 }
-__global__ void k_p2p_signal(unsigned long long *const *peer_flags, int nranks, int myrank, unsigned long long epoch) {
-  const int r = threadIdx.x;
-  if (r >= nranks) return;
-  __threadfence_system();
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_flags[r] + myrank), "l"(epoch) : "memory");
-}
-__global__ void k_p2p_wait(const unsigned long long *flags, int nranks, unsigned long long epoch, unsigned long long *err) {
-  const int r = threadIdx.x;
-  if (r >= nranks) return;
-  unsigned long long t0, t1, v;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  do {
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + r) : "memory");
-    if (v >= epoch) return;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-  } while (t1 - t0 < 20000000000ull);  // 20 s: a rank died; report instead of hanging the GPU
-  *err = epoch;
-}
-
 // store my slice (optionally normalised by 1/sqrt(*inv_norm2), optionally also into the local basis) into slot
 // `slot` of every rank's replicated buffer
 void p2p_scatter(Context &c, int which, const double *src_loc, int slot, const double *inv_norm2, double *basis_dst) {
@@ -94,11 +75,8 @@ void p2p_scatter(Context &c, int which, const double *src_loc, int slot, const d
 }
 // publish everything scattered so far and wait until every rank has published the same epoch
 void p2p_wait(Context &c) {
-  ++c.epoch;
-  k_p2p_signal<<<1, 32, 0, c.stream>>>(c.d_peer_flags.p, c.nranks, c.rank, c.epoch);
-  k_p2p_wait<<<1, 32, 0, c.stream>>>(c.d_flags.p, c.nranks, c.epoch, c.d_flags.p + 48);
-  BS_CUDA(cudaGetLastError());
-  count_launch(c, 2);
+  p2p_signal(c);  // the epoch is a device-resident counter (bs_gmres.cu), shared with the device-resident solver
+  p2p_wait_only(c, nullptr, nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -570,7 +548,8 @@ void lu_solve(Context &c, const double *LU, size_t n_, size_t ld, const int *piv
 // ---------------------------------------------------------------------------------------------------------
 // preconditioner application on the local slice
 // ---------------------------------------------------------------------------------------------------------
-void apply_precond(Context &c, const double *in_loc, double *out_loc) {
+void apply_precond(Context &c, const double *in_loc, double *out_loc, const int *skip) {
+  (void)skip;
   const size_t mloc = c.local_vec_len(c.prec_which);
   switch (c.prec_kind) {
     case BS_PREC_NONE:
@@ -657,6 +636,10 @@ int gmres_batched(Context &c, int which, int nrhs, const double *d_B, double *d_
                   int max_tmp, int *iters, double *final_res) {
   BS_REQUIRE(max_tmp >= 3, "max_n_tmp_vectors must be >= 3");
   BS_REQUIRE(nrhs >= 1, "nrhs must be positive");
+  // default: the device-resident iteration (bs_gmres.cu).  This host-driven loop remains for deal.II's modified
+  // Gram-Schmidt verbatim (host decisions every 5th iteration) and for callback communicators.
+  if (gmres_device_eligible(c, nrhs, max_tmp))
+    return gmres_device(c, which, nrhs, d_B, d_X, ldv, tol, max_steps, max_tmp, iters, final_res);
   const int m = max_tmp - 2;  // restart length (deal.II: n_tmp_vectors - 2 inner iterations)
   const size_t mloc = c.local_vec_len(which), mfull = c.full_vec_len(which);
   const size_t ldw = (mloc + 3) & ~(size_t)1, ldx = (mfull + 4) & ~(size_t)3;
@@ -866,7 +849,7 @@ int gmres_batched(Context &c, int which, int nrhs, const double *d_B, double *d_
   (void)sgrid;
   if (p2p) {  // a rank that timed out in the flag wait reports instead of hanging
     unsigned long long err = 0;
-    BS_CUDA(cudaMemcpyAsync(&err, c.d_flags.p + 48, sizeof(err), cudaMemcpyDeviceToHost, c.stream));
+    BS_CUDA(cudaMemcpyAsync(&err, c.d_flags.p + BS_FLAG_ERR, sizeof(err), cudaMemcpyDeviceToHost, c.stream));
     BS_CUDA(cudaStreamSynchronize(c.stream));
     if (err != 0) throw Error(BS_ERR_COMM, "peer exchange timed out waiting for epoch " + std::to_string(err));
   }

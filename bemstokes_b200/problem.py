@@ -227,6 +227,7 @@ class BEMProblem(FrameLoop):
         ctx = _lib.ctx_p()
         check(lib.bs_create(C.byref(ctx), self.device, self.fe_degree, self.map_degree))
         self._ctx = ctx
+        self._block_prec_ready = False
         if self.stream is not None:
             check(lib.bs_set_stream(ctx, C.c_void_p(self.stream)))
         if self.n_mpi_processes > 1:
@@ -397,6 +398,14 @@ class BEMProblem(FrameLoop):
         elif t in ("Direct",):
             if self.direct_trilinos_preconditioner._matrix is None or self.reassemble_preconditoner:
                 self.direct_trilinos_preconditioner.initialize(DeviceMatrix(self, which))
+                self.reassemble_preconditoner = False
+        elif t == "BlockDirect":
+            # block-Jacobi form of the DirectPreconditioner for row-sharded runs: every rank factorises its own diagonal
+            # block once and keeps the LU across frames, like the reference's reuse of direct_trilinos_preconditioner
+            # (bem_stokes.cc:5768-5779; refactorised when a solve needed more than 100 iterations, 4336-4339)
+            if not getattr(self, "_block_prec_ready", False) or self.reassemble_preconditoner:
+                check(lib.bs_precond_setup(self._ctx, which, _lib.PREC_BLOCK_DIRECT, 0))
+                self._block_prec_ready = True
                 self.reassemble_preconditoner = False
         elif t in ("ILU", "AMG"):
             # on these dense matrices ILU(0) is the exact LU and ML collapses to a direct coarse solve

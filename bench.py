@@ -7,7 +7,8 @@ One step = one pass of the hot path on a synthetic quad sphere:
 Headline `value` = assembly Gentries/s (2*(3N)^2 entries of V and K / assembly time, whole job, inputs resident
 in HBM); the line also carries the GMRES matvec HBM GB/s and the time-to-solution of the step — the three parts
 of BASELINE.json's metric.  `e2e` = the same assembly metric through the public BEMProblem / C-ABI call with
-HOST buffers (geometry H2D inside the timed region, V*n check vector D2H), plus the host-to-host time to solution.
+HOST buffers (geometry H2D inside the timed region, V*n check vector D2H), plus the host-to-host time to solution,
+both means over `--steps` repetitions.
 
 Workloads (config.workload): the default is the BASELINE config-4 family — synthetic cube-sphere, Q1, Gauss 8 /
 Lachat-Watson 10, translating sphere — with m = round(128 * (N/8)^(1/4)) subdivisions per face edge, i.e. the same
@@ -16,10 +17,17 @@ assembly).  At N=8 this is BASELINE config 4 exactly (98 306 nodes, 294 918 DoF,
 largest member one 180 GB B200 holds (34 658 nodes, 103 974 DoF).  These sizes use the fused no-K assembly
 (bs_assemble_fused: the double-layer tile is consumed in the tile epilogue, V and K would not fit together).
 --workload vk keeps both matrices (m = 64 * N^(1/4), 43.5 GB each per GPU); --workload q2 runs BASELINE config 3
-(Q2, Gauss 15 / singular 20).
+(Q2, Gauss 15 / singular 20); --workload c5 / c5ns the image kernels of BASELINE config 5.
 
-`--impl reference` times the reference's CPU path (the C/OpenMP restatement under oracle/, all host threads)
-on a bounded row sample of the same workload.
+`parity_at_scale`: at every N each rank re-assembles the raw operators and compares rows of the stored V (and K
+when it is stored) of collocation nodes it owns with the C port of the oracle (same mesh, same rules), entry by
+entry; the run fails (exit 3) above 1e-12 of the row scale.
+
+The default 1-GPU run also measures `secondary_workloads` (free-surface and no-slip image kernels, Q2 / config 3,
+6 batched right-hand sides / config 2) on smaller meshes, each with its own roofline fraction.
+
+`--impl reference` times the reference's CPU path (the C/OpenMP restatement under oracle/, all host threads
+regardless of OMP_NUM_THREADS) on a bounded row sample of the same workload.
 """
 import argparse
 import json
@@ -36,6 +44,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+METRIC = "assembly Gentries/s + GMRES matvec HBM GB/s; time-to-solution at 3N DoF"
+PARITY_TOL = 1e-12
+
 
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -45,17 +56,28 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
+def usable_cores():
+    """Host threads this process may use: the affinity mask, NOT OMP_NUM_THREADS (torchrun exports 1)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def workload(args, nranks):
-    if args.workload == "q2":
+    kind = args.workload
+    if kind == "q2":
         r = args.refine if args.refine is not None else 4
         return dict(kind="cubesphere", m=2 ** r, degree=2, quad=15, sing=20, fused=False,
                     name="BASELINE config 3: cube-sphere (sphere_2.inp topology) refined %dx, Q2, Gauss 15 / Mixed 20" % r)
-    if args.workload == "c5":
+    if kind in ("c5", "c5ns"):
         m = args.m if args.m else int(round(64 * nranks ** 0.25))
-        return dict(kind="cubesphere", m=m, degree=1, quad=8, sing=10, fused=False, kernel="free_surface",
-                    name="BASELINE config 5 kernel: synthetic cube-sphere m=%d, Q1, Gauss 8 / Lachat-Watson 10, "
-                         "FreeSurfaceStokesKernel (image system, wall y = 1.4), V and K both stored" % m)
-    if args.workload == "vk":
+        kern = "free_surface" if kind == "c5" else "no_slip"
+        return dict(kind="cubesphere", m=m, degree=1, quad=8, sing=10, fused=False, kernel=kern,
+                    name="BASELINE config 5 kernel: synthetic cube-sphere m=%d, Q1, Gauss 8 / Lachat-Watson 10, %s "
+                         "(image system, wall y = 1.4), V and K both stored"
+                         % (m, "FreeSurfaceStokesKernel" if kind == "c5" else "NoSlipWallStokesKernel"))
+    if kind == "vk":
         m = args.m if args.m else int(round(64 * nranks ** 0.25))
         return dict(kind="cubesphere", m=m, degree=1, quad=8, sing=10, fused=False,
                     name="synthetic cube-sphere m=%d (6*m^2 quads), Q1 collocation, Gauss 8 / Lachat-Watson 10, translating "
@@ -64,6 +86,24 @@ def workload(args, nranks):
     return dict(kind="cubesphere", m=m, degree=1, quad=8, sing=10, fused=not args.no_fused,
                 name="BASELINE config 4 family: synthetic cube-sphere m=%d (6*m^2 quads; m=128 at 8 GPUs = 98 306 nodes), Q1 "
                      "collocation, Gauss 8 / Lachat-Watson 10, translating sphere ImposedVelocity e_x, fused no-K assembly" % m)
+
+
+def mesh_sizes(wl):
+    """(nodes, cells) of the closed cube-sphere without building it."""
+    ncell = 6 * wl["m"] ** 2
+    return (ncell + 2 if wl["degree"] == 1 else 4 * ncell + 2), ncell
+
+
+def config_of(wl, world):
+    """Workload description, identical on both arms (the driver compares it)."""
+    N, ncell = mesh_sizes(wl)
+    n = 3 * N
+    return {"workload": wl["name"], "nodes": N, "cells": ncell, "dofs": n, "matrix_gb_each": 8.0 * n * n / 1e9,
+            "sharding": "rows (collocation nodes) over %d GPU(s), contiguous ranges of the locality order" % world,
+            "l2": "working set (%.1f GB of matrix per GPU) far larger than the 126 MB L2, no explicit flush needed"
+                  % (8.0 * n * n / 1e9 / world * (1 if wl.get("fused") else 2)),
+            "value_definition": "2*(3N)^2 entries of V and K evaluated / (K0+K1+K2 device time, CUDA events on the launching "
+                                "stream); ms_per_step is the whole step (assembly + corrections + monolithic build + GMRES)"}
 
 
 class ClockSampler:
@@ -110,23 +150,178 @@ class ClockSampler:
 
 
 def load_traffic(wl, world):
-    """ncu-measured DRAM traffic of the two dominant kernels for exactly this workload (profiles/r01_traffic.json)."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """ncu-measured DRAM traffic of the two dominant kernels for exactly this workload (profiles/*_traffic.json,
+    newest round first)."""
     key = "c4:m=%d:%s:n_gpus=%d" % (wl["m"], "fused" if wl.get("fused") else "vk", world)
-    try:
-        with open(path) as f:
-            t = json.load(f)
-        if t.get("workload_key") == key:
-            return t["k_gemv<2>"]["dram_bytes_per_launch"], t["k_assemble_regular"]["dram_bytes_per_assembly"]
-    except Exception:
-        pass
-    return None, None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f)
+            if t.get("workload_key") == key:
+                return t["k_gemv<2>"]["dram_bytes_per_launch"], t["k_assemble_regular"]["dram_bytes_per_assembly"], name
+        except Exception:
+            pass
+    return None, None, None
 
 
-def pairs_count(n_rows_nodes, ncell, nq, sing_pts_per_cell):
-    """(node, q-point) pairs: every (row node, cell) pair uses nq points, except the na singular pairs of each
-    cell, which use their singular rule."""
-    return n_rows_nodes * ncell * nq, sing_pts_per_cell * ncell
+def f_pair_of(wl):
+    """Algorithmic flops per (node, quadrature point) pair, SURVEY §8d."""
+    na = 4 if wl["degree"] == 1 else 9
+    k = wl.get("kernel")
+    if k == "free_surface":
+        return 95 + 36 * na
+    if k == "no_slip":
+        return 190 + 36 * na
+    return 50 + 24 * na
+
+
+def pairs_count(lib, _lib, wl):
+    N, ncell = mesh_sizes(wl)
+    na = 4 if wl["degree"] == 1 else 9
+    sing_pts = sum(lib.bs_make_singular_rule(_lib.SING_MIXED, wl["sing"], wl["degree"], a, 0, None, None) for a in range(na))
+    # every (row node, cell) pair uses nq points, except the na singular pairs of each cell, which use their rule
+    return N * ncell * wl["quad"] ** 2, sing_pts * ncell
+
+
+def oracle_kernel_spec(bo, wl):
+    k = wl.get("kernel")
+    if k == "free_surface":
+        return bo.KernelSpec(bo.FREE_SURFACE, 0.0, 1, (0.0, 1.4, 0.0))
+    if k == "no_slip":
+        return bo.KernelSpec(bo.NO_SLIP, 0.0, 1, (0.0, 1.4, 0.0))
+    return bo.KernelSpec()
+
+
+def set_problem_kernel(p, wl):
+    # tests/parameters_test_alpha_box.prm: wall 0 spans 80,0,80 at y = 1.4
+    if wl.get("kernel") == "free_surface":
+        p.reflect_kernel, p.wall_spans_0, p.wall_position_0 = True, (80.0, 0.0, 80.0), (0.0, 1.4, 0.0)
+    elif wl.get("kernel") == "no_slip":
+        p.no_slip_kernel, p.wall_spans_0, p.wall_position_0 = True, (80.0, 0.0, 80.0), (0.0, 1.4, 0.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def parity_at_scale(p, wl, geo, nodes_per_rank, extra_rows=None):
+    """Rows of the stored raw V (and K) of nodes this rank owns against the C port (the checker, not the product).
+    Returns (rows compared, max row-relative error of V, of K or None)."""
+    from oracle import bem_oracle as bo, port
+    from bemstokes_b200._lib import lib, check
+    from bemstokes_b200 import _lib
+    N = geo.N
+    n = 3 * N
+    if p.fused_assembly:   # raw operators again (the timed steps corrected V in place)
+        nh, mn = np.ascontiguousarray(p.normal_vector_pure), np.ascontiguousarray(p.M_normal_vector_pure)
+        Nr0 = np.ascontiguousarray(p.N_rigid[:p.num_rigid])
+        dp = _lib.c_double_p
+        check(lib.bs_assemble_fused(p._ctx, p.num_rigid, Nr0.ctypes.data_as(dp), nh.ctypes.data_as(dp), mn.ctypes.data_as(dp),
+                                    p.l2normGamma_pure, None))
+    else:
+        check(lib.bs_assemble_VK(p._ctx))
+    own = p.owned_nodes()
+    pick = own[np.unique(np.linspace(0, len(own) - 1, max(1, nodes_per_rank)).astype(np.int64))]
+    kspec = oracle_kernel_spec(bo, wl)
+    cols = np.arange(n, dtype=np.int32)
+    ev = ek = 0.0
+    have_k = not p.fused_assembly
+    count = 0
+
+    def compare(i, Vp, Kp):
+        nonlocal ev, ek, count
+        for c in range(3):
+            r = np.full(n, i + c * N, dtype=np.int32)
+            vg = p.V_matrix.entries(r, cols)
+            ev = max(ev, float(np.abs(vg - Vp[c]).max() / np.abs(Vp[c]).max()))
+            if have_k:
+                kg = p.K_matrix.entries(r, cols)
+                ek = max(ek, float(np.abs(kg - Kp[c]).max() / np.abs(Kp[c]).max()))
+            count += 1
+
+    for i in pick:
+        Vp, Kp, _ = port.assemble_VK(geo, kspec, wl["quad"], "Mixed", wl["sing"], int(i), int(i) + 1, 1)
+        compare(int(i), Vp, Kp)
+    if extra_rows is not None:   # the rows the cpu_baseline leg assembled anyway (single rank: all owned)
+        r0, Vp, Kp = extra_rows
+        nr = Vp.shape[0] // 3
+        ownset = set(int(x) for x in own)
+        for k in range(0, nr, max(1, nr // 16)):
+            if r0 + k in ownset:
+                compare(r0 + k, Vp[[k, k + nr, k + 2 * nr]], Kp[[k, k + nr, k + 2 * nr]])
+    return count, ev, (ek if have_k else None)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def secondary_workloads(device, fp64_peak, args):
+    """Smaller members of BASELINE configs 5, 3 and 2 measured in the same process (1 GPU), each with its own
+    roofline fraction (pairs x F_pair / K0+K1+K2 time / FP64 peak)."""
+    import bemstokes_b200 as bb
+    from bemstokes_b200 import _lib
+    from bemstokes_b200._lib import lib, check
+    import torch
+    out = {}
+
+    def assembly_case(tag, wl, reps=3):
+        mesh = bb.cubesphere(degree=wl["degree"], m=wl["m"])
+        p = bb.BEMProblem(device=device)
+        p.set_mesh(mesh)
+        p.quadrature_order, p.singular_quadrature_order = wl["quad"], wl["sing"]
+        set_problem_kernel(p, wl)
+        p.reinit()
+        check(lib.bs_assemble_VK(p._ctx))   # warm-up
+        p.reset_stats()
+        for _ in range(reps):
+            check(lib.bs_assemble_VK(p._ctx))
+        st = p.stats()
+        ms = (st["geometry_ms"] + st["assemble_regular_ms"] + st["assemble_singular_ms"]) / reps
+        n = 3 * mesh.n_nodes
+        pr, ps = pairs_count(lib, _lib, wl)
+        fp = f_pair_of(wl)
+        tf = (pr + ps) * fp / (ms * 1e-3) / 1e12
+        out[tag] = {"workload": wl["name"], "nodes": mesh.n_nodes, "value": 2.0 * n * n / (ms * 1e-3) / 1e9, "unit": "Gentries/s",
+                    "assembly_ms": ms, "flops_per_pair": fp, "achieved_tflops": tf, "frac": tf / fp64_peak}
+        p.close()
+
+    a = argparse.Namespace(workload="c5", m=args.secondary_m, refine=None, no_fused=False)
+    assembly_case("c5_free_surface", workload(a, 1))
+    a.workload = "c5ns"
+    assembly_case("c5_no_slip", workload(a, 1))
+    a.workload, a.refine = "q2", args.secondary_refine
+    assembly_case("q2_config3", workload(a, 1))
+    # ---- config 2: prolate spheroid (x scaled by 2), full 6x6 resistance matrix, 6 batched right-hand sides
+    m2 = args.secondary_m
+    mesh = bb.cubesphere(degree=1, m=m2, scale=(2.0, 1.0, 1.0))
+    p = bb.BEMProblem(device=device)
+    p.set_mesh(mesh)
+    p.quadrature_order, p.singular_quadrature_order = 8, 10
+    p.grid_type, p.imposed_component = "ImposedVelocity", 0
+    p.solve_directly, p.preconditioner_type, p.keep_VK = False, "None", False
+    p.solver_control.tolerance, p.solver_control.max_steps, p.gmres_restart = 1e-10, 1000, 200
+    p.reinit()
+    p.compute_center_of_mass_and_rigid_modes()
+    p.compute_normal_vector()
+    p.assemble_stokes_system(True)
+    n = p.n_dofs
+    p.resistance_matrix()   # warm-up (workspaces)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    Rm = p.resistance_matrix()
+    torch.cuda.synchronize()
+    t_b = time.perf_counter() - t0
+    its_b = list(p.last_steps)
+    t0 = time.perf_counter()
+    for r in range(6):
+        p.monolithic_rhs[:] = 0
+        p.monolithic_rhs[n + r] = 1
+        p.monolithic_solution[:] = 0
+        p.solve_system(True)
+    torch.cuda.synchronize()
+    t_s = time.perf_counter() - t0
+    out["resistance_6rhs"] = {"workload": "BASELINE config 2: synthetic prolate spheroid (cube-sphere m=%d, x scaled by 2), Q1, "
+                                          "6 x 6 resistance matrix, 6 batched right-hand sides" % m2,
+                              "nodes": mesh.n_nodes, "batched_s": t_b, "sequential_s": t_s, "speedup": t_s / t_b,
+                              "iterations": its_b, "R_diag": [float(Rm[i, i]) for i in range(6)],
+                              "R_offdiag_over_diag_max": float(np.abs(Rm - np.diag(np.diag(Rm))).max() / np.abs(np.diag(Rm)).min())}
+    p.close()
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -148,25 +343,20 @@ def run_ours(args):
     comm = None
     if world > 1:
         import datetime
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
         from bemstokes_b200.comm import TorchComm
         comm = TorchComm(device=dev)
-        # one explicit stream for the library's kernels AND torch's collectives (the legacy default stream is
-        # not ordered against the library's non-blocking stream)
-        side = torch.cuda.Stream(device=dev)
-        torch.cuda.set_stream(side)
     wl = workload(args, world)
     mesh = bb.cubesphere(degree=wl["degree"], m=wl["m"])
     N, ncell = mesh.n_nodes, mesh.n_cells
+    assert (N, ncell) == mesh_sizes(wl)
     n = 3 * N
-    stream = torch.cuda.current_stream().cuda_stream if world > 1 else None
-    p = bb.BEMProblem(device=local, rank=rank, nranks=world, comm=comm, stream=stream)
+    p = bb.BEMProblem(device=local, rank=rank, nranks=world, comm=comm)
     p.set_mesh(mesh)
     p.quadrature_order, p.singular_quadrature_order = wl["quad"], wl["sing"]
-    if wl.get("kernel") == "free_surface":   # tests/parameters_test_alpha_box.prm: wall 0 spans 80,0,80 at y = 1.4
-        p.reflect_kernel, p.wall_spans_0, p.wall_position_0 = True, (80.0, 0.0, 80.0), (0.0, 1.4, 0.0)
+    set_problem_kernel(p, wl)
     p.grid_type, p.imposed_component = "ImposedVelocity", 0
-    p.solve_directly, p.preconditioner_type = False, "None"
+    p.solve_directly, p.preconditioner_type = False, args.preconditioner
     p.keep_VK = False  # A aliases V's storage
     p.fused_assembly = bool(wl.get("fused"))
     p.use_peer_exchange = not args.no_peer_exchange
@@ -237,7 +427,6 @@ def run_ours(args):
     p.reset_stats()
     if comm is not None:
         comm.n_allgather = comm.n_allreduce = 0
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
     t0 = time.perf_counter()
     its = 0
@@ -247,150 +436,224 @@ def run_ours(args):
     sync()
     wall = time.perf_counter() - t0
     st = p.stats()
+    n_ag, n_ar = (comm.n_allgather, comm.n_allreduce) if comm else (0, 0)
     clocks = sampler.stop() if rank == 0 else None
     drag = float(p.rigid_total_forces[0])  # every rank holds the gathered solution
+    final_check = getattr(p, "final_check_0", (None, None))
     asm_ms = (st["geometry_ms"] + st["assemble_regular_ms"] + st["assemble_singular_ms"]) / args.steps
-    # ---- matvec bandwidth: device-resident GEMV loop on the monolithic matrix (L2 flushed by its own 43 GB) ----
+    # ---- matvec bandwidth: device-resident GEMV loop on the monolithic matrix (L2 flushed by its own 87 GB) ----
     ms_mv = C.c_double()
     check(lib.bs_bench_vmult(p._ctx, _lib.MAT_A, 10, C.byref(ms_mv)))
-    # ---- optional: BASELINE config-2 style batched solve (6 rigid-body right-hand sides in lockstep) ----
-    res6 = None
-    if args.resistance and world == 1:
-        torch.cuda.synchronize()
-        t6 = time.perf_counter()
-        Rm = p.resistance_matrix()
-        torch.cuda.synchronize()
-        t_batched = time.perf_counter() - t6
-        t6 = time.perf_counter()
-        for r in range(6):
-            p.monolithic_rhs[:] = 0
-            p.monolithic_rhs[n + r] = 1
-            p.monolithic_solution[:] = 0
-            p.solve_system(True)
-        torch.cuda.synchronize()
-        t_seq = time.perf_counter() - t6
-        res6 = {"batched_s": t_batched, "sequential_s": t_seq, "iterations": p.last_steps,
-                "R_diag_over_6pi_8pi": [float(Rm[i, i] / (6 * math.pi if i < 3 else 8 * math.pi)) for i in range(6)]}
-    # ---- e2e through host buffers ----
+    # ---- optional: frames with the frame-0 block LU reused as the preconditioner (ref: bem_stokes.cc:5768-5779) ----
+    frames = None
+    if args.frames > 0:
+        frames = run_frames(p, mesh, args, sync, torch)
+    # ---- e2e through host buffers: mean over `steps` ----
     e2e_asm, e2e_tts, e2e_pre = [], [], []
-    for _ in range(max(1, min(args.steps, 2))):
+    for _ in range(max(1, args.steps)):
         a, b, c_ = step_e2e()
         e2e_asm.append(a)
         e2e_tts.append(b)
         e2e_pre.append(c_)
     sync()
-    # max over ranks
-    vals = torch.tensor([wall, asm_ms, ms_mv.value, min(e2e_asm), min(e2e_tts)], dtype=torch.float64, device=dev)
+    # ---- parity at this size against the C port (checker) ----
+    cb = None
+    extra = None
+    geo = None
+    if not args.no_parity or (not args.no_cpu_baseline and world == 1 and rank == 0):
+        from oracle import bem_oracle as bo
+        nodes_o, conn_o = bo.cubesphere(degree=wl["degree"], m=wl["m"])   # the oracle's own mesh generator
+        geo = bo.Geometry(nodes_o, conn_o, wl["degree"])
+    if not args.no_cpu_baseline and world == 1:
+        cb, extra = cpu_baseline(wl, sample_seconds=args.cpu_seconds, geo=geo, keep_rows=True, iterations=its)
+    par = (0, 0.0, None)
+    if not args.no_parity:
+        par = parity_at_scale(p, wl, geo, args.parity_nodes, extra)
+    sync()
+    # max / sum over ranks
+    vals = torch.tensor([wall, asm_ms, ms_mv.value, float(np.mean(e2e_asm)), float(np.mean(e2e_tts)), par[1],
+                         par[2] if par[2] is not None else 0.0, st["solve_ms"] / args.steps], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([par[0]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-    wall, asm_ms, mv_ms, e2e_asm_s, e2e_tts_s = [float(v) for v in vals.cpu()]
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    wall, asm_ms, mv_ms, e2e_asm_s, e2e_tts_s, par_v, par_k, solve_ms = [float(v) for v in vals.cpu()]
+    par_rows = int(cnt.item())
     entries = 2.0 * n * n
     rows_loc = 3 * n_own + (6 if rank == world - 1 else 0)
+    parity_ok = True
     if rank == 0:
         peaks, peak_src = load_peaks()
-        fp64, fp64_burst = C.c_double(), C.c_double()
-        check(lib.bs_bench_fp64_peak(local, C.byref(fp64_burst)))
+        fp64 = C.c_double()
         check(lib.bs_bench_fp64_sustained(local, 1.0, C.byref(fp64)))  # K1 runs for 100s of ms under the power cap
-        na = 4 if wl["degree"] == 1 else 9
-        nq = wl["quad"] ** 2
-        sing_pts = sum(lib.bs_make_singular_rule(_lib.SING_MIXED, wl["sing"], wl["degree"], a, 0, None, None) for a in range(na))
-        pr, ps = pairs_count(N, ncell, nq, sing_pts)
-        f_pair = (95 + 36 * na) if wl.get("kernel") == "free_surface" else (50 + 24 * na)
+        sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+        fp64_silicon = 148 * 64 * 2 * sm_max * 1e6 / 1e12
+        pr, ps = pairs_count(lib, _lib, wl)
+        f_pair = f_pair_of(wl)
         asm_tflops = (pr + ps) * f_pair / (asm_ms * 1e-3) / 1e12   # whole job (all ranks assemble concurrently)
         mv_bytes = 8.0 * (n + 6) * (n + 6)                          # whole job: every rank streams its row block
         mv_gbs_job = mv_bytes / (mv_ms * 1e-3) / 1e9
         mv_gbs_gpu = mv_gbs_job / world
-        solve_ms = st["solve_ms"] / args.steps
-        traffic_mv, traffic_asm = load_traffic(wl, world)
+        traffic_mv, traffic_asm, traffic_src = load_traffic(wl, world)
         roof_mv = {"kernel": "k_gemv<2>", "bound": "hbm", "achieved": mv_gbs_gpu, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                    "frac": mv_gbs_gpu / peaks["hbm_gbs"], "traffic": traffic_mv, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
                    "algorithmic_bytes_per_launch": 8.0 * rows_loc * (n + 6), "launch_ms": mv_ms}
         roof_asm = {"kernel": "k_assemble_regular", "bound": "fp64", "achieved": asm_tflops / world, "peak": fp64.value,
                     "unit": "TFLOP/s", "frac": asm_tflops / world / fp64.value, "traffic": traffic_asm,
-                    "traffic_note": "DRAM bytes of one assembly (all colour launches); see profiles/r01_traffic.json",
+                    "traffic_note": "DRAM bytes of one assembly (all colour launches); profiles/%s" % traffic_src,
                     "peak_source": "measured in this run: 8-chain DFMA microbenchmark sustained for 1 s under the power cap "
-                                   "(bs_bench_fp64_sustained); burst figure in fp64_peak_tflops_burst",
+                                   "(bs_bench_fp64_sustained); silicon figure 148 SM x 64 DFMA x 2 x max clock in frac_of_silicon_peak",
+                    "peak_silicon": fp64_silicon, "frac_of_silicon_peak": asm_tflops / world / fp64_silicon,
                     "algorithmic_flops_per_pair": f_pair, "pairs_regular": pr, "pairs_singular": ps, "launch_ms": asm_ms}
         dominant_is_asm = asm_ms >= solve_ms
+        parity_ok = par_v <= PARITY_TOL and (par_k or 0.0) <= PARITY_TOL
+        parity = {"rows": par_rows, "max_row_rel_err_V": par_v, "max_row_rel_err_K": (par_k if not wl.get("fused") else None),
+                  "tolerance": PARITY_TOL, "ok": bool(parity_ok), "checker": "oracle/bem_port.c rows of nodes owned by every rank"}
+        if args.no_parity:
+            parity = None
+        gm_it = solve_ms / max(1, its)
+        summary = {"time_to_solution_s": wall / args.steps, "gmres_iterations": its, "gmres_ms_per_iteration": gm_it,
+                   "gmres_non_matvec_ms_per_iteration": gm_it - mv_ms, "ortho": p.gmres_orthogonalization,
+                   "preconditioner": args.preconditioner, "drag_over_6pi": drag / (6 * math.pi),
+                   "final_check": {"linf": final_check[0], "l2": final_check[1]},
+                   "phases_ms": {"assembly": asm_ms, "corrections": st["correct_ms"] / args.steps,
+                                 "monolithic": st["monolithic_ms"] / args.steps, "precond_setup": st["precond_setup_ms"] / args.steps,
+                                 "gmres": solve_ms},
+                   "matvec_hbm_gbs": mv_gbs_job, "matvec_hbm_gbs_per_gpu": mv_gbs_gpu,
+                   "collective_calls_in_timed_region": {"allgather": n_ag, "allreduce": n_ar},
+                   "exchange": ("none (1 GPU)" if world == 1 else (
+                       "NVLink peer stores (Krylov slices and Gram-Schmidt partial sums) from the producing kernels"
+                       if p.use_peer_exchange else "NCCL allgather + allreduce callbacks")),
+                   "parity_at_scale": parity}
         line = {
-            "metric": "assembly Gentries/s + GMRES matvec HBM GB/s; time-to-solution at 3N DoF",
-            "value": entries / (asm_ms * 1e-3) / 1e9, "unit": "Gentries/s",
-            "matvec_hbm_gbs": mv_gbs_job, "matvec_hbm_gbs_per_gpu": mv_gbs_gpu,
-            "time_to_solution_s": wall / args.steps, "gmres_iterations": its,
+            "metric": METRIC, "value": entries / (asm_ms * 1e-3) / 1e9, "unit": "Gentries/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["name"], "nodes": N, "cells": ncell, "dofs": n, "matrix_gb_each": 8.0 * n * n / 1e9,
-                       "sharding": "rows (collocation nodes) over %d GPU(s), contiguous ranges of the locality order" % world,
-                       "exchange": ("none (1 GPU)" if world == 1 else ("NVLink peer stores fused into the Krylov-vector kernel + "
-                                    "NCCL allreduce of the dots" if p.use_peer_exchange else "NCCL allgather + allreduce")),
-                       "collective_calls_in_timed_region": ({"allgather": comm.n_allgather, "allreduce": comm.n_allreduce} if comm else None),
-                       "timing": "CUDA events on the launching stream inside the library; working set (%.1f GB matrix per GPU) "
-                                 "far larger than the 126 MB L2, no explicit flush needed" % (8.0 * n * n / 1e9 / world),
-                       "value_definition": "2*(3N)^2 entries of V and K evaluated / (K0+K1+K2 device time); ms_per_step is the "
-                                           "whole step (assembly + corrections + monolithic build + GMRES)"
-                                           + ("; fused mode stores V only and consumes the K tile in the epilogue" if wl.get("fused") else "")},
-            "phases_ms": {"assembly": asm_ms, "assemble_regular": st["assemble_regular_ms"] / args.steps,
-                          "assemble_singular": st["assemble_singular_ms"] / args.steps, "cell_geometry": st["geometry_ms"] / args.steps,
-                          "corrections": st["correct_ms"] / args.steps, "monolithic": st["monolithic_ms"] / args.steps,
-                          "gmres": solve_ms},
-            "tiling": {"cell_blocks": int(st["n_cell_blocks"]), "colours": int(st["n_colours"]),
-                       "node_touch_ratio": st["node_touch_ratio"]},
-            "resistance_6rhs": res6,
-            "drag_over_6pi": (drag / (6 * math.pi)) if drag is not None else None,
-            "clocks": clocks,
+            "config": config_of(wl, world),
+            "summary": summary,
             "e2e": {"value": entries / e2e_asm_s / 1e9, "unit": "Gentries/s", "time_to_solution_s": e2e_tts_s,
-                    "prepass_s": min(e2e_pre), "prepass_cg_iterations": int(p._pre.cg_iterations),
+                    "repetitions": len(e2e_asm), "statistic": "mean",
+                    "prepass_s": float(np.mean(e2e_pre)), "prepass_cg_iterations": int(p._pre.cg_iterations),
+                    "gmres_iterations": its, "drag_over_6pi": drag / (6 * math.pi), "parity_at_scale": parity,
                     "note": "time_to_solution_s is host to host per frame: geometry H2D, device pre-pass (mass matrix, L2 "
                             "normals, rigid modes), assembly, corrections, monolithic build, GMRES, solution D2H; value "
                             "excludes the pre-pass",
-                    "h2d_bytes_per_step": int(8 * 3 * N + 4 * 2 * ncell * na + 8 * 2 * n + 8 * 12 * n + 8 * n),
+                    "h2d_bytes_per_step": int(8 * 3 * N + 4 * 2 * ncell * (4 if wl["degree"] == 1 else 9) + 8 * 2 * n + 8 * 12 * n + 8 * n),
                     "d2h_bytes_per_step": int(8 * n + 8 * (n + 6))},
             "gpu_launches": int(st["kernel_launches"]),
             "roofline": roof_asm if dominant_is_asm else roof_mv,
             "roofline_secondary": roof_mv if dominant_is_asm else roof_asm,
-            "fp64_peak_tflops_measured": fp64.value, "fp64_peak_tflops_burst": fp64_burst.value,
+            "tiling": {"cell_blocks": int(st["n_cell_blocks"]), "colours": int(st["n_colours"]),
+                       "node_touch_ratio": st["node_touch_ratio"]},
+            "fp64_peak_tflops_measured": fp64.value, "fp64_peak_tflops_silicon": fp64_silicon,
+            "frames": frames,
+            "clocks": clocks,
         }
-        if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(wl, sample_seconds=args.cpu_seconds)
-        print(json.dumps(line), flush=True)
+        if cb is not None:
+            line["cpu_baseline"] = cb
     p.close()
+    if rank == 0:
+        if world == 1 and not args.no_secondary and args.workload == "c4":
+            try:
+                line["secondary_workloads"] = secondary_workloads(local, line["fp64_peak_tflops_measured"], args)
+            except Exception as e:  # a secondary workload must never cost the headline line
+                line["secondary_workloads"] = {"error": repr(e)}
+        # the driver keeps the tail of a long line: repeat the figures that prove parity and the solve at the end
+        line["tail_summary"] = {"value": line["value"], "tts_s": summary["time_to_solution_s"], "gmres_its": its,
+                                "ms_per_it": summary["gmres_ms_per_iteration"], "non_matvec_ms_per_it": summary["gmres_non_matvec_ms_per_iteration"],
+                                "drag_over_6pi": summary["drag_over_6pi"], "parity_rows": par_rows, "parity_err_V": par_v,
+                                "parity_ok": bool(parity_ok), "allreduce_calls": n_ar, "allgather_calls": n_ag}
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if not parity_ok:
+        sys.exit(3)
+
+
+def run_frames(p, mesh, args, sync, torch):
+    """`--frames K`: K geometry-perturbed frames solved with the LU of frame 0 as the (block-Jacobi) preconditioner,
+    the reference's reuse logic (bem_stokes.cc:5768-5779, 4336-4339): time to solution per frame."""
+    import bemstokes_b200 as bb
+    base = mesh.nodes.copy()
+    p.preconditioner_type = "BlockDirect"
+    p.reassemble_preconditoner = True
+    out = []
+    for f in range(args.frames):
+        # rigid rotation about z by 0.02 rad per frame plus a 1 % breathing mode: same mesh, new coordinates
+        a = 0.02 * f
+        R = np.array([[math.cos(a), -math.sin(a), 0], [math.sin(a), math.cos(a), 0], [0, 0, 1.0]])
+        nodes = (base * (1.0 + 0.01 * math.sin(0.7 * f) * base[:, 2:3] ** 2)) @ R.T
+        sync()
+        t0 = time.perf_counter()
+        p.update_geometry(bb.QuadMesh(nodes, mesh.conn, mesh.degree))
+        p.compute_center_of_mass_and_rigid_modes()
+        p.compute_normal_vector()
+        p.reset_stats()
+        p.assemble_stokes_system(True)
+        p.monolithic_solution[:] = 0
+        p.solve_system(True)
+        sync()
+        st = p.stats()
+        out.append({"frame": f, "tts_s": time.perf_counter() - t0, "gmres_iterations": p.solver_control.last_step(),
+                    "lu_ms": st["precond_setup_ms"], "gmres_ms": st["solve_ms"]})
+    p.preconditioner_type = args.preconditioner
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_baseline(wl, sample_seconds=15.0, nthreads=0):
-    """The reference's CPU path (oracle/bem_port.c) on a bounded row sample of the same workload."""
+def cpu_baseline(wl, sample_seconds=15.0, geo=None, keep_rows=False, iterations=None):
+    """The reference's CPU path (oracle/bem_port.c) on a bounded row sample of the same workload: all usable host
+    threads (affinity mask; OMP_NUM_THREADS is ignored) and, as BASELINE.md §3 asks, one thread = one reference MPI rank."""
     from oracle import bem_oracle as bo, port
-    nodes, conn = bo.cubesphere(degree=wl["degree"], m=wl["m"])   # the oracle's own mesh generator: no product code here
-    geo = bo.Geometry(nodes, conn, wl["degree"])
-    cores = port.max_threads() if nthreads == 0 else nthreads
+    if geo is None:
+        nodes, conn = bo.cubesphere(degree=wl["degree"], m=wl["m"])   # the oracle's own mesh generator: no product code here
+        geo = bo.Geometry(nodes, conn, wl["degree"])
+    cores = usable_cores()
     N = geo.N
-    kspec = bo.KernelSpec(bo.FREE_SURFACE, 0.0, 1, (0.0, 1.4, 0.0)) if wl.get("kernel") == "free_surface" else bo.KernelSpec()
+    kspec = oracle_kernel_spec(bo, wl)
     # calibrate on one row per thread, then size the sample
     t0 = time.perf_counter()
-    _, _, pairs = port.assemble_VK(geo, kspec, wl["quad"], "Mixed", wl["sing"], 0, cores, nthreads)
+    port.assemble_VK(geo, kspec, wl["quad"], "Mixed", wl["sing"], 0, cores, cores)
     t_cal = time.perf_counter() - t0
     rows = int(max(cores, min(N, cores * max(1, int(sample_seconds / max(t_cal, 1e-3))))))
     t0 = time.perf_counter()
-    V, K, pairs = port.assemble_VK(geo, kspec, wl["quad"], "Mixed", wl["sing"], 0, rows, nthreads)
+    V, K, pairs = port.assemble_VK(geo, kspec, wl["quad"], "Mixed", wl["sing"], 0, rows, cores)
     t = time.perf_counter() - t0
     entries = 2.0 * 3 * rows * 3 * N
+    # one thread: what one reference MPI rank does (the reference has no threading in assembly)
+    rows1 = max(1, int(round(rows / cores * min(1.0, 4.0 / max(t, 1e-3)))))
+    t0 = time.perf_counter()
+    _, _, pairs1 = port.assemble_VK(geo, kspec, wl["quad"], "Mixed", wl["sing"], 0, rows1, 1)
+    t1 = time.perf_counter() - t0
     # matvec sample: the assembled row block itself
     x = np.random.default_rng(0).uniform(-1, 1, 3 * N)
-    port.gemv(V, x, nthreads)
-    t1 = time.perf_counter()
+    port.gemv(V, x, cores)
+    tm = time.perf_counter()
     reps = 5
     for _ in range(reps):
-        port.gemv(V, x, nthreads)
-    t_mv = (time.perf_counter() - t1) / reps
-    return {"value": entries / t / 1e9, "unit": "Gentries/s", "cores": cores, "kind": "port",
-            "sample": "%d of %d collocation nodes (all cells, all quadrature points), %.1f s; matvec on the %.2f GB row block"
-                      % (rows, N, t, V.nbytes / 1e9),
-            "pairs_per_s": pairs / t, "matvec_gbs": V.nbytes / t_mv / 1e9,
-            "note": "C/OpenMP restatement of bem_stokes.cc:2871-2998; flatters the reference (no Epetra per-entry "
-                    "insertion, threads over rows; the reference assembles single-threaded per MPI rank)"}
+        port.gemv(V, x, cores)
+    t_mv = (time.perf_counter() - tm) / reps
+    rate = entries / t / 1e9
+    mv_gbs = V.nbytes / t_mv / 1e9
+    out = {"value": rate, "unit": "Gentries/s", "cores": cores, "kind": "port",
+           "sample": "%d of %d collocation nodes (all cells, all quadrature points), %.1f s; matvec on the %.2f GB row block"
+                     % (rows, N, t, V.nbytes / 1e9),
+           "pairs_per_s": pairs / t, "matvec_gbs": mv_gbs,
+           "one_thread": {"value": 2.0 * 3 * rows1 * 3 * N / t1 / 1e9, "unit": "Gentries/s", "cores": 1,
+                          "sample": "%d nodes, %.1f s" % (rows1, t1)},
+           "omp_num_threads_env": os.environ.get("OMP_NUM_THREADS"),
+           "note": "C/OpenMP restatement of bem_stokes.cc:2871-2998; flatters the reference (no Epetra per-entry "
+                   "insertion, threads over rows; the reference assembles single-threaded per MPI rank)"}
+    if iterations:
+        n = 3.0 * N
+        out["time_to_solution_extrapolated_s"] = {
+            "assembly": 2.0 * n * n / 1e9 / rate, "gmres": iterations * 8.0 * n * n / 1e9 / mv_gbs,
+            "note": "extrapolated from the sample rates to the full 3N x 3N system and %d GMRES iterations "
+                    "(the full matrix is not assembled on the host)" % iterations}
+    if keep_rows:
+        return out, (0, V, K)
+    return out
 
 
 def run_reference(args):
@@ -398,20 +661,23 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
+    from oracle import bem_oracle as bo
     wl = workload(args, world)
+    nodes, conn = bo.cubesphere(degree=wl["degree"], m=wl["m"])
+    geo = bo.Geometry(nodes, conn, wl["degree"])
     vals = []
     per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     cb = None
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        cb = cpu_baseline(wl, sample_seconds=per_step)
+        cb = cpu_baseline(wl, sample_seconds=per_step, geo=geo)
         if i >= args.warmup:
             vals.append((cb["value"], time.perf_counter() - t0))
     v = float(np.mean([a for a, _ in vals]))
-    line = {"impl": "reference", "metric": "assembly Gentries/s + GMRES matvec HBM GB/s; time-to-solution at 3N DoF",
+    line = {"impl": "reference", "metric": METRIC,
             "value": v, "unit": "Gentries/s", "matvec_hbm_gbs": cb["matvec_gbs"], "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean([b for _, b in vals])), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": wl["name"]},
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_of(wl, world),
             "cpu_baseline": dict(cb, value=v),
             "e2e": {"value": v, "unit": "Gentries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -423,13 +689,19 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c4", choices=["c4", "vk", "q2", "c5"])
+    ap.add_argument("--workload", default="c4", choices=["c4", "vk", "q2", "c5", "c5ns"])
     ap.add_argument("--no-peer-exchange", action="store_true", help="multi-GPU: NCCL allgather callbacks instead of NVLink peer stores")
     ap.add_argument("--no-fused", action="store_true", help="c4 family with V and K both stored (needs 2x the memory)")
     ap.add_argument("--subdiv", dest="m", type=int, default=0, help="cube-sphere subdivisions per face edge (default 128*(N/8)^(1/4); 64*N^(1/4) for --workload vk)")
     ap.add_argument("--refine", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--resistance", action="store_true", help="also time the 6-RHS batched resistance solve")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity_at_scale row sample")
+    ap.add_argument("--parity-nodes", type=int, default=8, help="collocation nodes per rank compared with the C port")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads (configs 5, 3, 2)")
+    ap.add_argument("--secondary-m", type=int, default=48)
+    ap.add_argument("--secondary-refine", type=int, default=4)
+    ap.add_argument("--preconditioner", default="None", choices=["None", "Jacobi", "BlockDirect"])
+    ap.add_argument("--frames", type=int, default=0, help="also solve K perturbed frames with the frame-0 block LU as preconditioner")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":
