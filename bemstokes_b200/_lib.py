@@ -82,6 +82,7 @@ SIGNATURES = {
     "bs_reset_stats": (C.c_int, [ctx_p]),
     "bs_bench_vmult": (C.c_int, [ctx_p, C.c_int, C.c_int, c_double_p]),
     "bs_bench_vmult_multi": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, c_double_p]),
+    "bs_bench_lu": (C.c_int, [ctx_p, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]),
     "bs_bench_fp64_peak": (C.c_int, [C.c_int, c_double_p]),
     "bs_bench_fp64_sustained": (C.c_int, [C.c_int, C.c_double, c_double_p]),
 }

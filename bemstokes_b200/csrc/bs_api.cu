@@ -109,6 +109,16 @@ static void alloc_matrix(Context &c, DBuf<double> &store, DMat &M, size_t rows, 
 
 static int nextra_of(Context &c, int which) { return which == BS_MAT_A ? c.num_rigid : 0; }
 
+// the one accessor of the stored operators for every entry point: after bs_build_monolithic(keep_VK = 0) the
+// monolithic matrix lives in V's storage, so V (with -K columns and rigid columns written into it) is gone
+static const DMat &matrix_of(Context &c, int which) {
+  BS_REQUIRE(which == BS_MAT_V || which == BS_MAT_K || which == BS_MAT_A, "unknown matrix id");
+  if (which == BS_MAT_V && c.A_aliases_V) throw Error(BS_ERR_INVALID, "V was consumed by bs_build_monolithic(keep_VK=0)");
+  const DMat &M = which == BS_MAT_V ? c.V : (which == BS_MAT_K ? c.K : c.A);
+  BS_REQUIRE(M.valid(), which == BS_MAT_A ? "monolithic matrix not built" : "matrix not available");
+  return M;
+}
+
 }  // namespace bs
 
 using namespace bs;
@@ -289,7 +299,9 @@ int bs_set_geometry(bs_context *h, int n_map_nodes, const double *euler_vec, int
   build_geometry(c);
   extra(c).d_node_of_pos.upload(c.node_of_pos, c.stream);
   c.ld = ((c.n3() + MAX_RIGID + 15) / 16) * 16;
-  // a new geometry invalidates matrices
+  // a new geometry invalidates matrices and the factorised preconditioner (sizes and ordering changed)
+  c.prec_kind = BS_PREC_NONE;
+  c.lu_blocks.clear();
   c.V = DMat();
   c.K = DMat();
   c.A = DMat();
@@ -696,10 +708,7 @@ int bs_vmult_multi(bs_context *h, int which, int nrhs, const double *X, double *
   BS_API_BEGIN
   Context &c = ctx_of(h);
   BS_REQUIRE(which >= 0 && which <= 2 && nrhs >= 1 && X && Y, "bad vmult arguments");
-  const DMat &M = which == BS_MAT_V ? c.V : (which == BS_MAT_K ? c.K : c.A);
-  BS_REQUIRE(M.valid(), "matrix not available");
-  if (which != BS_MAT_A && c.A_aliases_V && which == BS_MAT_V)
-    throw Error(BS_ERR_INVALID, "V was consumed by bs_build_monolithic(keep_VK=0)");
+  const DMat &M = matrix_of(c, which);
   Extra &e = extra(c);
   const int nx = nextra_of(c, which);
   const size_t m = c.full_vec_len(which), mloc = c.local_vec_len(which);
@@ -725,8 +734,7 @@ int bs_vmult_multi(bs_context *h, int which, int nrhs, const double *X, double *
 int bs_get_entries(bs_context *h, int which, int n, const int *rows, const int *cols, double *out) {
   BS_API_BEGIN
   Context &c = ctx_of(h);
-  const DMat &M = which == BS_MAT_V ? c.V : (which == BS_MAT_K ? c.K : c.A);
-  BS_REQUIRE(M.valid(), "matrix not available");
+  const DMat &M = matrix_of(c, which);
   BS_REQUIRE(n >= 0 && rows && cols && out, "bad arguments");
   const int N = c.N, n3 = 3 * N;
   std::vector<int> ir(n), ic(n);
@@ -770,8 +778,12 @@ int bs_tangential_projector(bs_context *h, const double *in, double *out) {
 int bs_precond_setup(bs_context *h, int which, int kind, int param) {
   BS_API_BEGIN
   Context &c = ctx_of(h);
-  const DMat &M = which == BS_MAT_V ? c.V : (which == BS_MAT_K ? c.K : c.A);
-  BS_REQUIRE(kind == BS_PREC_NONE || M.valid(), "matrix not available");
+  if (kind == BS_PREC_NONE) {
+    c.prec_kind = kind;
+    c.prec_which = which;
+    return BS_OK;
+  }
+  const DMat &M = matrix_of(c, which);
   Timer t(c, c.stats.precond_setup_ms);
   c.prec_which = which;
   const size_t mloc = c.local_vec_len(which);
@@ -786,34 +798,23 @@ int bs_precond_setup(bs_context *h, int which, int kind, int param) {
     BS_CUDA(cudaMemcpyAsync(c.d_prec_diag.p, d.data(), mloc * sizeof(double), cudaMemcpyHostToDevice, c.stream));
     BS_CUDA(cudaStreamSynchronize(c.stream));
   } else if (kind == BS_PREC_DIRECT || kind == BS_PREC_BLOCK_DIRECT || kind == BS_PREC_BAND) {
-    size_t nb;
-    if (kind == BS_PREC_BLOCK_DIRECT) nb = c.rows_loc;  // node rows of this rank; rigid unknowns pass through
-    else {
+    // BLOCK_DIRECT: the node rows of this rank (rigid unknowns pass through), optionally cut into diagonal blocks of at
+    // most `param` rows; DIRECT / BAND: the whole matrix (one GPU).  ref: DirectPreconditioner::initialize
+    // (source/direct_preconditioner.cc:10-23), band copy assemble_monolithic_preconditioner (bem_stokes.cc:3437-3475)
+    size_t nb, max_block = 0;
+    int band = 0;
+    if (kind == BS_PREC_BLOCK_DIRECT) {
+      nb = c.rows_loc;
+      max_block = param > 0 ? (size_t)param : 0;
+    } else {
       BS_REQUIRE(c.nranks == 1, "full direct / band preconditioner needs the whole matrix on one GPU; use BS_PREC_BLOCK_DIRECT");
       nb = mloc;
+      if (kind == BS_PREC_BAND) {
+        BS_REQUIRE(param > 0, "band preconditioner needs a positive bandwidth");
+        band = param;
+      }
     }
-    c.lu_n = nb;
-    c.d_lu.alloc(nb * nb + 2);
-    c.d_piv.alloc(nb + 2);
-    BS_CUDA(cudaMemcpy2DAsync(c.d_lu.p, nb * sizeof(double), M.p + off, M.ld * sizeof(double), nb * sizeof(double), nb,
-                              cudaMemcpyDeviceToDevice, c.stream));
-    if (kind == BS_PREC_BAND) {
-      // ref: assemble_monolithic_preconditioner, bem_stokes.cc:3437-3475 (entries with |i-j| beyond the band dropped)
-      std::vector<double> hm(nb * nb);
-      BS_CUDA(cudaMemcpyAsync(hm.data(), c.d_lu.p, nb * nb * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
-      BS_CUDA(cudaStreamSynchronize(c.stream));
-      // the band is defined in the reference ordering; translate through the permutation
-      auto ref_of = [&](size_t i) { return i < c.n3() ? (size_t)c.node_of_pos[i / 3] + (i % 3) * c.N : i; };
-      for (size_t i = 0; i < nb; ++i)
-        for (size_t j = 0; j < nb; ++j) {
-          const long long ri = (long long)ref_of(i), rj = (long long)ref_of(j);
-          const long long lo = ri > param ? ri - param : 0, hi = ri + param;
-          if (!(rj >= lo && rj < hi)) hm[i * nb + j] = 0.0;
-        }
-      BS_CUDA(cudaMemcpyAsync(c.d_lu.p, hm.data(), nb * nb * sizeof(double), cudaMemcpyHostToDevice, c.stream));
-      BS_CUDA(cudaStreamSynchronize(c.stream));
-    }
-    lu_factor(c, c.d_lu.p, nb, nb, c.d_piv.p);
+    precond_factor_blocks(c, M, off, nb, max_block, band);
     BS_CUDA(cudaStreamSynchronize(c.stream));
   } else {
     BS_REQUIRE(kind == BS_PREC_NONE, "unknown preconditioner kind");
@@ -844,6 +845,7 @@ int bs_gmres(bs_context *h, int which, const double *b, double *x, double tol_ab
   BS_API_BEGIN
   Context &c = ctx_of(h);
   BS_REQUIRE(b && x, "null vectors");
+  matrix_of(c, which);
   BS_REQUIRE(c.prec_kind == BS_PREC_NONE || c.prec_which == which, "preconditioner was set up for another matrix");
   Timer t(c, c.stats.solve_ms, "bs_gmres");
   Extra &e = extra(c);
@@ -885,6 +887,7 @@ int bs_gmres_multi(bs_context *h, int which, int nrhs, const double *B, double *
   BS_API_BEGIN
   Context &c = ctx_of(h);
   BS_REQUIRE(B && X && nrhs >= 1, "bad arguments");
+  matrix_of(c, which);
   BS_REQUIRE(c.prec_kind == BS_PREC_NONE || c.prec_which == which, "preconditioner was set up for another matrix");
   Timer t(c, c.stats.solve_ms);
   const int nx = nextra_of(c, which);
@@ -918,21 +921,22 @@ int bs_direct_solve(bs_context *h, int which, const double *b, double *x) {
   BS_API_BEGIN
   Context &c = ctx_of(h);
   BS_REQUIRE(c.nranks == 1, "bs_direct_solve needs the whole matrix on one GPU");
-  const DMat &M = which == BS_MAT_V ? c.V : (which == BS_MAT_K ? c.K : c.A);
-  BS_REQUIRE(M.valid(), "matrix not available");
+  const DMat &M = matrix_of(c, which);
   Timer t(c, c.stats.solve_ms);
   const int nx = nextra_of(c, which);
   const size_t m = c.full_vec_len(which);
   struct P_ { double *p; } lu, dx;
   struct PI_ { int *p; } piv;
-  lu.p = c.wsd("direct.lu", m * m + 2);
+  const size_t ldl = (m + 15) & ~(size_t)15;  // 128-byte aligned rows: the trailing update runs on the tensor path
+  lu.p = c.wsd("direct.lu", m * ldl + 2);
   piv.p = c.wsi("direct.piv", m + 2);
   dx.p = c.wsd("api.x", m + 2);
-  BS_CUDA(cudaMemcpy2DAsync(lu.p, m * sizeof(double), M.p, M.ld * sizeof(double), m * sizeof(double), m,
+  BS_CUDA(cudaMemsetAsync(lu.p, 0, m * ldl * sizeof(double), c.stream));
+  BS_CUDA(cudaMemcpy2DAsync(lu.p, ldl * sizeof(double), M.p, M.ld * sizeof(double), m * sizeof(double), m,
                             cudaMemcpyDeviceToDevice, c.stream));
-  lu_factor(c, lu.p, m, m, piv.p);
+  lu_factor(c, lu.p, m, ldl, piv.p);
   to_internal(c, b, nx, dx.p);
-  lu_solve(c, lu.p, m, m, piv.p, dx.p);
+  lu_solve(c, lu.p, m, ldl, piv.p, dx.p);
   from_internal(c, dx.p, nx, x, 0, m);
   BS_CUDA(cudaStreamSynchronize(c.stream));
   BS_API_END
@@ -1112,6 +1116,61 @@ int bs_bench_vmult(bs_context *h, int which, int repeats, double *ms_per_call) {
   float ms = 0;
   cudaEventElapsedTime(&ms, c.ev0, c.ev1);
   if (ms_per_call) *ms_per_call = ms / repeats;
+  BS_API_END
+}
+
+// LU micro-benchmark on a synthetic matrix (uniform entries in [-1,1), n on the diagonal): factorisation and the
+// cooperative application timed with CUDA events on the context stream
+__global__ void k_fill_test_matrix(double *A, size_t ld, int n) {
+  const size_t i = blockIdx.y, j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n || j >= (size_t)n) return;
+  unsigned long long h = (i * 0x9E3779B97F4A7C15ull) ^ (j * 0xC2B2AE3D27D4EB4Full + 0x165667B19E3779F9ull);
+  h ^= h >> 29;
+  h *= 0xBF58476D1CE4E5B9ull;
+  h ^= h >> 32;
+  A[i * ld + j] = (double)(h >> 11) * (2.0 / 9007199254740992.0) - 1.0 + (i == j ? (double)n : 0.0);
+}
+int bs_bench_lu(bs_context *h, int n, int apply_repeats, double *factor_ms, double *apply_ms, double *residual) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(n > 0 && apply_repeats > 0, "bad arguments");
+  const size_t ld = ((size_t)n + 15) & ~(size_t)15;
+  double *A = c.wsd("benchlu.A", (size_t)n * ld + 2);
+  BS_CUDA(cudaMemsetAsync(A, 0, (size_t)n * ld * sizeof(double), c.stream));
+  k_fill_test_matrix<<<dim3((n + 255) / 256, n), 256, 0, c.stream>>>(A, ld, n);
+  DMat M;
+  M.p = A, M.rows = n, M.cols = n, M.ld = ld;
+  std::vector<Context::LuBlock> keep;
+  keep.swap(c.lu_blocks);  // the benchmark must not disturb a preconditioner that is set up (buffers are re-used: set up again afterwards)
+  cudaEventRecord(c.ev0, c.stream);
+  precond_factor_blocks(c, M, 0, (size_t)n, 0, 0);
+  cudaEventRecord(c.ev1, c.stream);
+  BS_CUDA(cudaEventSynchronize(c.ev1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c.ev0, c.ev1);
+  if (factor_ms) *factor_ms = ms;
+  double *x = c.wsd("benchlu.x", (size_t)n + 2), *y = c.wsd("benchlu.y", (size_t)n + 2), *r = c.wsd("benchlu.r", (size_t)n + 2);
+  fill(c, x, 1.0, n);
+  lu_apply_fast(c, c.lu_blocks[0], x, y, nullptr);
+  cudaEventRecord(c.ev0, c.stream);
+  for (int i = 0; i < apply_repeats; ++i) lu_apply_fast(c, c.lu_blocks[0], x, y, nullptr);
+  cudaEventRecord(c.ev1, c.stream);
+  BS_CUDA(cudaEventSynchronize(c.ev1));
+  cudaEventElapsedTime(&ms, c.ev0, c.ev1);
+  if (apply_ms) *apply_ms = ms / apply_repeats;
+  if (residual) {  // |A y - x|_inf / |x|_inf with the matrix regenerated (the factorisation ran in place on a copy)
+    k_fill_test_matrix<<<dim3((n + 255) / 256, n), 256, 0, c.stream>>>(A, ld, n);
+    gemv(c, M, y, r);
+    std::vector<double> hr(n);
+    BS_CUDA(cudaMemcpyAsync(hr.data(), r, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    BS_CUDA(cudaStreamSynchronize(c.stream));
+    double e = 0;
+    for (double v : hr) e = std::max(e, std::fabs(v - 1.0));
+    *residual = e;
+  }
+  c.lu_blocks.swap(keep);
+  if (!c.lu_blocks.empty()) c.prec_kind = BS_PREC_NONE;  // its buffers were overwritten
+  c.lu_blocks.clear();
   BS_API_END
 }
 

@@ -220,8 +220,24 @@ __global__ void __launch_bounds__(GM_THREADS) k_gm_pass(GmDev P) {
     if (MODE == GM_UPD_DOTS || MODE == GM_UPD_NORM) {
       const double *cf = (MODE == GM_UPD_DOTS ? P.c1 : P.c2) + (size_t)s * (P.m + 2);
       if (v0) {
-#pragma unroll 4
-        for (int k = 0; k < nb; ++k) {
+        // eight basis vectors per step: all loads are issued before the first FMA needs one (memory-level parallelism;
+        // the k loop is a dependent FMA chain per element otherwise paced by one load latency per vector)
+        int k = 0;
+        for (; k + 8 <= nb; k += 8) {
+          double2 b[8];
+          double cc[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            b[u] = *reinterpret_cast<const double2 *>(B + (size_t)(k + u) * P.ldb);
+            cc[u] = cf[k + u];
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            zz.x = fma(-cc[u], b[u].x, zz.x);
+            zz.y = fma(-cc[u], b[u].y, zz.y);
+          }
+        }
+        for (; k < nb; ++k) {
           const double2 b = *reinterpret_cast<const double2 *>(B + (size_t)k * P.ldb);
           const double cc = cf[k];
           zz.x = fma(-cc, b.x, zz.x);
@@ -234,15 +250,23 @@ __global__ void __launch_bounds__(GM_THREADS) k_gm_pass(GmDev P) {
     if (MODE == GM_DOTS || MODE == GM_UPD_DOTS) {
       for (int k0 = 0; k0 < nb; k0 += GM_KT) {
         const int kt = min(GM_KT, nb - k0);
-        for (int kk = 0; kk < kt; ++kk) {
-          double p = 0.0;
-          if (v0) {
-            const double2 b = *reinterpret_cast<const double2 *>(B + (size_t)(k0 + kk) * P.ldb);
-            p = b.x * zz.x;
-            if (v1) p = fma(b.y, zz.y, p);
+        for (int kk = 0; kk < kt; kk += 8) {  // eight loads in flight, then eight interleaved warp reductions
+          double p[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            p[u] = 0.0;
+            if (v0 && kk + u < kt) {
+              const double2 b = *reinterpret_cast<const double2 *>(B + (size_t)(k0 + kk + u) * P.ldb);
+              p[u] = v1 ? fma(b.y, zz.y, b.x * zz.x) : b.x * zz.x;
+            }
           }
-          p = warp_sum(p);
-          if (lane == 0) red[wid][kk] = p;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) p[u] = warp_sum(p[u]);
+          if (lane == 0) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (kk + u < kt) red[wid][kk + u] = p[u];
+          }
         }
         __syncthreads();
         if (tid < kt) {

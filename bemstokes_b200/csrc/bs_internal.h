@@ -227,9 +227,17 @@ struct Context {
   int prec_kind = BS_PREC_NONE;
   int prec_which = BS_MAT_A;
   DBuf<double> d_prec_diag;         // Jacobi
-  DBuf<double> d_lu;                // LU factors (full matrix, single GPU) or local diagonal block
+  // LU factors of the diagonal blocks the preconditioner solves with (one block = the whole matrix for
+  // BS_PREC_DIRECT / BAND, the rank's own row block or pieces of it for BS_PREC_BLOCK_DIRECT)
+  struct LuBlock {
+    size_t off = 0, n = 0, ld = 0;  // local row offset, size, leading dimension of LU
+    double *LU = nullptr;           // points into d_lu
+    int *piv = nullptr, *perm = nullptr;   // into d_piv: LAPACK-style pivot rows and the equivalent gather permutation
+    double *LinvT = nullptr, *UinvT = nullptr;  // into d_luinv: transposed inverses of the 128 x 128 diagonal blocks
+  };
+  std::vector<LuBlock> lu_blocks;
+  DBuf<double> d_lu, d_luinv;
   DBuf<int> d_piv;
-  size_t lu_n = 0;
 
   // comm
   bs_allgatherv_fn cb_allgatherv = nullptr;
@@ -320,6 +328,9 @@ void set_column(Context &c, DMat &A, size_t col, const double *v, double scale);
 void gather_entries(Context &c, const DMat &M, int n, const int *d_r, const int *d_c, double *d_out);
 // ---- solvers (bs_solve.cu) --------------------------------------------------------------------------------
 void lu_factor(Context &c, double *A, size_t n, size_t ld, int *piv);
+// factorise local diagonal blocks of `M` (copied; band > 0 drops entries outside the reference-ordered band) for the preconditioner
+void precond_factor_blocks(Context &c, const DMat &M, size_t col_off, size_t n_total, size_t max_block, int band);
+void lu_apply_fast(Context &c, const Context::LuBlock &b, const double *in, double *out, const int *skip);
 void lu_solve(Context &c, const double *LU, size_t n, size_t ld, const int *piv, double *x /* in/out */);
 void apply_operator(Context &c, int which, const double *x_full, double *y_loc);
 void exchange(Context &c, int which, const double *y_loc, double *x_full);

@@ -85,7 +85,7 @@ void p2p_wait(Context &c) {
 constexpr int LU_NB = 32;
 
 // factorise the panel A[k0:n, k0:k0+nb] with one CTA; piv[k0+j] = absolute pivot row
-__global__ void __launch_bounds__(1024) k_lu_panel(double *A, size_t ld, int n, int k0, int nb, int *piv) {
+__global__ void __launch_bounds__(1024) k_lu_panel(double *A, size_t ld, int n, int k0, int nb, int *piv, int *info) {
   __shared__ double s_val[32];
   __shared__ int s_idx[32];
   __shared__ int s_piv;
@@ -142,7 +142,9 @@ __global__ void __launch_bounds__(1024) k_lu_panel(double *A, size_t ld, int n, 
       A[(size_t)pr * ld + k0 + tid] = a;
     }
     __syncthreads();
-    const double dinv = 1.0 / A[(size_t)col * ld + col];
+    const double pv = A[(size_t)col * ld + col];
+    const double dinv = pv != 0.0 ? 1.0 / pv : 0.0;  // singular column: leave it, reported through `info`
+    if (pv == 0.0 && tid == 0) atomicCAS(info, 0, col + 1);
     // scale column and update the rest of the panel: thread <-> row
     for (int r = col + 1 + tid; r < n; r += blockDim.x) {
       double *row = A + (size_t)r * ld;
@@ -176,7 +178,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int
 constexpr int LU_RPT = 2;
 __global__ void __launch_bounds__(256) k_lu_panel_coop(double *A, size_t ld, int n, int k0, int nb, int *piv, double *cand_val,
                                                         int *cand_idx, double *xrow /*[2][32]*/, unsigned int *counter,
-                                                        int chunk) {
+                                                        int chunk, int *info) {
   __shared__ double s_val[8];
   __shared__ int s_idx[8];
   __shared__ int s_piv;
@@ -282,7 +284,8 @@ __global__ void __launch_bounds__(256) k_lu_panel_coop(double *A, size_t ld, int
           for (int jj = 0; jj < LU_NB; ++jj) a[rr][jj] = ((volatile double *)xrow)[jj];
         }
       }
-      const double dinv = 1.0 / s_prow[j];
+      const double dinv = s_prow[j] != 0.0 ? 1.0 / s_prow[j] : 0.0;
+      if (s_prow[j] == 0.0 && g == 0 && tid == 0) atomicCAS(info, 0, col + 1);
 #pragma unroll
       for (int rr = 0; rr < LU_RPT; ++rr)
         if (row[rr] > col) {
@@ -406,6 +409,124 @@ __global__ void __launch_bounds__(256) k_lu_gemm(double *A, size_t ld, int n, in
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Trailing update on the FP64 tensor path (DMMA m8n8k4):  C -= L * U  with the same index conventions as k_lu_gemm.
+// CTA tile 128 x 128, 8 warps as 2 x 4, warp tile 64 x 32 (8 x 4 MMA tiles, 64 accumulator registers per lane);
+// the k range runs through shared memory in slices of 16 columns, three stages deep (cp.async, zero-filled at the
+// matrix edges).  Fragment loads are bank-conflict free: A rows are padded to 20 doubles and B rows to 132 doubles,
+// so that the 16 lanes of a half-warp (4 rows x 4 k for A, 4 k x 4 columns for B) hit 16 different 8-byte banks.
+// Needs 16-byte aligned rows (ld, k0, col_begin even); k_lu_gemm stays as the fallback for odd edges.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int DG_BM = 128, DG_BN = 128, DG_KC = 16, DG_STAGES = 3;
+constexpr int DG_APAD = DG_KC + 4, DG_BPAD = DG_BN + 4;
+constexpr size_t DG_STAGE_DOUBLES = (size_t)DG_BM * DG_APAD + (size_t)DG_KC * DG_BPAD;
+constexpr size_t DG_SMEM = DG_STAGES * DG_STAGE_DOUBLES * sizeof(double);
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256) k_lu_gemm_dmma(double *A, size_t ld, int n, int k0, int kw, int row_begin, int col_begin,
+                                                      int col_end) {
+  extern __shared__ __align__(16) double dg_smem[];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int wm = wid >> 2, wn = wid & 3;
+  const int r0 = row_begin + blockIdx.y * DG_BM, c0 = col_begin + blockIdx.x * DG_BN;
+  const int nk = (kw + DG_KC - 1) / DG_KC;
+  auto load_stage = [&](int st, int kk) {
+    double *As = dg_smem + (size_t)st * DG_STAGE_DOUBLES, *Bs = As + (size_t)DG_BM * DG_APAD;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // L tile: 128 rows x 16 columns, 8 chunks of 16 bytes per row
+      const int ch = tid + i * 256, row = ch >> 3, cq = ch & 7;
+      const int gr = r0 + row, gk = kk + 2 * cq;
+      int valid = gr < n ? min(max(kw - gk, 0), 2) : 0;
+      const double *src = valid ? A + (size_t)gr * ld + k0 + gk : A;
+      cp_async16(As + (size_t)row * DG_APAD + 2 * cq, src, 8 * valid);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // U tile: 16 rows x 128 columns, 64 chunks per row
+      const int ch = tid + i * 256, row = ch >> 6, cq = ch & 63;
+      const int gk = kk + row, gc = c0 + 2 * cq;
+      int valid = gk < kw ? min(max(col_end - gc, 0), 2) : 0;
+      const double *src = valid ? A + (size_t)(k0 + gk) * ld + gc : A;
+      cp_async16(Bs + (size_t)row * DG_BPAD + 2 * cq, src, 8 * valid);
+    }
+  };
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+  for (int st = 0; st < DG_STAGES - 1; ++st) {
+    if (st < nk) load_stage(st, st * DG_KC);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(DG_STAGES - 2) : "memory");
+    __syncthreads();  // stage kt has landed for every thread; stage (kt-1) is free for the next prefetch
+    if (kt + DG_STAGES - 1 < nk) load_stage((kt + DG_STAGES - 1) % DG_STAGES, (kt + DG_STAGES - 1) * DG_KC);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const double *As = dg_smem + (size_t)(kt % DG_STAGES) * DG_STAGE_DOUBLES, *Bs = As + (size_t)DG_BM * DG_APAD;
+    const double *ap = As + (size_t)(wm * 64 + g) * DG_APAD + t;
+    const double *bp = Bs + (size_t)t * DG_BPAD + wn * 32 + g;
+#pragma unroll
+    for (int k4 = 0; k4 < DG_KC / 4; ++k4) {
+      double a[8], b[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = ap[(size_t)i * 8 * DG_APAD + 4 * k4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = bp[(size_t)4 * k4 * DG_BPAD + 8 * j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = r0 + wm * 64 + 8 * i + g;
+    if (r >= n) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cc = c0 + wn * 32 + 8 * j + 2 * t;
+      double *p = A + (size_t)r * ld + cc;
+      if (cc + 1 < col_end) {
+        double2 v = *reinterpret_cast<double2 *>(p);
+        v.x -= acc[i][j][0];
+        v.y -= acc[i][j][1];
+        *reinterpret_cast<double2 *>(p) = v;
+      } else if (cc < col_end) {
+        p[0] -= acc[i][j][0];
+      }
+    }
+  }
+}
+
+// C -= L U on the tensor path when the rows are 16-byte aligned, on the FMA kernel otherwise
+static void lu_trailing_update(Context &c, double *A, size_t ld, int n, int k0, int kw, int row_begin, int col_begin, int col_end) {
+  const int ncols = col_end - col_begin, nrows = n - row_begin;
+  if (ncols <= 0 || nrows <= 0 || kw <= 0) return;
+  const bool aligned = (ld % 2 == 0) && (k0 % 2 == 0) && (col_begin % 2 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0);
+  const dim3 grid((ncols + DG_BN - 1) / DG_BN, (nrows + DG_BM - 1) / DG_BM);
+  if (aligned && !std::getenv("BS_NO_DMMA")) {
+    static bool attr = false;
+    if (!attr) {
+      BS_CUDA(cudaFuncSetAttribute(k_lu_gemm_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DG_SMEM));
+      attr = true;
+    }
+    k_lu_gemm_dmma<<<grid, 256, DG_SMEM, c.stream>>>(A, ld, n, k0, kw, row_begin, col_begin, col_end);
+  } else {
+    k_lu_gemm<<<grid, 256, 0, c.stream>>>(A, ld, n, k0, kw, row_begin, col_begin, col_end);
+  }
+  count_launch(c);
+}
+
 // Right-looking blocked LU with partial pivoting: inner panels of 32 columns (one CTA each), immediate rank-32
 // updates only inside the current 128-column outer block, lazy U rows for the columns right of it, then one k=128
 // GEMM for the trailing matrix.
@@ -420,6 +541,8 @@ void lu_factor(Context &c, double *A, size_t n_, size_t ld, int *piv) {
     cudaStreamSynchronize(c.stream);
     tlast = tnow();
   }
+  int *info = c.wsi("lu.info", 4);
+  BS_CUDA(cudaMemsetAsync(info, 0, sizeof(int), c.stream));
   auto tick = [&](int k) {
     if (!trace) return;
     cudaStreamSynchronize(c.stream);
@@ -435,7 +558,7 @@ void lu_factor(Context &c, double *A, size_t n_, size_t ld, int *piv) {
       // rows per CTA: at most 256*LU_RPT (register-resident rows), at least 64 so that tiny panels use few CTAs
       int chunk = std::max(64, (rows_left + c.sm_count - 1) / c.sm_count);
       if (chunk > 256 * LU_RPT || rows_left <= 1024) {
-        k_lu_panel<<<1, 1024, 0, c.stream>>>(A, ld, n, j0, nb, piv);  // short panel, or taller than all SMs can hold
+        k_lu_panel<<<1, 1024, 0, c.stream>>>(A, ld, n, j0, nb, piv, info);  // short panel, or taller than all SMs can hold
       } else {
         const int G = (rows_left + chunk - 1) / chunk;
         double *cand_val = c.wsd("lu.cand", 256 + 2 * LU_NB);
@@ -445,7 +568,7 @@ void lu_factor(Context &c, double *A, size_t n_, size_t ld, int *piv) {
         BS_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), c.stream));
         int n_ = n, j0_ = j0, nb_ = nb;
         size_t ld_ = ld;
-        void *args[] = {&A, &ld_, &n_, &j0_, &nb_, &piv, &cand_val, &cand_idx, &xrow, &counter, &chunk};
+        void *args[] = {&A, &ld_, &n_, &j0_, &nb_, &piv, &cand_val, &cand_idx, &xrow, &counter, &chunk, &info};
         BS_CUDA(cudaLaunchCooperativeKernel((void *)k_lu_panel_coop, dim3(G), dim3(256), args, 0, c.stream));
       }
       tick(0);
@@ -459,24 +582,22 @@ void lu_factor(Context &c, double *A, size_t n_, size_t ld, int *piv) {
       }
       tick(2);
       const int inside = K0 + Bw - (j0 + nb), below = n - (j0 + nb);
-      if (inside > 0 && below > 0) {  // rank-32 update of the rest of the outer block
-        k_lu_gemm<<<dim3((inside + GM_T - 1) / GM_T, (below + GM_T - 1) / GM_T), 256, 0, c.stream>>>(A, ld, n, j0, nb, j0 + nb,
-                                                                                                   j0 + nb, K0 + Bw);
-        count_launch(c);
-      }
+      if (inside > 0 && below > 0) lu_trailing_update(c, A, ld, n, j0, nb, j0 + nb, j0 + nb, K0 + Bw);  // rank-32 update of the rest of the outer block
       tick(3);
     }
     const int rem = n - K0 - Bw;
-    if (rem > 0) {  // trailing matrix: one GEMM with k = Bw
-      k_lu_gemm<<<dim3((rem + GM_T - 1) / GM_T, (rem + GM_T - 1) / GM_T), 256, 0, c.stream>>>(A, ld, n, K0, Bw, K0 + Bw, K0 + Bw, n);
-      count_launch(c);
-    }
+    if (rem > 0) lu_trailing_update(c, A, ld, n, K0, Bw, K0 + Bw, K0 + Bw, n);  // trailing matrix: one GEMM with k = Bw
     tick(4);
   }
   if (trace)
     fprintf(stderr, "[bs trace] lu_factor n=%d: panel %.1f ms, swaps %.1f ms, U rows %.1f ms, inner GEMM %.1f ms, trailing GEMM %.1f ms\n", n,
             1e3 * tacc[0], 1e3 * tacc[1], 1e3 * tacc[2], 1e3 * tacc[3], 1e3 * tacc[4]);
   BS_CUDA(cudaGetLastError());
+  int h_info = 0;
+  BS_CUDA(cudaMemcpyAsync(&h_info, info, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  BS_CUDA(cudaStreamSynchronize(c.stream));
+  if (h_info != 0)
+    throw Error(BS_ERR_INVALID, "LU factorisation: the matrix is singular (zero pivot in column " + std::to_string(h_info - 1) + ")");
 }
 
 // x <- P x (sequential swaps, tiny kernel), then blocked forward / backward substitution
@@ -545,11 +666,229 @@ void lu_solve(Context &c, const double *LU, size_t n_, size_t ld, const int *piv
   BS_CUDA(cudaGetLastError());
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Preconditioner application  x = U^-1 L^-1 P b  as ONE cooperative kernel per diagonal block (the substitution
+// above takes four launches per 32 columns).  The triangular systems are solved in steps of 128 unknowns: the
+// 128 x 128 diagonal blocks of L and U are inverted once after the factorisation, so a step is
+//     x_k = inv(T_kk) r_k          one CTA (the owner of step k, rotating)
+//     r_i -= T_ik x_k              all warps of the grid, one row each, streaming the panel T[:, k] from HBM
+// with one grid barrier per step: the owner of step k+1 updates the 128 rows of its block first and solves it
+// while the other CTAs stream the rest of panel k.  Any fixed linear operator is admissible as a preconditioner,
+// so the explicit inverses of the diagonal blocks do not affect what GMRES converges to.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TB = 128;
+
+// perm = the gather form of LAPACK's sequential row interchanges: (P b)[i] = b[perm[i]]
+__global__ void k_piv_to_perm(const int *piv, int *perm, int n) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (int i = 0; i < n; ++i) perm[i] = i;
+  for (int i = 0; i < n; ++i) {
+    const int p = piv[i];
+    if (p != i) {
+      const int t = perm[i];
+      perm[i] = perm[p];
+      perm[p] = t;
+    }
+  }
+}
+
+// transposed inverses of the diagonal blocks: LinvT[k][j][i] = inv(L_kk)[i][j] (unit lower), UinvT likewise (upper)
+__global__ void __launch_bounds__(TB) k_tri_inverse(const double *LU, size_t ld, int n, double *LinvT, double *UinvT) {
+  extern __shared__ double X[];  // [TB][TB+1], X[i*(TB+1) + j] = inverse(i, j)
+  const int k0 = blockIdx.x * TB, kb = min(TB, n - k0), j = threadIdx.x;
+  const double *T = LU + (size_t)k0 * ld + k0;
+  constexpr int XL = TB + 1;
+  // ---- unit lower: column j of the inverse by forward substitution
+  for (int i = 0; i < TB; ++i) X[i * XL + j] = (i == j) ? 1.0 : 0.0;
+  if (j < kb)
+    for (int i = j + 1; i < kb; ++i) {
+      double sacc = 0.0;
+      for (int q = j; q < i; ++q) sacc = fma(T[(size_t)i * ld + q], X[q * XL + j], sacc);
+      X[i * XL + j] = -sacc;
+    }
+  __syncthreads();
+  double *out = LinvT + (size_t)blockIdx.x * TB * TB;
+  for (int q = 0; q < TB; ++q) out[(size_t)q * TB + j] = X[j * XL + q];  // out[q][i=j] = inv(i=j, q)
+  __syncthreads();
+  // ---- upper with diagonal: column j by backward substitution
+  for (int i = 0; i < TB; ++i) X[i * XL + j] = (i == j && j >= kb) ? 1.0 : 0.0;
+  if (j < kb) {
+    const double dj = T[(size_t)j * ld + j];
+    X[j * XL + j] = dj != 0.0 ? 1.0 / dj : 0.0;
+    for (int i = j - 1; i >= 0; --i) {
+      double sacc = 0.0;
+      for (int q = i + 1; q <= j; ++q) sacc = fma(T[(size_t)i * ld + q], X[q * XL + j], sacc);
+      const double di = T[(size_t)i * ld + i];
+      X[i * XL + j] = di != 0.0 ? -sacc / di : 0.0;
+    }
+  }
+  __syncthreads();
+  out = UinvT + (size_t)blockIdx.x * TB * TB;
+  for (int q = 0; q < TB; ++q) out[(size_t)q * TB + j] = X[j * XL + q];
+}
+
+__device__ __forceinline__ void tri_diag_apply(const double *MT, int k, int k0, int kb, double *x, double *sm) {
+  // x[k0 .. k0+kb) <- inv(T_kk) * x[k0 .. k0+kb); 256 threads: (row i, half of the columns)
+  const int tid = threadIdx.x, i = tid & (TB - 1), half = tid >> 7;
+  double *rs = sm, *part = sm + TB;
+  __syncthreads();
+  if (tid < TB) rs[tid] = tid < kb ? __ldcg(x + k0 + tid) : 0.0;
+  __syncthreads();
+  const double *Mk = MT + (size_t)k * TB * TB;
+  double a = 0.0;
+#pragma unroll 8
+  for (int jj = half * (TB / 2); jj < (half + 1) * (TB / 2); ++jj) a = fma(Mk[(size_t)jj * TB + i], rs[jj], a);
+  part[half * TB + i] = a;
+  __syncthreads();
+  if (tid < kb) __stcg(x + k0 + tid, part[tid] + part[TB + tid]);
+  __syncthreads();
+}
+// x[r] -= T[r][k0 .. k0+kb) . xk  (one warp per row; xk in registers, 4 values per lane)
+__device__ __forceinline__ void tri_row_update(const double *LU, size_t ld, int r, int k0, int kb, const double xk[4], double *x,
+                                               int lane) {
+  const double *row = LU + (size_t)r * ld + k0 + 4 * lane;
+  double s = 0.0;
+  if (4 * lane + 3 < kb) {
+    const double2 a = *reinterpret_cast<const double2 *>(row), b = *reinterpret_cast<const double2 *>(row + 2);
+    s = fma(a.x, xk[0], fma(a.y, xk[1], fma(b.x, xk[2], b.y * xk[3])));
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (4 * lane + u < kb) s = fma(row[u], xk[u], s);
+  }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+  if (lane == 0) __stcg(x + r, __ldcg(x + r) - s);
+}
+
+__global__ void __launch_bounds__(256) k_lu_apply_coop(const double *LU, size_t ld, int n, const int *perm, const double *LinvT,
+                                                       const double *UinvT, const double *in, double *x, unsigned int *counter,
+                                                       const int *skip) {
+  if (skip && *skip) return;
+  __shared__ double sm[3 * TB];
+  const int G = gridDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int gw = blockIdx.x * 8 + wid, total_warps = G * 8;
+  const int nblk = (n + TB - 1) / TB;
+  unsigned int nbar = 0;
+  for (int i = blockIdx.x * 256 + tid; i < n; i += G * 256) __stcg(x + i, in[perm[i]]);
+  grid_barrier(counter, (++nbar) * G);
+  // ---- forward: L y = P b
+  if ((int)blockIdx.x == 0 % G) tri_diag_apply(LinvT, 0, 0, min(TB, n), x, sm);
+  grid_barrier(counter, (++nbar) * G);
+  for (int k = 0; k + 1 < nblk; ++k) {
+    const int k0 = k * TB;  // kb == TB here (k is not the last block)
+    double xk[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) xk[u] = __ldcg(x + k0 + 4 * lane + u);
+    if ((int)blockIdx.x == (k + 1) % G) {  // owner of the next step: its rows first, then its diagonal solve
+      const int r1 = min(k0 + 2 * TB, n);
+      for (int r = k0 + TB + wid; r < r1; r += 8) tri_row_update(LU, ld, r, k0, TB, xk, x, lane);
+      tri_diag_apply(LinvT, k + 1, k0 + TB, r1 - (k0 + TB), x, sm);
+    }
+    for (int r = k0 + 2 * TB + gw; r < n; r += total_warps) tri_row_update(LU, ld, r, k0, TB, xk, x, lane);
+    grid_barrier(counter, (++nbar) * G);
+  }
+  // ---- backward: U x = y
+  {
+    const int kl = nblk - 1;
+    if ((int)blockIdx.x == kl % G) tri_diag_apply(UinvT, kl, kl * TB, n - kl * TB, x, sm);
+    grid_barrier(counter, (++nbar) * G);
+  }
+  for (int k = nblk - 1; k >= 1; --k) {
+    const int k0 = k * TB, kb = min(TB, n - k0);
+    double xk[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) xk[u] = (4 * lane + u < kb) ? __ldcg(x + k0 + 4 * lane + u) : 0.0;
+    if ((int)blockIdx.x == (k - 1) % G) {
+      for (int r = k0 - TB + wid; r < k0; r += 8) tri_row_update(LU, ld, r, k0, kb, xk, x, lane);
+      tri_diag_apply(UinvT, k - 1, k0 - TB, TB, x, sm);
+    }
+    for (int r = gw; r < k0 - TB; r += total_warps) tri_row_update(LU, ld, r, k0, kb, xk, x, lane);
+    grid_barrier(counter, (++nbar) * G);
+  }
+}
+
+void lu_apply_fast(Context &c, const Context::LuBlock &b, const double *in, double *out, const int *skip) {
+  static int max_per_sm = 0;
+  if (!max_per_sm) {
+    BS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_per_sm, k_lu_apply_coop, 256, 0));
+    max_per_sm = std::max(1, std::min(max_per_sm, 2));
+  }
+  int G = (int)std::min<size_t>((size_t)max_per_sm * c.sm_count, std::max<size_t>(1, (b.n + TB - 1) / TB));
+  unsigned int *counter = reinterpret_cast<unsigned int *>(c.wsi("lu.apply_counter", 4));
+  BS_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), c.stream));
+  const double *LU = b.LU;
+  size_t ld = b.ld;
+  int n = (int)b.n;
+  const int *perm = b.perm;
+  const double *Li = b.LinvT, *Ui = b.UinvT;
+  void *args[] = {&LU, &ld, &n, &perm, &Li, &Ui, &in, &out, &counter, &skip};
+  BS_CUDA(cudaLaunchCooperativeKernel((void *)k_lu_apply_coop, dim3(G), dim3(256), args, 0, c.stream));
+  count_launch(c);
+}
+
+// band filter of assemble_monolithic_preconditioner (ref: bem_stokes.cc:3437-3475): entries whose reference column index
+// lies outside [ri - band, ri + band) are dropped; ref_of maps local block index -> reference index
+__global__ void k_band_filter(double *LU, size_t ld, int n, const int *ref_of, int band) {
+  const int i = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || j >= n) return;
+  const long long ri = ref_of[i], rj = ref_of[j];
+  const long long lo = ri > band ? ri - band : 0, hi = ri + band;
+  if (!(rj >= lo && rj < hi)) LU[(size_t)i * ld + j] = 0.0;
+}
+
+void precond_factor_blocks(Context &c, const DMat &M, size_t col_off, size_t n_total, size_t max_block, int band) {
+  const size_t nblocks = (max_block == 0 || max_block >= n_total) ? 1 : (n_total + max_block - 1) / max_block;
+  c.lu_blocks.assign(nblocks, Context::LuBlock());
+  size_t lu_total = 0, inv_total = 0, piv_total = 0;
+  for (size_t b = 0; b < nblocks; ++b) {
+    Context::LuBlock &B = c.lu_blocks[b];
+    B.off = n_total * b / nblocks;
+    B.n = n_total * (b + 1) / nblocks - B.off;
+    B.ld = (B.n + 15) & ~(size_t)15;
+    lu_total += B.n * B.ld;
+    inv_total += 2 * ((B.n + TB - 1) / TB) * TB * TB;
+    piv_total += 2 * ((B.n + 3) & ~(size_t)3);
+  }
+  c.d_lu.alloc(lu_total + 2);
+  c.d_luinv.alloc(inv_total + 2);
+  c.d_piv.alloc(piv_total + 2);
+  size_t lu_at = 0, inv_at = 0, piv_at = 0;
+  BS_CUDA(cudaFuncSetAttribute(k_tri_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TB * (TB + 1) * sizeof(double))));
+  for (size_t b = 0; b < nblocks; ++b) {
+    Context::LuBlock &B = c.lu_blocks[b];
+    const size_t nt = (B.n + TB - 1) / TB, np = (B.n + 3) & ~(size_t)3;
+    B.LU = c.d_lu.p + lu_at, lu_at += B.n * B.ld;
+    B.LinvT = c.d_luinv.p + inv_at, B.UinvT = B.LinvT + nt * TB * TB, inv_at += 2 * nt * TB * TB;
+    B.piv = c.d_piv.p + piv_at, B.perm = B.piv + np, piv_at += 2 * np;
+    BS_CUDA(cudaMemsetAsync(B.LU, 0, B.n * B.ld * sizeof(double), c.stream));
+    BS_CUDA(cudaMemcpy2DAsync(B.LU, B.ld * sizeof(double), M.p + B.off * M.ld + col_off + B.off, M.ld * sizeof(double),
+                              B.n * sizeof(double), B.n, cudaMemcpyDeviceToDevice, c.stream));
+    if (band > 0) {
+      std::vector<int> ref(B.n);
+      for (size_t i = 0; i < B.n; ++i) {
+        const size_t gi = col_off + B.off + i;
+        ref[i] = gi < c.n3() ? (int)((size_t)c.node_of_pos[gi / 3] + (gi % 3) * c.N) : (int)gi;
+      }
+      int *d_ref = c.wsi("lu.band_ref", B.n + 2);
+      BS_CUDA(cudaMemcpyAsync(d_ref, ref.data(), B.n * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+      k_band_filter<<<dim3((unsigned)((B.n + 255) / 256), (unsigned)B.n), 256, 0, c.stream>>>(B.LU, B.ld, (int)B.n, d_ref, band);
+      BS_CUDA(cudaStreamSynchronize(c.stream));  // `ref` is a host temporary
+      count_launch(c);
+    }
+    lu_factor(c, B.LU, B.n, B.ld, B.piv);
+    k_piv_to_perm<<<1, 32, 0, c.stream>>>(B.piv, B.perm, (int)B.n);
+    k_tri_inverse<<<(unsigned)nt, TB, TB * (TB + 1) * sizeof(double), c.stream>>>(B.LU, B.ld, (int)B.n, B.LinvT, B.UinvT);
+    BS_CUDA(cudaGetLastError());
+    count_launch(c, 2);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // preconditioner application on the local slice
 // ---------------------------------------------------------------------------------------------------------
 void apply_precond(Context &c, const double *in_loc, double *out_loc, const int *skip) {
-  (void)skip;
   const size_t mloc = c.local_vec_len(c.prec_which);
   switch (c.prec_kind) {
     case BS_PREC_NONE:
@@ -560,10 +899,21 @@ void apply_precond(Context &c, const double *in_loc, double *out_loc, const int 
       break;
     case BS_PREC_DIRECT:
     case BS_PREC_BLOCK_DIRECT:
-    case BS_PREC_BAND:
-      copy(c, in_loc, out_loc, mloc);  // entries beyond the factorised block pass through (identity)
-      lu_solve(c, c.d_lu.p, c.lu_n, c.lu_n, c.d_piv.p, out_loc);
+    case BS_PREC_BAND: {
+      size_t covered = 0;
+      for (const Context::LuBlock &b : c.lu_blocks) {
+        BS_REQUIRE(b.off + b.n <= mloc, "preconditioner was factorised for a larger system: call bs_precond_setup again");
+        if (std::getenv("BS_LU_SUBSTITUTION")) {  // exact substitution (4 launches per 32 columns), for comparison
+          copy(c, in_loc + b.off, out_loc + b.off, b.n);
+          lu_solve(c, b.LU, b.n, b.ld, b.piv, out_loc + b.off);
+        } else {
+          lu_apply_fast(c, b, in_loc + b.off, out_loc + b.off, skip);
+        }
+        covered = b.off + b.n;
+      }
+      if (covered < mloc) copy(c, in_loc + covered, out_loc + covered, mloc - covered);  // rigid unknowns pass through
       break;
+    }
     default:
       throw Error(BS_ERR_INVALID, "unknown preconditioner kind");
   }

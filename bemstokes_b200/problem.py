@@ -193,6 +193,7 @@ class BEMProblem(FrameLoop):
         self.preconditioner_type = "Direct"
         self.bandwith_preconditioner = False
         self.bandwith = 100
+        self.preconditioner_block = 0     # "BlockDirect": largest diagonal block in rows (0 = the rank's whole row block)
         self.gmres_restart = 100
         self.gmres_orthogonalization = "CGS2"   # "MGS" = deal.II's modified Gram-Schmidt verbatim
         self.solver_control = SolverControl(1000, 1e-10)
@@ -404,7 +405,7 @@ class BEMProblem(FrameLoop):
             # block once and keeps the LU across frames, like the reference's reuse of direct_trilinos_preconditioner
             # (bem_stokes.cc:5768-5779; refactorised when a solve needed more than 100 iterations, 4336-4339)
             if not getattr(self, "_block_prec_ready", False) or self.reassemble_preconditoner:
-                check(lib.bs_precond_setup(self._ctx, which, _lib.PREC_BLOCK_DIRECT, 0))
+                check(lib.bs_precond_setup(self._ctx, which, _lib.PREC_BLOCK_DIRECT, int(self.preconditioner_block)))
                 self._block_prec_ready = True
                 self.reassemble_preconditoner = False
         elif t in ("ILU", "AMG"):

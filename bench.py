@@ -362,6 +362,7 @@ def run_ours(args):
     p.use_peer_exchange = not args.no_peer_exchange
     p.solver_control.tolerance, p.solver_control.max_steps = 1e-10, 1000
     p.gmres_restart = 200
+    p.preconditioner_block = args.prec_block
     p.reinit()
     # pre-pass (mass matrix, L2 normals, rigid modes; bs_prepass on the device): input of the hot path
     p.compute_center_of_mass_and_rigid_modes()
@@ -577,6 +578,7 @@ def run_frames(p, mesh, args, sync, torch):
     import bemstokes_b200 as bb
     base = mesh.nodes.copy()
     p.preconditioner_type = "BlockDirect"
+    p.preconditioner_block = args.prec_block
     p.reassemble_preconditoner = True
     out = []
     for f in range(args.frames):
@@ -702,6 +704,7 @@ def main():
     ap.add_argument("--secondary-refine", type=int, default=4)
     ap.add_argument("--preconditioner", default="None", choices=["None", "Jacobi", "BlockDirect"])
     ap.add_argument("--frames", type=int, default=0, help="also solve K perturbed frames with the frame-0 block LU as preconditioner")
+    ap.add_argument("--prec-block", type=int, default=26112, help="BlockDirect: largest diagonal block in rows (0 = the rank's whole row block)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":

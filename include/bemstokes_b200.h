@@ -158,6 +158,9 @@ int bs_tangential_projector(bs_context *ctx, const double *in, double *out);
 
 /* ---- preconditioner (ref: DirectPreconditioner, source/direct_preconditioner.cc:10-23; Jacobi 4296-4300;
  *      band copy assemble_monolithic_preconditioner 3437-3505) ---------------------------------------- */
+/* kind BS_PREC_BAND: param = band width; BS_PREC_BLOCK_DIRECT: param = largest diagonal block in rows (0 = the whole
+ * row block of the rank is one block); both ignored otherwise.  The LU factors persist until the next call: the host keeps
+ * them across frames exactly as the reference keeps direct_trilinos_preconditioner (bem_stokes.cc:5768-5779). */
 int bs_precond_setup(bs_context *ctx, int which, int kind, int bandwidth_or_block);
 int bs_precond_vmult(bs_context *ctx, const double *x, double *y);
 
@@ -226,6 +229,9 @@ int bs_reset_stats(bs_context *ctx);
 /* ---- benchmarking helpers: device-resident repeat loops timed with CUDA events on the context stream ---- */
 int bs_bench_vmult(bs_context *ctx, int which, int repeats, double *ms_per_call);
 int bs_bench_vmult_multi(bs_context *ctx, int which, int nrhs, int repeats, double *ms_per_call);
+/* dense LU (DirectPreconditioner's factorisation, (2/3) n^3 flops) and its application on a synthetic n x n matrix;
+ * residual = |A y - b|_inf for b = 1.  Invalidates a preconditioner that was set up on this context. */
+int bs_bench_lu(bs_context *ctx, int n, int apply_repeats, double *factor_ms, double *apply_ms, double *residual);
 int bs_bench_fp64_peak(int device, double *tflops);                              /* burst, best of 3 */
 int bs_bench_fp64_sustained(int device, double seconds, double *tflops);         /* back-to-back under the power cap */
 

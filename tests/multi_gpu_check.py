@@ -20,11 +20,10 @@ def main():
     import bemstokes_b200 as bb
     from bemstokes_b200.comm import TorchComm
     from oracle import bem_oracle as bo
-    side = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(side)
     comm = TorchComm(device=dev)
     mesh = bb.cubesphere(m=6)  # 218 nodes
-    p = bb.BEMProblem(device=local, rank=rank, nranks=world, comm=comm, stream=side.cuda_stream)
+    # no manual stream plumbing: the callbacks order torch's collectives on the context's own stream
+    p = bb.BEMProblem(device=local, rank=rank, nranks=world, comm=comm)
     p.use_peer_exchange = os.environ.get("BS_PEER_EXCHANGE", "1") == "1"
     p.set_mesh(mesh)
     p.quadrature_order, p.singular_quadrature_order = 6, 8
@@ -61,11 +60,28 @@ def main():
     assert abs(p.solver_control.last_step() - its) <= 1, (p.solver_control.last_step(), its)
     assert es < 1e-8, es
     assert p.final_check_0[0] < 1e-9
+    n_ar_solve = comm.n_allreduce
     if p.use_peer_exchange:
-        # the solve itself made no allgather call: only the monolithic build and the host-side checks did
+        # the solve itself made no collective call (Krylov slices and Gram-Schmidt sums go through peer memory): only the
+        # monolithic build and the host-side checks did
         assert comm.n_allgather <= 10, comm.n_allgather
     else:
         assert comm.n_allgather >= its
+    # block-Jacobi DirectPreconditioner: every rank factorises its own diagonal block (ref: direct_preconditioner.cc:10-23)
+    its_plain = p.solver_control.last_step()
+    p.preconditioner_type = "BlockDirect"
+    ar0 = comm.n_allreduce
+    p.monolithic_solution[:] = 0
+    p.solve_system(True)
+    esp = np.abs(p.monolithic_solution - xg).max() / np.abs(xg).max()
+    assert esp < 1e-8, esp
+    assert p.solver_control.last_step() < its_plain, (p.solver_control.last_step(), its_plain)
+    if p.use_peer_exchange:
+        assert comm.n_allreduce - ar0 <= 2, "the preconditioned solve made allreduce calls"   # _allsum of the solution only
+    its_block = p.solver_control.last_step()
+    p.preconditioner_type = "None"
+    from bemstokes_b200._lib import lib, check
+    check(lib.bs_precond_setup(p._ctx, 2, 0, 0))
     # six right-hand sides in lockstep through the same exchange path
     if world >= 1:
         nr = 6
@@ -80,9 +96,9 @@ def main():
         Xo = np.linalg.solve(A, Bm.T).T
         eb = np.abs(Xm - Xo).max() / np.abs(Xo).max()
         assert eb < 1e-7, eb
-    print("rank %d/%d ok: owned %d nodes, entry err K %.1e A %.1e, GMRES its %d (oracle %d), solution err %.1e, "
-          "allgathers %d allreduces %d" % (rank, world, len(own), ek, ea, p.solver_control.last_step(), its, es,
-                                           comm.n_allgather, comm.n_allreduce), flush=True)
+    print("rank %d/%d ok: owned %d nodes, entry err K %.1e A %.1e, GMRES its %d (oracle %d; block-Jacobi %d), solution err %.1e, "
+          "allgathers %d allreduces %d (%d up to the first solve)" % (rank, world, len(own), ek, ea, its_plain, its, its_block, es,
+                                           comm.n_allgather, comm.n_allreduce, n_ar_solve), flush=True)
     p.close()
     dist.barrier()
     dist.destroy_process_group()

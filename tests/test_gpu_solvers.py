@@ -1,0 +1,172 @@
+"""Device solvers behind DirectPreconditioner / SolverDirect (ref: source/direct_preconditioner.cc:10-23, call sites
+source/bem_stokes.cc:4109-4111, 4264-4266, 4312) and the device-resident GMRES iteration (ref: 4116, 4332): blocked LU with
+the trailing update on the FP64 tensor path, the cooperative block-triangular application, diagonal blocks and the band copy
+of assemble_monolithic_preconditioner (3437-3475), all against dense NumPy algebra on the matrix read back from the device."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import bemstokes_b200 as bb
+from bemstokes_b200 import _lib
+from bemstokes_b200._lib import lib, check
+from oracle import bem_oracle as bo
+from conftest import MESHES
+
+pytestmark = pytest.mark.gpu
+
+
+def make(mesh, **kw):
+    p = bb.BEMProblem()
+    p.set_mesh(mesh)
+    p.quadrature_order, p.singular_quadrature_order = 6, 8
+    p.grid_type, p.imposed_component = "ImposedVelocity", 0
+    p.solve_directly = False
+    for k, v in kw.items():
+        setattr(p, k, v)
+    p.reinit()
+    p.compute_center_of_mass_and_rigid_modes()
+    p.compute_normal_vector()
+    p.assemble_stokes_system(True)
+    return p
+
+
+@pytest.fixture(scope="module")
+def prob():
+    p = make(bb.cubesphere(m=10))   # 602 nodes, 1 812 unknowns: 15 trsv blocks, LU panels of every kind
+    A = p.monolithic_system_matrix.to_dense()
+    yield p, A
+    p.close()
+
+
+def test_lu_tensor_path_direct_solve(prob):
+    p, A = prob
+    n = A.shape[0]
+    rng = np.random.default_rng(1)
+    b = rng.uniform(-1, 1, n)
+    x = np.zeros(n)
+    check(lib.bs_direct_solve(p._ctx, _lib.MAT_A, b.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p)))
+    xo = np.linalg.solve(A, b)
+    assert np.abs(x - xo).max() <= 1e-9 * np.abs(xo).max()
+    assert np.abs(A @ x - b).max() <= 1e-11 * np.abs(b).max() * np.abs(A).sum(axis=1).max()
+
+
+@pytest.mark.parametrize("block", [0, 500])
+def test_block_direct_application_and_gmres(prob, block):
+    """BS_PREC_BLOCK_DIRECT: the node rows (optionally cut into diagonal blocks of at most `block` rows) are solved
+    exactly, the rigid unknowns pass through; the cooperative application equals the dense block solve."""
+    p, A = prob
+    n3, n = p.n_dofs, A.shape[0]
+    check(lib.bs_precond_setup(p._ctx, _lib.MAT_A, _lib.PREC_BLOCK_DIRECT, block))
+    rng = np.random.default_rng(2)
+    v = rng.uniform(-1, 1, n)
+    y = np.zeros(n)
+    check(lib.bs_precond_vmult(p._ctx, v.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p)))
+    # the blocks are contiguous in the library's own ordering: recover it from the application itself when block > 0
+    if block == 0:
+        yo = v.copy()
+        yo[:n3] = np.linalg.solve(A[:n3, :n3], v[:n3])
+        assert np.abs(y - yo).max() <= 1e-9 * np.abs(yo).max()
+    else:
+        # M^-1 is block diagonal: applying it and multiplying back with A's diagonal blocks is the identity; check the
+        # defining property instead of the ordering: M y = v on every block  <=>  y = M^-1 v, with M built from unit vectors
+        Minv = np.zeros((n, n))
+        for j in range(0, n, 64):   # 64 columns per call keep the test short
+            E = np.zeros((min(64, n - j), n))
+            E[np.arange(E.shape[0]), j + np.arange(E.shape[0])] = 1.0
+            Y = np.zeros_like(E)
+            for k in range(E.shape[0]):
+                check(lib.bs_precond_vmult(p._ctx, E[k].ctypes.data_as(C.c_void_p), Y[k].ctypes.data_as(C.c_void_p)))
+            Minv[:, j:j + E.shape[0]] = Y.T
+        M = np.linalg.inv(Minv)
+        mask = np.abs(M) > 1e-9 * np.abs(M).max()      # the sparsity pattern of M: diagonal blocks
+        assert np.abs(M - A)[mask].max() <= 1e-7 * np.abs(A).max()   # ... and on it M equals A
+        nblocks = -(-n3 // block)
+        assert mask[:n3, :n3].sum() <= 1.05 * nblocks * (n3 / nblocks) ** 2 + n3
+    # preconditioned GMRES converges to the solution of A x = b in fewer iterations than without
+    b = p.monolithic_rhs.copy()
+    x = np.zeros(n)
+    its = p.gmres(_lib.MAT_A, x, b)
+    xo = np.linalg.solve(A, b)
+    assert np.abs(x - xo).max() <= 1e-8 * np.abs(xo).max()
+    check(lib.bs_precond_setup(p._ctx, _lib.MAT_A, _lib.PREC_NONE, 0))
+    x0 = np.zeros(n)
+    its0 = p.gmres(_lib.MAT_A, x0, b)
+    assert its < its0, (its, its0)
+
+
+def test_fast_application_equals_substitution(prob, monkeypatch):
+    p, A = prob
+    n = A.shape[0]
+    check(lib.bs_precond_setup(p._ctx, _lib.MAT_A, _lib.PREC_DIRECT, 0))
+    v = np.random.default_rng(3).uniform(-1, 1, n)
+    y1, y2 = np.zeros(n), np.zeros(n)
+    check(lib.bs_precond_vmult(p._ctx, v.ctypes.data_as(C.c_void_p), y1.ctypes.data_as(C.c_void_p)))
+    monkeypatch.setenv("BS_LU_SUBSTITUTION", "1")
+    check(lib.bs_precond_vmult(p._ctx, v.ctypes.data_as(C.c_void_p), y2.ctypes.data_as(C.c_void_p)))
+    monkeypatch.delenv("BS_LU_SUBSTITUTION")
+    yo = np.linalg.solve(A, v)
+    assert np.abs(y2 - yo).max() <= 1e-9 * np.abs(yo).max()
+    assert np.abs(y1 - yo).max() <= 1e-9 * np.abs(yo).max()
+    check(lib.bs_precond_setup(p._ctx, _lib.MAT_A, _lib.PREC_NONE, 0))
+
+
+def test_band_preconditioner(prob):
+    """BS_PREC_BAND = assemble_monolithic_preconditioner with bandwith_preconditioner (ref: bem_stokes.cc:3437-3475):
+    entries with reference column index outside [i - band, i + band) are dropped before the factorisation."""
+    p, A = prob
+    n = A.shape[0]
+    band = 400
+    i, j = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    lo = np.where(i > band, i - band, 0)
+    B = np.where((j >= lo) & (j < i + band), A, 0.0)
+    check(lib.bs_precond_setup(p._ctx, _lib.MAT_A, _lib.PREC_BAND, band))
+    v = np.random.default_rng(4).uniform(-1, 1, n)
+    y = np.zeros(n)
+    check(lib.bs_precond_vmult(p._ctx, v.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p)))
+    yo = np.linalg.solve(B, v)
+    assert np.abs(y - yo).max() <= 1e-8 * np.abs(yo).max()
+    # through the reference's parameters: "ILU" with bandwith_preconditioner
+    p.preconditioner_type, p.bandwith_preconditioner, p.bandwith = "ILU", True, band
+    p.monolithic_solution[:] = 0
+    p.solve_system(True)
+    xo = np.linalg.solve(A, p.monolithic_rhs)
+    assert np.abs(p.monolithic_solution - xo).max() <= 1e-8 * np.abs(xo).max()
+    p.preconditioner_type, p.bandwith_preconditioner = "None", False
+    check(lib.bs_precond_setup(p._ctx, _lib.MAT_A, _lib.PREC_NONE, 0))
+
+
+def test_band_argument_checked():
+    p = make(bb.cubesphere(m=2))
+    assert lib.bs_precond_setup(p._ctx, _lib.MAT_A, _lib.PREC_BAND, 0) == -1   # a band needs a positive width
+    check(lib.bs_precond_setup(p._ctx, _lib.MAT_A, _lib.PREC_BAND, 1))          # the diagonal alone: regular
+    p.close()
+
+
+def test_device_gmres_restart_and_max_steps(prob):
+    """Restart cycles and the max_steps exit of the device-resident iteration against the oracle's GMRES."""
+    p, A = prob
+    n = A.shape[0]
+    b = p.monolithic_rhs.copy()
+    check(lib.bs_precond_setup(p._ctx, _lib.MAT_A, _lib.PREC_NONE, 0))
+    p.gmres_restart = 12   # 10 inner iterations per cycle
+    x = np.zeros(n)
+    its = p.gmres(_lib.MAT_A, x, b)
+    xo, its_o, _, ok = bo.gmres(lambda v: A @ v, b, tol=1e-10, max_n_tmp_vectors=12)
+    assert ok and abs(its - its_o) <= 2, (its, its_o)
+    assert np.abs(x - xo).max() <= 1e-8 * np.abs(xo).max()
+    p.solver_control.max_steps = 7
+    x = np.zeros(n)
+    with pytest.raises(_lib.BemStokesError) as e:
+        p.gmres(_lib.MAT_A, x, b)
+    assert e.value.code == _lib.ERR_NOT_CONVERGED and p.solver_control.last_step() == 7
+    p.solver_control.max_steps, p.gmres_restart = 1000, 100
+    # host-driven loop (deal.II's modified Gram-Schmidt verbatim) and the device-resident loop agree
+    x1, x2 = np.zeros(n), np.zeros(n)
+    p.gmres_orthogonalization = "MGS"
+    i1 = p.gmres(_lib.MAT_A, x1, b)
+    p.gmres_orthogonalization = "CGS2"
+    i2 = p.gmres(_lib.MAT_A, x2, b)
+    assert abs(i1 - i2) <= 1
+    assert np.abs(x1 - x2).max() <= 1e-9 * np.abs(x2).max()
