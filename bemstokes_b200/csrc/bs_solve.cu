@@ -319,7 +319,7 @@ __global__ void k_lu_swap(double *A, size_t ld, int n, int k0, int nb, const int
   }
 }
 
-constexpr int LU_OUT = 128;  // outer block: trailing update of the columns right of it is one k=128 GEMM
+constexpr int LU_OUT = 256;  // outer block: trailing update of the columns right of it is one k=256 GEMM (halves the C traffic of k=128)
 
 // Rows [j0, j0+nb) of U for every column c >= j0+nb:  u = L_jj^{-1} (A[j-rows][c] - L[j-rows][K0:j0) * U[K0:j0)[c]).
 // Columns inside the current outer block [K0, K0+Bw) already carry the rank-32 updates of the earlier inner panels
@@ -412,13 +412,12 @@ __global__ void __launch_bounds__(256) k_lu_gemm(double *A, size_t ld, int n, in
 
 // ---------------------------------------------------------------------------------------------------------
 // Trailing update on the FP64 tensor path (DMMA m8n8k4):  C -= L * U  with the same index conventions as k_lu_gemm.
-// CTA tile 128 x 128, 8 warps as 2 x 4, warp tile 64 x 32 (8 x 4 MMA tiles, 64 accumulator registers per lane);
-// the k range runs through shared memory in slices of 16 columns, three stages deep (cp.async, zero-filled at the
-// matrix edges).  Fragment loads are bank-conflict free: A rows are padded to 20 doubles and B rows to 132 doubles,
+// The k range runs through shared memory in slices of 16 columns, three stages deep (cp.async, zero-filled at the
+// matrix edges).  Fragment loads are bank-conflict free: A rows are padded to 20 doubles and B rows to 68 doubles,
 // so that the 16 lanes of a half-warp (4 rows x 4 k for A, 4 k x 4 columns for B) hit 16 different 8-byte banks.
 // Needs 16-byte aligned rows (ld, k0, col_begin even); k_lu_gemm stays as the fallback for odd edges.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int DG_BM = 128, DG_BN = 128, DG_KC = 16, DG_STAGES = 3;
+constexpr int DG_BM = 128, DG_BN = 64, DG_KC = 16, DG_STAGES = 3;
 constexpr int DG_APAD = DG_KC + 4, DG_BPAD = DG_BN + 4;
 constexpr size_t DG_STAGE_DOUBLES = (size_t)DG_BM * DG_APAD + (size_t)DG_KC * DG_BPAD;
 constexpr size_t DG_SMEM = DG_STAGES * DG_STAGE_DOUBLES * sizeof(double);
@@ -431,11 +430,13 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(256) k_lu_gemm_dmma(double *A, size_t ld, int n, int k0, int kw, int row_begin, int col_begin,
-                                                      int col_end) {
+// CTA tile 128 x 64, 8 warps as 4 x 2, warp tile 32 x 32 (4 x 4 MMA tiles, 32 accumulators = 64 registers per lane): two
+// CTAs are resident per SM, so that the C read-modify-write of one tile overlaps the MMAs of the other
+__global__ void __launch_bounds__(256, 2) k_lu_gemm_dmma(double *A, size_t ld, int n, int k0, int kw, int row_begin, int col_begin,
+                                                         int col_end) {
   extern __shared__ __align__(16) double dg_smem[];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, g = lane >> 2, t = lane & 3;
-  const int wm = wid >> 2, wn = wid & 3;
+  const int wm = wid >> 1, wn = wid & 1;
   const int r0 = row_begin + blockIdx.y * DG_BM, c0 = col_begin + blockIdx.x * DG_BN;
   const int nk = (kw + DG_KC - 1) / DG_KC;
   auto load_stage = [&](int st, int kk) {
@@ -444,22 +445,22 @@ __global__ void __launch_bounds__(256) k_lu_gemm_dmma(double *A, size_t ld, int 
     for (int i = 0; i < 4; ++i) {  // L tile: 128 rows x 16 columns, 8 chunks of 16 bytes per row
       const int ch = tid + i * 256, row = ch >> 3, cq = ch & 7;
       const int gr = r0 + row, gk = kk + 2 * cq;
-      int valid = gr < n ? min(max(kw - gk, 0), 2) : 0;
+      const int valid = gr < n ? min(max(kw - gk, 0), 2) : 0;
       const double *src = valid ? A + (size_t)gr * ld + k0 + gk : A;
       cp_async16(As + (size_t)row * DG_APAD + 2 * cq, src, 8 * valid);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {  // U tile: 16 rows x 128 columns, 64 chunks per row
-      const int ch = tid + i * 256, row = ch >> 6, cq = ch & 63;
+    for (int i = 0; i < 2; ++i) {  // U tile: 16 rows x 64 columns, 32 chunks per row
+      const int ch = tid + i * 256, row = ch >> 5, cq = ch & 31;
       const int gk = kk + row, gc = c0 + 2 * cq;
-      int valid = gk < kw ? min(max(col_end - gc, 0), 2) : 0;
+      const int valid = gk < kw ? min(max(col_end - gc, 0), 2) : 0;
       const double *src = valid ? A + (size_t)(k0 + gk) * ld + gc : A;
       cp_async16(Bs + (size_t)row * DG_BPAD + 2 * cq, src, 8 * valid);
     }
   };
-  double acc[8][4][2];
+  double acc[4][4][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 #pragma unroll
@@ -473,24 +474,24 @@ __global__ void __launch_bounds__(256) k_lu_gemm_dmma(double *A, size_t ld, int 
     if (kt + DG_STAGES - 1 < nk) load_stage((kt + DG_STAGES - 1) % DG_STAGES, (kt + DG_STAGES - 1) * DG_KC);
     asm volatile("cp.async.commit_group;" ::: "memory");
     const double *As = dg_smem + (size_t)(kt % DG_STAGES) * DG_STAGE_DOUBLES, *Bs = As + (size_t)DG_BM * DG_APAD;
-    const double *ap = As + (size_t)(wm * 64 + g) * DG_APAD + t;
+    const double *ap = As + (size_t)(wm * 32 + g) * DG_APAD + t;
     const double *bp = Bs + (size_t)t * DG_BPAD + wn * 32 + g;
 #pragma unroll
     for (int k4 = 0; k4 < DG_KC / 4; ++k4) {
-      double a[8], b[4];
+      double a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = ap[(size_t)i * 8 * DG_APAD + 4 * k4];
+      for (int i = 0; i < 4; ++i) a[i] = ap[(size_t)i * 8 * DG_APAD + 4 * k4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) b[j] = bp[(size_t)4 * k4 * DG_BPAD + 8 * j];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = r0 + wm * 64 + 8 * i + g;
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + wm * 32 + 8 * i + g;
     if (r >= n) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -513,8 +514,8 @@ static void lu_trailing_update(Context &c, double *A, size_t ld, int n, int k0, 
   const int ncols = col_end - col_begin, nrows = n - row_begin;
   if (ncols <= 0 || nrows <= 0 || kw <= 0) return;
   const bool aligned = (ld % 2 == 0) && (k0 % 2 == 0) && (col_begin % 2 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0);
-  const dim3 grid((ncols + DG_BN - 1) / DG_BN, (nrows + DG_BM - 1) / DG_BM);
   if (aligned && !std::getenv("BS_NO_DMMA")) {
+    const dim3 grid((ncols + DG_BN - 1) / DG_BN, (nrows + DG_BM - 1) / DG_BM);
     static bool attr = false;
     if (!attr) {
       BS_CUDA(cudaFuncSetAttribute(k_lu_gemm_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DG_SMEM));
@@ -522,6 +523,7 @@ static void lu_trailing_update(Context &c, double *A, size_t ld, int n, int k0, 
     }
     k_lu_gemm_dmma<<<grid, 256, DG_SMEM, c.stream>>>(A, ld, n, k0, kw, row_begin, col_begin, col_end);
   } else {
+    const dim3 grid((ncols + GM_T - 1) / GM_T, (nrows + GM_T - 1) / GM_T);
     k_lu_gemm<<<grid, 256, 0, c.stream>>>(A, ld, n, k0, kw, row_begin, col_begin, col_end);
   }
   count_launch(c);
@@ -533,6 +535,7 @@ static void lu_trailing_update(Context &c, double *A, size_t ld, int n, int k0, 
 void lu_factor(Context &c, double *A, size_t n_, size_t ld, int *piv) {
   const int n = (int)n_;
   const size_t sm_u12 = (size_t)LU_NB * (LU_OUT + 1) * sizeof(double);
+  if (sm_u12 > 48 * 1024) BS_CUDA(cudaFuncSetAttribute(k_lu_u12_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_u12));
   const bool trace = std::getenv("BS_TRACE") != nullptr;
   double tacc[5] = {0, 0, 0, 0, 0};
   auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -728,20 +731,49 @@ __global__ void __launch_bounds__(TB) k_tri_inverse(const double *LU, size_t ld,
   for (int q = 0; q < TB; ++q) out[(size_t)q * TB + j] = X[j * XL + q];
 }
 
-__device__ __forceinline__ void tri_diag_apply(const double *MT, int k, int k0, int kb, double *x, double *sm) {
-  // x[k0 .. k0+kb) <- inv(T_kk) * x[k0 .. k0+kb); 256 threads: (row i, half of the columns)
-  const int tid = threadIdx.x, i = tid & (TB - 1), half = tid >> 7;
-  double *rs = sm, *part = sm + TB;
-  __syncthreads();
-  if (tid < TB) rs[tid] = tid < kb ? __ldcg(x + k0 + tid) : 0.0;
-  __syncthreads();
-  const double *Mk = MT + (size_t)k * TB * TB;
-  double a = 0.0;
+// 128 x 128 block times vector for the owner CTA: thread (row i, half h) sums 64 columns; `colmajor` says whether
+// consecutive threads read consecutive addresses (the transposed inverses) or every thread walks its own row (T itself)
+__device__ __forceinline__ double tri_block_dot(const double *Mk, size_t ldm, bool colmajor, int i, int half, int ncols,
+                                                const double *v) {
+  const int j0 = half * (TB / 2), j1 = min(j0 + TB / 2, ncols);
+  double a0 = 0.0, a1 = 0.0;
+  if (colmajor) {
 #pragma unroll 8
-  for (int jj = half * (TB / 2); jj < (half + 1) * (TB / 2); ++jj) a = fma(Mk[(size_t)jj * TB + i], rs[jj], a);
-  part[half * TB + i] = a;
+    for (int j = j0; j < j1; ++j) a0 = fma(Mk[(size_t)j * ldm + i], v[j], a0);
+  } else {
+    const double *row = Mk + (size_t)i * ldm;
+    int j = j0;
+#pragma unroll 8
+    for (; j + 1 < j1; j += 2) {
+      const double2 m2 = *reinterpret_cast<const double2 *>(row + j);
+      a0 = fma(m2.x, v[j], a0);
+      a1 = fma(m2.y, v[j + 1], a1);
+    }
+    if (j < j1) a0 = fma(row[j], v[j], a0);
+  }
+  return a0 + a1;
+}
+// owner step: r_blk -= T[blk rows][k0 .. k0+kb) x_k (skipped when T == nullptr), then x_blk = inv(T_bb) r_blk.
+// sm: xs[TB] | rs[TB] | part[2 TB]
+__device__ __forceinline__ void tri_owner_step(const double *T, size_t ld, int k0, int kb, const double *MT, int blk, int b0, int bb,
+                                               double *x, double *sm) {
+  const int tid = threadIdx.x, i = tid & (TB - 1), half = tid >> 7;
+  double *xs = sm, *rs = sm + TB, *part = sm + 2 * TB;
   __syncthreads();
-  if (tid < kb) __stcg(x + k0 + tid, part[tid] + part[TB + tid]);
+  if (tid < TB) {
+    rs[tid] = tid < bb ? __ldcg(x + b0 + tid) : 0.0;
+    if (T) xs[tid] = tid < kb ? __ldcg(x + k0 + tid) : 0.0;
+  }
+  __syncthreads();
+  if (T) {
+    part[half * TB + i] = i < bb ? tri_block_dot(T + (size_t)b0 * ld + k0, ld, false, i, half, kb, xs) : 0.0;
+    __syncthreads();
+    if (tid < TB) rs[tid] -= part[tid] + part[TB + tid];
+    __syncthreads();
+  }
+  part[half * TB + i] = tri_block_dot(MT + (size_t)blk * TB * TB, TB, true, i, half, TB, rs);
+  __syncthreads();
+  if (tid < bb) __stcg(x + b0 + tid, part[tid] + part[TB + tid]);
   __syncthreads();
 }
 // x[r] -= T[r][k0 .. k0+kb) . xk  (one warp per row; xk in registers, 4 values per lane)
@@ -766,7 +798,7 @@ __global__ void __launch_bounds__(256) k_lu_apply_coop(const double *LU, size_t 
                                                        const double *UinvT, const double *in, double *x, unsigned int *counter,
                                                        const int *skip) {
   if (skip && *skip) return;
-  __shared__ double sm[3 * TB];
+  __shared__ double sm[4 * TB];
   const int G = gridDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int gw = blockIdx.x * 8 + wid, total_warps = G * 8;
   const int nblk = (n + TB - 1) / TB;
@@ -774,25 +806,22 @@ __global__ void __launch_bounds__(256) k_lu_apply_coop(const double *LU, size_t 
   for (int i = blockIdx.x * 256 + tid; i < n; i += G * 256) __stcg(x + i, in[perm[i]]);
   grid_barrier(counter, (++nbar) * G);
   // ---- forward: L y = P b
-  if ((int)blockIdx.x == 0 % G) tri_diag_apply(LinvT, 0, 0, min(TB, n), x, sm);
+  if ((int)blockIdx.x == 0 % G) tri_owner_step(nullptr, ld, 0, 0, LinvT, 0, 0, min(TB, n), x, sm);
   grid_barrier(counter, (++nbar) * G);
   for (int k = 0; k + 1 < nblk; ++k) {
     const int k0 = k * TB;  // kb == TB here (k is not the last block)
     double xk[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) xk[u] = __ldcg(x + k0 + 4 * lane + u);
-    if ((int)blockIdx.x == (k + 1) % G) {  // owner of the next step: its rows first, then its diagonal solve
-      const int r1 = min(k0 + 2 * TB, n);
-      for (int r = k0 + TB + wid; r < r1; r += 8) tri_row_update(LU, ld, r, k0, TB, xk, x, lane);
-      tri_diag_apply(LinvT, k + 1, k0 + TB, r1 - (k0 + TB), x, sm);
-    }
+    if ((int)blockIdx.x == (k + 1) % G)  // owner of the next step: its rows first, then its diagonal solve
+      tri_owner_step(LU, ld, k0, TB, LinvT, k + 1, k0 + TB, min(k0 + 2 * TB, n) - (k0 + TB), x, sm);
     for (int r = k0 + 2 * TB + gw; r < n; r += total_warps) tri_row_update(LU, ld, r, k0, TB, xk, x, lane);
     grid_barrier(counter, (++nbar) * G);
   }
   // ---- backward: U x = y
   {
     const int kl = nblk - 1;
-    if ((int)blockIdx.x == kl % G) tri_diag_apply(UinvT, kl, kl * TB, n - kl * TB, x, sm);
+    if ((int)blockIdx.x == kl % G) tri_owner_step(nullptr, ld, 0, 0, UinvT, kl, kl * TB, n - kl * TB, x, sm);
     grid_barrier(counter, (++nbar) * G);
   }
   for (int k = nblk - 1; k >= 1; --k) {
@@ -800,10 +829,7 @@ __global__ void __launch_bounds__(256) k_lu_apply_coop(const double *LU, size_t 
     double xk[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) xk[u] = (4 * lane + u < kb) ? __ldcg(x + k0 + 4 * lane + u) : 0.0;
-    if ((int)blockIdx.x == (k - 1) % G) {
-      for (int r = k0 - TB + wid; r < k0; r += 8) tri_row_update(LU, ld, r, k0, kb, xk, x, lane);
-      tri_diag_apply(UinvT, k - 1, k0 - TB, TB, x, sm);
-    }
+    if ((int)blockIdx.x == (k - 1) % G) tri_owner_step(LU, ld, k0, kb, UinvT, k - 1, k0 - TB, TB, x, sm);
     for (int r = gw; r < k0 - TB; r += total_warps) tri_row_update(LU, ld, r, k0, kb, xk, x, lane);
     grid_barrier(counter, (++nbar) * G);
   }

@@ -400,7 +400,7 @@ class FrameLoop:
                 self.update_system_state(True, i, self.bool_rot, self.bool_dipl, "Forward")
                 self.reinit_for_new_time((i + 1) % self.n_frames)
                 self.next_euler_vec = self.compute_euler_vector((i + 2) % self.n_frames, True)
-                self._solve_frame(i)
+                self._solve_frame(i + 1)   # ref 5797: compute_center_of_mass_and_rigid_modes(i+1)
                 self.update_system_state(True, i, self.bool_rot, self.bool_dipl, self.res_strategy)
             self.total_velocities = self.shape_velocities + self.rigid_puntual_velocities + self.wall_velocities
             self.rigid_puntual_displacements = self.next_rigid_puntual_displacements

@@ -260,7 +260,7 @@ public:
   Vector normal_vector_pure, M_normal_vector_pure, V_x_normals_body, monolithic_rhs, monolithic_solution, stokes_forces,
       shape_velocities;
   std::vector<Vector> N_rigid, N_rigid_dual;
-  Vector rigid_velocities, rigid_total_forces;
+  Vector rigid_velocities, rigid_total_forces, baricenter_rigid_velocities;
   Matrix3 rotation_matrix = identity3(), old_rotation_matrix = identity3();
   Vector old_rigid_velocities, old_rigid_displacements_for_sim;
   Vector next_euler_vec, rigid_puntual_velocities, rigid_puntual_translation_velocities, next_rigid_puntual_displacements,
@@ -393,6 +393,7 @@ public:
       rigid_velocities[r] = monolithic_solution[n_dofs + r] * assemble_scaling;
       rigid_total_forces[r] = dot(stokes_forces, N_rigid_dual[r]);
     }
+    baricenter_rigid_velocities = rigid_velocities;  // this solve's velocities about the pole (bem_stokes.cc:4479-4492)
   }
 
   // DN(u) = P V^{-1} (P K P u)   (bem_stokes.cc:4072-4129)
@@ -527,12 +528,14 @@ public:
       old_rotation_matrix = rotation_matrix;
       old_rigid_displacements_for_sim = rigid_displacements_for_sim;
     }
+    // the punctual velocities come from the LAST solve (baricenter_rigid_velocities, ref 4784-4789); Heun's mean enters
+    // only through omega in update_rotation_matrix
     rigid_puntual_velocities.assign(n_dofs, 0.);
     for (unsigned int r = 0; r < 3; ++r)
-      for (unsigned int i = 0; i < n_dofs; ++i) rigid_puntual_velocities[i] += assemble_scaling * rigid_velocities[r] * N_rigid[r][i];
+      for (unsigned int i = 0; i < n_dofs; ++i) rigid_puntual_velocities[i] += assemble_scaling * baricenter_rigid_velocities[r] * N_rigid[r][i];
     rigid_puntual_translation_velocities = rigid_puntual_velocities;
     for (unsigned int r = 3; r < num_rigid; ++r)
-      for (unsigned int i = 0; i < n_dofs; ++i) rigid_puntual_velocities[i] += assemble_scaling * rigid_velocities[r] * N_rigid[r][i];
+      for (unsigned int i = 0; i < n_dofs; ++i) rigid_puntual_velocities[i] += assemble_scaling * baricenter_rigid_velocities[r] * N_rigid[r][i];
     if (consider_rotations) update_rotation_matrix(rotation_matrix, {{rigid_velocities[3], rigid_velocities[4], rigid_velocities[5]}}, time_step);
     next_rigid_puntual_displacements.assign(n_dofs, 0.);
     for (unsigned int i = 0; i < n_dofs; ++i) next_rigid_puntual_displacements[i] = time_step * rigid_puntual_translation_velocities[i];
@@ -601,7 +604,7 @@ public:
         update_system_state(true, i, bool_rot, bool_dipl, "Forward");
         compute_euler_vector(frame_euler, (i + 1) % n_frames, true);
         compute_euler_vector(next_euler_vec, (i + 2) % n_frames, true);
-        solve_frame(i);
+        solve_frame(i + 1);  // ref 5797: compute_center_of_mass_and_rigid_modes(i+1)
         update_system_state(true, i, bool_rot, bool_dipl, "Heun");
       }
       total_velocities = shape_velocities;

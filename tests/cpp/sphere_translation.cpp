@@ -72,5 +72,23 @@ int main(int argc, char **argv) {
   looped.run(0, 1);
   std::cout.precision(12);
   std::cout << "run frame 1 velocity ratio " << looped.rigid_velocities[0] / u0 << std::endl;
+
+  // Heun predictor-corrector (bem_stokes.cc:5780-5830) on the same grids, one frame: result files into <out>/heun
+  if (argc > 3) {
+    BEMProblem<3> heun;
+    heun.quadrature_order = 8;
+    heun.singular_quadrature_order = 10;
+    heun.grid_type = "Real";
+    heun.solve_directly = true;
+    heun.res_strategy = "Heun";
+    heun.input_grid_path = bem_problem_3d.input_grid_path;
+    heun.input_grid_base_name = "sphere_translation_";
+    heun.output_dir = argv[3];
+    heun.n_frames = 2;
+    heun.pcout = &sink;
+    heun.run(0, 0);
+    std::cout << "heun mean velocity " << heun.rigid_velocities[0] << " predictor " << heun.old_rigid_velocities[0]
+              << " last solve " << heun.baricenter_rigid_velocities[0] << std::endl;
+  }
   return 0;
 }

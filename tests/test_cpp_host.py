@@ -72,7 +72,9 @@ def test_cpp_sphere_translation_and_frame_loop(tmp_path, goldens):
     import numpy as np
     from bemstokes_b200 import frontend as fe
     exe = build_exe(str(tmp_path), os.path.join(ROOT, "tests", "cpp", "sphere_translation.cpp"))
-    r = subprocess.run([exe, MESHES, str(tmp_path)], capture_output=True, text=True, timeout=300)
+    hdir = os.path.join(str(tmp_path), "heun_cpp")
+    os.makedirs(hdir)
+    r = subprocess.run([exe, MESHES, str(tmp_path), hdir], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     out = r.stdout
     G = goldens["sphere_translation"]
@@ -90,3 +92,26 @@ def test_cpp_sphere_translation_and_frame_loop(tmp_path, goldens):
     N = len(d0) // 3
     assert np.abs(d0[:N] - 0.1 * G["rigid_velocity_0"]).max() < 1e-7
     assert os.path.exists(os.path.join(str(tmp_path), "rotation_matrix_1.bin"))
+    # ---- the C++ Heun branch on the device against the Python frame loop (same grids, same parameters), file by file
+    import bemstokes_b200 as bb
+    pdir = os.path.join(str(tmp_path), "heun_py")
+    os.makedirs(pdir)
+    ph = bb.BEMProblem()
+    ph.quadrature_order, ph.singular_quadrature_order = 8, 10
+    ph.grid_type, ph.res_strategy, ph.solve_directly = "Real", "Heun", True
+    ph.input_grid_path, ph.input_grid_base_name, ph.input_grid_format = MESHES, "sphere_translation_", "msh"
+    ph.n_frames, ph.output_dir = 2, pdir
+    ph.log = lambda *_: None
+    ph.run(0, 0)
+    for name in ("4_6_rigid_velocities_0.bin", "stokes_rigid_vel_0.bin", "stokes_rigid_displ_0.bin", "rotation_matrix_0.bin",
+                 "stokes_forces_0.bin", "total_velocities_0.bin"):
+        a = fe.vector_block_read(os.path.join(hdir, name))
+        b = fe.vector_block_read(os.path.join(pdir, name))
+        assert a.shape == b.shape and np.abs(a - b).max() <= 1e-9 * max(1.0, np.abs(b).max()), name
+    # the punctual velocities are those of the second (corrector) solve, not of the Heun mean (ref 4784-4789)
+    m = re.search(r"heun mean velocity ([-0-9.e+]+) predictor ([-0-9.e+]+) last solve ([-0-9.e+]+)", out)
+    mean, pred, last = (float(m.group(k)) for k in (1, 2, 3))
+    assert abs(mean - 0.5 * (pred + last)) < 1e-12 and abs(last + pred) < 2e-2 * abs(pred)
+    vel = fe.vector_block_read(os.path.join(hdir, "stokes_rigid_vel_0.bin"))
+    assert abs(vel[0] - last) < 1e-9
+    ph.close()
