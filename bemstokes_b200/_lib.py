@@ -71,6 +71,7 @@ SIGNATURES = {
     "bs_set_gmres_orthogonalization": (C.c_int, [ctx_p, C.c_int]),
     "bs_gmres_multi": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, c_int_p,
                                  c_double_p]),
+    "bs_dn_operator_multi": (C.c_int, [ctx_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, c_int_p]),
     "bs_direct_solve": (C.c_int, [ctx_p, C.c_int, C.c_void_p, C.c_void_p]),
     "bs_evaluate_bie": (C.c_int, [ctx_p, C.c_int, c_double_p, c_double_p, c_double_p, c_double_p, C.c_int]),
     "bs_kernel_eval": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p,

@@ -1176,6 +1176,89 @@ int bs_bench_lu(bs_context *h, int n, int apply_repeats, double *factor_ms, doub
 
 }  // extern "C"
 
+// ---- DN-operator route (ref: dirichlet_to_neumann_operator bem_stokes.cc:4072-4129, solve_system(false) 4163-4258) ----
+// F_k = P V^-1 P K P u_k for nvec input velocities at once: one projection kernel, one multi-right-hand-side sweep over K
+// (FP64 tensor path from 4 vectors), nvec V-solves advanced in lockstep (one sweep over V per iteration for all of them,
+// or one LU for all with solve_directly), one projection.
+__global__ void k_project_apply(double *X, size_t ldx, int nvec, const double *dots, const double *nhat, double inv_l2, size_t n) {
+  const int k = blockIdx.y;
+  const double d = dots[k] * inv_l2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    X[(size_t)k * ldx + i] -= d * nhat[i];
+}
+namespace bs {
+// X_k <- P X_k = X_k - (Mnhat . X_k) / l2 * nhat for nvec full internal vectors
+static void project_multi(Context &c, double *X, size_t ldx, int nvec) {
+  const size_t n = c.n3();
+  double *dots = c.wsd("dn.dots", 16);
+  multi_dot(c, X, ldx, nvec, c.d_Mnhat.p, n, dots);
+  k_project_apply<<<dim3((unsigned)std::min<size_t>((n + 255) / 256, 592), nvec), 256, 0, c.stream>>>(X, ldx, nvec, dots, c.d_nhat.p,
+                                                                                                  1.0 / c.l2gamma, n);
+  BS_CUDA(cudaGetLastError());
+  count_launch(c);
+}
+}  // namespace bs
+
+extern "C" int bs_dn_operator_multi(bs_context *h, int nvec, const double *U, double *F, int solve_directly, double tol_abs,
+                                    int max_steps, int max_n_tmp_vectors, int *iterations) {
+  int rc = BS_OK;
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(nvec >= 1 && nvec <= Context::XCHG_SLOTS && U && F, "1 <= nvec <= 8 input velocities");
+  BS_REQUIRE(c.have_projector, "projector data not set (bs_correct_V / bs_build_monolithic)");
+  const DMat &K = matrix_of(c, BS_MAT_K);
+  const DMat &V = matrix_of(c, BS_MAT_V);
+  BS_REQUIRE(!solve_directly || c.nranks == 1, "solve_directly needs the whole matrix on one GPU");
+  BS_REQUIRE(c.prec_kind == BS_PREC_NONE || c.prec_which == BS_MAT_V, "preconditioner was set up for another matrix");
+  Timer t(c, c.stats.solve_ms, "bs_dn_operator_multi");
+  const size_t n = c.n3(), off = c.slice_offset(BS_MAT_V), mloc = c.rows_loc;
+  const size_t ldx = (n + 4) & ~(size_t)3;
+  double *X = c.wsd("dn.x", (size_t)nvec * ldx), *Y = c.wsd("dn.y", (size_t)nvec * ldx), *Fv = c.wsd("dn.f", (size_t)nvec * ldx);
+  BS_CUDA(cudaMemsetAsync(Y, 0, (size_t)nvec * ldx * sizeof(double), c.stream));
+  BS_CUDA(cudaMemsetAsync(Fv, 0, (size_t)nvec * ldx * sizeof(double), c.stream));
+  for (int k = 0; k < nvec; ++k) to_internal(c, U + (size_t)k * n, 0, X + (size_t)k * ldx);
+  project_multi(c, X, ldx, nvec);                                       // P u
+  gemv_multi(c, K, nvec, X, ldx, Y + off, ldx);                         // K P u on the owned rows
+  if (c.nranks > 1)
+    for (int k = 0; k < nvec; ++k) exchange(c, BS_MAT_K, Y + (size_t)k * ldx + off, Y + (size_t)k * ldx);
+  project_multi(c, Y, ldx, nvec);                                       // P K P u
+  if (solve_directly) {
+    const size_t ldl = (n + 15) & ~(size_t)15;
+    double *lu = c.wsd("direct.lu", n * ldl + 2);
+    int *piv = c.wsi("direct.piv", n + 2);
+    BS_CUDA(cudaMemsetAsync(lu, 0, n * ldl * sizeof(double), c.stream));
+    BS_CUDA(cudaMemcpy2DAsync(lu, ldl * sizeof(double), V.p, V.ld * sizeof(double), n * sizeof(double), n, cudaMemcpyDeviceToDevice, c.stream));
+    lu_factor(c, lu, n, ldl, piv);
+    for (int k = 0; k < nvec; ++k) {
+      copy(c, Y + (size_t)k * ldx, Fv + (size_t)k * ldx, n);
+      lu_solve(c, lu, n, ldl, piv, Fv + (size_t)k * ldx);
+    }
+    if (iterations)
+      for (int k = 0; k < nvec; ++k) iterations[k] = 1;
+  } else {
+    std::vector<int> its(nvec, 0);
+    rc = gmres_batched(c, BS_MAT_V, nvec, Y + off, Fv + off, ldx, tol_abs, max_steps, max_n_tmp_vectors, its.data(), nullptr);
+    if (iterations) std::copy(its.begin(), its.end(), iterations);
+    if (c.nranks > 1)
+      for (int k = 0; k < nvec; ++k) exchange(c, BS_MAT_V, Fv + (size_t)k * ldx + off, Fv + (size_t)k * ldx);
+  }
+  (void)mloc;
+  project_multi(c, Fv, ldx, nvec);                                      // P V^-1 P K P u
+  for (int k = 0; k < nvec; ++k) from_internal(c, Fv + (size_t)k * ldx, 0, F + (size_t)k * n, 0, n);
+  BS_CUDA(cudaStreamSynchronize(c.stream));
+  if (rc == BS_ERR_NOT_CONVERGED) bs::set_last_error("GMRES did not converge within max_steps for at least one DN right-hand side");
+  }
+  catch (const bs::Error &e) {
+    bs::set_last_error(e.what());
+    return e.code;
+  }
+  catch (const std::exception &e) {
+    bs::set_last_error(e.what());
+    return BS_ERR_INVALID;
+  }
+  return rc;
+}
+
 // ---- FP64 FMA-chain microbenchmark: the denominator of the assembly roofline (not in MEASURED_PEAKS.json) ----
 __global__ void k_fp64_peak(double *out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;

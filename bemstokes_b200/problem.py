@@ -495,35 +495,61 @@ class BEMProblem(FrameLoop):
             self.rigid_velocities[:3] += np.cross(self.baricenter_rigid_velocities[3:6], -pole)
         return self
 
+    def dirichlet_to_neumann_operator_multi(self, input_vels):
+        """DN(u_k) = P V^{-1} (P K P u_k) for up to 8 velocities in one device call (bs_dn_operator_multi): one
+        multi-right-hand-side sweep over K and the V-systems advanced in lockstep (ref: bem_stokes.cc:4072-4129 called
+        6 + 1 times by solve_system(false), 4163-4258)."""
+        U = np.ascontiguousarray(np.atleast_2d(input_vels), dtype=np.float64)
+        F = np.zeros_like(U)
+        its = (C.c_int * U.shape[0])()
+        if not self.solve_directly:
+            self._setup_preconditioner(_lib.MAT_V)
+            check(lib.bs_set_gmres_orthogonalization(
+                self._ctx, _lib.ORTHO_MGS if self.gmres_orthogonalization == "MGS" else _lib.ORTHO_CGS2))
+        rc = lib.bs_dn_operator_multi(self._ctx, U.shape[0], _vp(U), _vp(F), 1 if self.solve_directly else 0,
+                                      self.solver_control.tolerance, self.solver_control.max_steps, self.gmres_restart, its)
+        self.last_steps = [its[k] for k in range(U.shape[0])]
+        self.solver_control._last_step = max(self.last_steps)
+        check(rc)
+        return F
+
     def dirichlet_to_neumann_operator(self, input_vel, output_force=None):
         """DN(u) = P V^{-1} (P K P u)   (ref: bem_stokes.cc:4072-4129)."""
-        v1 = self.tangential_projector_body(input_vel)
-        v2 = self.K_matrix @ v1
-        v1 = self.tangential_projector_body(v2)
-        f = np.zeros(self.n_dofs)
-        if self.solve_directly:
-            check(lib.bs_direct_solve(self._ctx, _lib.MAT_V, _vp(v1), _vp(f)))
-        else:
-            self._setup_preconditioner(_lib.MAT_V)
-            self.gmres(_lib.MAT_V, f, v1)
-        out = self.tangential_projector_body(f, output_force)
-        return out
+        F = self.dirichlet_to_neumann_operator_multi(np.asarray(input_vel, dtype=np.float64)[None, :])[0]
+        if output_force is not None:
+            output_force[:] = F
+            return output_force
+        return F
 
-    def solve_dn(self):
-        """solve_system(false): resistance problem through the DN operator (bem_stokes.cc:4163-4258)."""
+    def solve_dn(self, batched=True):
+        """solve_system(false): the rigid-body problem through the DN operator (ref: bem_stokes.cc:4163-4258).  The
+        reference calls the operator once for the shape velocities and once per rigid mode; here the 1 + num_rigid
+        systems are one batch (`batched=False` keeps the sequential calls, for timing)."""
         nr = self.num_rigid
-        DN = [self.dirichlet_to_neumann_operator(self.N_rigid[r]) for r in range(nr)]
-        F = np.array([[self.N_rigid_dual[i] @ DN[j] for j in range(nr)] for i in range(nr)])
-        self.final_matrix = F
-        rhs = -np.array([self.N_rigid_dual[i] @ self.dirichlet_to_neumann_operator(self.shape_velocities)
-                         for i in range(nr)]) if np.any(self.shape_velocities) else np.zeros(nr)
-        if not np.any(rhs):
-            self.rigid_velocities = np.zeros(nr)
-            self.stokes_forces = np.zeros(self.n_dofs)
-            return
-        U = np.linalg.solve(F, rhs)
-        self.rigid_velocities = U
-        self.stokes_forces = sum(U[r] * DN[r] for r in range(nr)) + self.dirichlet_to_neumann_operator(self.shape_velocities)
+        inputs = np.vstack([np.asarray(self.shape_velocities, dtype=np.float64)[None, :], self.N_rigid[:nr]])
+        if batched:
+            out = self.dirichlet_to_neumann_operator_multi(inputs)
+        else:
+            out = np.vstack([self.dirichlet_to_neumann_operator(u)[None, :] for u in inputs])
+        self.stokes_forces = out[0].copy()
+        self.DN_N_rigid = out[1:]
+        final_rhs = -np.array([self.N_rigid_dual[i] @ self.stokes_forces for i in range(nr)])
+        F = np.zeros((nr, nr))
+        for i in range(nr):
+            if self.grid_type == "ImposedForce":
+                if i == self.imposed_component:
+                    final_rhs[i] += 1.0
+                F[i] = [self.N_rigid_dual[i] @ self.DN_N_rigid[j] for j in range(nr)]
+            elif self.grid_type == "ImposedVelocity":
+                F[i, i] = 1.0
+                final_rhs[i] = 1.0 if i == self.imposed_component else 0.0
+            else:
+                F[i] = [self.N_rigid_dual[i] @ self.DN_N_rigid[j] for j in range(nr)]
+        self.final_matrix, self.final_rhs = F, final_rhs
+        # the reference hands the 6 x 6 system to GMRES with the identity preconditioner (4244); it is solved directly here
+        self.rigid_velocities = np.linalg.solve(F, final_rhs)
+        self.stokes_forces = self.stokes_forces + self.rigid_velocities @ self.DN_N_rigid
+        self.reassemble_preconditoner = True
 
     # ---- field evaluation ---------------------------------------------------------------------------------
     def evaluate_stokes_bie(self, val_points, vel, forces, val_velocities=None):

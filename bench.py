@@ -321,6 +321,37 @@ def secondary_workloads(device, fp64_peak, args):
                               "iterations": its_b, "R_diag": [float(Rm[i, i]) for i in range(6)],
                               "R_offdiag_over_diag_max": float(np.abs(Rm - np.diag(np.diag(Rm))).max() / np.abs(np.diag(Rm)).min())}
     p.close()
+    # ---- DN-operator route: 1 + 6 V-systems of solve_system(false) as one device batch against the
+    # reference's sequence of single calls; V and K both stored
+    p = bb.BEMProblem(device=device)
+    p.set_mesh(mesh)
+    p.quadrature_order, p.singular_quadrature_order = 8, 10
+    p.grid_type, p.monolithic_bool = "Real", False
+    p.solve_directly, p.preconditioner_type = False, "None"
+    p.solver_control.tolerance, p.solver_control.max_steps, p.gmres_restart = 1e-10, 1000, 200
+    p.reinit()
+    p.compute_center_of_mass_and_rigid_modes()
+    p.compute_normal_vector()
+    x = mesh.nodes
+    p.shape_velocities = np.concatenate([np.sin(x[:, 0]) * x[:, 1], 0.5 * x[:, 1] * x[:, 2], 0.3 * x[:, 0] * x[:, 1] - 0.1])
+    p.assemble_stokes_system(True)
+    p.solve_dn(batched=True)   # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    p.solve_dn(batched=True)
+    torch.cuda.synchronize()
+    t_b = time.perf_counter() - t0
+    its_b = list(p.last_steps)
+    Ub = p.rigid_velocities.copy()
+    t0 = time.perf_counter()
+    p.solve_dn(batched=False)
+    torch.cuda.synchronize()
+    t_s = time.perf_counter() - t0
+    out["dn_route_7rhs"] = {"workload": "solve_system(false): DN operator of the swimming stroke and of the 6 rigid modes on the same "
+                                        "prolate mesh (V and K stored)", "nodes": mesh.n_nodes, "batched_s": t_b, "sequential_s": t_s,
+                            "speedup": t_s / t_b, "iterations": its_b,
+                            "rigid_velocities_batched_vs_sequential": float(np.abs(Ub - p.rigid_velocities).max())}
+    p.close()
     return out
 
 

@@ -174,6 +174,13 @@ int bs_set_gmres_orthogonalization(bs_context *ctx, int kind);
 /* nrhs independent systems (the 6 rigid-body resistance problems), B and X nrhs x size. */
 int bs_gmres_multi(bs_context *ctx, int which, int nrhs, const double *B, double *X, double tol_abs, int max_steps,
                    int max_n_tmp_vectors, int *iterations, double *final_residuals);
+/* DN-operator route, batched (ref: dirichlet_to_neumann_operator bem_stokes.cc:4072-4129, its 6 + 1 calls in
+ * solve_system(false) 4163-4258): F_k = P V^-1 P K P u_k for nvec <= 8 velocities at once (U, F: nvec x 3N).  One
+ * multi-right-hand-side sweep over K, then the nvec V-systems advanced in lockstep by one multi-right-hand-side sweep over
+ * V per GMRES iteration (solve_directly = 0; the preconditioner set up for BS_MAT_V applies), or one LU of V for all of them
+ * (solve_directly = 1).  Needs V and K both stored and corrected, and the projector data.  iterations: nvec counts (may be NULL). */
+int bs_dn_operator_multi(bs_context *ctx, int nvec, const double *U, double *F, int solve_directly, double tol_abs,
+                         int max_steps, int max_n_tmp_vectors, int *iterations);
 /* ref: TrilinosWrappers::SolverDirect (4261-4267): dense LU with partial pivoting on the device. */
 int bs_direct_solve(bs_context *ctx, int which, const double *b, double *x);
 

@@ -16,6 +16,7 @@
 #pragma once
 #include "bemstokes_b200.h"
 
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <fstream>
@@ -261,6 +262,8 @@ public:
       shape_velocities;
   std::vector<Vector> N_rigid, N_rigid_dual;
   Vector rigid_velocities, rigid_total_forces, baricenter_rigid_velocities;
+  std::vector<Vector> DN_N_rigid;   // DN(N_rigid[r]) of the last solve_system(false)
+  std::vector<double> final_matrix; // num_rigid x num_rigid, row-major
   Matrix3 rotation_matrix = identity3(), old_rotation_matrix = identity3();
   Vector old_rigid_velocities, old_rigid_displacements_for_sim;
   Vector next_euler_vec, rigid_puntual_velocities, rigid_puntual_translation_velocities, next_rigid_puntual_displacements,
@@ -352,7 +355,10 @@ public:
 
   // ref: BEMProblem::solve_system (bem_stokes.cc:4158-4508)
   void solve_system(bool monolithic_booly = true) {
-    if (!monolithic_booly) throw Error(BS_ERR_UNSUPPORTED, "use dirichlet_to_neumann_operator for the DN route");
+    if (!monolithic_booly) {
+      solve_system_dn();
+      return;
+    }
     if (solve_directly) {
       check(bs_direct_solve(ctx, BS_MAT_A, monolithic_rhs.data(), monolithic_solution.data()));
       solver_control.last_step_ = 1;
@@ -396,20 +402,74 @@ public:
     baricenter_rigid_velocities = rigid_velocities;  // this solve's velocities about the pole (bem_stokes.cc:4479-4492)
   }
 
-  // DN(u) = P V^{-1} (P K P u)   (bem_stokes.cc:4072-4129)
+  // DN(u_k) = P V^{-1} (P K P u_k) for up to 8 velocities in one device call (bem_stokes.cc:4072-4129)
+  void dirichlet_to_neumann_operator_multi(const std::vector<Vector> &input_vels, std::vector<Vector> &output_forces) {
+    const int nvec = (int)input_vels.size();
+    Vector U((size_t)nvec * n_dofs), F((size_t)nvec * n_dofs, 0.);
+    for (int k = 0; k < nvec; ++k) std::copy(input_vels[k].begin(), input_vels[k].end(), U.begin() + (size_t)k * n_dofs);
+    std::vector<int> its(nvec, 0);
+    if (!solve_directly) check(bs_precond_setup(ctx, BS_MAT_V, BS_PREC_NONE, 0));
+    check(bs_dn_operator_multi(ctx, nvec, U.data(), F.data(), solve_directly ? 1 : 0, solver_control.tolerance,
+                               (int)solver_control.max_steps, (int)gmres_restart, its.data()));
+    solver_control.last_step_ = (unsigned int)*std::max_element(its.begin(), its.end());
+    *pcout << "   Iterations needed to solve DN:         " << solver_control.last_step_ << std::endl;
+    output_forces.assign(nvec, Vector(n_dofs));
+    for (int k = 0; k < nvec; ++k) std::copy(F.begin() + (size_t)k * n_dofs, F.begin() + (size_t)(k + 1) * n_dofs, output_forces[k].begin());
+  }
   void dirichlet_to_neumann_operator(const Vector &input_vel, Vector &output_force) {
-    Vector v1, v2, f(n_dofs, 0.);
-    tangential_projector_body(input_vel, v1);
-    K_matrix.vmult(v2, v1);
-    tangential_projector_body(v2, v1);
-    if (solve_directly) check(bs_direct_solve(ctx, BS_MAT_V, v1.data(), f.data()));
-    else {
-      check(bs_precond_setup(ctx, BS_MAT_V, BS_PREC_NONE, 0));
-      int its;
-      double res;
-      check(bs_gmres(ctx, BS_MAT_V, v1.data(), f.data(), solver_control.tolerance, (int)solver_control.max_steps, (int)gmres_restart, &its, &res));
+    std::vector<Vector> out;
+    dirichlet_to_neumann_operator_multi({input_vel}, out);
+    output_force = out[0];
+  }
+  // solve_system(false): the rigid-body problem through the DN operator, the 1 + num_rigid systems as one batch
+  // (bem_stokes.cc:4163-4258); the 6 x 6 system, which the reference hands to GMRES, is solved by Gaussian elimination
+  void solve_system_dn() {
+    std::vector<Vector> in, out;
+    in.push_back(shape_velocities);
+    for (unsigned int r = 0; r < num_rigid; ++r) in.push_back(N_rigid[r]);
+    dirichlet_to_neumann_operator_multi(in, out);
+    stokes_forces = out[0];
+    DN_N_rigid.assign(out.begin() + 1, out.end());
+    const unsigned int nr = num_rigid;
+    std::vector<double> Fm((size_t)nr * nr, 0.), rhs(nr, 0.);
+    for (unsigned int i = 0; i < nr; ++i) rhs[i] = -dot(N_rigid_dual[i], stokes_forces);
+    for (unsigned int i = 0; i < nr; ++i) {
+      if (grid_type == "ImposedVelocity") {
+        Fm[(size_t)i * nr + i] = 1.;
+        rhs[i] = (i == imposed_component) ? 1. : 0.;
+      } else {
+        if (grid_type == "ImposedForce" && i == imposed_component) rhs[i] += 1.;
+        for (unsigned int j = 0; j < nr; ++j) Fm[(size_t)i * nr + j] = dot(N_rigid_dual[i], DN_N_rigid[j]);
+      }
     }
-    tangential_projector_body(f, output_force);
+    final_matrix = Fm;
+    // Gaussian elimination with partial pivoting on the nr x nr system
+    std::vector<double> a = Fm, x = rhs;
+    for (unsigned int k = 0; k < nr; ++k) {
+      unsigned int pv = k;
+      for (unsigned int i = k + 1; i < nr; ++i)
+        if (std::fabs(a[(size_t)i * nr + k]) > std::fabs(a[(size_t)pv * nr + k])) pv = i;
+      if (pv != k) {
+        for (unsigned int j = 0; j < nr; ++j) std::swap(a[(size_t)k * nr + j], a[(size_t)pv * nr + j]);
+        std::swap(x[k], x[pv]);
+      }
+      for (unsigned int i = k + 1; i < nr; ++i) {
+        const double l = a[(size_t)i * nr + k] / a[(size_t)k * nr + k];
+        for (unsigned int j = k; j < nr; ++j) a[(size_t)i * nr + j] -= l * a[(size_t)k * nr + j];
+        x[i] -= l * x[k];
+      }
+    }
+    for (int k = (int)nr - 1; k >= 0; --k) {
+      for (unsigned int j = k + 1; j < nr; ++j) x[k] -= a[(size_t)k * nr + j] * x[j];
+      x[k] /= a[(size_t)k * nr + k];
+    }
+    rigid_velocities = x;
+    baricenter_rigid_velocities = x;
+    for (unsigned int r = 0; r < nr; ++r)
+      for (unsigned int i = 0; i < n_dofs; ++i) stokes_forces[i] += x[r] * DN_N_rigid[r][i];
+    rigid_total_forces.assign(nr, 0.);
+    for (unsigned int r = 0; r < nr; ++r) rigid_total_forces[r] = dot(stokes_forces, N_rigid_dual[r]);
+    reassemble_preconditoner = true;
   }
 
   // ref: evaluate_stokes_bie (bem_stokes.cc:5366-5451); val_points [P][3], result component-major

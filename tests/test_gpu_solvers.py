@@ -172,3 +172,57 @@ def test_device_gmres_restart_and_max_steps(prob):
     i2 = p.gmres(_lib.MAT_A, x2, b)
     assert abs(i1 - i2) <= 1
     assert np.abs(x1 - x2).max() <= 1e-9 * np.abs(x2).max()
+
+
+@pytest.mark.parametrize("meshname,grid_type", [("sphere_half_refined_0.inp", "Real"),
+                                                ("prolate_spheroid_lambda_2_ref_0.msh", "ImposedForce")])
+def test_dn_route_batched(meshname, grid_type):
+    """solve_system(false) with the 1 + 6 DN systems as ONE device batch (bs_dn_operator_multi; ref: bem_stokes.cc:4073-4129,
+    4163-4258): final_matrix, rigid velocities and stokes_forces against the oracle's dense algebra, <= 1e-9."""
+    from oracle import port
+    mesh = bb.read_mesh(os.path.join(MESHES, meshname))
+    p = bb.BEMProblem()
+    p.set_mesh(mesh)
+    p.quadrature_order, p.singular_quadrature_order = 8, 10
+    p.grid_type, p.imposed_component = grid_type, 2
+    p.monolithic_bool, p.solve_directly, p.preconditioner_type = False, False, "None"
+    p.solver_control.tolerance = 1e-12
+    p.reinit()
+    p.compute_center_of_mass_and_rigid_modes()
+    p.compute_normal_vector()
+    x = mesh.nodes
+    if grid_type == "Real":   # a smooth swimming stroke
+        p.shape_velocities = np.concatenate([np.sin(x[:, 0]) * x[:, 1], 0.5 * x[:, 1] * x[:, 2], 0.3 * x[:, 0] * x[:, 1] - 0.1])
+    p.assemble_stokes_system(True)
+    p.solve_system(False)
+    its_batched = list(p.last_steps)
+    geo = bo.Geometry(mesh.nodes, mesh.conn.astype(np.int64), 1)
+    Vo, Ko, _ = port.assemble_VK(geo, bo.KernelSpec(), 8, "Mixed", 10)
+    pre = bo.Prepass(geo, 8)
+    Vc, _ = bo.correct_V(Vo, pre)
+    Kc = bo.correct_K(Ko, geo.N)
+    import scipy.linalg as sla
+    lu = sla.lu_factor(Vc)
+    DN = lambda u: pre.P(sla.lu_solve(lu, pre.P(Kc @ pre.P(u))))
+    f0 = DN(p.shape_velocities)
+    DNr = [DN(pre.N_rigid[r]) for r in range(6)]
+    Fo = np.array([[pre.N_rigid_dual[i] @ DNr[j] for j in range(6)] for i in range(6)])
+    rhs = -np.array([pre.N_rigid_dual[i] @ f0 for i in range(6)])
+    if grid_type == "ImposedForce":
+        rhs[2] += 1.0
+    Uo = np.linalg.solve(Fo, rhs)
+    fo = f0 + sum(Uo[r] * DNr[r] for r in range(6))
+    assert np.abs(p.final_matrix - Fo).max() <= 1e-9 * np.abs(Fo).max()
+    assert np.abs(p.rigid_velocities - Uo).max() <= 1e-9 * max(1e-30, np.abs(Uo).max()) + 1e-13
+    assert np.abs(p.stokes_forces - fo).max() <= 1e-9 * np.abs(fo).max()
+    # batched == the reference's sequence of single calls
+    F1 = p.final_matrix.copy()
+    p.solve_dn(batched=False)
+    assert np.abs(p.final_matrix - F1).max() <= 1e-9 * np.abs(F1).max()
+    assert max(its_batched) >= 1
+    # one LU for all seven systems (solve_directly)
+    p.solve_directly = True
+    p.solve_system(False)
+    assert np.abs(p.final_matrix - Fo).max() <= 1e-9 * np.abs(Fo).max()
+    assert np.abs(p.stokes_forces - fo).max() <= 1e-9 * np.abs(fo).max()
+    p.close()
