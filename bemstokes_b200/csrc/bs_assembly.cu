@@ -422,6 +422,141 @@ __device__ __forceinline__ void integrate_free(const double *__restrict__ c8, co
   }
 }
 
+// Free-space kernel, Q1 unknowns on a bilinear (Q1) mapping, Gauss 8 (N1C == -8): rows of the tensor rule are straight
+// lines, y(xi, eta_q) = y(0, eta_q) + xi b(eta_q), hence R = R0 + xi B and every product R_i R_j is the quadratic
+// A_v + xi C_v + xi^2 D_v with A = R0 (x) R0, C = R0 (x) B + B (x) R0, D = B (x) B constant along the row.  With
+// l_0 = 1 - xi, l_1 = xi the x-direction sums sum_q c_q l_b(xi_q) R_i R_j collapse to the four scalar moments
+// m_k = sum_q c_q xi_q^k (k = 0..3) per layer: 10 FMAs per point (4 + 4 + 2 for the isotropic part) instead of 6
+// products and 26 FMAs, and one expansion per row (3 FMAs per value and shape function).  r^2, 1/r and R.n keep
+// the per-point R = y_q - x, so the coefficients c_q are the same numbers as before; per point 29 FP64 instructions
+// instead of 55, per row of 8 points about 380 instead of 490.
+//   xi_s: [8][4] = xi_q, xi_q^2, xi_q^3, - ; xi_s[32] = xi_0, xi_s[33] = 1 / (xi_7 - xi_0)
+template <int MODE>
+__device__ __forceinline__ void free_stage_c_lin(const FreeB &b, const double *__restrict__ xq, double (&mg)[4], double (&mk)[4],
+                                                 double (&mi)[2]) {
+  const double2 x12 = *reinterpret_cast<const double2 *>(xq);
+  const double x3 = xq[2];
+  if (MODE != 1) {
+    mg[0] += b.c3;
+    mg[1] = fma(b.c3, x12.x, mg[1]);
+    mg[2] = fma(b.c3, x12.y, mg[2]);
+    mg[3] = fma(b.c3, x3, mg[3]);
+    mi[0] += b.c1;
+    mi[1] = fma(b.c1, x12.x, mi[1]);
+  }
+  if (MODE != 0) {
+    mk[0] += b.ck;
+    mk[1] = fma(b.ck, x12.x, mk[1]);
+    mk[2] = fma(b.ck, x12.y, mk[2]);
+    mk[3] = fma(b.ck, x3, mk[3]);
+  }
+}
+
+template <int MODE, int QS, int NACC>
+__device__ __forceinline__ void integrate_free_lin(const double *__restrict__ c8, const double *__restrict__ xi_s,
+                                                   const double *__restrict__ ly_s, const double (&x)[3], int part,
+                                                   double (&acc)[4][NACC]) {
+  constexpr int N1 = 8;
+  constexpr int KO = (MODE == 2) ? 6 : 0;  // offset of the double-layer values in acc
+  const bool flip = (QS == 2) && (part == 1);  // odd partner: accumulator slot s holds shape function s^1 (see cell_pass)
+  const double xi0 = xi_s[32], inv_dxi = xi_s[33];
+  double accI[4] = {0.0, 0.0, 0.0, 0.0};
+  FreeA sa;
+  FreeB sb;
+  if (part < N1) {
+    FreeA a0;
+    free_stage_a<MODE>(c8 + (size_t)8 * part * N1, x, a0);
+    free_stage_b<MODE>(a0, sb);
+    free_stage_a<MODE>(c8 + (size_t)8 * (part * N1 + 1), x, sa);
+  }
+  for (int qy = part; qy < N1; qy += QS) {
+    double mg[4] = {0.0, 0.0, 0.0, 0.0}, mk[4] = {0.0, 0.0, 0.0, 0.0}, mi[2] = {0.0, 0.0};
+    const double *crow = c8 + (size_t)8 * qy * N1;
+    const int qyn = (qy + QS < N1) ? qy + QS : qy;  // this thread's next row (or a harmless re-read at the end)
+    const double *nrow = c8 + (size_t)8 * qyn * N1;
+#pragma unroll
+    for (int qx = 0; qx < N1; ++qx) {
+      FreeB nb;
+      free_stage_b<MODE>(sa, nb);                                                                  // point qx+1
+      FreeA na;
+      free_stage_a<MODE>(qx + 2 < N1 ? crow + 8 * (qx + 2) : nrow + 8 * (qx + 2 - N1), x, na);      // point qx+2
+      free_stage_c_lin<MODE>(sb, xi_s + 4 * qx, mg, mk, mi);                                       // point qx
+      sb = nb;
+      sa = na;
+    }
+    // ---- the row's straight line and the expansion of the moments
+    double R0[3], B[3];
+    {
+      const double2 u0 = *reinterpret_cast<const double2 *>(crow), u7 = *reinterpret_cast<const double2 *>(crow + 8 * (N1 - 1));
+      const double z0 = crow[2], z7 = crow[8 * (N1 - 1) + 2];
+      B[0] = (u7.x - u0.x) * inv_dxi;
+      B[1] = (u7.y - u0.y) * inv_dxi;
+      B[2] = (z7 - z0) * inv_dxi;
+      R0[0] = fma(-xi0, B[0], u0.x - x[0]);
+      R0[1] = fma(-xi0, B[1], u0.y - x[1]);
+      R0[2] = fma(-xi0, B[2], z0 - x[2]);
+    }
+    // moments of l_b xi^k: l_0 = 1 - xi, l_1 = xi; slot order swapped for the odd partner
+    double Mg[3][2], Mk[3][2], Mi[2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (MODE != 1) {
+        const double d = mg[k] - mg[k + 1], e = mg[k + 1];
+        Mg[k][0] = flip ? e : d;
+        Mg[k][1] = flip ? d : e;
+      }
+      if (MODE != 0) {
+        const double d = mk[k] - mk[k + 1], e = mk[k + 1];
+        Mk[k][0] = flip ? e : d;
+        Mk[k][1] = flip ? d : e;
+      }
+    }
+    if (MODE != 1) {
+      const double d = mi[0] - mi[1], e = mi[1];
+      Mi[0] = flip ? e : d;
+      Mi[1] = flip ? d : e;
+    }
+    const double ly0 = ly_s[qy * 2], ly1 = ly_s[qy * 2 + 1];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = i; j < 3; ++j) {
+        const int v = (i == 0) ? j : (i == 1 ? 2 + j : 5);
+        const double Av = R0[i] * R0[j];
+        const double Cv = (i == j) ? 2.0 * (R0[i] * B[i]) : fma(R0[i], B[j], B[i] * R0[j]);
+        const double Dv = B[i] * B[j];
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          if (MODE != 1) {
+            const double tg = fma(Dv, Mg[2][b], fma(Cv, Mg[1][b], Av * Mg[0][b]));
+            acc[b][v] = fma(tg, ly0, acc[b][v]);
+            acc[b + 2][v] = fma(tg, ly1, acc[b + 2][v]);
+          }
+          if (MODE != 0) {
+            const double tk = fma(Dv, Mk[2][b], fma(Cv, Mk[1][b], Av * Mk[0][b]));
+            acc[b][KO + v] = fma(tk, ly0, acc[b][KO + v]);
+            acc[b + 2][KO + v] = fma(tk, ly1, acc[b + 2][KO + v]);
+          }
+        }
+      }
+    if (MODE != 1) {
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        accI[b] = fma(Mi[b], ly0, accI[b]);
+        accI[b + 2] = fma(Mi[b], ly1, accI[b + 2]);
+      }
+    }
+  }
+  if (MODE != 1) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      acc[a][0] += accI[a];
+      acc[a][3] += accI[a];
+      acc[a][5] += accI[a];
+    }
+  }
+}
+
 // Free-surface image system on the same fast path: G_fs = G(R) + s_i G(R_im), K likewise, with s_i = -1 on the row of
 // the wall normal and +1 otherwise (ref: source/free_surface_kernel.cc:19-72, 135-209).  Both terms are free-space
 // kernels, so one layer at a time (MODE 0 or 1, the layer-split launches) is accumulated as two symmetric 6-vectors
@@ -518,7 +653,12 @@ __device__ __forceinline__ void cell_pass(const double *__restrict__ cq, const d
   if (FAST) {
     const double *lx_s = FLIP ? l1d_s + part * (n1 * NB1) : l1d_s;  // odd partner: x-flipped copy of the table
     if constexpr (KT == BS_KERNEL_FREE) {
-      if (ok) integrate_free<NA, MODE, QS, N1C, NACC>(cq, lx_s, l1d_s, n1, x, part, acc);
+      if constexpr (N1C < 0) {
+        static_assert(NA == 4 && N1C == -8, "linear-row fast path: Q1, Gauss 8");
+        if (ok) integrate_free_lin<MODE, QS, NACC>(cq, l1d_s + 32, l1d_s, x, part, acc);
+      } else {
+        if (ok) integrate_free<NA, MODE, QS, N1C, NACC>(cq, lx_s, l1d_s, n1, x, part, acc);
+      }
     } else {
       if constexpr (KT == BS_KERNEL_FREE_SURFACE && MODE != 2) {
         if (ok) integrate_free_surface<NA, MODE, QS>(cq, lx_s, l1d_s, n1, x, xim, o, part, acc);
@@ -659,6 +799,19 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
     const double l = P.l1d[i];
     l1d_s[i] = l;
     if (FLIP) l1d_s[n1 * NB1 + (i ^ 1)] = l;  // columns swapped (NB1 == 2)
+  }
+  if (N1C < 0 && t < 8) {  // linear-row fast path: powers of the 1-D rule points xi_q = l_1(x_q), end points of a row
+    const double xi = P.l1d[2 * t + 1];
+    double *xt = l1d_s + 32 + 4 * t;
+    xt[0] = xi;
+    xt[1] = xi * xi;
+    xt[2] = xi * xi * xi;
+    xt[3] = 0.0;
+    if (t == 0) {
+      const double x0 = P.l1d[1], x7 = P.l1d[2 * 7 + 1];
+      l1d_s[64] = x0;
+      l1d_s[65] = 1.0 / (x7 - x0);
+    }
   }
   for (int i = t; i < (ce - cs) * NA; i += NT) {
     const int cell = P.blk_cells[cs + i / NA];
@@ -836,10 +989,15 @@ static void launch_reg_layer(Context &c, RegParams P, int nrow_tiles, size_t sme
   // reference's parameter files): fully unrolled, software-pipelined rows
   const bool n8 = (KT == BS_KERNEL_FREE) && c.kp.eps == 0.0 && P.n1d == 8;
   constexpr int N8 = (KT == BS_KERNEL_FREE) ? 8 : 0;
-  auto kern = c.fused ? ((c.kp.eps == 0.0) ? (n8 ? k_assemble_regular<NA, KT, LAYER, QS, VS, false, true, N8>
+  // Q1 unknowns on a Q1 (bilinear) mapping: the rows of the rule are straight lines -> moment formulation (N1C = -8)
+  constexpr int L8 = (KT == BS_KERNEL_FREE && NA == 4) ? -8 : N8;
+  const bool lin = n8 && NA == 4 && c.na_map == 4 && !std::getenv("BS_NO_LINROWS");
+  auto kern = c.fused ? ((c.kp.eps == 0.0) ? (n8 ? (lin ? k_assemble_regular<NA, KT, LAYER, QS, VS, false, true, L8>
+                                                        : k_assemble_regular<NA, KT, LAYER, QS, VS, false, true, N8>)
                                                  : k_assemble_regular<NA, KT, LAYER, QS, VS, false, true, 0>)
                                            : k_assemble_regular<NA, KT, LAYER, QS, VS, true, true, 0>)
-                      : ((c.kp.eps == 0.0) ? (n8 ? k_assemble_regular<NA, KT, LAYER, QS, VS, false, false, N8>
+                      : ((c.kp.eps == 0.0) ? (n8 ? (lin ? k_assemble_regular<NA, KT, LAYER, QS, VS, false, false, L8>
+                                                        : k_assemble_regular<NA, KT, LAYER, QS, VS, false, false, N8>)
                                                  : k_assemble_regular<NA, KT, LAYER, QS, VS, false, false, 0>)
                                            : k_assemble_regular<NA, KT, LAYER, QS, VS, true, false, 0>);
   BS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
