@@ -100,6 +100,7 @@ static void alloc_matrix(Context &c, DBuf<double> &store, DMat &M, size_t rows, 
   if (c.rows_loc)
     BS_CUDA(cudaMemset2DAsync(store.p + c.n3(), c.ld * sizeof(double), 0, (c.ld - c.n3()) * sizeof(double), c.rows_loc, c.stream));
   BS_CUDA(cudaMemsetAsync(store.p + c.rows_loc * c.ld, 0, (MAX_RIGID * c.ld + 2) * sizeof(double), c.stream));
+  M = DMat();  // also drops an implicit rank-1 term of the previous assembly
   M.p = store.p;
   M.rows = rows;
   M.cols = cols;
@@ -486,14 +487,29 @@ int bs_correct_V(bs_context *h, const double *nhat, const double *Mnhat, double 
   Extra &e = extra(c);
   e.vout.alloc(std::max(e.vout.n, c.n3() + MAX_RIGID + 2));
   double *vn_loc = e.vout.p + 3 * (size_t)c.p0;
+  c.V.r1_u = c.V.r1_w = nullptr;  // V nhat of the raw operator (the correction is idempotent)
+  c.V.r1_ncols = 0;
   gemv(c, c.V, c.d_nhat.p, vn_loc);
   mark("gemv V*nhat");
   if (Vn_out) from_internal(c, e.vout.p, 0, Vn_out, 3 * (size_t)c.p0, 3 * (size_t)c.p1, true);
   mark("Vn to host");
-  // u = nhat - V nhat on the owned rows
+  // u = (nhat - V nhat) / l2 on the owned rows, w = M nhat:  V + u w^T.  Kept as the two vectors (DMat::r1_*): every reader of
+  // the matrix applies the term, the read-modify-write pass over the whole matrix (86 GB at the benchmark size) is gone
   e.vin.alloc(std::max(e.vin.n, c.n3() + MAX_RIGID + 2));
   sub(c, c.d_nhat.p + 3 * (size_t)c.p0, vn_loc, e.vin.p, c.rows_loc);
-  rank1_update(c, c.V, e.vin.p, c.d_Mnhat.p, 1.0 / l2gamma);
+  if (std::getenv("BS_EXPLICIT_RANK1")) {
+    rank1_update(c, c.V, e.vin.p, c.d_Mnhat.p, 1.0 / l2gamma);
+  } else {
+    c.d_r1u.alloc(c.rows_loc + MAX_RIGID + 2);
+    c.d_r1u.zero(c.stream);
+    c.d_r1w.alloc(c.n3() + 2);
+    copy(c, e.vin.p, c.d_r1u.p, c.rows_loc);
+    scal(c, 1.0 / l2gamma, c.d_r1u.p, c.rows_loc);
+    copy(c, c.d_Mnhat.p, c.d_r1w.p, c.n3());
+    c.V.r1_u = c.d_r1u.p;
+    c.V.r1_w = c.d_r1w.p;
+    c.V.r1_ncols = c.n3();
+  }
   BS_CUDA(cudaStreamSynchronize(c.stream));
   mark("rank-1 update");
   BS_API_END
@@ -645,6 +661,21 @@ int bs_build_monolithic(bs_context *h, const unsigned char *col_is_K, int num_ri
     Vv.rows = c.rows_loc;
     Vv.cols = n;
     select_columns(c, c.A, Vv, c.K, d_flag, c.A_aliases_V);
+    // the implicit V correction carries over to the V columns of A
+    c.A.r1_u = c.V.r1_u;
+    c.A.r1_w = c.V.r1_w;
+    c.A.r1_ncols = c.V.r1_ncols;
+    if (c.V.r1_u && col_is_K) {
+      std::vector<double> wm(n);
+      BS_CUDA(cudaMemcpyAsync(wm.data(), c.V.r1_w, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+      BS_CUDA(cudaStreamSynchronize(c.stream));
+      for (size_t p = 0; p < (size_t)c.N; ++p)
+        for (int k = 0; k < 3; ++k)
+          if (col_is_K[(size_t)c.node_of_pos[p] + (size_t)k * c.N]) wm[3 * p + k] = 0.0;
+      c.d_r1wA.upload(wm, c.stream);
+      BS_CUDA(cudaStreamSynchronize(c.stream));
+      c.A.r1_w = c.d_r1wA.p;
+    }
   }
   // rigid columns A(i, 3N+r) = -scaling * tmpN[r][i]  (ref: bem_stokes.cc:3247-3251)
   struct P2_ { double *p; } colbuf;
@@ -934,6 +965,7 @@ int bs_direct_solve(bs_context *h, int which, const double *b, double *x) {
   BS_CUDA(cudaMemsetAsync(lu.p, 0, m * ldl * sizeof(double), c.stream));
   BS_CUDA(cudaMemcpy2DAsync(lu.p, ldl * sizeof(double), M.p, M.ld * sizeof(double), m * sizeof(double), m,
                             cudaMemcpyDeviceToDevice, c.stream));
+  add_rank1_block(c, M, 0, 0, m, lu.p, ldl);
   lu_factor(c, lu.p, m, ldl, piv.p);
   to_internal(c, b, nx, dx.p);
   lu_solve(c, lu.p, m, ldl, piv.p, dx.p);
@@ -1228,6 +1260,7 @@ extern "C" int bs_dn_operator_multi(bs_context *h, int nvec, const double *U, do
     int *piv = c.wsi("direct.piv", n + 2);
     BS_CUDA(cudaMemsetAsync(lu, 0, n * ldl * sizeof(double), c.stream));
     BS_CUDA(cudaMemcpy2DAsync(lu, ldl * sizeof(double), V.p, V.ld * sizeof(double), n * sizeof(double), n, cudaMemcpyDeviceToDevice, c.stream));
+    add_rank1_block(c, V, 0, 0, n, lu, ldl);
     lu_factor(c, lu, n, ldl, piv);
     for (int k = 0; k < nvec; ++k) {
       copy(c, Y + (size_t)k * ldx, Fv + (size_t)k * ldx, n);

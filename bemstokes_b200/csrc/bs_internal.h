@@ -75,10 +75,16 @@ struct DBuf {
 };
 
 // Row-block of a dense matrix, row-major, leading dimension ld (doubles), internal (node-major) ordering.
+// Optional implicit rank-1 term: the matrix stands for  M + r1_u r1_w^T  on the columns < r1_ncols (the V correction of
+// ref bem_stokes.cc:3017-3032 kept as two vectors instead of a read-modify-write pass over the whole matrix; every
+// reader below - matvec, entry reads, diagonal, LU copies - applies it).
 struct DMat {
   double *p = nullptr;
   size_t rows = 0, cols = 0, ld = 0;
   bool owned = false;
+  const double *r1_u = nullptr;  // [rows] (zero on the rigid rows)
+  const double *r1_w = nullptr;  // [r1_ncols]
+  size_t r1_ncols = 0;
   bool valid() const { return p != nullptr; }
 };
 
@@ -219,6 +225,7 @@ struct Context {
   int fused_alpha = 0;
   // projector data (internal ordering, full length 3N)
   DBuf<double> d_nhat, d_Mnhat;
+  DBuf<double> d_r1u, d_r1w, d_r1wA;  // implicit V correction: u = (nhat - V nhat) / l2 on the owned rows, w = M nhat (masked copy for A)
   double l2gamma = 0.0;
   bool have_projector = false;
 
@@ -326,6 +333,8 @@ void extract_diag(Context &c, const DMat &M, size_t row_offset, double *d_out);
 void select_columns(Context &c, DMat &A, const DMat &V, const DMat &K, const unsigned char *d_flag, bool alias);
 void set_column(Context &c, DMat &A, size_t col, const double *v, double scale);
 void gather_entries(Context &c, const DMat &M, int n, const int *d_r, const int *d_c, double *d_out);
+// dst[i][j] (n x n, leading dimension ldd) += r1_u[row_off + i] * r1_w[col_off + j] of M's implicit term (after a plain copy of a block of M)
+void add_rank1_block(Context &c, const DMat &M, size_t row_off, size_t col_off, size_t n, double *dst, size_t ldd);
 // ---- solvers (bs_solve.cu) --------------------------------------------------------------------------------
 void lu_factor(Context &c, double *A, size_t n, size_t ld, int *piv);
 // factorise local diagonal blocks of `M` (copied; band > 0 drops entries outside the reference-ordered band) for the preconditioner

@@ -22,7 +22,8 @@ __device__ __forceinline__ double2 ld_stream2(const double *p) {
 template <int RPW>
 __global__ void __launch_bounds__(32 * GEMV_WARPS) k_gemv(const double *__restrict__ A, size_t ld, size_t rows, size_t cols,
                                                           const double *__restrict__ x, double *__restrict__ y,
-                                                          const int *skip) {
+                                                          const int *skip, const double *__restrict__ r1_u,
+                                                          const double *__restrict__ r1_dot) {
   if (skip && *skip) return;
   const int lane = threadIdx.x & 31;
   const size_t warp = (size_t)blockIdx.x * GEMV_WARPS + (threadIdx.x >> 5);
@@ -67,16 +68,25 @@ __global__ void __launch_bounds__(32 * GEMV_WARPS) k_gemv(const double *__restri
     double s = acc[r];
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-    if (lane == 0 && r0 + r < rows) y[r0 + r] = s;
+    if (lane == 0 && r0 + r < rows) y[r0 + r] = r1_u ? fma(r1_u[r0 + r], *r1_dot, s) : s;  // + u (w . x): implicit rank-1 term
   }
+}
+
+// dots[k] = r1_w . X_k for the implicit rank-1 term of M (nullptr when M has none)
+static const double *rank1_dots(Context &c, const DMat &M, int nrhs, const double *X, size_t ldx) {
+  if (!M.r1_u) return nullptr;
+  double *dots = c.wsd("r1.dots", 16);
+  multi_dot(c, X, ldx, nrhs, M.r1_w, M.r1_ncols, dots);
+  return dots;
 }
 
 void gemv(Context &c, const DMat &M, const double *x, double *y, const int *skip) {
   if (M.rows == 0) return;
   BS_REQUIRE((M.ld & 1) == 0, "matrix ld must be even");
+  const double *r1_dot = rank1_dots(c, M, 1, x, 0);
   const size_t warps = (M.rows + GEMV_RPW - 1) / GEMV_RPW;
   const unsigned grid = (unsigned)((warps + GEMV_WARPS - 1) / GEMV_WARPS);
-  k_gemv<GEMV_RPW><<<grid, 32 * GEMV_WARPS, 0, c.stream>>>(M.p, M.ld, M.rows, M.cols, x, y, skip);
+  k_gemv<GEMV_RPW><<<grid, 32 * GEMV_WARPS, 0, c.stream>>>(M.p, M.ld, M.rows, M.cols, x, y, skip, M.r1_u, r1_dot);
   BS_CUDA(cudaGetLastError());
   count_launch(c);
 }
@@ -87,7 +97,8 @@ void gemv(Context &c, const DMat &M, const double *x, double *y, const int *skip
 template <int NR, int RPW, int U>
 __global__ void __launch_bounds__(32 * GEMV_WARPS) k_gemv_multi(const double *__restrict__ A, size_t ld, size_t rows,
                                                                 size_t cols, const double *__restrict__ X, size_t ldx,
-                                                                double *__restrict__ Y, size_t ldy, const int *skip) {
+                                                                double *__restrict__ Y, size_t ldy, const int *skip,
+                                                                const double *__restrict__ r1_u, const double *__restrict__ r1_dots) {
   if (skip && *skip) return;
   const int lane = threadIdx.x & 31;
   const size_t warp = (size_t)blockIdx.x * GEMV_WARPS + (threadIdx.x >> 5);
@@ -142,7 +153,7 @@ __global__ void __launch_bounds__(32 * GEMV_WARPS) k_gemv_multi(const double *__
       double s = acc[r][k];
 #pragma unroll
       for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-      if (lane == 0 && r0 + r < rows) Y[(size_t)k * ldy + r0 + r] = s;
+      if (lane == 0 && r0 + r < rows) Y[(size_t)k * ldy + r0 + r] = r1_u ? fma(r1_u[r0 + r], r1_dots[k], s) : s;
     }
 }
 
@@ -154,11 +165,12 @@ __global__ void __launch_bounds__(32 * GEMV_WARPS) k_gemv_multi(const double *__
 #endif
 
 template <int NR>
-static void launch_gemv_multi(Context &c, const DMat &M, const double *X, size_t ldx, double *Y, size_t ldy, const int *skip) {
+static void launch_gemv_multi(Context &c, const DMat &M, const double *X, size_t ldx, double *Y, size_t ldy, const int *skip,
+                              const double *r1_dots) {
   constexpr int RPW = BS_GEMVM_RPW, U = BS_GEMVM_U;
   const size_t warps = (M.rows + RPW - 1) / RPW;
   const unsigned grid = (unsigned)((warps + GEMV_WARPS - 1) / GEMV_WARPS);
-  k_gemv_multi<NR, RPW, U><<<grid, 32 * GEMV_WARPS, 0, c.stream>>>(M.p, M.ld, M.rows, M.cols, X, ldx, Y, ldy, skip);
+  k_gemv_multi<NR, RPW, U><<<grid, 32 * GEMV_WARPS, 0, c.stream>>>(M.p, M.ld, M.rows, M.cols, X, ldx, Y, ldy, skip, M.r1_u, r1_dots);
   BS_CUDA(cudaGetLastError());
   count_launch(c);
 }
@@ -240,14 +252,14 @@ __global__ void __launch_bounds__(32 * DMMA_WARPS) k_gemm_dmma(const double *__r
 }
 
 __global__ void k_sum_ksplit(size_t rows, int nrhs, int ksplit, const double *__restrict__ P, size_t ldp, double *__restrict__ Y,
-                             size_t ldy, const int *skip) {
+                             size_t ldy, const int *skip, const double *__restrict__ r1_u, const double *__restrict__ r1_dots) {
   if (skip && *skip) return;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y;
   if (i >= rows || n >= nrhs) return;
   double s = 0.0;
   for (int k = 0; k < ksplit; ++k) s += P[((size_t)k * 8 + n) * ldp + i];
-  Y[(size_t)n * ldy + i] = s;
+  Y[(size_t)n * ldy + i] = r1_u ? fma(r1_u[i], r1_dots[n], s) : s;
 }
 
 #ifndef BS_DMMA_MB
@@ -257,7 +269,8 @@ __global__ void k_sum_ksplit(size_t rows, int nrhs, int ksplit, const double *__
 #define BS_DMMA_U 4
 #endif
 
-static void gemm_dmma(Context &c, const DMat &M, int nrhs, const double *X, size_t ldx, double *Y, size_t ldy, const int *skip) {
+static void gemm_dmma(Context &c, const DMat &M, int nrhs, const double *X, size_t ldx, double *Y, size_t ldy, const int *skip,
+                      const double *r1_dots) {
   constexpr int MB = BS_DMMA_MB, U = BS_DMMA_U;
   const size_t row_warps = (M.rows + 8 * MB - 1) / (8 * MB);
   const unsigned gx = (unsigned)((row_warps + DMMA_WARPS - 1) / DMMA_WARPS);
@@ -271,7 +284,7 @@ static void gemm_dmma(Context &c, const DMat &M, int nrhs, const double *X, size
   double *P = c.wsd("gemm.partial", (size_t)ksplit * 8 * ldp);
   k_gemm_dmma<MB, U><<<dim3(gx, ksplit), 32 * DMMA_WARPS, 0, c.stream>>>(M.p, M.ld, M.rows, M.cols, X, ldx, nrhs, P, ldp, kchunk, skip);
   BS_CUDA(cudaGetLastError());
-  k_sum_ksplit<<<dim3((unsigned)((M.rows + 255) / 256), nrhs), 256, 0, c.stream>>>(M.rows, nrhs, ksplit, P, ldp, Y, ldy, skip);
+  k_sum_ksplit<<<dim3((unsigned)((M.rows + 255) / 256), nrhs), 256, 0, c.stream>>>(M.rows, nrhs, ksplit, P, ldp, Y, ldy, skip, M.r1_u, r1_dots);
   BS_CUDA(cudaGetLastError());
   count_launch(c, 2);
 }
@@ -284,22 +297,23 @@ void gemv_multi(Context &c, const DMat &M, int nrhs, const double *X, size_t ldx
     const int nr = std::min(8, nrhs - done);
     const double *Xp = X + (size_t)done * ldx;
     double *Yp = Y + (size_t)done * ldy;
+    const double *r1_dots = rank1_dots(c, M, nr, Xp, ldx);
     const bool aligned16 = (ldx % 2 == 0) && (reinterpret_cast<uintptr_t>(Xp) % 16 == 0) && (M.ld % 8 == 0) &&
                            (reinterpret_cast<uintptr_t>(M.p) % 16 == 0);
     if (nr >= 4 && aligned16 && !std::getenv("BS_NO_DMMA")) {  // FP64 tensor path; up to 3 right-hand sides the FMA kernel is HBM bound
-      gemm_dmma(c, M, nr, Xp, ldx, Yp, ldy, skip);
+      gemm_dmma(c, M, nr, Xp, ldx, Yp, ldy, skip, r1_dots);
       done += nr;
       continue;
     }
     switch (nr) {
-      case 1: launch_gemv_multi<1>(c, M, Xp, ldx, Yp, ldy, skip); break;
-      case 2: launch_gemv_multi<2>(c, M, Xp, ldx, Yp, ldy, skip); break;
-      case 3: launch_gemv_multi<3>(c, M, Xp, ldx, Yp, ldy, skip); break;
-      case 4: launch_gemv_multi<4>(c, M, Xp, ldx, Yp, ldy, skip); break;
-      case 5: launch_gemv_multi<5>(c, M, Xp, ldx, Yp, ldy, skip); break;
-      case 6: launch_gemv_multi<6>(c, M, Xp, ldx, Yp, ldy, skip); break;
-      case 7: launch_gemv_multi<7>(c, M, Xp, ldx, Yp, ldy, skip); break;
-      default: launch_gemv_multi<8>(c, M, Xp, ldx, Yp, ldy, skip); break;
+      case 1: launch_gemv_multi<1>(c, M, Xp, ldx, Yp, ldy, skip, r1_dots); break;
+      case 2: launch_gemv_multi<2>(c, M, Xp, ldx, Yp, ldy, skip, r1_dots); break;
+      case 3: launch_gemv_multi<3>(c, M, Xp, ldx, Yp, ldy, skip, r1_dots); break;
+      case 4: launch_gemv_multi<4>(c, M, Xp, ldx, Yp, ldy, skip, r1_dots); break;
+      case 5: launch_gemv_multi<5>(c, M, Xp, ldx, Yp, ldy, skip, r1_dots); break;
+      case 6: launch_gemv_multi<6>(c, M, Xp, ldx, Yp, ldy, skip, r1_dots); break;
+      case 7: launch_gemv_multi<7>(c, M, Xp, ldx, Yp, ldy, skip, r1_dots); break;
+      default: launch_gemv_multi<8>(c, M, Xp, ldx, Yp, ldy, skip, r1_dots); break;
     }
     done += nr;
   }
@@ -350,13 +364,17 @@ void k_correct_diag(Context &c, DMat &K, const double *Ck, int use_internal_alph
   count_launch(c);
 }
 
-__global__ void k_extract_diag(const double *M, size_t ld, size_t rows, size_t row_offset, double *out) {
+__global__ void k_extract_diag(const double *M, size_t ld, size_t rows, size_t row_offset, double *out, const double *r1_u,
+                               const double *r1_w, size_t r1_ncols) {
   const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < rows) out[r] = M[r * ld + row_offset + r];
+  if (r >= rows) return;
+  double v = M[r * ld + row_offset + r];
+  if (r1_u && row_offset + r < r1_ncols) v = fma(r1_u[r], r1_w[row_offset + r], v);
+  out[r] = v;
 }
 void extract_diag(Context &c, const DMat &M, size_t row_offset, double *d_out) {
   if (!M.rows) return;
-  k_extract_diag<<<(unsigned)((M.rows + 255) / 256), 256, 0, c.stream>>>(M.p, M.ld, M.rows, row_offset, d_out);
+  k_extract_diag<<<(unsigned)((M.rows + 255) / 256), 256, 0, c.stream>>>(M.p, M.ld, M.rows, row_offset, d_out, M.r1_u, M.r1_w, M.r1_ncols);
   BS_CUDA(cudaGetLastError());
   count_launch(c);
 }
@@ -400,15 +418,37 @@ void set_column(Context &c, DMat &A, size_t col, const double *v, double scale) 
   count_launch(c);
 }
 
-__global__ void k_gather_entries(const double *M, size_t ld, int n, const int *r, const int *cidx, double *out) {
+__global__ void k_gather_entries(const double *M, size_t ld, int n, const int *r, const int *cidx, double *out, const double *r1_u,
+                                 const double *r1_w, size_t r1_ncols) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = M[(size_t)r[i] * ld + cidx[i]];
+  if (i >= n) return;
+  double v = M[(size_t)r[i] * ld + cidx[i]];
+  if (r1_u && (size_t)cidx[i] < r1_ncols) v = fma(r1_u[r[i]], r1_w[cidx[i]], v);
+  out[i] = v;
 }
 void gather_entries(Context &c, const DMat &M, int n, const int *d_r, const int *d_c, double *d_out) {
   if (!n) return;
-  k_gather_entries<<<(n + 255) / 256, 256, 0, c.stream>>>(M.p, M.ld, n, d_r, d_c, d_out);
+  k_gather_entries<<<(n + 255) / 256, 256, 0, c.stream>>>(M.p, M.ld, n, d_r, d_c, d_out, M.r1_u, M.r1_w, M.r1_ncols);
   BS_CUDA(cudaGetLastError());
   count_launch(c);
+}
+
+__global__ void k_add_rank1_block(double *dst, size_t ldd, size_t n, const double *__restrict__ u, const double *__restrict__ w,
+                                  size_t wcols) {
+  const size_t i = blockIdx.y;
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n && j < wcols; j += (size_t)gridDim.x * blockDim.x)
+    dst[i * ldd + j] = fma(u[i], w[j], dst[i * ldd + j]);
+}
+void add_rank1_block(Context &c, const DMat &M, size_t row_off, size_t col_off, size_t n, double *dst, size_t ldd) {
+  if (!M.r1_u || n == 0 || col_off >= M.r1_ncols) return;
+  const unsigned gx = (unsigned)std::min<size_t>((n + 255) / 256, 64);
+  for (size_t done = 0; done < n; done += 65535) {
+    const size_t nr = std::min<size_t>(n - done, 65535);
+    k_add_rank1_block<<<dim3(gx, (unsigned)nr), 256, 0, c.stream>>>(dst + done * ldd, ldd, n, M.r1_u + row_off + done, M.r1_w + col_off,
+                                                                  M.r1_ncols - col_off);
+    BS_CUDA(cudaGetLastError());
+    count_launch(c);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -917,6 +917,7 @@ void precond_factor_blocks(Context &c, const DMat &M, size_t col_off, size_t n_t
     BS_CUDA(cudaMemsetAsync(B.LU, 0, B.n * B.ld * sizeof(double), c.stream));
     BS_CUDA(cudaMemcpy2DAsync(B.LU, B.ld * sizeof(double), M.p + B.off * M.ld + col_off + B.off, M.ld * sizeof(double),
                               B.n * sizeof(double), B.n, cudaMemcpyDeviceToDevice, c.stream));
+    add_rank1_block(c, M, B.off, col_off + B.off, B.n, B.LU, B.ld);  // implicit V correction of M, if any
     if (band > 0) {
       std::vector<int> ref(B.n);
       for (size_t i = 0; i < B.n; ++i) {
