@@ -146,6 +146,8 @@ static Context &ctx_of(bs_context *h) {
 
 extern "C" {
 
+static void build_constraint_tables(Context &c);
+
 const char *bs_last_error(void) { return bs::get_last_error().c_str(); }
 int bs_version(void) { return 100; }
 
@@ -298,6 +300,7 @@ int bs_set_geometry(bs_context *h, int n_map_nodes, const double *euler_vec, int
   c.material.assign(ncell, 0);
   if (material_id) c.material.assign(material_id, material_id + ncell);
   build_geometry(c);
+  build_constraint_tables(c);  // constraints given before the geometry
   extra(c).d_node_of_pos.upload(c.node_of_pos, c.stream);
   c.ld = ((c.n3() + MAX_RIGID + 15) / 16) * 16;
   // a new geometry invalidates matrices and the factorised preconditioner (sizes and ordering changed)
@@ -396,6 +399,80 @@ int bs_set_kernel(bs_context *h, int type, double eps, int wall_orientation, con
   BS_API_END
 }
 
+// internal tables of the owned constrained rows (after geometry + constraints are known)
+static void build_constraint_tables(Context &c) {
+  c.n_cons_owned = 0;
+  if (c.cons_dof.empty() || !c.have_geometry) return;
+  const int N = c.N;
+  auto to_int = [&](int ref) { return 3 * c.pos_of_node[ref % N] + ref / N; };
+  std::vector<int> rows, ptr(1, 0), cols;
+  std::vector<double> coefs;
+  std::vector<unsigned char> node(std::max(1, c.p1 - c.p0), 0);
+  for (size_t k = 0; k < c.cons_dof.size(); ++k) {
+    const int ref = c.cons_dof[k];
+    BS_REQUIRE(ref >= 0 && ref < 3 * N, "constrained dof out of range");
+    const int gi = to_int(ref), li = gi - 3 * c.p0;
+    if (li < 0 || li >= (int)c.rows_loc) continue;  // another rank's row
+    rows.push_back(li);
+    for (int q = c.cons_ptr[k]; q < c.cons_ptr[k + 1]; ++q) {
+      BS_REQUIRE(c.cons_col[q] >= 0 && c.cons_col[q] < 3 * N, "constraining dof out of range");
+      cols.push_back(to_int(c.cons_col[q]));
+      coefs.push_back(c.cons_coef[q]);
+    }
+    ptr.push_back((int)cols.size());
+    if (ref < N) node[li / 3] = 1;  // the reference tests the x-component dof of the node (bem_stokes.cc:3078)
+  }
+  c.n_cons_owned = (int)rows.size();
+  if (!c.n_cons_owned) return;
+  if (cols.empty()) {
+    cols.push_back(0);
+    coefs.push_back(0.0);
+  }
+  c.d_cons_row.upload(rows, c.stream);
+  c.d_cons_ptr.upload(ptr, c.stream);
+  c.d_cons_col.upload(cols, c.stream);
+  c.d_cons_coef.upload(coefs, c.stream);
+  c.d_cons_node.upload(node, c.stream);
+  BS_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+extern "C" int bs_set_constraints(bs_context *h, int n_constrained, const int *dof, const int *ptr, const int *cols, const double *coefs) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  BS_REQUIRE(n_constrained >= 0, "negative count");
+  c.cons_dof.clear();
+  c.cons_ptr.clear();
+  c.cons_col.clear();
+  c.cons_coef.clear();
+  if (n_constrained > 0) {
+    BS_REQUIRE(dof && ptr, "constraint arrays missing");
+    BS_REQUIRE(ptr[n_constrained] == 0 || (cols && coefs), "constraint entries missing");
+    c.cons_dof.assign(dof, dof + n_constrained);
+    c.cons_ptr.assign(ptr, ptr + n_constrained + 1);
+    c.cons_col.assign(cols, cols + ptr[n_constrained]);
+    c.cons_coef.assign(coefs, coefs + ptr[n_constrained]);
+  }
+  build_constraint_tables(c);
+  BS_API_END
+}
+
+extern "C" int bs_set_torque_mode(bs_context *h, const double *N_torque, const double *N_torque_dual, double rhs_value) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  if (!N_torque) {
+    c.torque_on = false;
+    c.torque_mode.clear();
+    c.torque_dual.clear();
+    return BS_OK;
+  }
+  BS_REQUIRE(c.have_geometry && N_torque_dual, "geometry first; both vectors are needed");
+  c.torque_mode.assign(N_torque, N_torque + c.n3());
+  c.torque_dual.assign(N_torque_dual, N_torque_dual + c.n3());
+  c.torque_rhs = rhs_value;
+  c.torque_on = true;
+  BS_API_END
+}
+
 static void assemble_common(Context &c, bool fused) {
   BS_REQUIRE(c.have_geometry && c.have_quadrature && c.have_singular, "geometry, quadrature and singular quadrature must be set");
   c.fused = fused;
@@ -420,6 +497,11 @@ static void assemble_common(Context &c, bool fused) {
   {
     Timer t(c, c.stats.assemble_singular_ms);
     launch_assembly_singular(c);
+  }
+  if (c.n_cons_owned) {  // constrained rows are not integrated: they hold the constraint equation (ref: 2970-2995)
+    BS_REQUIRE(!fused, "hanging-node constraints are not supported by the fused (no-K) assembly");
+    apply_constraint_rows(c, c.V, c.n3());
+    apply_constraint_rows(c, c.K, c.n3());
   }
   BS_CUDA(cudaStreamSynchronize(c.stream));
 }
@@ -497,6 +579,7 @@ int bs_correct_V(bs_context *h, const double *nhat, const double *Mnhat, double 
   // the matrix applies the term, the read-modify-write pass over the whole matrix (86 GB at the benchmark size) is gone
   e.vin.alloc(std::max(e.vin.n, c.n3() + MAX_RIGID + 2));
   sub(c, c.d_nhat.p + 3 * (size_t)c.p0, vn_loc, e.vin.p, c.rows_loc);
+  zero_constrained_entries(c, e.vin.p);  // "We correct only if we don't have constraints" (ref: 3024-3025)
   if (std::getenv("BS_EXPLICIT_RANK1")) {
     rank1_update(c, c.V, e.vin.p, c.d_Mnhat.p, 1.0 / l2gamma);
   } else {
@@ -563,12 +646,18 @@ int bs_build_monolithic(bs_context *h, const unsigned char *col_is_K, int num_ri
     keep_VK = 0;
   }
   BS_REQUIRE(num_rigid == 0 || (N_rigid && N_rigid_dual), "rigid modes missing");
+  BS_REQUIRE(!(c.fused && (c.torque_on || c.n_cons_owned)), "torque unknown / constraints are not supported by the fused (no-K) assembly");
+  BS_REQUIRE(!c.torque_on || num_rigid + 1 <= MAX_RIGID, "no room for the torque unknown");
   Timer t(c, c.stats.monolithic_ms, "bs_build_monolithic");
   set_projector(c, nhat, Mnhat, l2gamma);
   Extra &e = extra(c);
   const size_t n = c.n3();
-  const int nr = num_rigid;
-  const int nvec = nr + 1;  // rigid modes + shape velocity
+  // with solve_with_torque the flagellum's angular velocity is one more unknown after the rigid ones: same column
+  // (-scaling P K P N) and row (scaling N_dual) as a rigid mode of a Real grid (ref: 3143-3147, 3252-3256, 3340-3352)
+  const int nr = num_rigid + (c.torque_on ? 1 : 0);
+  auto mode = [&](int r) { return r < num_rigid ? N_rigid + (size_t)r * n : c.torque_mode.data(); };
+  auto dual = [&](int r) { return r < num_rigid ? N_rigid_dual + (size_t)r * n : c.torque_dual.data(); };
+  const int nvec = nr + 1;  // rigid modes (+ torque mode) + shape velocity
   c.num_rigid = nr;
   c.mono_size = n + nr;
   const bool last = (c.rank == c.nranks - 1);
@@ -585,7 +674,7 @@ int bs_build_monolithic(bs_context *h, const unsigned char *col_is_K, int num_ri
         dst_int[3 * p + k] = v[ref] - d * nhat[ref];
       }
   };
-  for (int r = 0; r < nr; ++r) project_into(N_rigid + (size_t)r * n, &X[(size_t)r * ldx]);
+  for (int r = 0; r < nr; ++r) project_into(mode(r), &X[(size_t)r * ldx]);
   const bool use_shape = (grid_type == BS_GRID_REAL && shape_vel != nullptr);
   if (use_shape) project_into(shape_vel, &X[(size_t)nr * ldx]);
   e.vout.alloc(std::max(e.vout.n, (size_t)nvec * c.rows_loc + 2));
@@ -690,12 +779,16 @@ int bs_build_monolithic(bs_context *h, const unsigned char *col_is_K, int num_ri
   }
   // rigid rows (ref: 3297-3339), stored after the last rank's node rows
   std::vector<double> rhs_int(n + nr, 0.0);
-  if (use_shape)
+  if (use_shape && !c.torque_on)  // solve_with_torque: zero right-hand side on every node row (ref: 3190-3192)
     for (size_t i = 0; i < n; ++i) rhs_int[i] = Y[(size_t)nr * n + i];
   if (nr > 0) {
     std::vector<double> rows((size_t)nr * c.ld, 0.0);
     for (int r = 0; r < nr; ++r) {
-      if (grid_type != BS_GRID_REAL) {
+      if (r >= num_rigid) {  // torque row
+        rhs_int[n + r] = c.torque_rhs;
+        for (size_t p = 0; p < (size_t)c.N; ++p)
+          for (int k = 0; k < 3; ++k) rows[(size_t)r * c.ld + 3 * p + k] = scaling * dual(r)[c.node_of_pos[p] + (size_t)k * c.N];
+      } else if (grid_type != BS_GRID_REAL) {
         rhs_int[n + r] = (r == imposed_component) ? 1.0 : 0.0;
         if (grid_type == BS_GRID_IMPOSED_VELOCITY) {
           rows[(size_t)r * c.ld + n + r] = scaling;
@@ -714,6 +807,16 @@ int bs_build_monolithic(bs_context *h, const unsigned char *col_is_K, int num_ri
       BS_CUDA(cudaMemcpyAsync(c.A.p + c.rows_loc * c.ld, rows.data(), rows.size() * sizeof(double), cudaMemcpyHostToDevice,
                               c.stream));
     BS_CUDA(cudaStreamSynchronize(c.stream));
+  }
+  if (c.n_cons_owned) {  // constrained rows: 1 on the diagonal, -coefficients, nothing else; rhs 0 (ref: 3156-3183)
+    DMat Arow = c.A;
+    Arow.rows = c.rows_loc;
+    apply_constraint_rows(c, Arow, n + nr);
+    BS_CUDA(cudaStreamSynchronize(c.stream));
+  }
+  {
+    const int N = c.N;
+    for (size_t k = 0; k < c.cons_dof.size(); ++k) rhs_int[3 * (size_t)c.pos_of_node[c.cons_dof[k] % N] + c.cons_dof[k] / N] = 0.0;
   }
   if (rhs_out) {
     for (size_t p = 0; p < (size_t)c.N; ++p)

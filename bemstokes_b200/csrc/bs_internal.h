@@ -229,6 +229,18 @@ struct Context {
   double l2gamma = 0.0;
   bool have_projector = false;
 
+  // hanging-node constraints (ref: bem_stokes.cc:2970-2995, 3156-3183), reference ordering as given by the host
+  std::vector<int> cons_dof, cons_ptr, cons_col;
+  std::vector<double> cons_coef;
+  DBuf<int> d_cons_row, d_cons_ptr, d_cons_col;   // owned constrained rows (local row index), CSR of (internal column, coefficient)
+  DBuf<double> d_cons_coef;
+  DBuf<unsigned char> d_cons_node;                // [p1-p0] 1 = the node's x-component dof is constrained (K correction skips it)
+  int n_cons_owned = 0;
+  // flagellum torque unknown (ref: solve_with_torque, bem_stokes.cc:3191, 3252-3256, 3340-3352)
+  std::vector<double> torque_mode, torque_dual;
+  double torque_rhs = 0.0;
+  bool torque_on = false;
+
   int gmres_ortho = BS_ORTHO_CGS2;
   // preconditioner
   int prec_kind = BS_PREC_NONE;
@@ -329,6 +341,8 @@ void sub(Context &c, const double *a, const double *b, double *out, size_t n);  
 void mul_elem(Context &c, const double *a, const double *d, double *out, size_t n); // out = a*d
 void fill(Context &c, double *x, double v, size_t n);
 void k_correct_diag(Context &c, DMat &K, const double *Ck /*[3][rows] internal*/, int use_internal_alpha);
+void apply_constraint_rows(Context &c, DMat &M, size_t ncols);   // constrained owned rows: 0 ... 1 (diagonal) ... -coefficient ...
+void zero_constrained_entries(Context &c, double *v_loc);         // v_loc[row] = 0 on the constrained owned rows
 void extract_diag(Context &c, const DMat &M, size_t row_offset, double *d_out);
 void select_columns(Context &c, DMat &A, const DMat &V, const DMat &K, const unsigned char *d_flag, bool alias);
 void set_column(Context &c, DMat &A, size_t col, const double *v, double scale);

@@ -346,10 +346,12 @@ void rank1_update(Context &c, DMat &M, const double *u, const double *w, double 
 }
 
 // K(3k+j, 3(p0+k)+m) -= C[m][3k+j] ; += delta_jm unless use_internal_alpha   (ref: bem_stokes.cc:3076-3092)
-__global__ void k_correct_diag(double *K, size_t ld, int nloc, int p0, const double *__restrict__ C, size_t ldc, int alpha) {
+__global__ void k_correct_diag(double *K, size_t ld, int nloc, int p0, const double *__restrict__ C, size_t ldc, int alpha,
+                               const unsigned char *__restrict__ skip_node) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nloc * 9) return;
   const int k = idx / 9, jm = idx - 9 * k, j = jm / 3, m = jm - 3 * j;
+  if (skip_node && skip_node[k]) return;  // constrained node (ref: bem_stokes.cc:3078)
   const size_t row = (size_t)3 * k + j;
   double v = K[row * ld + (size_t)3 * (p0 + k) + m] - C[(size_t)m * ldc + row];
   if (j == m && !alpha) v += 1.0;
@@ -359,7 +361,8 @@ __global__ void k_correct_diag(double *K, size_t ld, int nloc, int p0, const dou
 void k_correct_diag(Context &c, DMat &K, const double *Ck, int use_internal_alpha) {
   const int nloc = c.p1 - c.p0;
   if (nloc == 0) return;
-  k_correct_diag<<<(nloc * 9 + 255) / 256, 256, 0, c.stream>>>(K.p, K.ld, nloc, c.p0, Ck, c.rows_loc, use_internal_alpha);
+  k_correct_diag<<<(nloc * 9 + 255) / 256, 256, 0, c.stream>>>(K.p, K.ld, nloc, c.p0, Ck, c.rows_loc, use_internal_alpha,
+                                                               c.n_cons_owned ? c.d_cons_node.p : nullptr);
   BS_CUDA(cudaGetLastError());
   count_launch(c);
 }
@@ -429,6 +432,36 @@ __global__ void k_gather_entries(const double *M, size_t ld, int n, const int *r
 void gather_entries(Context &c, const DMat &M, int n, const int *d_r, const int *d_c, double *d_out) {
   if (!n) return;
   k_gather_entries<<<(n + 255) / 256, 256, 0, c.stream>>>(M.p, M.ld, n, d_r, d_c, d_out, M.r1_u, M.r1_w, M.r1_ncols);
+  BS_CUDA(cudaGetLastError());
+  count_launch(c);
+}
+
+// one CTA per constrained owned row: the row becomes the constraint equation x_ii - sum coef_k x_k = 0
+__global__ void k_constraint_rows(double *M, size_t ld, size_t ncols, size_t diag_off, const int *rows, const int *ptr, const int *cols,
+                                  const double *coefs) {
+  const int r = rows[blockIdx.x];
+  double *row = M + (size_t)r * ld;
+  for (size_t j = threadIdx.x; j < ncols; j += blockDim.x) row[j] = 0.0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    row[diag_off + r] = 1.0;
+    for (int k = ptr[blockIdx.x]; k < ptr[blockIdx.x + 1]; ++k) row[cols[k]] = -coefs[k];
+  }
+}
+void apply_constraint_rows(Context &c, DMat &M, size_t ncols) {
+  if (!c.n_cons_owned) return;
+  k_constraint_rows<<<c.n_cons_owned, 256, 0, c.stream>>>(M.p, M.ld, ncols, (size_t)3 * c.p0, c.d_cons_row.p, c.d_cons_ptr.p,
+                                                          c.d_cons_col.p, c.d_cons_coef.p);
+  BS_CUDA(cudaGetLastError());
+  count_launch(c);
+}
+__global__ void k_zero_rows(double *v, const int *rows, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[rows[i]] = 0.0;
+}
+void zero_constrained_entries(Context &c, double *v_loc) {
+  if (!c.n_cons_owned) return;
+  k_zero_rows<<<(c.n_cons_owned + 255) / 256, 256, 0, c.stream>>>(v_loc, c.d_cons_row.p, c.n_cons_owned);
   BS_CUDA(cudaGetLastError());
   count_launch(c);
 }

@@ -205,6 +205,12 @@ class BEMProblem(FrameLoop):
         self.col_is_K = None           # per dof: True -> the unknown is a wall velocity, column -K (index-set logic 3194-3245)
         self.use_peer_exchange = True  # multi-GPU: NVLink peer stores fused into the Krylov-vector kernel (else NCCL allgather)
         self.num_rigid = 6
+        self.constraints = None        # hanging nodes: {dof: [(dof, coefficient), ...]} (reference ordering; ref 2970-2995)
+        self.solve_with_torque = False # "Impose a torque on the flagellum" (ref 216, 3252-3256, 3340-3352)
+        self.N_flagellum_torque = None
+        self.N_flagellum_torque_dual = None
+        self.torque_rhs = -2.0         # the reference's hard-coded motor torque (3352)
+        self.flagellum_omega = 0.0
         self._ctx = None
         self.mesh = None
         self.direct_trilinos_preconditioner = DirectPreconditioner()
@@ -265,6 +271,30 @@ class BEMProblem(FrameLoop):
         check(lib.bs_set_geometry(self._ctx, mm.n_nodes, _dp(euler), self.mesh.n_cells, _ip(mm.conn), self.mesh.n_nodes,
                                   _ip(self.mesh.conn), None))
         return self
+
+    def _push_constraints_and_torque(self):
+        ctx = self._ctx
+        if self.constraints:
+            dofs = sorted(self.constraints)
+            ptr = np.zeros(len(dofs) + 1, dtype=np.int32)
+            cols, coefs = [], []
+            for k, d in enumerate(dofs):
+                for col, coef in self.constraints[d]:
+                    cols.append(col)
+                    coefs.append(coef)
+                ptr[k + 1] = len(cols)
+            dof = np.ascontiguousarray(dofs, dtype=np.int32)
+            cols = np.ascontiguousarray(cols if cols else [0], dtype=np.int32)
+            coefs = np.ascontiguousarray(coefs if coefs else [0.0], dtype=np.float64)
+            check(lib.bs_set_constraints(ctx, len(dofs), _ip(dof), _ip(ptr), _ip(cols), _dp(coefs)))
+        else:
+            check(lib.bs_set_constraints(ctx, 0, None, None, None, None))
+        if self.solve_with_torque:
+            nt = np.ascontiguousarray(self.N_flagellum_torque, dtype=np.float64)
+            ntd = np.ascontiguousarray(self.N_flagellum_torque_dual, dtype=np.float64)
+            check(lib.bs_set_torque_mode(ctx, _dp(nt), _dp(ntd), float(self.torque_rhs)))
+        else:
+            check(lib.bs_set_torque_mode(ctx, None, None, 0.0))
 
     def _set_kernel(self):
         # ref: kernel_wall_orientation = last axis with wall_spans[0][axis]==0 (bem_stokes.cc:2861-2866)
@@ -353,6 +383,7 @@ class BEMProblem(FrameLoop):
         """ref: BEMProblem::assemble_stokes_system (bem_stokes.cc:2840-3435)."""
         ctx = self._ctx
         self._set_kernel()
+        self._push_constraints_and_torque()
         nh = np.ascontiguousarray(self.normal_vector_pure)
         mn = np.ascontiguousarray(self.M_normal_vector_pure)
         if self.fused_assembly:
@@ -370,7 +401,8 @@ class BEMProblem(FrameLoop):
         check(lib.bs_correct_K(ctx, 1 if self.use_internal_alpha else 0))
         if self.monolithic_bool:
             nr = self.num_rigid
-            self.monolithic_rhs = np.zeros(self.n_dofs + nr)
+            nx = nr + (1 if self.solve_with_torque else 0)   # + the flagellum's angular velocity
+            self.monolithic_rhs = np.zeros(self.n_dofs + nx)
             Nr = np.ascontiguousarray(self.N_rigid[:nr])
             Nd = np.ascontiguousarray(self.N_rigid_dual[:nr])
             sv = np.ascontiguousarray(self.shape_velocities, dtype=np.float64)
@@ -381,8 +413,8 @@ class BEMProblem(FrameLoop):
                                           nr, _dp(Nr), _dp(Nd), _dp(nh), _dp(mn), self.l2normGamma_pure,
                                           _GRID[self.grid_type], self.imposed_component, self.assemble_scaling, _dp(sv),
                                           1 if self.keep_VK else 0, _dp(self.monolithic_rhs)))
-            if getattr(self, "monolithic_solution", None) is None or len(self.monolithic_solution) != self.n_dofs + nr:
-                self.monolithic_solution = np.zeros(self.n_dofs + nr)
+            if getattr(self, "monolithic_solution", None) is None or len(self.monolithic_solution) != self.n_dofs + nx:
+                self.monolithic_solution = np.zeros(self.n_dofs + nx)
         return self
 
     def tangential_projector_body(self, input_vel, output_vel=None):
@@ -470,7 +502,7 @@ class BEMProblem(FrameLoop):
             else:
                 self._setup_preconditioner(_lib.MAT_A)
                 if self.n_mpi_processes > 1:
-                    own = self._owned_mask(nr)
+                    own = self._owned_mask(len(x) - n)
                     x[~own] = 0.0
                 its = self.gmres(_lib.MAT_A, x, b)
                 self._allsum(x)
@@ -484,6 +516,8 @@ class BEMProblem(FrameLoop):
             self.stokes_forces = np.where(isK, 0.0, x[:n])
             self.wall_velocities = np.where(isK, x[:n], 0.0)
             self.rigid_velocities = x[n:n + nr].copy() * self.assemble_scaling
+            if self.solve_with_torque:   # ref 4398-4409: the new shape velocity is omega * N_flagellum_torque
+                self.flagellum_omega = float(x[n + nr])
         else:
             self.solve_dn()
         self.rigid_total_forces = np.array([self.stokes_forces @ self.N_rigid_dual[r] for r in range(nr)])

@@ -118,6 +118,18 @@ int bs_prepass(bs_context *ctx, int pole_kind, const double *pole, double *nhat,
                double *N_rigid, double *N_rigid_dual, double *area, double *support_points, double *center_of_mass,
                double *pole_used, int *cg_iterations);
 
+/* Hanging-node constraints (ref: the AffineConstraints of dh_stokes, bem_stokes.cc:2970-2995 in the assembly loop,
+ * 3024-3025 / 3078 in the corrections, 3156-3183 in the monolithic build).  dof[k] (reference ordering, i + c*N) is
+ * constrained to sum_q coefs[q] * x[cols[q]], q in [ptr[k], ptr[k+1]).  The row of a constrained dof is not integrated: in
+ * V, K and A it holds the constraint equation (1 on the diagonal, -coef at the constraining dofs, rhs 0), and the V / K
+ * corrections skip it.  Call before bs_assemble_VK; n_constrained = 0 clears.  Not available with bs_assemble_fused. */
+int bs_set_constraints(bs_context *ctx, int n_constrained, const int *dof, const int *ptr, const int *cols, const double *coefs);
+/* solve_with_torque (ref: bem_stokes.cc:1612-1634, 3143-3147, 3191, 3252-3256, 3340-3352): one more unknown after the
+ * rigid ones - the flagellum's angular velocity - with the column -scaling P K P N_torque, the row scaling N_torque_dual
+ * and the right-hand side rhs_value (-2 in the reference); every node row then has a zero right-hand side.  Takes effect in
+ * the next bs_build_monolithic (whose vectors get num_rigid + 1 trailing entries); N_torque = NULL switches it off. */
+int bs_set_torque_mode(bs_context *ctx, const double *N_torque, const double *N_torque_dual, double rhs_value);
+
 /* ---- assembly (ref: BEMProblem::assemble_stokes_system, bem_stokes.cc:2840-3435) ----------------------- */
 /* K1 (regular Gauss pass) + K2 (singular pass) -> row-block of V and K on the device (2871-3000). */
 int bs_assemble_VK(bs_context *ctx);
@@ -135,7 +147,7 @@ int bs_assemble_fused(bs_context *ctx, int num_rigid, const double *N_rigid, con
 int bs_correct_V(bs_context *ctx, const double *nhat, const double *Mnhat, double l2gamma, double *Vn_out);
 /* K(i+jN, i+kN) -= (K e_k)[i+jN]; += delta_jk unless use_internal_alpha (3044-3098). */
 int bs_correct_K(bs_context *ctx, int use_internal_alpha);
-/* Monolithic matrix + rhs (3120-3357) for a problem without hanging-node constraints.
+/* Monolithic matrix + rhs (3120-3357); constrained rows as set by bs_set_constraints, torque unknown by bs_set_torque_mode.
  * col_is_K[3N] (NULL = all V): column j of A is -K(:,j) when set, V(:,j) otherwise (the reference derives it
  * from the body / wall index sets, 3194-3245).  N_rigid, N_rigid_dual: num_rigid x 3N row-major.
  * shape_vel (3N, may be NULL) is used for grid_type Real.  rhs_out: 3N+num_rigid.

@@ -595,15 +595,36 @@ class Prepass:
 # --------------------------------------------------------------------------------------------------------
 
 
-def correct_V(V, pre):
+def apply_constraints(V, K, constraints):
+    """Constrained (hanging-node) rows of V and K as the assembly loop leaves them (bem_stokes.cc:2970-2995): the row of a
+    constrained dof ii is not integrated; it holds 1 on the diagonal and -coefficient at the constraining dofs.
+    constraints: {dof ii (reference ordering): [(dof, coefficient), ...]}."""
+    V, K = V.copy(), K.copy()
+    for ii, entries in constraints.items():
+        for M in (V, K):
+            M[ii, :] = 0.0
+            M[ii, ii] = 1.0
+            for col, coef in entries:
+                M[ii, col] = -coef
+    return V, K
+
+
+def correct_V(V, pre, constraints=None):
+    """V correction on the unconstrained rows only (bem_stokes.cc:3017-3032, "We correct only if we don't have constraints")."""
     Vn = V @ pre.nhat
-    return V + np.outer(pre.nhat - Vn, pre.Mnhat) / pre.l2, Vn
+    u = pre.nhat - Vn
+    if constraints:
+        u[list(constraints.keys())] = 0.0
+    return V + np.outer(u, pre.Mnhat) / pre.l2, Vn
 
 
-def correct_K(K, N, use_internal_alpha=False):
+def correct_K(K, N, use_internal_alpha=False, constraints=None):
+    """K correction; nodes whose x-component dof is constrained are skipped (bem_stokes.cc:3078, is_constrained(i))."""
     K = K.copy()
     C = np.stack([K[:, k * N:(k + 1) * N].sum(1) for k in range(3)], 0)  # C[k] = K e_k
     idx = np.arange(N)
+    if constraints:
+        idx = np.array([i for i in range(N) if i not in constraints], dtype=np.int64)
     for j in range(3):
         for k in range(3):
             K[idx + j * N, idx + k * N] -= C[k][idx + j * N]
@@ -612,13 +633,20 @@ def correct_K(K, N, use_internal_alpha=False):
     return K
 
 
-def monolithic(V, K, pre, grid_type="ImposedForce", imposed_component=1, scaling=1.0, shape_vel=None, col_is_K=None):
-    """Monolithic matrix / rhs without constraints.  col_is_K[j] set: column j belongs to a wall unknown whose
+def monolithic(V, K, pre, grid_type="ImposedForce", imposed_component=1, scaling=1.0, shape_vel=None, col_is_K=None,
+               constraints=None, torque=None):
+    """Monolithic matrix / rhs.  col_is_K[j] set: column j belongs to a wall unknown whose
     velocity is solved for, A(:,j) = -K(:,j) (neumann / free-surface tangential sets, bem_stokes.cc:3194-3245);
-    otherwise A(:,j) = V(:,j) (body, no-slip, dirichlet sets)."""
+    otherwise A(:,j) = V(:,j) (body, no-slip, dirichlet sets).
+    constraints {dof: [(dof, coef)]}: the row of a constrained dof is 1 on the diagonal, -coef at the constraining dofs,
+    nothing in the rigid columns, rhs 0 (bem_stokes.cc:3156-3183).
+    torque = (N_torque, N_torque_dual, rhs_value): solve_with_torque (bem_stokes.cc:3191, 3252-3256, 3340-3352): one more
+    unknown (the flagellum's angular velocity) with the column -scaling P K P N_torque, the row scaling N_torque_dual,
+    right-hand side rhs_value (-2 in the reference), and ZERO right-hand side on every node row."""
     n = V.shape[0]
-    A = np.zeros((n + 6, n + 6))
-    b = np.zeros(n + 6)
+    nx = 6 + (1 if torque is not None else 0)
+    A = np.zeros((n + nx, n + nx))
+    b = np.zeros(n + nx)
     A[:n, :n] = V
     if col_is_K is not None:
         f = np.asarray(col_is_K, dtype=bool)
@@ -627,6 +655,19 @@ def monolithic(V, K, pre, grid_type="ImposedForce", imposed_component=1, scaling
         A[:n, n + r] = -scaling * pre.P(K @ pre.P(pre.N_rigid[r]))
     if grid_type == "Real" and shape_vel is not None:
         b[:n] = pre.P(K @ pre.P(shape_vel))
+    if torque is not None:
+        Nt, Ntd, tval = torque
+        A[:n, n + 6] = -scaling * pre.P(K @ pre.P(Nt))
+        A[n + 6, :n] = scaling * np.asarray(Ntd)
+        b[:n] = 0.0
+        b[n + 6] = tval
+    if constraints:
+        for ii, entries in constraints.items():
+            A[ii, :] = 0.0
+            A[ii, ii] = 1.0
+            for col, coef in entries:
+                A[ii, col] = -coef
+            b[ii] = 0.0
     for r in range(6):
         if grid_type != "Real":
             b[n + r] = 1.0 if r == imposed_component else 0.0

@@ -226,3 +226,61 @@ def test_dn_route_batched(meshname, grid_type):
     assert np.abs(p.final_matrix - Fo).max() <= 1e-9 * np.abs(Fo).max()
     assert np.abs(p.stokes_forces - fo).max() <= 1e-9 * np.abs(fo).max()
     p.close()
+
+
+def test_constrained_rows_and_torque_unknown():
+    """The two boundary extras of bs_build_monolithic: hanging-node constraint rows (ref: bem_stokes.cc:2970-2995, 3024-3025,
+    3078, 3156-3183) and the flagellum torque unknown of solve_with_torque (ref: 3143-3147, 3191, 3252-3256, 3340-3352), against
+    the oracle's restatement: entries <= 1e-12 of the row scale, solution <= 1e-9."""
+    mesh = bb.read_mesh(os.path.join(MESHES, "sphere_half_refined_0.inp"))
+    N = mesh.n_nodes
+    # artificial hanging nodes: node 5 is the mean of nodes 7 and 11 (all three components), node 20 follows node 3 (x only)
+    cons = {5 + c * N: [(7 + c * N, 0.5), (11 + c * N, 0.5)] for c in range(3)}
+    cons[20] = [(3, 1.0)]
+    p = bb.BEMProblem()
+    p.set_mesh(mesh)
+    p.quadrature_order, p.singular_quadrature_order = 8, 10
+    p.grid_type, p.solve_directly = "Real", True
+    p.constraints = cons
+    p.reinit()
+    p.compute_center_of_mass_and_rigid_modes()
+    p.compute_normal_vector()
+    x = mesh.nodes
+    p.shape_velocities = np.concatenate([np.sin(x[:, 0]) * x[:, 1], 0.5 * x[:, 1] * x[:, 2], 0.3 * x[:, 0] * x[:, 1] - 0.1])
+    # torque mode: a rotation about z restricted to the "flagellum" half z < 0, dual = mass matrix times it
+    geo = bo.Geometry(mesh.nodes, mesh.conn.astype(np.int64), 1)
+    pre = bo.Prepass(geo, 8)
+    Nt = pre.N_rigid[5] * np.tile(x[:, 2] < 0, 3)
+    M = bo.mass_matrix(geo, 8)[0]
+    Ntd = np.concatenate([M @ Nt[c * N:(c + 1) * N] for c in range(3)])
+    for torque in (False, True):
+        p.solve_with_torque = torque
+        p.N_flagellum_torque, p.N_flagellum_torque_dual = Nt, Ntd
+        p.assemble_stokes_system(True)
+        Vo, Ko = bo.assemble_VK(geo, bo.KernelSpec(), 8, "Mixed", 10)
+        Vo, Ko = bo.apply_constraints(Vo, Ko, cons)
+        Vc, _ = bo.correct_V(Vo, pre, cons)
+        Kc = bo.correct_K(Ko, N, False, cons)
+        Ao, bvec = bo.monolithic(Vc, Kc, pre, "Real", 1, 1.0, p.shape_velocities, None, cons,
+                                 (Nt, Ntd, -2.0) if torque else None)
+        scale = lambda B: np.maximum(np.abs(B).max(axis=1, keepdims=True), 1e-300)
+        assert (np.abs(p.V_matrix.to_dense() - Vc) / scale(Vc)).max() < 1e-12
+        assert (np.abs(p.K_matrix.to_dense() - Kc) / scale(Kc)).max() < 1e-12
+        A = p.monolithic_system_matrix.to_dense()
+        assert A.shape == Ao.shape == (3 * N + 6 + torque, 3 * N + 6 + torque)
+        assert (np.abs(A - Ao) / scale(Ao)).max() < 1e-12
+        assert np.abs(p.monolithic_rhs - bvec).max() <= 1e-12 * max(1.0, np.abs(bvec).max())
+        p.monolithic_solution[:] = 0
+        p.solve_system(True)
+        xo = np.linalg.solve(Ao, bvec)
+        assert np.abs(p.monolithic_solution - xo).max() <= 1e-9 * np.abs(xo).max()
+        for ii, entries in cons.items():     # the constraint equations hold in the solution
+            assert abs(p.monolithic_solution[ii] - sum(cf * p.monolithic_solution[cl] for cl, cf in entries)) < 1e-9 * np.abs(xo).max()
+        if torque:
+            assert abs(p.flagellum_omega - xo[-1]) <= 1e-9 * abs(xo[-1])
+            assert abs(Ntd @ p.stokes_forces - (-2.0)) < 1e-8      # the imposed motor torque
+    # the fused (no-K) assembly refuses both
+    p.fused_assembly = True
+    with pytest.raises(_lib.BemStokesError):
+        p.assemble_stokes_system(True)
+    p.close()
