@@ -30,6 +30,16 @@ void exchange(Context &c, int which, const double *y_loc, double *x_full) {
     if (y_loc != x_full) copy(c, y_loc, x_full, mloc);
     return;
   }
+  if (c.p2p && c.full_vec_len(which) <= c.xchg_ld) {
+    // peer stores over NVLink instead of a collective call: every rank writes its slice into slot 0 of all replicated
+    // buffers, publishes it and waits for the others
+    p2p_scatter(c, which, y_loc, 0, nullptr, nullptr);
+    p2p_wait(c);
+    copy(c, c.d_xchg.p, x_full, c.full_vec_len(which));
+    // the next scatter into slot 0 must not overtake a peer that is still copying: a second handshake closes the epoch
+    p2p_wait(c);
+    return;
+  }
   BS_REQUIRE(c.cb_allgatherv != nullptr, "nranks > 1 but no communicator callbacks set (bs_set_comm)");
   std::vector<int> counts(c.nranks), displs(c.nranks);
   for (int r = 0; r < c.nranks; ++r) {
