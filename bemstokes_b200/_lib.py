@@ -57,6 +57,7 @@ SIGNATURES = {
     "bs_set_constraints": (C.c_int, [ctx_p, C.c_int, c_int_p, c_int_p, c_int_p, c_double_p]),
     "bs_set_torque_mode": (C.c_int, [ctx_p, c_double_p, c_double_p, C.c_double]),
     "bs_assemble_VK": (C.c_int, [ctx_p]),
+    "bs_set_column_flags": (C.c_int, [ctx_p, c_ubyte_p]),
     "bs_assemble_fused": (C.c_int, [ctx_p, C.c_int, c_double_p, c_double_p, c_double_p, C.c_double, c_double_p]),
     "bs_correct_V": (C.c_int, [ctx_p, c_double_p, c_double_p, C.c_double, c_double_p]),
     "bs_correct_K": (C.c_int, [ctx_p, C.c_int]),

@@ -473,6 +473,34 @@ extern "C" int bs_set_torque_mode(bs_context *h, const double *N_torque, const d
   BS_API_END
 }
 
+// flags of the wall-velocity unknowns for the fused (no-K) assembly; see Context::col_flags
+static void build_flag_tables(Context &c) {
+  c.n_flagged = 0;
+  if (c.col_flags.empty() || !c.have_geometry) return;
+  BS_REQUIRE(c.col_flags.size() == c.n3(), "column flags: 3N entries expected");
+  std::vector<int> kcol(c.n3(), -1);
+  int nf = 0;
+  for (size_t p = 0; p < (size_t)c.N; ++p)
+    for (int k = 0; k < 3; ++k)
+      if (c.col_flags[(size_t)c.node_of_pos[p] + (size_t)k * c.N]) kcol[3 * p + k] = nf++;
+  c.n_flagged = nf;
+  c.ldk = ((size_t)nf + 1) & ~(size_t)1;
+  if (nf) c.d_kcol.upload(kcol, c.stream);
+  BS_CUDA(cudaStreamSynchronize(c.stream));
+}
+
+extern "C" int bs_set_column_flags(bs_context *h, const unsigned char *col_is_K) {
+  BS_API_BEGIN
+  Context &c = ctx_of(h);
+  c.col_flags.clear();
+  if (col_is_K) {
+    BS_REQUIRE(c.have_geometry, "geometry first");
+    c.col_flags.assign(col_is_K, col_is_K + c.n3());
+  }
+  build_flag_tables(c);
+  BS_API_END
+}
+
 static void assemble_common(Context &c, bool fused) {
   BS_REQUIRE(c.have_geometry && c.have_quadrature && c.have_singular, "geometry, quadrature and singular quadrature must be set");
   c.fused = fused;
@@ -483,6 +511,7 @@ static void assemble_common(Context &c, bool fused) {
     c.storeK.release();  // the point of the fused mode: the double-layer matrix is never materialised
     c.d_KX.alloc(c.rows_loc * c.panel_p + 2);
     c.d_KX.zero(c.stream);
+    if (c.n_flagged > 0) c.d_Kflag.alloc(c.rows_loc * c.ldk + 2);  // every entry is stored by its first colour before anything reads it
   }
   c.A = DMat();
   c.A_aliases_V = false;
@@ -641,7 +670,12 @@ int bs_build_monolithic(bs_context *h, const unsigned char *col_is_K, int num_ri
   BS_REQUIRE(c.V.valid() && (c.K.valid() || c.fused), "V and K must be assembled (and corrected) first");
   BS_REQUIRE(num_rigid >= 0 && num_rigid <= MAX_RIGID, "num_rigid out of range");
   if (c.fused) {
-    BS_REQUIRE(col_is_K == nullptr, "fused (no-K) assembly supports body-only systems: every column of A is a V column");
+    if (col_is_K) {
+      BS_REQUIRE(c.n_flagged > 0 && c.col_flags.size() == c.n3() && std::equal(c.col_flags.begin(), c.col_flags.end(), col_is_K),
+                 "fused (no-K) assembly with mixed boundary conditions: hand the same flags to bs_set_column_flags before bs_assemble_fused");
+    } else {
+      BS_REQUIRE(c.n_flagged == 0, "bs_set_column_flags was given flags, bs_build_monolithic none");
+    }
     BS_REQUIRE(num_rigid == c.panel_nr && c.h_C.size() == 3 * c.rows_loc, "fused mode: call bs_assemble_fused and bs_correct_K first");
     keep_VK = 0;
   }
@@ -745,11 +779,20 @@ int bs_build_monolithic(bs_context *h, const unsigned char *col_is_K, int num_ri
     e.d_flag.upload(f, c.stream);
     d_flag = e.d_flag.p;
   }
-  {
+  if (c.fused && col_is_K) {
+    // the flagged columns of A = the compact -K columns kept by the assembly, with the K correction of their 3 x 3
+    // diagonal blocks: -(K - C_k + delta (1 - alpha))  (ref: 3076-3092 then 3194-3245)
+    double *dC = c.wsd("mono.C", 3 * c.rows_loc + 2);
+    BS_CUDA(cudaMemcpyAsync(dC, c.h_C.data(), 3 * c.rows_loc * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    scatter_flagged_columns(c, c.A, c.d_Kflag.p, c.ldk, c.d_kcol.p, dC, c.fused_alpha);
+    BS_CUDA(cudaStreamSynchronize(c.stream));
+  } else {
     DMat Vv = c.V;
     Vv.rows = c.rows_loc;
     Vv.cols = n;
     select_columns(c, c.A, Vv, c.K, d_flag, c.A_aliases_V);
+  }
+  {
     // the implicit V correction carries over to the V columns of A
     c.A.r1_u = c.V.r1_u;
     c.A.r1_w = c.V.r1_w;

@@ -166,6 +166,10 @@ struct RegParams {
   const double *panel;
   double *KX;
   int pp;
+  // fused mode with mixed boundary conditions: -K of the flagged columns goes to the compact matrix Kflag
+  const int *kcol;   // [3N] internal column -> compact column, -1 = not flagged; nullptr = no flags
+  double *Kflag;
+  size_t ldk;
 };
 
 constexpr int ACC_LD = TI + 1;  // padded row-node stride of the shared accumulators (bank-conflict free both ways)
@@ -631,6 +635,138 @@ __device__ __forceinline__ void integrate_free_surface(const double *__restrict_
     }
 }
 
+// Free-surface image system with the moment formulation of integrate_free_lin (Q1 on bilinear cells, Gauss 8): the direct
+// part R = y - x and the image part R_im = y - x_im are both free-space kernels along the same straight rows (same B,
+// different R0), one layer per launch (MODE 0 or 1).  Three-stage software pipeline over the points as in integrate_free.
+template <int MODE, int QS>
+__device__ __forceinline__ void integrate_free_surface_lin(const double *__restrict__ c8, const double *__restrict__ xi_s,
+                                                           const double *__restrict__ ly_s, const double (&x)[3],
+                                                           const double (&xim)[3], int o, int part, double (&out)[4][9]) {
+  static_assert(MODE == 0 || MODE == 1, "one layer per launch");
+  constexpr int N1 = 8;
+  const bool flip = (QS == 2) && (part == 1);
+  const double xi0 = xi_s[32], inv_dxi = xi_s[33];
+  double acc[4][12], accI[4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    accI[a][0] = accI[a][1] = 0.0;
+#pragma unroll
+    for (int v = 0; v < 12; ++v) acc[a][v] = 0.0;
+  }
+  FreeA saA, saB;
+  FreeB sbA, sbB;
+  if (part < N1) {
+    FreeA a0;
+    const double *r0 = c8 + (size_t)8 * part * N1;
+    free_stage_a<MODE>(r0, x, a0);
+    free_stage_b<MODE>(a0, sbA);
+    free_stage_a<MODE>(r0, xim, a0);
+    free_stage_b<MODE>(a0, sbB);
+    free_stage_a<MODE>(r0 + 8, x, saA);
+    free_stage_a<MODE>(r0 + 8, xim, saB);
+  }
+  for (int qy = part; qy < N1; qy += QS) {
+    double mA[4] = {0.0, 0.0, 0.0, 0.0}, mB[4] = {0.0, 0.0, 0.0, 0.0}, iA[2] = {0.0, 0.0}, iB[2] = {0.0, 0.0};
+    double dummy[4] = {0.0, 0.0, 0.0, 0.0};
+    const double *crow = c8 + (size_t)8 * qy * N1;
+    const int qyn = (qy + QS < N1) ? qy + QS : qy;
+    const double *nrow = c8 + (size_t)8 * qyn * N1;
+#pragma unroll
+    for (int qx = 0; qx < N1; ++qx) {
+      FreeB nbA, nbB;
+      free_stage_b<MODE>(saA, nbA);
+      free_stage_b<MODE>(saB, nbB);
+      FreeA naA, naB;
+      const double *rec = qx + 2 < N1 ? crow + 8 * (qx + 2) : nrow + 8 * (qx + 2 - N1);
+      free_stage_a<MODE>(rec, x, naA);
+      free_stage_a<MODE>(rec, xim, naB);
+      if (MODE == 0) {
+        free_stage_c_lin<0>(sbA, xi_s + 4 * qx, mA, dummy, iA);
+        free_stage_c_lin<0>(sbB, xi_s + 4 * qx, mB, dummy, iB);
+      } else {
+        free_stage_c_lin<1>(sbA, xi_s + 4 * qx, dummy, mA, iA);
+        free_stage_c_lin<1>(sbB, xi_s + 4 * qx, dummy, mB, iB);
+      }
+      sbA = nbA;
+      sbB = nbB;
+      saA = naA;
+      saB = naB;
+    }
+    double R0a[3], R0b[3], B[3];
+    {
+      const double2 u0 = *reinterpret_cast<const double2 *>(crow), u7 = *reinterpret_cast<const double2 *>(crow + 8 * (N1 - 1));
+      const double z0 = crow[2], z7 = crow[8 * (N1 - 1) + 2];
+      B[0] = (u7.x - u0.x) * inv_dxi;
+      B[1] = (u7.y - u0.y) * inv_dxi;
+      B[2] = (z7 - z0) * inv_dxi;
+      const double y0[3] = {u0.x, u0.y, z0};
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        R0a[d] = fma(-xi0, B[d], y0[d] - x[d]);
+        R0b[d] = fma(-xi0, B[d], y0[d] - xim[d]);
+      }
+    }
+    double MA[3][2], MB[3][2], IA[2], IB[2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double dA = mA[k] - mA[k + 1], eA = mA[k + 1], dB = mB[k] - mB[k + 1], eB = mB[k + 1];
+      MA[k][0] = flip ? eA : dA;
+      MA[k][1] = flip ? dA : eA;
+      MB[k][0] = flip ? eB : dB;
+      MB[k][1] = flip ? dB : eB;
+    }
+    if (MODE == 0) {
+      const double dA = iA[0] - iA[1], eA = iA[1], dB = iB[0] - iB[1], eB = iB[1];
+      IA[0] = flip ? eA : dA;
+      IA[1] = flip ? dA : eA;
+      IB[0] = flip ? eB : dB;
+      IB[1] = flip ? dB : eB;
+    }
+    const double ly0 = ly_s[qy * 2], ly1 = ly_s[qy * 2 + 1];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = i; j < 3; ++j) {
+        const int v = (i == 0) ? j : (i == 1 ? 2 + j : 5);
+        const double Dv = B[i] * B[j];
+        const double AvA = R0a[i] * R0a[j], AvB = R0b[i] * R0b[j];
+        const double CvA = (i == j) ? 2.0 * (R0a[i] * B[i]) : fma(R0a[i], B[j], B[i] * R0a[j]);
+        const double CvB = (i == j) ? 2.0 * (R0b[i] * B[i]) : fma(R0b[i], B[j], B[i] * R0b[j]);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const double tA = fma(Dv, MA[2][b], fma(CvA, MA[1][b], AvA * MA[0][b]));
+          const double tB = fma(Dv, MB[2][b], fma(CvB, MB[1][b], AvB * MB[0][b]));
+          acc[b][v] = fma(tA, ly0, acc[b][v]);
+          acc[b + 2][v] = fma(tA, ly1, acc[b + 2][v]);
+          acc[b][6 + v] = fma(tB, ly0, acc[b][6 + v]);
+          acc[b + 2][6 + v] = fma(tB, ly1, acc[b + 2][6 + v]);
+        }
+      }
+    if (MODE == 0) {
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        accI[b][0] = fma(IA[b], ly0, accI[b][0]);
+        accI[b + 2][0] = fma(IA[b], ly1, accI[b + 2][0]);
+        accI[b][1] = fma(IB[b], ly0, accI[b][1]);
+        accI[b + 2][1] = fma(IB[b], ly1, accI[b + 2][1]);
+      }
+    }
+  }
+  // G_fs = G(R) + s_i G(R_im), s_i = -1 on the row of the wall normal (ref: source/free_surface_kernel.cc:19-72, 135-209)
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double sg = (i == o) ? -1.0 : 1.0;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        double v = fma(sg, acc[a][6 + vidx<6>(i, j)], acc[a][vidx<6>(i, j)]);
+        if (MODE == 0 && i == j) v += fma(sg, accI[a][1], accI[a][0]);
+        out[a][3 * i + j] = v;
+      }
+    }
+}
+
 // One (row, cell) integration over this thread's share of the tensor rule.  MODE 0: single layer only, 1: double
 // layer only, 2: both.  Sum-factorised: x-direction into NB1 temporaries per value, y-direction once per row of
 // the rule; then the QS partial sums of a row (adjacent lanes) are combined by shuffles and lane `part` adds its
@@ -661,7 +797,12 @@ __device__ __forceinline__ void cell_pass(const double *__restrict__ cq, const d
       }
     } else {
       if constexpr (KT == BS_KERNEL_FREE_SURFACE && MODE != 2) {
-        if (ok) integrate_free_surface<NA, MODE, QS>(cq, lx_s, l1d_s, n1, x, xim, o, part, acc);
+        if constexpr (N1C < 0) {
+          static_assert(NA == 4 && N1C == -8, "linear-row fast path: Q1, Gauss 8");
+          if (ok) integrate_free_surface_lin<MODE, QS>(cq, l1d_s + 32, l1d_s, x, xim, o, part, acc);
+        } else {
+          if (ok) integrate_free_surface<NA, MODE, QS>(cq, lx_s, l1d_s, n1, x, xim, o, part, acc);
+        }
       }
     }
   } else {
@@ -896,8 +1037,9 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
   const int E = 3 * tj;
   // per-lane column metadata, loop invariant: shared-tile offset of the value for each matrix-row component i (+ row
   // of the pair), global column, and what to do with it (0 nothing, 1 store, 2 reduce) -- the row loop is branch free
-  int soff[MAXSTEP][3], gcol[MAXSTEP], todo[MAXSTEP];
+  int soff[MAXSTEP][3], gcol[MAXSTEP], todo[MAXSTEP], kc[MAXSTEP];
   bool second[MAXSTEP];
+  const bool mixed = FUSED && LAYER != 1 && P.kcol != nullptr;  // uniform: -K of the flagged columns is kept (mixed BC)
 #pragma unroll
   for (int sidx = 0; sidx < MAXSTEP; ++sidx) {
     const int e2 = lane + 32 * sidx;
@@ -908,6 +1050,7 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
     const bool valid = node >= 0;
     todo[sidx] = valid ? (first[sl] != 0 ? 1 : 2) : 0;
     gcol[sidx] = valid ? 3 * node + j : 0;
+    kc[sidx] = (mixed && valid) ? P.kcol[3 * node + j] : -1;
 #pragma unroll
     for (int i = 0; i < 3; ++i) soff[sidx][i] = valid ? vidx<NV>(i, j) * vs + sl * ACC_LD + (second[sidx] ? 1 : 0) : 0;
   }
@@ -924,6 +1067,10 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
         const double *as = acc_s + soff[sidx][i] + r_;
         if (LAYER != 2) store_or_reduce(P.V + off, as[0], what);
         if (!FUSED && LAYER != 1) store_or_reduce(P.K + off, as[(size_t)KPL * vs], what);
+        if (mixed) {
+          const size_t offk = ((size_t)3 * (by * TI + r_) + i + (second[sidx] ? 3 : 0)) * P.ldk + (kc[sidx] >= 0 ? kc[sidx] : 0);
+          store_or_reduce(P.Kflag + offk, -as[(size_t)KPL * vs], kc[sidx] >= 0 ? what : 0);
+        }
       }
     }
   }
@@ -990,15 +1137,16 @@ static void launch_reg_layer(Context &c, RegParams P, int nrow_tiles, size_t sme
   const bool n8 = (KT == BS_KERNEL_FREE) && c.kp.eps == 0.0 && P.n1d == 8;
   constexpr int N8 = (KT == BS_KERNEL_FREE) ? 8 : 0;
   // Q1 unknowns on a Q1 (bilinear) mapping: the rows of the rule are straight lines -> moment formulation (N1C = -8)
-  constexpr int L8 = (KT == BS_KERNEL_FREE && NA == 4) ? -8 : N8;
-  const bool lin = n8 && NA == 4 && c.na_map == 4 && !std::getenv("BS_NO_LINROWS");
-  auto kern = c.fused ? ((c.kp.eps == 0.0) ? (n8 ? (lin ? k_assemble_regular<NA, KT, LAYER, QS, VS, false, true, L8>
-                                                        : k_assemble_regular<NA, KT, LAYER, QS, VS, false, true, N8>)
-                                                 : k_assemble_regular<NA, KT, LAYER, QS, VS, false, true, 0>)
+  constexpr bool LINK = (KT == BS_KERNEL_FREE) || (KT == BS_KERNEL_FREE_SURFACE && LAYER != 0);  // kernels with the moment formulation
+  constexpr int L8 = (LINK && NA == 4) ? -8 : N8;
+  const bool lin8 = LINK && NA == 4 && c.na_map == 4 && c.kp.eps == 0.0 && P.n1d == 8 && !std::getenv("BS_NO_LINROWS");
+  auto kern = c.fused ? ((c.kp.eps == 0.0) ? (lin8 ? k_assemble_regular<NA, KT, LAYER, QS, VS, false, true, L8>
+                                                   : (n8 ? k_assemble_regular<NA, KT, LAYER, QS, VS, false, true, N8>
+                                                         : k_assemble_regular<NA, KT, LAYER, QS, VS, false, true, 0>))
                                            : k_assemble_regular<NA, KT, LAYER, QS, VS, true, true, 0>)
-                      : ((c.kp.eps == 0.0) ? (n8 ? (lin ? k_assemble_regular<NA, KT, LAYER, QS, VS, false, false, L8>
-                                                        : k_assemble_regular<NA, KT, LAYER, QS, VS, false, false, N8>)
-                                                 : k_assemble_regular<NA, KT, LAYER, QS, VS, false, false, 0>)
+                      : ((c.kp.eps == 0.0) ? (lin8 ? k_assemble_regular<NA, KT, LAYER, QS, VS, false, false, L8>
+                                                   : (n8 ? k_assemble_regular<NA, KT, LAYER, QS, VS, false, false, N8>
+                                                         : k_assemble_regular<NA, KT, LAYER, QS, VS, false, false, 0>))
                                            : k_assemble_regular<NA, KT, LAYER, QS, VS, true, false, 0>);
   BS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const std::vector<int> &cs = c.blocks.colour_start;
@@ -1054,6 +1202,9 @@ void launch_assembly_regular(Context &c) {
   P.panel = c.fused ? c.d_panel.p : nullptr;
   P.KX = c.fused ? c.d_KX.p : nullptr;
   P.pp = c.panel_p;
+  P.kcol = (c.fused && c.n_flagged > 0) ? c.d_kcol.p : nullptr;
+  P.Kflag = c.d_Kflag.p;
+  P.ldk = c.ldk;
   const int nrow_tiles = (c.p1 - c.p0 + TI - 1) / TI;
   if (nrow_tiles == 0) return;
   
@@ -1096,6 +1247,9 @@ struct SingParams {
   const double *panel;  // fused mode (K not stored)
   double *KX;
   int pp;
+  const int *kcol;      // fused mode, mixed boundary conditions (see RegParams)
+  double *Kflag;
+  size_t ldk;
 };
 
 constexpr int SING_WARPS = 4;
@@ -1191,6 +1345,11 @@ __global__ void __launch_bounds__(32 * SING_WARPS) k_assemble_singular(const Sin
           double *M = mat == 0 ? P.V : P.K;
           M[(row0 + i) * P.ld + (size_t)3 * cpos + j] += val;
         }
+        if (FUSED && mat == 1 && a0 + a < NA && P.kcol) {  // mixed BC: -K of the flagged columns
+          const int cpos = P.conn_pos[(size_t)cell * NA + a0 + a];
+          const int kcc = P.kcol[3 * cpos + j];
+          if (kcc >= 0) P.Kflag[(row0 + i) * P.ldk + kcc] -= red[wid][a * NV2 + NV + vidx<NV>(i, j)];
+        }
       }
       if (FUSED) {
         // K block of this (node, cell) pair times the panel rows of the cell's nodes; this warp owns the rows
@@ -1253,6 +1412,9 @@ void launch_assembly_singular(Context &c) {
   P.panel = c.fused ? c.d_panel.p : nullptr;
   P.KX = c.fused ? c.d_KX.p : nullptr;
   P.pp = c.panel_p;
+  P.kcol = (c.fused && c.n_flagged > 0) ? c.d_kcol.p : nullptr;
+  P.Kflag = c.d_Kflag.p;
+  P.ldk = c.ldk;
   switch (c.kp.type) {
     case BS_KERNEL_FREE: launch_sing_kt<BS_KERNEL_FREE>(c, P); break;
     case BS_KERNEL_FREE_SURFACE: launch_sing_kt<BS_KERNEL_FREE_SURFACE>(c, P); break;

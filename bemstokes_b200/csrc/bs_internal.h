@@ -223,6 +223,14 @@ struct Context {
   std::vector<double> h_panel;      // host copy of X
   std::vector<double> h_C;          // [3][rows_loc] K e_k on the owned rows (after bs_correct_K in fused mode)
   int fused_alpha = 0;
+  // mixed boundary conditions in the fused mode: the unknowns flagged here are wall velocities, whose columns of the
+  // monolithic matrix are -K columns (ref: bem_stokes.cc:3194-3245).  K is not stored in this mode, so the assembly keeps
+  // -K for exactly these columns in a compact side matrix.
+  std::vector<unsigned char> col_flags;   // [3N] reference ordering (empty = none)
+  DBuf<int> d_kcol;                       // [3N] internal column -> compact column of Kflag, -1 = not flagged
+  DBuf<double> d_Kflag;                   // [rows_loc][ldk] = -K(:, flagged) (uncorrected)
+  size_t ldk = 0;
+  int n_flagged = 0;
   // projector data (internal ordering, full length 3N)
   DBuf<double> d_nhat, d_Mnhat;
   DBuf<double> d_r1u, d_r1w, d_r1wA;  // implicit V correction: u = (nhat - V nhat) / l2 on the owned rows, w = M nhat (masked copy for A)
@@ -346,6 +354,8 @@ void zero_constrained_entries(Context &c, double *v_loc);         // v_loc[row] 
 void extract_diag(Context &c, const DMat &M, size_t row_offset, double *d_out);
 void select_columns(Context &c, DMat &A, const DMat &V, const DMat &K, const unsigned char *d_flag, bool alias);
 void set_column(Context &c, DMat &A, size_t col, const double *v, double scale);
+// A(:, c) = Kflag(:, kcol[c]) for the flagged columns (Kflag = -K uncorrected), K correction applied on the node's own 3 x 3 block
+void scatter_flagged_columns(Context &c, DMat &A, const double *Kflag, size_t ldk, const int *kcol, const double *Ck, int alpha);
 void gather_entries(Context &c, const DMat &M, int n, const int *d_r, const int *d_c, double *d_out);
 // dst[i][j] (n x n, leading dimension ldd) += r1_u[row_off + i] * r1_w[col_off + j] of M's implicit term (after a plain copy of a block of M)
 void add_rank1_block(Context &c, const DMat &M, size_t row_off, size_t col_off, size_t n, double *dst, size_t ldd);

@@ -410,6 +410,37 @@ void select_columns(Context &c, DMat &A, const DMat &V, const DMat &K, const uns
   }
 }
 
+// rows of this rank x all columns; flagged columns only are written.  Ck[m][row] = (K e_m)[row] on the owned rows.
+__global__ void k_scatter_flagged(double *A, size_t ld, size_t rows, size_t ncols, const double *__restrict__ Kflag, size_t ldk,
+                                  const int *__restrict__ kcol, const double *__restrict__ Ck, size_t ldc, int p0, int alpha) {
+  const size_t r = blockIdx.y;
+  if (r >= rows) return;
+  const size_t node_row = r / 3, jrow = r - 3 * node_row;  // row = (local node, component j)
+  for (size_t cc = (size_t)blockIdx.x * blockDim.x + threadIdx.x; cc < ncols; cc += (size_t)gridDim.x * blockDim.x) {
+    const int kc = kcol[cc];
+    if (kc < 0) continue;
+    double v = Kflag[r * ldk + kc];  // = -K(r, cc)
+    const size_t node_col = cc / 3, m = cc - 3 * node_col;
+    if (node_col == (size_t)p0 + node_row) {  // own diagonal block: -(K - C_m[r] + delta_jm (1 - alpha))
+      v += Ck[m * ldc + r];
+      if (jrow == m && !alpha) v -= 1.0;
+    }
+    A[r * ld + cc] = v;
+  }
+}
+void scatter_flagged_columns(Context &c, DMat &A, const double *Kflag, size_t ldk, const int *kcol, const double *Ck, int alpha) {
+  const size_t rows = c.rows_loc, ncols = c.n3();
+  if (!rows) return;
+  const unsigned gx = (unsigned)std::min<size_t>((ncols + 255) / 256, 64);
+  for (size_t done = 0; done < rows; done += 65535) {
+    const size_t nr = std::min<size_t>(rows - done, 65535);
+    k_scatter_flagged<<<dim3(gx, (unsigned)nr), 256, 0, c.stream>>>(A.p + done * A.ld, A.ld, nr, ncols, Kflag + done * ldk, ldk, kcol,
+                                                                  Ck + done, rows, c.p0 + (int)(done / 3), alpha);
+    BS_CUDA(cudaGetLastError());
+    count_launch(c);
+  }
+}
+
 __global__ void k_set_column(double *A, size_t ld, size_t rows, size_t col, const double *__restrict__ v, double scale) {
   const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r < rows) A[r * ld + col] = v ? scale * v[r] : scale;

@@ -389,6 +389,8 @@ class BEMProblem(FrameLoop):
         if self.fused_assembly:
             Nr0 = np.ascontiguousarray(self.N_rigid[:self.num_rigid])
             sv0 = np.ascontiguousarray(self.shape_velocities, dtype=np.float64)
+            fl = None if self.col_is_K is None else np.ascontiguousarray(self.col_is_K, dtype=np.uint8)
+            check(lib.bs_set_column_flags(ctx, fl.ctypes.data_as(_lib.c_ubyte_p) if fl is not None else None))
             check(lib.bs_assemble_fused(ctx, self.num_rigid, _dp(Nr0), _dp(nh), _dp(mn), self.l2normGamma_pure,
                                         _dp(sv0) if self.grid_type == "Real" else None))
         else:

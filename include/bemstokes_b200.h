@@ -137,8 +137,13 @@ int bs_assemble_VK(bs_context *ctx);
  * matrix): same K1/K2 passes, but the double-layer tile is multiplied in the tile epilogue with the panel
  * [e_0 e_1 e_2 | P N_r | P u_shape] instead of being stored, which is all the monolithic system of a body-only
  * problem needs from K (K correction 3044-3098, projected rigid columns 3120-3148, rhs 3127-3132).  Afterwards
- * call bs_correct_V, bs_correct_K and bs_build_monolithic as usual (col_is_K must be NULL, A aliases V);
- * BS_MAT_K is not available. */
+ * call bs_correct_V, bs_correct_K and bs_build_monolithic as usual (A aliases V; col_is_K as given to
+ * bs_set_column_flags); BS_MAT_K is not available. */
+/* Mixed boundary conditions with the fused assembly: col_is_K[3N] flags the unknowns that are wall velocities, whose
+ * columns of the monolithic matrix are -K columns (ref: the index-set logic of bem_stokes.cc:3194-3245).  K is not stored in
+ * the fused mode, so bs_assemble_fused keeps -K for exactly these columns in a compact side matrix (rows x flagged columns)
+ * and bs_build_monolithic, called with the same flags, moves them into A.  NULL clears.  Call before bs_assemble_fused. */
+int bs_set_column_flags(bs_context *ctx, const unsigned char *col_is_K);
 int bs_assemble_fused(bs_context *ctx, int num_rigid, const double *N_rigid, const double *nhat, const double *Mnhat,
                       double l2gamma, const double *shape_vel);
 /* V <- V + (nhat - V nhat)(M nhat)^T / l2 on owned rows (3004-3036). nhat = normal_vector_pure,

@@ -601,6 +601,22 @@ def test_config_C5_free_surface_kernel_mixed_columns(half):
     q.assemble_stokes_system(True)
     assert rel_rows(q.monolithic_system_matrix.to_dense(), Ao) < ENTRY_TOL
     q.close()
+    # fused (no-K) assembly with the same mixed boundary conditions: -K is kept for the flagged columns only
+    for kern in (kw, {}):
+        f = make_problem(half, grid_type="ImposedForce", imposed_component=0, col_is_K=flags, fused_assembly=True,
+                         solve_directly=False, preconditioner_type="None", **kern)
+        f.assemble_stokes_system(True)
+        if kern:
+            Af = Ao
+        else:   # free-space kernel through the pipelined fast path
+            geo2, (V2, K2) = oracle_VK(f)
+            Vc2, _ = bo.correct_V(V2, pre)
+            Af, _ = bo.monolithic(Vc2, bo.correct_K(K2, geo2.N), pre, "ImposedForce", 0, 1.0, None, flags)
+        assert rel_rows(f.monolithic_system_matrix.to_dense(), Af) < ENTRY_TOL
+        f.solve_system(True)
+        xf = np.linalg.solve(Af, bvec)
+        assert np.abs(f.monolithic_solution - xf).max() <= 1e-6 * np.abs(xf).max()
+        f.close()
 
 
 def test_config_C3_Q2_reference_quadrature():

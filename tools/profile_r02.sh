@@ -29,4 +29,13 @@ done
 C="python bench.py --workload q2 --steps 1 --warmup 1 --no-cpu-baseline --no-secondary --no-parity"
 $C > $O/p_q2_plain.log 2>&1 && \
 $NCU --set full -k regex:k_assemble_regular -s 7 -c 1 -o $O/r02_k1_q2 -f $C > $O/p_ncu_q2.log 2>&1; echo "q2 rc=$?"
-ls -la $O/*.ncu-rep $O/r02_*.csv 2>/dev/null
+# export the pages on the box (gpurun merges at most 64 MiB back) and drop the reports
+for R in r02_k1 r02_gmres_iter r02_lu_gemm r02_k1_c5 r02_k1_c5ns r02_k1_q2; do
+  [ -f $O/$R.ncu-rep ] || continue
+  ncu -i $O/$R.ncu-rep --page raw --csv > $O/${R}_raw.csv 2>/dev/null
+  rm -f $O/$R.ncu-rep.keep
+done
+ncu -i $O/r02_k1.ncu-rep --page source --csv > $O/r02_k1_source.csv 2>/dev/null
+ncu -i $O/r02_k1_c5.ncu-rep --page source --csv > $O/r02_k1_c5_source.csv 2>/dev/null
+rm -f $O/*.ncu-rep
+ls -la $O/r02_* 2>/dev/null
