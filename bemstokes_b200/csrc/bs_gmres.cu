@@ -565,11 +565,29 @@ int gmres_device(Context &c, int which, int nrhs, const double *d_B, double *d_X
     BS_CUDA(cudaFuncSetAttribute(k_gm_pass<GM_UPD_NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   const int *skip = &st->all_done;
 
+  // BS_TRACE: CUDA events around every sweep over the matrix, so that the solve time splits into matvec and the rest
+  const bool trace = std::getenv("BS_TRACE") != nullptr;
+  std::vector<cudaEvent_t> tev;
   auto matvec = [&]() {  // w = A_loc * (replicated vectors of the slots)
     if (p2p) p2p_wait_only(c, skip, st);
+    if (trace) {
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0, c.stream);
+      tev.push_back(e0);
+      tev.push_back(e1);
+    }
     if (nrhs == 1) gemv(c, M, xfull, w, skip);
     else gemv_multi(c, M, nrhs, xfull, xld, w, ldw, skip);
+    if (trace) cudaEventRecord(tev.back(), c.stream);
   };
+  cudaEvent_t tr0 = nullptr, tr1 = nullptr;
+  if (trace) {
+    cudaEventCreate(&tr0);
+    cudaEventCreate(&tr1);
+    cudaEventRecord(tr0, c.stream);
+  }
   auto precondition = [&]() {  // z = M^-1 w
     switch (c.prec_kind) {
       case BS_PREC_NONE: break;  // z aliases w
@@ -639,6 +657,29 @@ int gmres_device(Context &c, int which, int nrhs, const double *d_B, double *d_X
     last = gh.pinned[0];
     BS_CUDA(cudaGetLastError());
     if (last.all_done) stop_all = true;
+  }
+  if (trace) {
+    cudaEventRecord(tr1, c.stream);
+    cudaEventSynchronize(tr1);
+    float total = 0, mv = 0, mv_max = 0;
+    cudaEventElapsedTime(&total, tr0, tr1);
+    int nmv = 0;
+    for (size_t i = 0; i + 1 < tev.size(); i += 2) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, tev[i], tev[i + 1]);
+      if (ms > 0.05f) {  // sweeps queued behind the convergence point return at once
+        mv += ms;
+        ++nmv;
+        mv_max = std::max(mv_max, ms);
+      }
+      cudaEventDestroy(tev[i]);
+      cudaEventDestroy(tev[i + 1]);
+    }
+    cudaEventDestroy(tr0);
+    cudaEventDestroy(tr1);
+    fprintf(stderr, "[bs trace rank %d] device GMRES: %d iterations, %.2f ms on the stream; %d sweeps over the matrix %.2f ms (max %.3f ms); "
+                    "everything else %.3f ms = %.4f ms per iteration\n", c.rank, last.its[0], total, nmv, mv, mv_max, total - mv,
+            (total - mv) / std::max(1, last.its[0]));
   }
   if (failed(last)) throw Error(BS_ERR_COMM, "peer exchange timed out during the GMRES iteration (a rank stopped answering)");
   int rc = BS_OK;

@@ -260,7 +260,7 @@ struct Context {
     size_t off = 0, n = 0, ld = 0;  // local row offset, size, leading dimension of LU
     double *LU = nullptr;           // points into d_lu
     int *piv = nullptr, *perm = nullptr;   // into d_piv: LAPACK-style pivot rows and the equivalent gather permutation
-    double *LinvT = nullptr, *UinvT = nullptr;  // into d_luinv: transposed inverses of the 128 x 128 diagonal blocks
+    double *LinvT = nullptr, *UinvT = nullptr;  // into d_luinv: row-major inverses of the 512 x 512 diagonal blocks of L and U
   };
   std::vector<LuBlock> lu_blocks;
   DBuf<double> d_lu, d_luinv;

@@ -682,15 +682,16 @@ void lu_solve(Context &c, const double *LU, size_t n_, size_t ld, const int *piv
 
 // ---------------------------------------------------------------------------------------------------------
 // Preconditioner application  x = U^-1 L^-1 P b  as ONE cooperative kernel per diagonal block (the substitution
-// above takes four launches per 32 columns).  The triangular systems are solved in steps of 128 unknowns: the
-// 128 x 128 diagonal blocks of L and U are inverted once after the factorisation, so a step is
-//     x_k = inv(T_kk) r_k          one CTA (the owner of step k, rotating)
-//     r_i -= T_ik x_k              all warps of the grid, one row each, streaming the panel T[:, k] from HBM
-// with one grid barrier per step: the owner of step k+1 updates the 128 rows of its block first and solves it
-// while the other CTAs stream the rest of panel k.  Any fixed linear operator is admissible as a preconditioner,
-// so the explicit inverses of the diagonal blocks do not affect what GMRES converges to.
+// above takes four launches per 32 columns).  The triangular systems are solved in steps of TB = 512 unknowns whose
+// diagonal blocks are inverted once after the factorisation, so that BOTH halves of a step are matrix-vector products
+// spread over the whole grid and the sweep is bandwidth bound instead of latency bound:
+//     x_k = inv(T_kk) r_k          512 rows, one warp each
+//     r_i -= T_ik x_k              all remaining rows, one warp per row, TRB rows in flight per warp
+// with a grid barrier after each half (2 n / 512 barriers per sweep; 128-unknown steps solved by one owner CTA took
+// 13 ms at 36 864 unknowns, dominated by the 578 dependent owner steps).  Any fixed linear operator is admissible as a
+// preconditioner, so the explicit inverses of the diagonal blocks do not affect what GMRES converges to.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int TB = 128;
+constexpr int TB = 512;
 
 // perm = the gather form of LAPACK's sequential row interchanges: (P b)[i] = b[perm[i]]
 __global__ void k_piv_to_perm(const int *piv, int *perm, int n) {
@@ -706,116 +707,68 @@ __global__ void k_piv_to_perm(const int *piv, int *perm, int n) {
   }
 }
 
-// transposed inverses of the diagonal blocks: LinvT[k][j][i] = inv(L_kk)[i][j] (unit lower), UinvT likewise (upper)
-__global__ void __launch_bounds__(TB) k_tri_inverse(const double *LU, size_t ld, int n, double *LinvT, double *UinvT) {
-  extern __shared__ double X[];  // [TB][TB+1], X[i*(TB+1) + j] = inverse(i, j)
+// inverses of the TB x TB diagonal blocks, row-major: Linv[k][i][j] = inv(L_kk)(i, j) (unit lower), Uinv likewise (upper).
+// One CTA per diagonal block, thread j builds column j by substitution directly in the output (its own column only).
+__global__ void __launch_bounds__(TB) k_tri_inverse(const double *LU, size_t ld, int n, double *Linv, double *Uinv) {
   const int k0 = blockIdx.x * TB, kb = min(TB, n - k0), j = threadIdx.x;
   const double *T = LU + (size_t)k0 * ld + k0;
-  constexpr int XL = TB + 1;
-  // ---- unit lower: column j of the inverse by forward substitution
-  for (int i = 0; i < TB; ++i) X[i * XL + j] = (i == j) ? 1.0 : 0.0;
+  double *X = Linv + (size_t)blockIdx.x * TB * TB;
+  for (int i = 0; i < TB; ++i) X[(size_t)i * TB + j] = (i == j) ? 1.0 : 0.0;
   if (j < kb)
     for (int i = j + 1; i < kb; ++i) {
       double sacc = 0.0;
-      for (int q = j; q < i; ++q) sacc = fma(T[(size_t)i * ld + q], X[q * XL + j], sacc);
-      X[i * XL + j] = -sacc;
+      for (int q = j; q < i; ++q) sacc = fma(T[(size_t)i * ld + q], X[(size_t)q * TB + j], sacc);
+      X[(size_t)i * TB + j] = -sacc;
     }
-  __syncthreads();
-  double *out = LinvT + (size_t)blockIdx.x * TB * TB;
-  for (int q = 0; q < TB; ++q) out[(size_t)q * TB + j] = X[j * XL + q];  // out[q][i=j] = inv(i=j, q)
-  __syncthreads();
-  // ---- upper with diagonal: column j by backward substitution
-  for (int i = 0; i < TB; ++i) X[i * XL + j] = (i == j && j >= kb) ? 1.0 : 0.0;
+  X = Uinv + (size_t)blockIdx.x * TB * TB;
+  for (int i = 0; i < TB; ++i) X[(size_t)i * TB + j] = (i == j && j >= kb) ? 1.0 : 0.0;
   if (j < kb) {
     const double dj = T[(size_t)j * ld + j];
-    X[j * XL + j] = dj != 0.0 ? 1.0 / dj : 0.0;
+    X[(size_t)j * TB + j] = dj != 0.0 ? 1.0 / dj : 0.0;
     for (int i = j - 1; i >= 0; --i) {
       double sacc = 0.0;
-      for (int q = i + 1; q <= j; ++q) sacc = fma(T[(size_t)i * ld + q], X[q * XL + j], sacc);
+      for (int q = i + 1; q <= j; ++q) sacc = fma(T[(size_t)i * ld + q], X[(size_t)q * TB + j], sacc);
       const double di = T[(size_t)i * ld + i];
-      X[i * XL + j] = di != 0.0 ? -sacc / di : 0.0;
+      X[(size_t)i * TB + j] = di != 0.0 ? -sacc / di : 0.0;
     }
   }
-  __syncthreads();
-  out = UinvT + (size_t)blockIdx.x * TB * TB;
-  for (int q = 0; q < TB; ++q) out[(size_t)q * TB + j] = X[j * XL + q];
 }
 
-// 128 x 128 block times vector for the owner CTA: thread (row i, half h) sums 64 columns; `colmajor` says whether
-// consecutive threads read consecutive addresses (the transposed inverses) or every thread walks its own row (T itself)
-__device__ __forceinline__ double tri_block_dot(const double *Mk, size_t ldm, bool colmajor, int i, int half, int ncols,
-                                                const double *v) {
-  const int j0 = half * (TB / 2), j1 = min(j0 + TB / 2, ncols);
-  double a0 = 0.0, a1 = 0.0;
-  if (colmajor) {
-#pragma unroll 8
-    for (int j = j0; j < j1; ++j) a0 = fma(Mk[(size_t)j * ldm + i], v[j], a0);
-  } else {
-    const double *row = Mk + (size_t)i * ldm;
-    int j = j0;
-#pragma unroll 8
-    for (; j + 1 < j1; j += 2) {
-      const double2 m2 = *reinterpret_cast<const double2 *>(row + j);
-      a0 = fma(m2.x, v[j], a0);
-      a1 = fma(m2.y, v[j + 1], a1);
-    }
-    if (j < j1) a0 = fma(row[j], v[j], a0);
-  }
-  return a0 + a1;
-}
-// owner step: r_blk -= T[blk rows][k0 .. k0+kb) x_k (skipped when T == nullptr), then x_blk = inv(T_bb) r_blk.
-// sm: xs[TB] | rs[TB] | part[2 TB]
-__device__ __forceinline__ void tri_owner_step(const double *T, size_t ld, int k0, int kb, const double *MT, int blk, int b0, int bb,
-                                               double *x, double *sm) {
-  const int tid = threadIdx.x, i = tid & (TB - 1), half = tid >> 7;
-  double *xs = sm, *rs = sm + TB, *part = sm + 2 * TB;
-  __syncthreads();
-  if (tid < TB) {
-    rs[tid] = tid < bb ? __ldcg(x + b0 + tid) : 0.0;
-    if (T) xs[tid] = tid < kb ? __ldcg(x + k0 + tid) : 0.0;
-  }
-  __syncthreads();
-  if (T) {
-    part[half * TB + i] = i < bb ? tri_block_dot(T + (size_t)b0 * ld + k0, ld, false, i, half, kb, xs) : 0.0;
-    __syncthreads();
-    if (tid < TB) rs[tid] -= part[tid] + part[TB + tid];
-    __syncthreads();
-  }
-  part[half * TB + i] = tri_block_dot(MT + (size_t)blk * TB * TB, TB, true, i, half, TB, rs);
-  __syncthreads();
-  if (tid < bb) __stcg(x + b0 + tid, part[tid] + part[TB + tid]);
-  __syncthreads();
-}
-// x[r] -= T[r][k0 .. k0+kb) . xk for the rows r0, r0 + stride, ... < r_end of one warp; xk in registers (4 values per
-// lane).  TRB rows are in flight together: all their loads are issued before the first reduction, otherwise a warp pays
-// one DRAM latency per row (measured: 32 us per 128-column step at 36 864 unknowns, 18 ms per application)
-constexpr int TRB = 8;
-__device__ __forceinline__ void tri_rows_update(const double *LU, size_t ld, int r0, int stride, int r_end, int k0, int kb,
-                                                const double xk[4], double *x, int lane) {
-  const bool full = (4 * lane + 3 < kb);
+// dot products of TRB matrix rows (row r0 + u * stride, columns [0, ncols) of a TB-wide block starting at `base`) with
+// the vector v (shared memory); all loads of a batch are issued before the first reduction.  Lane 0 of the warp hands
+// the TRB results to `sink(row, value)`.
+constexpr int TRB = 4;
+template <class Sink>
+__device__ __forceinline__ void tri_rows_dot(const double *base, size_t ld, int r0, int stride, int r_end, int ncols,
+                                             const double *__restrict__ v, int lane, Sink sink) {
   for (int rb = r0; rb < r_end; rb += TRB * stride) {
-    double2 a[TRB], b[TRB];
-    double xr = 0.0;
-#pragma unroll
-    for (int u = 0; u < TRB; ++u) {
-      const int r = rb + u * stride;
-      a[u] = b[u] = make_double2(0.0, 0.0);
-      if (r < r_end) {
-        const double *row = LU + (size_t)r * ld + k0 + 4 * lane;
-        if (full) {
-          a[u] = *reinterpret_cast<const double2 *>(row);
-          b[u] = *reinterpret_cast<const double2 *>(row + 2);
-        } else {
-          if (4 * lane + 0 < kb) a[u].x = row[0];
-          if (4 * lane + 1 < kb) a[u].y = row[1];
-          if (4 * lane + 2 < kb) b[u].x = row[2];
-        }
-        if (lane == u) xr = __ldcg(x + r);
-      }
-    }
     double s[TRB];
 #pragma unroll
-    for (int u = 0; u < TRB; ++u) s[u] = fma(a[u].x, xk[0], fma(a[u].y, xk[1], fma(b[u].x, xk[2], b[u].y * xk[3])));
+    for (int u = 0; u < TRB; ++u) s[u] = 0.0;
+#pragma unroll
+    for (int h = 0; h < TB / 256; ++h) {  // 256 columns per pass: 8 doubles per lane and row
+      const int c0 = 256 * h + 8 * lane;
+      double2 a[TRB][4];
+#pragma unroll
+      for (int u = 0; u < TRB; ++u) {
+        const int r = rb + u * stride;
+        const double *row = base + (size_t)r * ld + c0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          a[u][q] = make_double2(0.0, 0.0);
+          if (r < r_end) {
+            if (c0 + 2 * q + 1 < ncols) a[u][q] = *reinterpret_cast<const double2 *>(row + 2 * q);
+            else if (c0 + 2 * q < ncols) a[u][q].x = row[2 * q];
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double2 vv = *reinterpret_cast<const double2 *>(v + c0 + 2 * q);
+#pragma unroll
+        for (int u = 0; u < TRB; ++u) s[u] = fma(a[u][q].x, vv.x, fma(a[u][q].y, vv.y, s[u]));
+      }
+    }
 #pragma unroll
     for (int u = 0; u < TRB; ++u) {
 #pragma unroll
@@ -826,48 +779,42 @@ __device__ __forceinline__ void tri_rows_update(const double *LU, size_t ld, int
     for (int u = 0; u < TRB; ++u)
       if (lane == u) mine = s[u];
     const int r = rb + lane * stride;
-    if (lane < TRB && r < r_end) __stcg(x + r, xr - mine);
+    if (lane < TRB && r < r_end) sink(r, mine);
   }
 }
 
-__global__ void __launch_bounds__(256) k_lu_apply_coop(const double *LU, size_t ld, int n, const int *perm, const double *LinvT,
-                                                       const double *UinvT, const double *in, double *x, unsigned int *counter,
-                                                       const int *skip) {
+__global__ void __launch_bounds__(256) k_lu_apply_coop(const double *LU, size_t ld, int n, const int *perm, const double *Linv,
+                                                       const double *Uinv, const double *in, double *x, double *xk_g /*[TB]*/,
+                                                       unsigned int *counter, const int *skip) {
   if (skip && *skip) return;
-  __shared__ double sm[4 * TB];
+  __shared__ __align__(16) double vs[TB];
   const int G = gridDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int gw = blockIdx.x * 8 + wid, total_warps = G * 8;
   const int nblk = (n + TB - 1) / TB;
   unsigned int nbar = 0;
   for (int i = blockIdx.x * 256 + tid; i < n; i += G * 256) __stcg(x + i, in[perm[i]]);
   grid_barrier(counter, (++nbar) * G);
-  // ---- forward: L y = P b
-  if ((int)blockIdx.x == 0 % G) tri_owner_step(nullptr, ld, 0, 0, LinvT, 0, 0, min(TB, n), x, sm);
-  grid_barrier(counter, (++nbar) * G);
-  for (int k = 0; k + 1 < nblk; ++k) {
-    const int k0 = k * TB;  // kb == TB here (k is not the last block)
-    double xk[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) xk[u] = __ldcg(x + k0 + 4 * lane + u);
-    if ((int)blockIdx.x == (k + 1) % G)  // owner of the next step: its rows first, then its diagonal solve
-      tri_owner_step(LU, ld, k0, TB, LinvT, k + 1, k0 + TB, min(k0 + 2 * TB, n) - (k0 + TB), x, sm);
-    tri_rows_update(LU, ld, k0 + 2 * TB + gw, total_warps, n, k0, TB, xk, x, lane);
-    grid_barrier(counter, (++nbar) * G);
-  }
-  // ---- backward: U x = y
-  {
-    const int kl = nblk - 1;
-    if ((int)blockIdx.x == kl % G) tri_owner_step(nullptr, ld, 0, 0, UinvT, kl, kl * TB, n - kl * TB, x, sm);
-    grid_barrier(counter, (++nbar) * G);
-  }
-  for (int k = nblk - 1; k >= 1; --k) {
-    const int k0 = k * TB, kb = min(TB, n - k0);
-    double xk[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) xk[u] = (4 * lane + u < kb) ? __ldcg(x + k0 + 4 * lane + u) : 0.0;
-    if ((int)blockIdx.x == (k - 1) % G) tri_owner_step(LU, ld, k0, kb, UinvT, k - 1, k0 - TB, TB, x, sm);
-    tri_rows_update(LU, ld, gw, total_warps, k0 - TB, k0, kb, xk, x, lane);
-    grid_barrier(counter, (++nbar) * G);
+  for (int sweep = 0; sweep < 2; ++sweep) {  // 0: L y = P b forwards, 1: U x = y backwards
+    const double *Minv = sweep == 0 ? Linv : Uinv;
+    for (int kk = 0; kk < nblk; ++kk) {
+      const int k = sweep == 0 ? kk : nblk - 1 - kk;
+      const int k0 = k * TB, kb = min(TB, n - k0);
+      // ---- x_k = inv(T_kk) r_k into the staging vector (r_k = x[k0 ..] is still being read by other CTAs)
+      __syncthreads();
+      for (int i = tid; i < TB; i += 256) vs[i] = i < kb ? __ldcg(x + k0 + i) : 0.0;
+      __syncthreads();
+      tri_rows_dot(Minv + (size_t)k * TB * TB, TB, gw, total_warps, kb, TB, vs, lane, [&](int r, double v) { __stcg(xk_g + r, v); });
+      grid_barrier(counter, (++nbar) * G);
+      // ---- r_i -= T_ik x_k on the rows still to be solved; CTA 0 moves x_k to its place
+      for (int i = tid; i < TB; i += 256) vs[i] = i < kb ? __ldcg(xk_g + i) : 0.0;
+      __syncthreads();
+      if (blockIdx.x == 0)
+        for (int i = tid; i < kb; i += 256) __stcg(x + k0 + i, vs[i]);
+      const int r_lo = sweep == 0 ? k0 + TB : 0, r_hi = sweep == 0 ? n : k0;
+      if (r_lo < r_hi)
+        tri_rows_dot(LU + k0, ld, r_lo + gw, total_warps, r_hi, kb, vs, lane, [&](int r, double v) { __stcg(x + r, __ldcg(x + r) - v); });
+      grid_barrier(counter, (++nbar) * G);
+    }
   }
 }
 
@@ -877,15 +824,16 @@ void lu_apply_fast(Context &c, const Context::LuBlock &b, const double *in, doub
     BS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_per_sm, k_lu_apply_coop, 256, 0));
     max_per_sm = std::max(1, std::min(max_per_sm, 2));
   }
-  int G = (int)std::min<size_t>((size_t)max_per_sm * c.sm_count, std::max<size_t>(1, (b.n + TB - 1) / TB));
+  int G = (int)std::min<size_t>((size_t)max_per_sm * c.sm_count, std::max<size_t>(1, (b.n + 63) / 64));
   unsigned int *counter = reinterpret_cast<unsigned int *>(c.wsi("lu.apply_counter", 4));
   BS_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), c.stream));
+  double *xk = c.wsd("lu.apply_xk", TB + 2);
   const double *LU = b.LU;
   size_t ld = b.ld;
   int n = (int)b.n;
   const int *perm = b.perm;
   const double *Li = b.LinvT, *Ui = b.UinvT;
-  void *args[] = {&LU, &ld, &n, &perm, &Li, &Ui, &in, &out, &counter, &skip};
+  void *args[] = {&LU, &ld, &n, &perm, &Li, &Ui, &in, &out, &xk, &counter, &skip};
   BS_CUDA(cudaLaunchCooperativeKernel((void *)k_lu_apply_coop, dim3(G), dim3(256), args, 0, c.stream));
   count_launch(c);
 }
@@ -917,7 +865,6 @@ void precond_factor_blocks(Context &c, const DMat &M, size_t col_off, size_t n_t
   c.d_luinv.alloc(inv_total + 2);
   c.d_piv.alloc(piv_total + 2);
   size_t lu_at = 0, inv_at = 0, piv_at = 0;
-  BS_CUDA(cudaFuncSetAttribute(k_tri_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TB * (TB + 1) * sizeof(double))));
   for (size_t b = 0; b < nblocks; ++b) {
     Context::LuBlock &B = c.lu_blocks[b];
     const size_t nt = (B.n + TB - 1) / TB, np = (B.n + 3) & ~(size_t)3;
@@ -942,7 +889,7 @@ void precond_factor_blocks(Context &c, const DMat &M, size_t col_off, size_t n_t
     }
     lu_factor(c, B.LU, B.n, B.ld, B.piv);
     k_piv_to_perm<<<1, 32, 0, c.stream>>>(B.piv, B.perm, (int)B.n);
-    k_tri_inverse<<<(unsigned)nt, TB, TB * (TB + 1) * sizeof(double), c.stream>>>(B.LU, B.ld, (int)B.n, B.LinvT, B.UinvT);
+    k_tri_inverse<<<(unsigned)nt, TB, 0, c.stream>>>(B.LU, B.ld, (int)B.n, B.LinvT, B.UinvT);
     BS_CUDA(cudaGetLastError());
     count_launch(c, 2);
   }

@@ -284,6 +284,38 @@ def secondary_workloads(device, fp64_peak, args):
                     "assembly_ms": ms, "flops_per_pair": fp, "achieved_tflops": tf, "frac": tf / fp64_peak}
         p.close()
 
+    # ---- config 1: the reference's own CPU-runnable case (debug_grids/sphere_mesh_3d_0.msh, 386 nodes): whole step
+    try:
+        m1 = bb.read_mesh(os.path.join(ROOT, "tests", "golden", "meshes", "sphere_mesh_3d_0.msh"))
+        p = bb.BEMProblem(device=device)
+        p.set_mesh(m1)
+        p.quadrature_order, p.singular_quadrature_order = 8, 10
+        p.grid_type, p.imposed_component = "ImposedVelocity", 0
+        p.solve_directly, p.preconditioner_type = False, "None"
+        p.solver_control.tolerance, p.gmres_restart = 1e-10, 200
+        p.reinit()
+
+        def c1_step():
+            p.compute_center_of_mass_and_rigid_modes()
+            p.compute_normal_vector()
+            p.assemble_stokes_system(True)
+            p.monolithic_solution[:] = 0
+            p.solve_system(True)
+        c1_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            c1_step()
+        torch.cuda.synchronize()
+        out["c1_sphere_mesh_3d"] = {"workload": "BASELINE config 1: debug_grids/sphere_mesh_3d_0.msh, Q1, Gauss 8 / Lachat-Watson 10, "
+                                                "translating body, pre-pass + assembly + GMRES through the public API",
+                                    "nodes": m1.n_nodes, "time_to_solution_ms": 1e3 * (time.perf_counter() - t0) / 5,
+                                    "gmres_iterations": p.solver_control.last_step(),
+                                    "drag_over_6pi_a_eq": float(p.rigid_total_forces[0] / (6 * math.pi * 0.861)),
+                                    "note": "node radii 0.849-0.874: equivalent radius 0.861 (SURVEY §8)"}
+        p.close()
+    except Exception as e:
+        out["c1_sphere_mesh_3d"] = {"error": repr(e)}
     a = argparse.Namespace(workload="c5", m=args.secondary_m, refine=None, no_fused=False)
     assembly_case("c5_free_surface", workload(a, 1))
     a.workload = "c5ns"

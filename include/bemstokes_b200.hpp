@@ -245,6 +245,13 @@ public:
   unsigned int bandwith = 100, gmres_restart = 100, num_rigid = 6;
   SolverControl solver_control;
   bool keep_VK = true;
+  bool fused_assembly = false;                     // never store K (bs_assemble_fused): sizes where V and K do not fit together
+  std::vector<unsigned char> col_is_K;             // per dof: the unknown is a wall velocity, column -K (index sets of 3194-3245)
+  // hanging-node constraints: dof -> (constraining dof, coefficient) (ref: the AffineConstraints of 2970-2995, 3156-3183)
+  std::map<unsigned int, std::vector<std::pair<unsigned int, double>>> constraints;
+  bool solve_with_torque = false;                  // "Impose a torque on the flagellum" (216, 3252-3256, 3340-3352)
+  Vector N_flagellum_torque, N_flagellum_torque_dual;
+  double torque_rhs = -2., flagellum_omega = 0.;
   // frame loop (bem_stokes.cc:215-216, 222-229, 282-300, 327-329)
   unsigned int n_frames = 120, delta_frame = 1;
   bool bool_rot = true, bool_dipl = false, bool_dipl_x = false, bool_dipl_y = false, bool_dipl_z = false;
@@ -316,7 +323,31 @@ public:
   // ref: BEMProblem::assemble_stokes_system (bem_stokes.cc:2840-3435), same log lines
   void assemble_stokes_system(bool correction_on_V = true) {
     set_kernel();
-    check(bs_assemble_VK(ctx));
+    {  // constraints and the torque unknown take effect in the calls below
+      std::vector<int> dof, ptr(1, 0), cols;
+      std::vector<double> coefs;
+      for (const auto &kv : constraints) {
+        dof.push_back((int)kv.first);
+        for (const auto &e : kv.second) {
+          cols.push_back((int)e.first);
+          coefs.push_back(e.second);
+        }
+        ptr.push_back((int)cols.size());
+      }
+      check(bs_set_constraints(ctx, (int)dof.size(), dof.data(), ptr.data(), cols.data(), coefs.data()));
+      if (solve_with_torque) check(bs_set_torque_mode(ctx, N_flagellum_torque.data(), N_flagellum_torque_dual.data(), torque_rhs));
+      else check(bs_set_torque_mode(ctx, nullptr, nullptr, 0.));
+    }
+    const unsigned char *flags = col_is_K.size() == n_dofs ? col_is_K.data() : nullptr;
+    if (fused_assembly) {
+      std::vector<double> nr0;
+      for (unsigned int r = 0; r < num_rigid; ++r) nr0.insert(nr0.end(), N_rigid[r].begin(), N_rigid[r].end());
+      check(bs_set_column_flags(ctx, flags));
+      check(bs_assemble_fused(ctx, (int)num_rigid, nr0.data(), normal_vector_pure.data(), M_normal_vector_pure.data(), l2normGamma_pure,
+                              grid_type == "Real" ? shape_velocities.data() : nullptr));
+    } else {
+      check(bs_assemble_VK(ctx));
+    }
     V_x_normals_body.assign(n_dofs, 0.);
     if (correction_on_V)
       check(bs_correct_V(ctx, normal_vector_pure.data(), M_normal_vector_pure.data(), l2normGamma_pure, V_x_normals_body.data()));
@@ -327,7 +358,7 @@ public:
     V_matrix.vmult(post, normal_vector_pure);
     *pcout << "Check on the V operator Norm post (should be one) pure: " << dot(post, normal_vector_pure) / N << std::endl;
     check(bs_correct_K(ctx, use_internal_alpha ? 1 : 0));
-    for (unsigned int k = 0; k < 3; ++k) {
+    for (unsigned int k = 0; k < 3 && !fused_assembly; ++k) {
       Vector e(n_dofs, 0.), ke;
       for (unsigned int i = 0; i < N; ++i) e[i + k * N] = 1.;
       K_matrix.vmult(ke, e);
@@ -339,9 +370,9 @@ public:
         nr.insert(nr.end(), N_rigid[r].begin(), N_rigid[r].end());
         nd.insert(nd.end(), N_rigid_dual[r].begin(), N_rigid_dual[r].end());
       }
-      monolithic_rhs.assign(n_dofs + num_rigid, 0.);
+      monolithic_rhs.assign(n_dofs + num_rigid + (solve_with_torque ? 1 : 0), 0.);
       const int gt = grid_type == "ImposedForce" ? BS_GRID_IMPOSED_FORCE : grid_type == "ImposedVelocity" ? BS_GRID_IMPOSED_VELOCITY : BS_GRID_REAL;
-      check(bs_build_monolithic(ctx, nullptr, (int)num_rigid, nr.data(), nd.data(), normal_vector_pure.data(),
+      check(bs_build_monolithic(ctx, flags, (int)num_rigid, nr.data(), nd.data(), normal_vector_pure.data(),
                                 M_normal_vector_pure.data(), l2normGamma_pure, gt, (int)imposed_component, assemble_scaling,
                                 shape_velocities.data(), keep_VK ? 1 : 0, monolithic_rhs.data()));
       if (monolithic_solution.size() != monolithic_rhs.size()) monolithic_solution.assign(monolithic_rhs.size(), 0.);
@@ -400,6 +431,7 @@ public:
       rigid_total_forces[r] = dot(stokes_forces, N_rigid_dual[r]);
     }
     baricenter_rigid_velocities = rigid_velocities;  // this solve's velocities about the pole (bem_stokes.cc:4479-4492)
+    if (solve_with_torque) flagellum_omega = monolithic_solution[n_dofs + num_rigid];  // ref 4398-4401
   }
 
   // DN(u_k) = P V^{-1} (P K P u_k) for up to 8 velocities in one device call (bem_stokes.cc:4072-4129)
