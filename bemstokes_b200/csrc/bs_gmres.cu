@@ -480,6 +480,8 @@ __global__ void __launch_bounds__(GM_THREADS) k_gm_update_x(GmDev P, double *X, 
 struct GmHost {  // per-context pinned status mirror (created on first use)
   GmStatus *pinned = nullptr;  // [2]
   cudaEvent_t ev[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> sweep_ev;  // pool: start / stop events around every sweep over the matrix (timing only)
+  cudaEvent_t span[2] = {nullptr, nullptr};
 };
 
 bool gmres_device_eligible(Context &c, int nrhs, int max_tmp) {
@@ -565,29 +567,28 @@ int gmres_device(Context &c, int which, int nrhs, const double *d_B, double *d_X
     BS_CUDA(cudaFuncSetAttribute(k_gm_pass<GM_UPD_NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   const int *skip = &st->all_done;
 
-  // BS_TRACE: CUDA events around every sweep over the matrix, so that the solve time splits into matvec and the rest
+  // CUDA events around every sweep over the matrix: the solve time on the stream splits into matvec and the rest
+  // (bs_stats gmres_*_last; two event records per sweep, no synchronisation)
   const bool trace = std::getenv("BS_TRACE") != nullptr;
-  std::vector<cudaEvent_t> tev;
+  size_t nev = 0;
   auto matvec = [&]() {  // w = A_loc * (replicated vectors of the slots)
     if (p2p) p2p_wait_only(c, skip, st);
-    if (trace) {
-      cudaEvent_t e0, e1;
-      cudaEventCreate(&e0);
-      cudaEventCreate(&e1);
-      cudaEventRecord(e0, c.stream);
-      tev.push_back(e0);
-      tev.push_back(e1);
+    if (gh.sweep_ev.size() < nev + 2) {
+      gh.sweep_ev.resize(nev + 2, nullptr);
+      cudaEventCreate(&gh.sweep_ev[nev]);
+      cudaEventCreate(&gh.sweep_ev[nev + 1]);
     }
+    cudaEventRecord(gh.sweep_ev[nev], c.stream);
     if (nrhs == 1) gemv(c, M, xfull, w, skip);
     else gemv_multi(c, M, nrhs, xfull, xld, w, ldw, skip);
-    if (trace) cudaEventRecord(tev.back(), c.stream);
+    cudaEventRecord(gh.sweep_ev[nev + 1], c.stream);
+    nev += 2;
   };
-  cudaEvent_t tr0 = nullptr, tr1 = nullptr;
-  if (trace) {
-    cudaEventCreate(&tr0);
-    cudaEventCreate(&tr1);
-    cudaEventRecord(tr0, c.stream);
+  if (!gh.span[0]) {
+    cudaEventCreate(&gh.span[0]);
+    cudaEventCreate(&gh.span[1]);
   }
+  cudaEventRecord(gh.span[0], c.stream);
   auto precondition = [&]() {  // z = M^-1 w
     switch (c.prec_kind) {
       case BS_PREC_NONE: break;  // z aliases w
@@ -658,28 +659,28 @@ int gmres_device(Context &c, int which, int nrhs, const double *d_B, double *d_X
     BS_CUDA(cudaGetLastError());
     if (last.all_done) stop_all = true;
   }
-  if (trace) {
-    cudaEventRecord(tr1, c.stream);
-    cudaEventSynchronize(tr1);
+  {
+    cudaEventRecord(gh.span[1], c.stream);
+    cudaEventSynchronize(gh.span[1]);
     float total = 0, mv = 0, mv_max = 0;
-    cudaEventElapsedTime(&total, tr0, tr1);
-    int nmv = 0;
-    for (size_t i = 0; i + 1 < tev.size(); i += 2) {
+    cudaEventElapsedTime(&total, gh.span[0], gh.span[1]);
+    int nmv = 0, its_max = 0;
+    for (int s = 0; s < nrhs; ++s) its_max = std::max(its_max, last.its[s]);
+    const int real_sweeps = its_max + (its_max == 0 ? 1 : (its_max + m - 1) / m);  // one per iteration + one residual per cycle
+    for (size_t i = 0; i + 1 < nev && nmv < real_sweeps; i += 2) {  // sweeps queued behind the convergence point returned at once
       float ms = 0;
-      cudaEventElapsedTime(&ms, tev[i], tev[i + 1]);
-      if (ms > 0.05f) {  // sweeps queued behind the convergence point return at once
-        mv += ms;
-        ++nmv;
-        mv_max = std::max(mv_max, ms);
-      }
-      cudaEventDestroy(tev[i]);
-      cudaEventDestroy(tev[i + 1]);
+      cudaEventElapsedTime(&ms, gh.sweep_ev[i], gh.sweep_ev[i + 1]);
+      mv += ms;
+      ++nmv;
+      mv_max = std::max(mv_max, ms);
     }
-    cudaEventDestroy(tr0);
-    cudaEventDestroy(tr1);
-    fprintf(stderr, "[bs trace rank %d] device GMRES: %d iterations, %.2f ms on the stream; %d sweeps over the matrix %.2f ms (max %.3f ms); "
-                    "everything else %.3f ms = %.4f ms per iteration\n", c.rank, last.its[0], total, nmv, mv, mv_max, total - mv,
-            (total - mv) / std::max(1, last.its[0]));
+    c.stats.gmres_stream_ms_last = total;
+    c.stats.gmres_matvec_ms_last = mv;
+    c.stats.gmres_sweeps_last = nmv;
+    if (trace)
+      fprintf(stderr, "[bs trace rank %d] device GMRES: %d iterations, %.2f ms on the stream; %d sweeps over the matrix %.2f ms (max %.3f ms); "
+                      "everything else %.3f ms = %.4f ms per iteration\n", c.rank, its_max, total, nmv, mv, mv_max, total - mv,
+              (total - mv) / std::max(1, its_max));
   }
   if (failed(last)) throw Error(BS_ERR_COMM, "peer exchange timed out during the GMRES iteration (a rank stopped answering)");
   int rc = BS_OK;
@@ -697,6 +698,10 @@ void gm_host_release(Context &c) {
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->ev[0]) cudaEventDestroy(h->ev[0]);
   if (h->ev[1]) cudaEventDestroy(h->ev[1]);
+  for (cudaEvent_t e : h->sweep_ev)
+    if (e) cudaEventDestroy(e);
+  if (h->span[0]) cudaEventDestroy(h->span[0]);
+  if (h->span[1]) cudaEventDestroy(h->span[1]);
   delete h;
   c.gm_host = nullptr;
 }

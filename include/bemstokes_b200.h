@@ -246,6 +246,9 @@ typedef struct {
   /* tiling of the regular pass: disjoint cell blocks, colours (launches), tile traffic amplification */
   long long n_cell_blocks, n_colours;
   double node_touch_ratio;
+  /* last device-resident GMRES solve: time on the stream, of which in the sweeps over the matrix (CUDA events around each) */
+  double gmres_stream_ms_last, gmres_matvec_ms_last;
+  long long gmres_sweeps_last;
 } bs_stats;
 int bs_get_stats(bs_context *ctx, bs_stats *out);
 int bs_reset_stats(bs_context *ctx);
