@@ -1018,11 +1018,9 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
     st = (st + 1 == ns) ? 0 : st + 1;
     st_fill = (st_fill + 1 == ns) ? 0 : st_fill + 1;
   }
-  // With one thread set (VS == 1) every tile row is written by the threads of ONE warp (the QS threads of a row node are
-  // adjacent lanes), and the write-out below gives each warp exactly its own rows: no CTA barrier here - a warp that is
-  // done with its cells starts writing while the others still integrate (the barrier skew was 8 % of the samples).
-  if (VS == 1) __syncwarp();
-  else __syncthreads();  // V warps and K warps fill different planes of the same rows
+  __syncthreads();  // the tile is complete.  (Tried: every tile row belongs to one warp when VS == 1, so each warp could write out its
+                    // own rows after a __syncwarp and skip this barrier, whose skew is 8 % of the samples - measured 782 ms
+                    // instead of 470 ms per assembly: the warps of a CTA drift into different code regions of a 68 KB kernel.)
 
   // ---- combine the tile with global memory: rows 3*(p-p0)+i, columns 3*node(slot)+j.  The first colour that
   // touches a node column stores, later colours (launched after this one) add: fixed summation order.
@@ -1058,12 +1056,8 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
 #pragma unroll
     for (int i = 0; i < 3; ++i) soff[sidx][i] = valid ? vidx<NV>(i, j) * vs + sl * ACC_LD + (second[sidx] ? 1 : 0) : 0;
   }
-  constexpr int ROWS_PER_WARP = 32 / QS;  // VS == 1: the rows this warp integrated
-  const int r_begin = (VS == 1) ? ROWS_PER_WARP * warp : 2 * warp;
-  const int r_stop = (VS == 1) ? min(rows_tile, ROWS_PER_WARP * (warp + 1)) : rows_tile;
-  const int r_step = (VS == 1) ? 2 : 2 * NWARP;
-  for (int r_ = r_begin; r_ < r_stop; r_ += r_step) {
-    const bool has2 = r_ + 1 < r_stop;
+  for (int r_ = 2 * warp; r_ < rows_tile; r_ += 2 * NWARP) {
+    const bool has2 = r_ + 1 < rows_tile;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const size_t rowoff = ((size_t)3 * (by * TI + r_) + i) * P.ld;
