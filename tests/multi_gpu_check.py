@@ -81,6 +81,11 @@ def main():
     p.preconditioner_type = "None"
     from bemstokes_b200._lib import lib, check
     check(lib.bs_precond_setup(p._ctx, 2, 0, 0))
+    # DN operator of a rigid mode on the sharded V and K (bs_dn_operator_multi: sweep over K, gather, lockstep V-solve, gather)
+    dn = p.dirichlet_to_neumann_operator(pre.N_rigid[0])
+    dn_o = pre.P(np.linalg.solve(Vc, pre.P(Kc @ pre.P(pre.N_rigid[0]))))
+    edn = np.abs(dn - dn_o).max() / np.abs(dn_o).max()
+    assert edn < 1e-8, edn
     # six right-hand sides in lockstep through the same exchange path
     if world >= 1:
         nr = 6
