@@ -390,11 +390,13 @@ int bs_set_kernel(bs_context *h, int type, double eps, int wall_orientation, con
   Context &c = ctx_of(h);
   BS_REQUIRE(type >= 0 && type <= 2, "unknown kernel type");
   BS_REQUIRE(wall_orientation >= 0 && wall_orientation < 3, "wall orientation must be 0,1,2");
-  const bool retile = (type == BS_KERNEL_FREE) != (c.kp.type == BS_KERNEL_FREE);
+  bool retile = (type == BS_KERNEL_FREE) != (c.kp.type == BS_KERNEL_FREE);
+  const int cs_before = cell_sets(c);
   c.kp.type = type;
   c.kp.eps = eps;
   c.kp.o = wall_orientation;
   c.kp.wall_pos = wall_position ? wall_position[wall_orientation] : 0.0;
+  retile = retile || cell_sets(c) != cs_before;  // the cell blocks depend on the K1 variant (tile size, cell pairs)
   if (retile && c.have_geometry && c.have_quadrature) build_tables(c);
   BS_API_END
 }

@@ -158,6 +158,7 @@ struct RegParams {
   const signed char *blk_slots;
   const int *blk_nodes;            // [nblocks][tj] node position per slot, -1 unused
   const unsigned char *blk_first;  // [nblocks][tj] first-touch flag
+  const unsigned *blk_sync;        // [nblocks] cell-split mode: steps that start with a CTA barrier (bit = step)
   int blk_begin;                   // first block of the colour being launched
   double *V, *K;
   size_t ld;
@@ -172,6 +173,7 @@ struct RegParams {
   size_t ldk;
 };
 
+constexpr int TJ_CS2 = 15;      // nodes per cell block in the cell-split mode of K1 (see cell_sets)
 constexpr int ACC_LD = TI + 1;  // padded row-node stride of the shared accumulators (bank-conflict free both ways)
 // stride between consecutive values of the shared tile [value][slot][row]; the +5 spreads the three values a
 // write-out lane group reads for one node over different banks
@@ -192,19 +194,33 @@ int tile_planes(int na, int kernel_type) {
   return (na == 4 && kernel_type != BS_KERNEL_FREE) ? nv : 2 * nv;
 }
 
-size_t assembly_smem_bytes(int na, int planes, int tj, int nq_pad) {
+// Cell-split mode (cs == 2; Q1 free-space kernel on bilinear cells, Gauss 8): one thread per collocation node integrates
+// a whole cell (all rows of the rule, all four shape functions) and the CTA's two thread sets work on two cells of the
+// block that share no node, so nothing is exchanged between threads and the per-cell tile update is paid once per
+// 8 rule rows instead of once per 4.  A ring stage then holds a pair of cell records.
+int cell_sets(const Context &c) {
+  const bool lin8 = c.na == 4 && c.na_map == 4 && c.kp.type == BS_KERNEL_FREE && c.kp.eps == 0.0 && c.x1d.size() == 8;
+  return (lin8 && !std::getenv("BS_NO_LINROWS") && !std::getenv("BS_NO_CELLSPLIT")) ? 2 : 1;
+}
+__host__ __device__ inline int ring_stages(int nq_pad, int cs) { return cs == 2 ? 2 : cell_stages(nq_pad); }
+
+size_t assembly_smem_bytes(int na, int planes, int tj, int nq_pad, int cs) {
   (void)na;
-  size_t ring = (size_t)cell_stages(nq_pad) * 8 * nq_pad * 8;
+  size_t ring = (size_t)ring_stages(nq_pad, cs) * cs * 8 * nq_pad * 8;
   ring = std::max(ring, (size_t)3 * tj * MAX_PANEL * 8);  // K-only launches stage the fused panel rows in the ring
   return (size_t)planes * acc_vstride(tj) * 8 + ring + (size_t)l1d_doubles(nq_pad) * 8 + 64;  // tile, ring, shape table, mbarriers
 }
 
-int choose_tj(int na, int kernel_type, int nq_pad) {
+int choose_tj(int na, int kernel_type, int nq_pad, int cs) {
   const int planes = tile_planes(na, kernel_type);
   const size_t budget = (227 * 1024) / CTAS_PER_SM - 1024 - 1024;  // minus static arrays (768 B) / per-CTA reserve
+  if (cs == 2) {  // cell-split blocks are 2 x 4 patches (15 nodes); the block size is a compile-time constant of that kernel
+    BS_REQUIRE(assembly_smem_bytes(na, planes, TJ_CS2, nq_pad, cs) <= budget, "cell-split tile does not fit (BS_TI / BS_CTAS_PER_SM changed?)");
+    return TJ_CS2;
+  }
   int tj = 2;
   for (int t = 2; t <= 32; t += 2)
-    if (assembly_smem_bytes(na, planes, t, nq_pad) <= budget) tj = t;
+    if (assembly_smem_bytes(na, planes, t, nq_pad, cs) <= budget) tj = t;
   return tj;
 }
 
@@ -772,7 +788,9 @@ __device__ __forceinline__ void integrate_free_surface_lin(const double *__restr
 // the rule; then the QS partial sums of a row (adjacent lanes) are combined by shuffles and lane `part` adds its
 // share of the shape functions into the shared tile [value][slot][row].
 // FAST: free-space kernel without regularisation, `cq` is the point-major prescaled record.
-template <int NA, int KT, int MODE, int QS, bool HAS_EPS, bool FAST, int N1C, bool KLOW = false>
+// TILE_ACC (cell-split mode, QS == 1): the thread owns its tile entries for the duration of the cell, so the accumulators
+// start from the tile values and are stored back - no zeroing, no add pass.
+template <int NA, int KT, int MODE, int QS, bool HAS_EPS, bool FAST, int N1C, bool KLOW = false, bool TILE_ACC = false>
 __device__ __forceinline__ void cell_pass(const double *__restrict__ cq, const double *__restrict__ l1d_s, int n1, int nqp,
                                           const double (&x)[3], const double (&xim)[3], double eps, int o, bool ok,
                                           int part, const int (&slot)[NA], double *__restrict__ acc_s, int tj, int rl) {
@@ -781,6 +799,25 @@ __device__ __forceinline__ void cell_pass(const double *__restrict__ cq, const d
   constexpr int NACC = (MODE == 2) ? 2 * NV : NV;
   constexpr int VOFF = (MODE == 1 && !KLOW) ? NV : 0;  // KLOW: double-layer-only launch, K lives in planes 0..NV-1
   double acc[NA][NACC];
+  if constexpr (TILE_ACC) {
+    static_assert(FAST && QS == 1 && NA == 4 && N1C == -8 && KT == BS_KERNEL_FREE, "tile accumulators: cell-split fast path");
+    if (ok) {
+      const int vs = acc_vstride(tj);
+      double *dst[NA];
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        dst[a] = acc_s + (size_t)VOFF * vs + (size_t)slot[a] * ACC_LD + rl;
+#pragma unroll
+        for (int v = 0; v < NACC; ++v) acc[a][v] = dst[a][(size_t)v * vs];
+      }
+      integrate_free_lin<MODE, QS, NACC>(cq, l1d_s + 32, l1d_s, x, part, acc);
+#pragma unroll
+      for (int a = 0; a < NA; ++a)
+#pragma unroll
+        for (int v = 0; v < NACC; ++v) dst[a][(size_t)v * vs] = acc[a][v];
+    }
+    return;
+  }
 #pragma unroll
   for (int a = 0; a < NA; ++a)
 #pragma unroll
@@ -883,8 +920,9 @@ __device__ __forceinline__ void cell_pass(const double *__restrict__ cq, const d
 constexpr int MAXC = 32;  // cells per block (a block touches at most tj <= 32 nodes)
 
 // LAYER 0: both layers in one tile; 1: single layer only; 2: double layer only (two launches, half the tile per node).
-template <int NA, int KT, int LAYER, int QS, int VS, bool HAS_EPS, bool FUSED, int N1C>
-__global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(const RegParams P) {
+// CS == 2: cell-split mode (see cell_sets): QS == VS == 1, thread set t / TI integrates cell 2*step + set of the block.
+template <int NA, int KT, int LAYER, int QS, int VS, bool HAS_EPS, bool FUSED, int N1C, int CS = 1>
+__global__ void __launch_bounds__(TI *QS *VS *CS, CTAS_PER_SM) k_assemble_regular(const RegParams P) {
   // point-major prescaled cell records, pipelined points: free space, and the Q1 free-surface image system (its two
   // layers are integrated by separate launches; with Q2 the 9 x 12 partial sums would not fit the register file)
   constexpr bool FAST = !HAS_EPS && (KT == BS_KERNEL_FREE || (KT == BS_KERNEL_FREE_SURFACE && NA == 4 && LAYER != 0));
@@ -893,13 +931,14 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
   constexpr int NV2 = (LAYER == 0) ? 2 * NV : NV;  // value planes of the tile
   constexpr int KPL = (LAYER == 0) ? NV : 0;       // first plane of the double layer
   static_assert(LAYER == 0 || VS == 1, "layer-split launches use one thread set");
+  static_assert(CS == 1 || (CS == 2 && QS == 1 && VS == 1), "cell-split mode: one thread per node and cell");
   constexpr int NB1 = (NA == 4) ? 2 : 3;
-  constexpr int NT = TI * QS * VS;
+  constexpr int NT = TI * QS * VS * CS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int tj = P.tj, nqp = P.nq_pad, n1 = P.n1d;
-  const int ns = cell_stages(nqp);
-  double *cellbuf = reinterpret_cast<double *>(smem_raw);                   // [ns][7][nqp] or [ns][nqp][8]
-  const size_t ring_doubles = max((size_t)ns * 8 * nqp, (size_t)3 * tj * MAX_PANEL);
+  const int tj = (CS == 2) ? TJ_CS2 : P.tj, nqp = (CS == 2) ? 64 : P.nq_pad, n1 = (CS == 2) ? 8 : P.n1d;
+  const int ns = ring_stages(nqp, CS);
+  double *cellbuf = reinterpret_cast<double *>(smem_raw);                   // [ns][CS][7][nqp] or [ns][CS][nqp][8]
+  const size_t ring_doubles = max((size_t)ns * CS * 8 * nqp, (size_t)3 * tj * MAX_PANEL);
   double *l1d_s = cellbuf + ring_doubles;                                   // [n1][NB1] 1-D shape values (+ x-flipped copy)
   double *acc_s = l1d_s + l1d_doubles(nqp);                                 // [NV2][tj][ACC_LD]
   uint64_t *bars = reinterpret_cast<uint64_t *>(acc_s + (size_t)NV2 * acc_vstride(tj));  // full[3], empty[3]
@@ -911,7 +950,8 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
 
   const int t = threadIdx.x;
   const int vpart = (VS == 2) ? t / (TI * QS) : 0;   // warp-uniform role: 0 single layer, 1 double layer
-  const int tt = t - vpart * (TI * QS);
+  const int cset = (CS == 2) ? t / TI : 0;           // warp-uniform: which cell of a pair this thread integrates
+  const int tt = t - (vpart + cset) * (TI * QS);
   const int rl = tt / QS, part = tt - rl * QS;
   // row tile fastest: co-resident CTAs integrate the same cell block for different rows, so its cell records and
   // metadata stay in L1/L2 instead of being re-streamed from HBM per row tile
@@ -931,9 +971,18 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // first records of the ring right away: their HBM latency hides behind the tile clear and the metadata staging
-    for (int i = 0; i < ns - 1 && cs + i < ce; ++i) {
-      mbar_expect_tx(&full[i], cell_bytes);
-      bulk_g2s(cellbuf + (size_t)i * CQ * nqp, cell_src + (size_t)P.blk_cells[cs + i] * CQ * nqp, cell_bytes, &full[i]);
+    for (int i = 0; i < ns - 1 && cs + CS * i < ce; ++i) {
+      int cid[CS], nvalid = 0;
+#pragma unroll
+      for (int u = 0; u < CS; ++u) {
+        cid[u] = P.blk_cells[cs + CS * i + u];
+        nvalid += cid[u] >= 0;
+      }
+      mbar_expect_tx(&full[i], nvalid * cell_bytes);
+#pragma unroll
+      for (int u = 0; u < CS; ++u)
+        if (cid[u] >= 0)
+          bulk_g2s(cellbuf + (size_t)(i * CS + u) * CQ * nqp, cell_src + (size_t)cid[u] * CQ * nqp, cell_bytes, &full[i]);
     }
   }
   for (int i = t; i < n1 * NB1; i += NT) {
@@ -955,9 +1004,9 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
     }
   }
   for (int i = t; i < (ce - cs) * NA; i += NT) {
-    const int cell = P.blk_cells[cs + i / NA];
+    const int cell = P.blk_cells[cs + i / NA];  // -1: no partner cell in this step (cell-split mode)
     if (i % NA == 0) s_cells[i / NA] = cell;
-    s_conn[i] = P.conn_pos[(size_t)cell * NA + i % NA];
+    s_conn[i] = cell >= 0 ? P.conn_pos[(size_t)cell * NA + i % NA] : -1;
     s_slots[i] = P.blk_slots[(size_t)cs * NA + i];
   }
   for (int i = t; i < NV2 * acc_vstride(tj); i += NT) acc_s[i] = 0.0;
@@ -981,19 +1030,33 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
   // every warp has released it (empty barrier) - warps are not held in lock step by a CTA barrier per cell.
   int st = 0, st_fill = ns - 1;             // stage of cell `it`, stage of cell `it + ns - 1`
   uint32_t ph_full = 0, ph_empty = 0;       // parity bits, one per stage
-  for (int kc = cs; kc < ce; ++kc) {
-    const int it = kc - cs;
-    if (t == 0 && kc + ns - 1 < ce) {
-      if (it >= 1) {  // the stage was last used by cell it-1
+  const int nsteps = (ce - cs) / CS;  // cell-split mode: the host pads the cell list of a block to whole pairs
+  // Cell-split mode: the two cells of a step share no node, but the thread sets may be one step apart (two ring stages);
+  // where a cell shares a node with the other set's cell of the previous step (flagged by the host, about one step per
+  // block), all warps finish that step first.
+  const unsigned sync_mask = (CS == 2) ? P.blk_sync[blk] : 0u;
+  for (int step = 0; step < nsteps; ++step) {
+    if (CS == 2 && ((sync_mask >> step) & 1u)) __syncthreads();
+    if (t == 0 && step + ns - 1 < nsteps) {
+      if (step >= 1) {  // the stage was last used by step-1
         mbar_wait(&empty[st_fill], (ph_empty >> st_fill) & 1u);
         ph_empty ^= 1u << st_fill;
       }
-      mbar_expect_tx(&full[st_fill], cell_bytes);
-      bulk_g2s(cellbuf + (size_t)st_fill * CQ * nqp, cell_src + (size_t)s_cells[it + ns - 1] * CQ * nqp, cell_bytes,
-               &full[st_fill]);
+      int nvalid = 0;
+#pragma unroll
+      for (int u = 0; u < CS; ++u) nvalid += s_cells[(step + ns - 1) * CS + u] >= 0;
+      mbar_expect_tx(&full[st_fill], nvalid * cell_bytes);
+#pragma unroll
+      for (int u = 0; u < CS; ++u) {
+        const int cid = s_cells[(step + ns - 1) * CS + u];
+        if (cid >= 0)
+          bulk_g2s(cellbuf + (size_t)(st_fill * CS + u) * CQ * nqp, cell_src + (size_t)cid * CQ * nqp, cell_bytes,
+                   &full[st_fill]);
+      }
     }
+    const int it = step * CS + cset;  // this thread's cell of the step
     int slot[NA];
-    bool sing = false;
+    bool sing = (CS == 2) && s_cells[it] < 0;
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
       slot[a] = s_slots[it * NA + (FLIP ? (a ^ part) : a)];
@@ -1001,7 +1064,7 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
     }
     mbar_wait(&full[st], (ph_full >> st) & 1u);
     ph_full ^= 1u << st;
-    const double *cq = cellbuf + (size_t)st * CQ * nqp;
+    const double *cq = cellbuf + (size_t)(st * CS + cset) * CQ * nqp;
     const bool ok = row_ok && !sing;  // singular (node in cell) pairs are integrated by K2 (ref: 2885-2908)
     if (VS == 2) {
       if (vpart == 0) cell_pass<NA, KT, 0, QS, HAS_EPS, FAST, N1C>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
@@ -1010,6 +1073,8 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
       cell_pass<NA, KT, 0, QS, HAS_EPS, FAST, N1C>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
     } else if (LAYER == 2) {
       cell_pass<NA, KT, 1, QS, HAS_EPS, FAST, N1C, true>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
+    } else if (CS == 2) {
+      cell_pass<NA, KT, 2, QS, HAS_EPS, FAST, N1C, false, CS == 2>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
     } else {
       cell_pass<NA, KT, 2, QS, HAS_EPS, FAST, N1C>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
     }
@@ -1132,8 +1197,25 @@ __global__ void __launch_bounds__(TI *QS *VS, CTAS_PER_SM) k_assemble_regular(co
   }
 }
 
-template <int NA, int KT, int LAYER, int QS, int VS>
+template <int NA, int KT, int LAYER, int QS, int VS, int CS = 1>
 static void launch_reg_layer(Context &c, RegParams P, int nrow_tiles, size_t smem, int colour) {
+  if constexpr (CS == 2) {  // cell-split mode exists for the moment formulation only (cell_sets)
+    static_assert(NA == 4 && KT == BS_KERNEL_FREE && LAYER == 0, "cell-split mode: Q1 free-space kernel");
+    BS_REQUIRE(cell_sets(c) == 2 && c.blocks.cs == 2, "cell blocks were not built for the cell-split kernel");
+    BS_REQUIRE(P.tj == TJ_CS2 && P.nq_pad == 64 && P.n1d == 8, "cell-split kernel: compile-time block and rule sizes");
+    auto kern = c.fused ? k_assemble_regular<NA, KT, LAYER, QS, VS, false, true, -8, 2>
+                        : k_assemble_regular<NA, KT, LAYER, QS, VS, false, false, -8, 2>;
+    BS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const std::vector<int> &cs = c.blocks.colour_start;
+    const int nb = cs[colour + 1] - cs[colour];
+    for (int b0 = 0; b0 < nb; b0 += 65535) {  // gridDim.y limit
+      P.blk_begin = cs[colour] + b0;
+      kern<<<dim3(nrow_tiles, std::min(nb - b0, 65535)), TI * QS * VS * CS, smem, c.stream>>>(P);
+      BS_CUDA(cudaGetLastError());
+      count_launch(c);
+    }
+    return;
+  } else {
   // the free-space kernel has a variant with the 1-D rule size fixed at compile time (Gauss 8, the order of the
   // reference's parameter files): fully unrolled, software-pipelined rows
   const bool n8 = (KT == BS_KERNEL_FREE) && c.kp.eps == 0.0 && P.n1d == 8;
@@ -1159,10 +1241,11 @@ static void launch_reg_layer(Context &c, RegParams P, int nrow_tiles, size_t sme
     BS_CUDA(cudaGetLastError());
     count_launch(c);
   }
+  }
 }
 
 // SPLIT: the two layers in two launches per colour (single layer, then double layer)
-template <int NA, int KT, bool SPLIT, int QS, int VS>
+template <int NA, int KT, bool SPLIT, int QS, int VS, int CS = 1>
 static void launch_reg(Context &c, RegParams P, int nrow_tiles, size_t smem) {
   BS_REQUIRE(c.blocks.max_cells <= MAXC, "cell block larger than MAXC");
   const std::vector<int> &cs = c.blocks.colour_start;
@@ -1172,7 +1255,7 @@ static void launch_reg(Context &c, RegParams P, int nrow_tiles, size_t smem) {
       launch_reg_layer<NA, KT, 1, QS, VS>(c, P, nrow_tiles, smem, (int)k);
       launch_reg_layer<NA, KT, 2, QS, VS>(c, P, nrow_tiles, smem, (int)k);
     } else {
-      launch_reg_layer<NA, KT, 0, QS, VS>(c, P, nrow_tiles, smem, (int)k);
+      launch_reg_layer<NA, KT, 0, QS, VS, CS>(c, P, nrow_tiles, smem, (int)k);
     }
   }
 }
@@ -1196,6 +1279,7 @@ void launch_assembly_regular(Context &c) {
   P.blk_slots = c.d_blk_slots.p;
   P.blk_nodes = c.d_blk_nodes.p;
   P.blk_first = c.d_blk_first.p;
+  P.blk_sync = c.d_blk_sync.p;
   P.blk_begin = 0;
   P.V = c.V.p;
   P.K = c.K.p;
@@ -1211,13 +1295,15 @@ void launch_assembly_regular(Context &c) {
   if (nrow_tiles == 0) return;
   
   const int grid = nrow_tiles;
-  const size_t smem = assembly_smem_bytes(c.na, tile_planes(c.na, c.kp.type), c.blocks.tj, c.nq_pad);
+  const size_t smem = assembly_smem_bytes(c.na, tile_planes(c.na, c.kp.type), c.blocks.tj, c.nq_pad, c.blocks.cs);
+  BS_REQUIRE(c.blocks.cs == cell_sets(c), "cell blocks out of date (kernel or quadrature changed after the tables were built)");
   const bool q2 = (c.na == 9);
   switch (c.kp.type) {
     // <NA, kernel, two sequential passes?, threads per row over q, thread sets over {V,K}>
     case BS_KERNEL_FREE:
       if (q2) launch_reg<9, BS_KERNEL_FREE, false, 1, 2>(c, P, grid, smem);      // 256 threads
-      else launch_reg<4, BS_KERNEL_FREE, false, 2, 1>(c, P, grid, smem);         // 256 threads (V/K thread split measured slower)
+      else if (c.blocks.cs == 2) launch_reg<4, BS_KERNEL_FREE, false, 1, 1, 2>(c, P, grid, smem);  // cell-split pairs
+      else launch_reg<4, BS_KERNEL_FREE, false, 2, 1>(c, P, grid, smem);         // 128 threads (V/K thread split measured slower)
       break;
     case BS_KERNEL_FREE_SURFACE:
       if (q2) launch_reg<9, BS_KERNEL_FREE_SURFACE, false, 1, 2>(c, P, grid, smem);

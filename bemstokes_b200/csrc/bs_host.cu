@@ -4,6 +4,7 @@
 #include "bs_internal.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <numeric>
 
 namespace bs {
@@ -283,8 +284,9 @@ static void compute_support(Context &c) {
   for (int i = 0; i < N; ++i) BS_REQUIRE(seen[i], "node without a cell");
 }
 
-void build_geometry(Context &c) {
-  const int N = c.N, na = c.na;
+// Support points, their Morton order and the row partition: host only (no device call)
+void compute_node_order(Context &c) {
+  const int N = c.N;
   compute_support(c);
 
   // Morton order of the support points -> spatially compact column blocks and row partitions
@@ -330,6 +332,11 @@ void build_geometry(Context &c) {
   c.p0 = c.part_start[c.rank];
   c.p1 = c.part_start[c.rank + 1];
   c.rows_loc = (size_t)3 * (c.p1 - c.p0);
+}
+
+void build_geometry(Context &c) {
+  const int N = c.N, na = c.na;
+  compute_node_order(c);
 
   // upload
   std::vector<double> sup_int((size_t)3 * N);
@@ -375,44 +382,113 @@ void build_geometry(Context &c) {
 // ---------------------------------------------------------------------------------------------------------
 // tables depending on quadrature: regular shape tables, column blocks, singular rule tables
 // ---------------------------------------------------------------------------------------------------------
-void build_tables(Context &c) {
-  BS_REQUIRE(c.have_geometry && c.have_quadrature, "geometry and quadrature must be set first");
-  const int na = c.na, nam = c.na_map, nq = c.reg.size();
-  c.nq = nq;
-  c.nq_pad = (nq + 1) & ~1;  // keep every 7*nq_pad*8-byte cell record a multiple of 16 B for bulk copies
-  std::vector<double> phi((size_t)nq * na), tab((size_t)nq * nam * 3);
-  std::vector<double> ph(MAX_NA), dph(2 * MAX_NA);
-  for (int q = 0; q < nq; ++q) {
-    shape_eval(c.fe_degree, c.reg.xi[2 * q], c.reg.xi[2 * q + 1], ph.data(), nullptr);
-    for (int a = 0; a < na; ++a) phi[(size_t)q * na + a] = ph[a];
-    shape_eval(c.map_degree, c.reg.xi[2 * q], c.reg.xi[2 * q + 1], ph.data(), dph.data());
-    for (int a = 0; a < nam; ++a) {
-      tab[((size_t)q * nam + a) * 3 + 0] = ph[a];
-      tab[((size_t)q * nam + a) * 3 + 1] = dph[2 * a];
-      tab[((size_t)q * nam + a) * 3 + 2] = dph[2 * a + 1];
+// Cell-split mode of K1: order the cells of a block as a sequence of pairs that share no node (the two thread sets of a CTA
+// update their cells' tile entries concurrently), -1 where a cell has no partner.  Matching on the "shares no node" graph
+// of the block: greedy start, then augmentation over pair swaps (blocks have <= 16 cells).  The thread sets may be one
+// step apart, so a cell must not share a node with the other set's cell of the previous step either; the pairs are
+// ordered (and oriented) to make that rare, and the steps where it cannot be avoided are flagged in `sync` (bit = step).
+static std::vector<int> match_cells(const std::vector<int> &cells, const std::vector<int> &cpos, int na) {
+  const int n = (int)cells.size();
+  auto compatible = [&](int x, int y) {
+    for (int a = 0; a < na; ++a)
+      for (int b = 0; b < na; ++b)
+        if (cpos[(size_t)cells[x] * na + a] == cpos[(size_t)cells[y] * na + b]) return false;
+    return true;
+  };
+  std::vector<std::vector<char>> ok(n, std::vector<char>(n, 0));
+  for (int x = 0; x < n; ++x)
+    for (int y = x + 1; y < n; ++y) ok[x][y] = ok[y][x] = compatible(x, y) ? 1 : 0;
+  std::vector<int> mate(n, -1);
+  for (int x = 0; x < n; ++x) {  // greedy start: the compatible free cell with the fewest compatible alternatives
+    if (mate[x] >= 0) continue;
+    int best = -1, best_deg = 1 << 30;
+    for (int y = 0; y < n; ++y) {
+      if (y == x || mate[y] >= 0 || !ok[x][y]) continue;
+      int deg = 0;
+      for (int z = 0; z < n; ++z) deg += (z != x && mate[z] < 0 && ok[y][z]);
+      if (deg < best_deg) best = y, best_deg = deg;
+    }
+    if (best >= 0) mate[x] = best, mate[best] = x;
+  }
+  // improve: two free cells x, y and a matched pair (u, v) with x-u and y-v compatible -> two pairs instead of one
+  for (bool changed = true; changed;) {
+    changed = false;
+    for (int x = 0; x < n && !changed; ++x) {
+      if (mate[x] >= 0) continue;
+      for (int y = x + 1; y < n && !changed; ++y) {
+        if (mate[y] >= 0) continue;
+        for (int u = 0; u < n && !changed; ++u) {
+          const int v = mate[u];
+          if (v < 0) continue;
+          if (ok[x][u] && ok[y][v]) {
+            mate[x] = u, mate[u] = x, mate[y] = v, mate[v] = y;
+            changed = true;
+          }
+        }
+      }
     }
   }
-  c.d_phi_reg.upload(phi, c.stream);
-  c.d_map_tab_reg.upload(tab, c.stream);
-  {  // 1-D factors of the tensor-product shape functions: phi_a(q) = l_ix(a)(x_qx) * l_iy(a)(x_qy)
-    const int n1 = (int)c.x1d.size(), nb1 = c.fe_degree + 1;
-    std::vector<double> l1((size_t)n1 * nb1);
-    for (int i = 0; i < n1; ++i) {
-      double l[3], d[3];
-      lagrange_1d(c.fe_degree, c.x1d[i], l, d);
-      for (int b = 0; b < nb1; ++b) l1[(size_t)i * nb1 + b] = l[b];
-    }
-    c.d_l1d.upload(l1, c.stream);
-  }
+  return mate;
+}
 
+static std::vector<int> pair_cells(const std::vector<int> &cells, const std::vector<int> &cpos, int na, int &unpaired,
+                                   unsigned &sync) {
+  const int n = (int)cells.size();
+  auto compatible = [&](int x, int y) {
+    if (x < 0 || y < 0) return true;
+    for (int a = 0; a < na; ++a)
+      for (int b = 0; b < na; ++b)
+        if (cpos[(size_t)cells[x] * na + a] == cpos[(size_t)cells[y] * na + b]) return false;
+    return true;
+  };
+  const std::vector<int> mate = match_cells(cells, cpos, na);
+  std::vector<std::pair<int, int>> pairs;  // local indices, second = -1: no partner
+  for (int x = 0; x < n; ++x) {
+    if (mate[x] >= 0 && mate[x] < x) continue;
+    pairs.emplace_back(x, mate[x]);
+    if (mate[x] < 0) ++unpaired;
+  }
+  // order: next = a remaining pair (either orientation) without a cross conflict with the previous step, if there is one
+  std::vector<int> out;
+  std::vector<char> used(pairs.size(), 0);
+  int pa = -1, pb = -1;
+  sync = 0;
+  for (size_t step = 0; step < pairs.size(); ++step) {
+    int pick = -1;
+    bool swap = false, clean = false;
+    for (size_t k = 0; k < pairs.size() && !clean; ++k) {
+      if (used[k]) continue;
+      for (int o = 0; o < 2 && !clean; ++o) {
+        const int a = o ? pairs[k].second : pairs[k].first, b = o ? pairs[k].first : pairs[k].second;
+        if (a < 0) continue;  // the first set always has a cell
+        const bool good = compatible(a, pb) && compatible(b, pa);
+        if (pick < 0 || good) pick = (int)k, swap = (o == 1), clean = good;
+      }
+    }
+    used[pick] = 1;
+    const int a = swap ? pairs[pick].second : pairs[pick].first, b = swap ? pairs[pick].first : pairs[pick].second;
+    if (!clean && step > 0) sync |= 1u << step;
+    out.push_back(cells[a]);
+    out.push_back(b >= 0 ? cells[b] : -1);
+    pa = a;
+    pb = b;
+  }
+  return out;
+}
+
+// Cell blocks of K1 (host only, no device call)
+void build_cell_blocks(Context &c) {
   // ---- cell blocks --------------------------------------------------------------------------------------
   // Disjoint, spatially compact clusters of cells touching at most tj distinct nodes each: every (row node,
   // cell) pair is integrated exactly once.  Blocks that share a node get different colours; colours are
   // launched one after another, so the partial tiles of a shared node column are combined in a fixed order
   // (first colour stores, later colours read-modify-write) without atomics.
   ColumnBlocks &B = c.blocks;
-  B.tj = choose_tj(na, c.kp.type, c.nq_pad);
+  const int na = c.na;
+  B.cs = cell_sets(c);
+  B.tj = choose_tj(na, c.kp.type, c.nq_pad, B.cs);
   const int tj = B.tj;
+  const int max_block_cells = (B.cs == 2) ? 16 : 32;  // padded to pairs, a block still has at most 32 cell slots
   BS_REQUIRE(tj >= na, "shared memory too small for one cell per block");
   std::vector<int> cpos((size_t)c.ncell * na);
   for (size_t k = 0; k < cpos.size(); ++k) cpos[k] = c.pos_of_node[c.conn[k]];
@@ -441,55 +517,142 @@ void build_tables(Context &c) {
       for (int d = 0; d < 3; ++d) ccen[(size_t)3 * cell + d] += c.support[(size_t)3 * c.conn[(size_t)cell * na + a] + d] / na;
   std::vector<int> block_of(c.ncell, -1);
   std::vector<std::vector<int>> bcells, bnodes;
-  std::vector<int> mark(c.N, -1);  // mark[node] == current block id when the node is in the block
-  for (int seed : corder) {
-    if (block_of[seed] >= 0) continue;
-    const int b = (int)bcells.size();
-    bcells.emplace_back();
-    bnodes.emplace_back();
-    double bsum[3] = {0, 0, 0};  // sum of the centroids of the block's cells
+  std::vector<int> mark(c.N, -1);  // mark[node] == stamp of the growth in progress when the node is in it
+  int stamp = 0;
+  // Growth from a seed: repeatedly the unassigned neighbour cell adding the fewest new nodes.  Ties, strategy 0: closest
+  // to the block's centre (3 x 3 patches), then lowest key.  Strategies 1-4 (cell-split mode, where a block should be a
+  // 2 x 4 strip so that its cells pair up): closest to a line along one of the seed's two local axes through the
+  // middle of one of its edges (the strip's two rows lie on either side of that line), then closest to the seed along it.
+  auto grow = [&](int seed, int strategy, std::vector<int> &cells, std::vector<int> &nodes) {
+    ++stamp;
+    cells.clear();
+    nodes.clear();
+    double bsum[3] = {0, 0, 0}, org[3] = {0, 0, 0}, ax[3] = {0, 0, 0}, pe[3] = {0, 0, 0}, wu = 1.0, wv = 1.0;
+    if (strategy > 0) {
+      const int *sn = &c.conn[(size_t)seed * na];
+      const int axis = (strategy - 1) >> 1, side = (strategy - 1) & 1;  // axis 0: local nodes 0->1, axis 1: 0->2
+      const int e0 = 0, e1 = axis == 0 ? 1 : 2, f0 = axis == 0 ? 2 : 1, f1 = 3;  // edge (e0,e1) and the opposite edge (f0,f1)
+      const int m0 = side ? f0 : e0, m1 = side ? f1 : e1;
+      double an = 0, pd = 0;
+      for (int d = 0; d < 3; ++d) {
+        const double *X = c.support.data();
+        org[d] = 0.5 * (X[(size_t)3 * sn[m0] + d] + X[(size_t)3 * sn[m1] + d]);
+        ax[d] = X[(size_t)3 * sn[e1] + d] - X[(size_t)3 * sn[e0] + d];
+        pe[d] = X[(size_t)3 * sn[f0] + d] - X[(size_t)3 * sn[e0] + d];
+        an += ax[d] * ax[d];
+      }
+      an = std::sqrt(std::max(an, 1e-300));
+      for (int d = 0; d < 3; ++d) ax[d] /= an, pd += pe[d] * ax[d];
+      double pn = 0;
+      for (int d = 0; d < 3; ++d) pe[d] -= pd * ax[d], pn += pe[d] * pe[d];
+      pn = std::sqrt(std::max(pn, 1e-300));
+      for (int d = 0; d < 3; ++d) pe[d] /= pn;
+      wu = an;  // cell size along and across the strip: distances are compared in whole cells
+      wv = pn;
+    }
     auto add_cell = [&](int cell) {
-      block_of[cell] = b;
-      bcells[b].push_back(cell);
+      cells.push_back(cell);
       for (int d = 0; d < 3; ++d) bsum[d] += ccen[(size_t)3 * cell + d];
       for (int a = 0; a < na; ++a) {
         const int p = cpos[(size_t)cell * na + a];
-        if (mark[p] != b) {
-          mark[p] = b;
-          bnodes[b].push_back(p);
+        if (mark[p] != stamp) {
+          mark[p] = stamp;
+          nodes.push_back(p);
         }
       }
     };
     add_cell(seed);
     while (true) {
-      // candidate = unassigned neighbour cell adding the fewest new nodes (ties: closest to the block centre, lowest key)
       int best = -1, best_new = 1 << 30, best_key = 1 << 30;
-      double best_d2 = 1e300;
-      const double inv = 1.0 / (double)bcells[b].size();
-      for (size_t in = 0; in < bnodes[b].size(); ++in) {
-        const int p = bnodes[b][in];
+      double best_d1 = 1e300, best_d2 = 1e300;
+      const double inv = 1.0 / (double)cells.size();
+      for (size_t in = 0; in < nodes.size(); ++in) {
+        const int p = nodes[in];
         for (int e = nptr[p]; e < nptr[p + 1]; ++e) {
           const int cell = ncells[e];
-          if (block_of[cell] >= 0) continue;
+          if (block_of[cell] >= 0 || std::find(cells.begin(), cells.end(), cell) != cells.end()) continue;
           int nn = 0;
-          for (int a = 0; a < na; ++a) nn += (mark[cpos[(size_t)cell * na + a]] != b);
-          double d2 = 0;
-          for (int d = 0; d < 3; ++d) {
-            const double t = ccen[(size_t)3 * cell + d] - bsum[d] * inv;
-            d2 += t * t;
+          for (int a = 0; a < na; ++a) nn += (mark[cpos[(size_t)cell * na + a]] != stamp);
+          double d1 = 0, d2 = 0;  // primary and secondary tie-break distances
+          if (strategy == 0) {
+            for (int d = 0; d < 3; ++d) {
+              const double t = ccen[(size_t)3 * cell + d] - bsum[d] * inv;
+              d1 += t * t;
+            }
+          } else {
+            double u = 0, v = 0;
+            for (int d = 0; d < 3; ++d) {
+              const double t = ccen[(size_t)3 * cell + d] - org[d];
+              u += t * ax[d];
+              v += t * pe[d];
+            }
+            d1 = std::floor(std::fabs(v) / wv);        // 0: one of the two rows next to the line
+            d2 = std::floor(std::fabs(u) / wu + 0.5);  // column distance from the seed
           }
-          const bool closer = d2 < best_d2 * (1.0 - 1e-9), same = !closer && d2 <= best_d2 * (1.0 + 1e-9);
-          if (nn < best_new || (nn == best_new && (closer || (same && ckey[cell] < best_key)))) {
+          const bool closer = d1 < best_d1 * (1.0 - 1e-6), same = !closer && d1 <= best_d1 * (1.0 + 1e-6);
+          const bool closer2 = same && d2 < best_d2 * (1.0 - 1e-6), same2 = same && !closer2 && d2 <= best_d2 * (1.0 + 1e-6);
+          if (nn < best_new || (nn == best_new && (closer || closer2 || (same2 && ckey[cell] < best_key)))) {
             best = cell;
             best_new = nn;
             best_key = ckey[cell];
+            best_d1 = d1;
             best_d2 = d2;
           }
         }
       }
-      if (best < 0 || (int)bnodes[b].size() + best_new > tj || (int)bcells[b].size() >= 32) break;
+      if (best < 0 || (int)nodes.size() + best_new > tj || (int)cells.size() >= max_block_cells) break;
       add_cell(best);
     }
+  };
+  const int nstrategies = (B.cs == 2 && !std::getenv("BS_GROW_COMPACT")) ? 5 : 1;
+  std::vector<int> tcells, tnodes, gcells, gnodes;
+  // Seeds: cell-split mode continues next to the blocks already made (advancing front, first in first out), so that
+  // the strips of a structured region line up end to end instead of leaving gaps shorter than a strip; otherwise, and
+  // whenever the front is empty, the next unassigned cell of the Morton order.
+  std::vector<int> front;
+  size_t front_head = 0, next_morton = 0;
+  std::vector<char> queued(c.ncell, 0);
+  const bool use_front = nstrategies > 1 && !std::getenv("BS_NO_FRONT");
+  while (true) {
+    int seed = -1;
+    while (use_front && front_head < front.size()) {
+      const int cand = front[front_head++];
+      if (block_of[cand] < 0) {
+        seed = cand;
+        break;
+      }
+    }
+    if (seed < 0) {
+      while (next_morton < corder.size() && block_of[corder[next_morton]] >= 0) ++next_morton;
+      if (next_morton == corder.size()) break;
+      seed = corder[next_morton];
+    }
+    // cell-split mode: the growth whose cells pair up best (fewest steps per cell), then the larger one
+    double best_score = 1e300;
+    for (int st = 0; st < nstrategies; ++st) {
+      grow(seed, st, tcells, tnodes);
+      double score = 0.0;
+      if (nstrategies > 1) {
+        const std::vector<int> mate = match_cells(tcells, cpos, na);
+        int single = 0;
+        for (int m : mate) single += (m < 0);
+        const double steps = 0.5 * (double)(tcells.size() + single);
+        // cost model per cell: a step (two cells' rule rows), a touched node column (write-out, fused product) and
+        // the fixed cost of a CTA (prologue, barriers), in the proportions of the measured profile
+        score = (0.16 * steps + 0.0094 * (double)tnodes.size() + 0.2) / (double)tcells.size() + 1e-6 * st;
+      }
+      if (score < best_score) best_score = score, gcells = tcells, gnodes = tnodes;
+    }
+    const int b = (int)bcells.size();
+    bcells.push_back(gcells);
+    bnodes.push_back(gnodes);
+    for (int cell : gcells) block_of[cell] = b;
+    if (use_front)
+      for (int p : gnodes)
+        for (int e = nptr[p]; e < nptr[p + 1]; ++e) {
+          const int cell = ncells[e];
+          if (block_of[cell] < 0 && !queued[cell]) queued[cell] = 1, front.push_back(cell);
+        }
   }
   B.nblocks = (int)bcells.size();
   // greedy colouring of the block conflict graph (blocks sharing a node)
@@ -524,6 +687,9 @@ void build_tables(Context &c) {
   B.nodes.assign((size_t)B.nblocks * tj, -1);
   B.first.assign((size_t)B.nblocks * tj, 0);
   B.max_cells = 0;
+  B.unpaired = 0;
+  B.sync.assign(B.nblocks, 0u);
+  B.sync_steps = B.steps = 0;
   long long touched = 0;
   for (int nb = 0; nb < B.nblocks; ++nb) {
     const int b = border[nb];
@@ -537,23 +703,73 @@ void build_tables(Context &c) {
       for (int ob : blocks_of_node[p]) minc = std::min(minc, colour[ob]);
       B.first[(size_t)nb * tj + sidx] = (minc == colour[b]) ? 1 : 0;
     }
-    for (int cell : bcells[b]) {
+    std::vector<int> order = bcells[b];
+    if (B.cs == 2) {
+      unsigned sync = 0;
+      order = pair_cells(bcells[b], cpos, na, B.unpaired, sync);
+      B.sync[nb] = sync;
+      B.steps += (long long)order.size() / 2;
+      for (unsigned m = sync; m; m &= m - 1) ++B.sync_steps;
+    }
+    for (int cell : order) {
       B.cells.push_back(cell);
       for (int a = 0; a < na; ++a) {
+        if (cell < 0) {  // no partner in this step
+          B.slots.push_back(0);
+          continue;
+        }
         const int p = cpos[(size_t)cell * na + a];
         const int sidx = (int)(std::lower_bound(nodes.begin(), nodes.end(), p) - nodes.begin());
         B.slots.push_back((signed char)sidx);
       }
     }
     B.cell_ptr.push_back((int)B.cells.size());
-    B.max_cells = std::max(B.max_cells, (int)bcells[b].size());
+    B.max_cells = std::max(B.max_cells, (int)order.size());
   }
   B.node_touch_ratio = (double)touched / std::max(1, c.N);
+}
+
+void build_tables(Context &c) {
+  BS_REQUIRE(c.have_geometry && c.have_quadrature, "geometry and quadrature must be set first");
+  const int na = c.na, nam = c.na_map, nq = c.reg.size();
+  c.nq = nq;
+  c.nq_pad = (nq + 1) & ~1;  // keep every 7*nq_pad*8-byte cell record a multiple of 16 B for bulk copies
+  std::vector<double> phi((size_t)nq * na), tab((size_t)nq * nam * 3);
+  std::vector<double> ph(MAX_NA), dph(2 * MAX_NA);
+  for (int q = 0; q < nq; ++q) {
+    shape_eval(c.fe_degree, c.reg.xi[2 * q], c.reg.xi[2 * q + 1], ph.data(), nullptr);
+    for (int a = 0; a < na; ++a) phi[(size_t)q * na + a] = ph[a];
+    shape_eval(c.map_degree, c.reg.xi[2 * q], c.reg.xi[2 * q + 1], ph.data(), dph.data());
+    for (int a = 0; a < nam; ++a) {
+      tab[((size_t)q * nam + a) * 3 + 0] = ph[a];
+      tab[((size_t)q * nam + a) * 3 + 1] = dph[2 * a];
+      tab[((size_t)q * nam + a) * 3 + 2] = dph[2 * a + 1];
+    }
+  }
+  c.d_phi_reg.upload(phi, c.stream);
+  c.d_map_tab_reg.upload(tab, c.stream);
+  {  // 1-D factors of the tensor-product shape functions: phi_a(q) = l_ix(a)(x_qx) * l_iy(a)(x_qy)
+    const int n1 = (int)c.x1d.size(), nb1 = c.fe_degree + 1;
+    std::vector<double> l1((size_t)n1 * nb1);
+    for (int i = 0; i < n1; ++i) {
+      double l[3], d[3];
+      lagrange_1d(c.fe_degree, c.x1d[i], l, d);
+      for (int b = 0; b < nb1; ++b) l1[(size_t)i * nb1 + b] = l[b];
+    }
+    c.d_l1d.upload(l1, c.stream);
+  }
+
+  build_cell_blocks(c);
+  ColumnBlocks &B = c.blocks;
   c.d_blk_cell_ptr.upload(B.cell_ptr, c.stream);
   c.d_blk_cells.upload(B.cells, c.stream);
   c.d_blk_slots.upload(B.slots, c.stream);
   c.d_blk_nodes.upload(B.nodes, c.stream);
   c.d_blk_first.upload(B.first, c.stream);
+  c.d_blk_sync.upload(B.sync, c.stream);
+  if (std::getenv("BS_TRACE"))
+    fprintf(stderr, "[bs] cell blocks: %d blocks, tj %d, cell sets %d, %lld steps (%d cells without partner, %lld steps behind a barrier), touch ratio %.3f\n",
+            B.nblocks, B.tj, B.cs, B.steps, B.unpaired, B.sync_steps, B.node_touch_ratio);
 
   // singular rule tables: per rule, per point: phi[na], then (phi_map, dphi_x, dphi_y)[na_map], then weight
   if (c.have_singular) {

@@ -148,6 +148,12 @@ struct ColumnBlocks {
   std::vector<unsigned char> first; // [nblocks][tj] 1 = this block's colour is the first to touch the node column
   std::vector<int> colour_start;    // [ncolours+1] block ranges per colour (blocks are sorted by colour)
   int max_cells = 0;
+  int cs = 1;                       // cell sets: with cs == 2 the cell list of a block is a sequence of pairs of cells that
+                                    // share no node (-1 = no partner), integrated concurrently by the two thread sets of K1
+  int unpaired = 0;                 // cells without a partner (cs == 2)
+  std::vector<unsigned> sync;       // [nblocks] cs == 2: bit s set = a cell of step s shares a node with the other set's cell
+                                    // of step s-1 (the thread sets may be one step apart): CTA barrier before step s
+  long long sync_steps = 0, steps = 0;
   double node_touch_ratio = 0;      // sum over blocks of touched nodes / N  (tile traffic amplification)
 };
 
@@ -198,6 +204,7 @@ struct Context {
   DBuf<signed char> d_blk_slots;
   DBuf<int> d_blk_nodes;
   DBuf<unsigned char> d_blk_first;
+  DBuf<unsigned> d_blk_sync;
   // singular pass tables
   DBuf<int> d_patch_ptr, d_patch_cell, d_patch_local;   // per internal position (CSR)
   DBuf<double> d_sing_tab;          // concatenated per rule: [nqs][ (na + 3*na_map + 1) ]
@@ -318,6 +325,8 @@ void host_prepass(int fe_degree, int map_degree, int n_map_nodes, const double *
 // same quantities on the device from the context's geometry (bs_prepass.cu); results in internal ordering
 void device_prepass(Context &c, int pole_kind, const double pole_in[3], double *d_nhat, double *d_Mnhat, double *d_Nr,
                     double *d_Nrd, double *h_l2, double *h_area, double *h_center_of_mass, double *h_pole_used, int *cg_iterations);
+void compute_node_order(Context &c);    // host part of build_geometry: support points, Morton order, row partition
+void build_cell_blocks(Context &c);     // host part of build_tables: cell blocks of K1 (colours, pairs)
 void build_geometry(Context &c);
 void update_coordinates(Context &c);    // same mesh, new map_nodes
 void build_tables(Context &c);          // after geometry + quadrature known
@@ -327,8 +336,9 @@ void launch_assembly_regular(Context &c);
 void launch_assembly_singular(Context &c);
 constexpr int MAX_PANEL = 12;
 int tile_planes(int na, int kernel_type);
-size_t assembly_smem_bytes(int na, int planes, int tj, int nq_pad);
-int choose_tj(int na, int kernel_type, int nq_pad);
+size_t assembly_smem_bytes(int na, int planes, int tj, int nq_pad, int cs = 1);
+int choose_tj(int na, int kernel_type, int nq_pad, int cs = 1);
+int cell_sets(const Context &c);        // 2: K1 runs two thread sets on different cells of a block (see ColumnBlocks::cs)
 void kernel_eval_device(int type, double eps, int o, int npts, const double *d_p, const double *d_pim, double *d_G,
                         double *d_W, cudaStream_t s);
 // ---- linear algebra (bs_linalg.cu) ------------------------------------------------------------------------
