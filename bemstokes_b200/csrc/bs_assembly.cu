@@ -173,7 +173,8 @@ struct RegParams {
   size_t ldk;
 };
 
-constexpr int TJ_CS2 = 15;      // nodes per cell block in the cell-split mode of K1 (see cell_sets)
+// nodes per cell block in the cell-split mode of K1 (see cell_sets)
+__host__ __device__ constexpr int tj_cell_split(int kernel_type) { return kernel_type == BS_KERNEL_FREE ? 15 : 20; }
 constexpr int ACC_LD = TI + 1;  // padded row-node stride of the shared accumulators (bank-conflict free both ways)
 // stride between consecutive values of the shared tile [value][slot][row]; the +5 spreads the three values a
 // write-out lane group reads for one node over different banks
@@ -194,13 +195,14 @@ int tile_planes(int na, int kernel_type) {
   return (na == 4 && kernel_type != BS_KERNEL_FREE) ? nv : 2 * nv;
 }
 
-// Cell-split mode (cs == 2; Q1 free-space kernel on bilinear cells, Gauss 8): one thread per collocation node integrates
+// Cell-split mode (cs == 2; Q1 unknowns, Gauss 8, no regularisation): one thread per collocation node integrates
 // a whole cell (all rows of the rule, all four shape functions) and the CTA's two thread sets work on two cells of the
 // block that share no node, so nothing is exchanged between threads and the per-cell tile update is paid once per
 // 8 rule rows instead of once per 4.  A ring stage then holds a pair of cell records.
 int cell_sets(const Context &c) {
-  const bool lin8 = c.na == 4 && c.na_map == 4 && c.kp.type == BS_KERNEL_FREE && c.kp.eps == 0.0 && c.x1d.size() == 8;
-  return (lin8 && !std::getenv("BS_NO_LINROWS") && !std::getenv("BS_NO_CELLSPLIT")) ? 2 : 1;
+  if (c.na != 4 || c.kp.eps != 0.0 || c.x1d.size() != 8 || std::getenv("BS_NO_CELLSPLIT")) return 1;
+  if (c.kp.type == BS_KERNEL_NO_SLIP) return 2;                    // per-point Green evaluation, any mapping
+  return (c.na_map == 4 && !std::getenv("BS_NO_LINROWS")) ? 2 : 1;  // free space / free surface: moment formulation
 }
 __host__ __device__ inline int ring_stages(int nq_pad, int cs) { return cs == 2 ? 2 : cell_stages(nq_pad); }
 
@@ -214,9 +216,11 @@ size_t assembly_smem_bytes(int na, int planes, int tj, int nq_pad, int cs) {
 int choose_tj(int na, int kernel_type, int nq_pad, int cs) {
   const int planes = tile_planes(na, kernel_type);
   const size_t budget = (227 * 1024) / CTAS_PER_SM - 1024 - 1024;  // minus static arrays (768 B) / per-CTA reserve
-  if (cs == 2) {  // cell-split blocks are 2 x 4 patches (15 nodes); the block size is a compile-time constant of that kernel
-    BS_REQUIRE(assembly_smem_bytes(na, planes, TJ_CS2, nq_pad, cs) <= budget, "cell-split tile does not fit (BS_TI / BS_CTAS_PER_SM changed?)");
-    return TJ_CS2;
+  if (cs == 2) {  // cell-split blocks: 2 x 4 cells (15 nodes) with the 12-plane tile of the free-space kernel, 3 x 4 cells
+                  // (20 nodes) with the 9-plane tiles of the image kernels; compile-time constants of those kernels
+    const int t = tj_cell_split(kernel_type);
+    BS_REQUIRE(assembly_smem_bytes(na, planes, t, nq_pad, cs) <= budget, "cell-split tile does not fit (BS_TI / BS_CTAS_PER_SM changed?)");
+    return t;
   }
   int tj = 2;
   for (int t = 2; t <= 32; t += 2)
@@ -646,7 +650,7 @@ __device__ __forceinline__ void integrate_free_surface(const double *__restrict_
       for (int j = 0; j < 3; ++j) {
         double v = fma(sg, acc[a][6 + vidx<6>(i, j)], acc[a][vidx<6>(i, j)]);
         if (MODE == 0 && i == j) v += fma(sg, accI[a][1], accI[a][0]);
-        out[a][3 * i + j] = v;
+        out[a][3 * i + j] += v;  // the caller's accumulators (zero, or the tile values in the cell-split mode)
       }
     }
 }
@@ -778,7 +782,7 @@ __device__ __forceinline__ void integrate_free_surface_lin(const double *__restr
       for (int j = 0; j < 3; ++j) {
         double v = fma(sg, acc[a][6 + vidx<6>(i, j)], acc[a][vidx<6>(i, j)]);
         if (MODE == 0 && i == j) v += fma(sg, accI[a][1], accI[a][0]);
-        out[a][3 * i + j] = v;
+        out[a][3 * i + j] += v;  // the caller's accumulators (zero, or the tile values in the cell-split mode)
       }
     }
 }
@@ -799,29 +803,27 @@ __device__ __forceinline__ void cell_pass(const double *__restrict__ cq, const d
   constexpr int NACC = (MODE == 2) ? 2 * NV : NV;
   constexpr int VOFF = (MODE == 1 && !KLOW) ? NV : 0;  // KLOW: double-layer-only launch, K lives in planes 0..NV-1
   double acc[NA][NACC];
-  if constexpr (TILE_ACC) {
-    static_assert(FAST && QS == 1 && NA == 4 && N1C == -8 && KT == BS_KERNEL_FREE, "tile accumulators: cell-split fast path");
+  double *dst[NA];
+  // the free-surface integrators keep their own partial sums and combine them into acc at the end: preloading acc would
+  // only lengthen its live range there, so that kernel adds to the tile after the cell
+  constexpr bool PRELOAD = TILE_ACC && KT != BS_KERNEL_FREE_SURFACE;
+  if constexpr (PRELOAD) {
+    static_assert(QS == 1, "tile accumulators: one thread per node and cell");
     if (ok) {
       const int vs = acc_vstride(tj);
-      double *dst[NA];
 #pragma unroll
       for (int a = 0; a < NA; ++a) {
         dst[a] = acc_s + (size_t)VOFF * vs + (size_t)slot[a] * ACC_LD + rl;
 #pragma unroll
         for (int v = 0; v < NACC; ++v) acc[a][v] = dst[a][(size_t)v * vs];
       }
-      integrate_free_lin<MODE, QS, NACC>(cq, l1d_s + 32, l1d_s, x, part, acc);
-#pragma unroll
-      for (int a = 0; a < NA; ++a)
-#pragma unroll
-        for (int v = 0; v < NACC; ++v) dst[a][(size_t)v * vs] = acc[a][v];
     }
-    return;
+  } else {
+#pragma unroll
+    for (int a = 0; a < NA; ++a)
+#pragma unroll
+      for (int v = 0; v < NACC; ++v) acc[a][v] = 0.0;
   }
-#pragma unroll
-  for (int a = 0; a < NA; ++a)
-#pragma unroll
-    for (int v = 0; v < NACC; ++v) acc[a][v] = 0.0;
   constexpr bool FLIP = FAST && QS == 2 && NA == 4;
   if (FAST) {
     const double *lx_s = FLIP ? l1d_s + part * (n1 * NB1) : l1d_s;  // odd partner: x-flipped copy of the table
@@ -884,6 +886,21 @@ __device__ __forceinline__ void cell_pass(const double *__restrict__ cq, const d
     }
   }
   }
+  if constexpr (TILE_ACC) {
+    if (ok) {
+      const int vs = acc_vstride(tj);
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        if constexpr (!PRELOAD) dst[a] = acc_s + (size_t)VOFF * vs + (size_t)slot[a] * ACC_LD + rl;
+#pragma unroll
+        for (int v = 0; v < NACC; ++v) {
+          if constexpr (PRELOAD) dst[a][(size_t)v * vs] = acc[a][v];
+          else dst[a][(size_t)v * vs] += acc[a][v];
+        }
+      }
+    }
+    return;
+  }
   if (FLIP) {
     // slots 1 and 3 hold the partner's shape functions (0^1, 2^1 in its numbering): send them, finalise 0 and 2
     const int vs = acc_vstride(tj);
@@ -935,7 +952,7 @@ __global__ void __launch_bounds__(TI *QS *VS *CS, CTAS_PER_SM) k_assemble_regula
   constexpr int NB1 = (NA == 4) ? 2 : 3;
   constexpr int NT = TI * QS * VS * CS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int tj = (CS == 2) ? TJ_CS2 : P.tj, nqp = (CS == 2) ? 64 : P.nq_pad, n1 = (CS == 2) ? 8 : P.n1d;
+  const int tj = (CS == 2) ? tj_cell_split(KT) : P.tj, nqp = (CS == 2) ? 64 : P.nq_pad, n1 = (CS == 2) ? 8 : P.n1d;
   const int ns = ring_stages(nqp, CS);
   double *cellbuf = reinterpret_cast<double *>(smem_raw);                   // [ns][CS][7][nqp] or [ns][CS][nqp][8]
   const size_t ring_doubles = max((size_t)ns * CS * 8 * nqp, (size_t)3 * tj * MAX_PANEL);
@@ -1070,13 +1087,11 @@ __global__ void __launch_bounds__(TI *QS *VS *CS, CTAS_PER_SM) k_assemble_regula
       if (vpart == 0) cell_pass<NA, KT, 0, QS, HAS_EPS, FAST, N1C>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
       else cell_pass<NA, KT, 1, QS, HAS_EPS, FAST, N1C>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
     } else if (LAYER == 1) {
-      cell_pass<NA, KT, 0, QS, HAS_EPS, FAST, N1C>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
+      cell_pass<NA, KT, 0, QS, HAS_EPS, FAST, N1C, false, CS == 2>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
     } else if (LAYER == 2) {
-      cell_pass<NA, KT, 1, QS, HAS_EPS, FAST, N1C, true>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
-    } else if (CS == 2) {
-      cell_pass<NA, KT, 2, QS, HAS_EPS, FAST, N1C, false, CS == 2>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
+      cell_pass<NA, KT, 1, QS, HAS_EPS, FAST, N1C, true, CS == 2>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
     } else {
-      cell_pass<NA, KT, 2, QS, HAS_EPS, FAST, N1C>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
+      cell_pass<NA, KT, 2, QS, HAS_EPS, FAST, N1C, false, CS == 2>(cq, l1d_s, n1, nqp, x, xim, eps, o, ok, part, slot, acc_s, tj, rl);
     }
     __syncwarp();
     if ((t & 31) == 0) mbar_arrive(&empty[st]);  // this warp is done with the record
@@ -1199,12 +1214,13 @@ __global__ void __launch_bounds__(TI *QS *VS *CS, CTAS_PER_SM) k_assemble_regula
 
 template <int NA, int KT, int LAYER, int QS, int VS, int CS = 1>
 static void launch_reg_layer(Context &c, RegParams P, int nrow_tiles, size_t smem, int colour) {
-  if constexpr (CS == 2) {  // cell-split mode exists for the moment formulation only (cell_sets)
-    static_assert(NA == 4 && KT == BS_KERNEL_FREE && LAYER == 0, "cell-split mode: Q1 free-space kernel");
+  if constexpr (CS == 2) {  // cell-split mode (cell_sets): Gauss 8, no regularisation; moment formulation except for no-slip
+    static_assert(NA == 4 && (LAYER == 0) == (KT == BS_KERNEL_FREE), "cell-split mode: Q1 unknowns");
     BS_REQUIRE(cell_sets(c) == 2 && c.blocks.cs == 2, "cell blocks were not built for the cell-split kernel");
-    BS_REQUIRE(P.tj == TJ_CS2 && P.nq_pad == 64 && P.n1d == 8, "cell-split kernel: compile-time block and rule sizes");
-    auto kern = c.fused ? k_assemble_regular<NA, KT, LAYER, QS, VS, false, true, -8, 2>
-                        : k_assemble_regular<NA, KT, LAYER, QS, VS, false, false, -8, 2>;
+    BS_REQUIRE(P.tj == tj_cell_split(KT) && P.nq_pad == 64 && P.n1d == 8, "cell-split kernel: compile-time block and rule sizes");
+    constexpr int NC = (KT == BS_KERNEL_NO_SLIP) ? 0 : -8;
+    auto kern = c.fused ? k_assemble_regular<NA, KT, LAYER, QS, VS, false, true, NC, 2>
+                        : k_assemble_regular<NA, KT, LAYER, QS, VS, false, false, NC, 2>;
     BS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const std::vector<int> &cs = c.blocks.colour_start;
     const int nb = cs[colour + 1] - cs[colour];
@@ -1252,8 +1268,8 @@ static void launch_reg(Context &c, RegParams P, int nrow_tiles, size_t smem) {
   for (size_t k = 0; k + 1 < cs.size(); ++k) {  // one launch (pair) per colour, stream order = summation order
     if (cs[k + 1] - cs[k] <= 0) continue;
     if constexpr (SPLIT) {
-      launch_reg_layer<NA, KT, 1, QS, VS>(c, P, nrow_tiles, smem, (int)k);
-      launch_reg_layer<NA, KT, 2, QS, VS>(c, P, nrow_tiles, smem, (int)k);
+      launch_reg_layer<NA, KT, 1, QS, VS, CS>(c, P, nrow_tiles, smem, (int)k);
+      launch_reg_layer<NA, KT, 2, QS, VS, CS>(c, P, nrow_tiles, smem, (int)k);
     } else {
       launch_reg_layer<NA, KT, 0, QS, VS, CS>(c, P, nrow_tiles, smem, (int)k);
     }
@@ -1307,10 +1323,12 @@ void launch_assembly_regular(Context &c) {
       break;
     case BS_KERNEL_FREE_SURFACE:
       if (q2) launch_reg<9, BS_KERNEL_FREE_SURFACE, false, 1, 2>(c, P, grid, smem);
+      else if (c.blocks.cs == 2) launch_reg<4, BS_KERNEL_FREE_SURFACE, true, 1, 1, 2>(c, P, grid, smem);
       else launch_reg<4, BS_KERNEL_FREE_SURFACE, true, 2, 1>(c, P, grid, smem);
       break;
     case BS_KERNEL_NO_SLIP:
       if (q2) launch_reg<9, BS_KERNEL_NO_SLIP, false, 1, 2>(c, P, grid, smem);
+      else if (c.blocks.cs == 2) launch_reg<4, BS_KERNEL_NO_SLIP, true, 1, 1, 2>(c, P, grid, smem);
       else launch_reg<4, BS_KERNEL_NO_SLIP, true, 2, 1>(c, P, grid, smem);
       break;
     default:
