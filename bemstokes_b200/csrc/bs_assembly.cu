@@ -17,6 +17,9 @@
 #include "bs_internal.h"
 #include "bs_green.cuh"
 
+#ifndef BS_MOM2D
+#define BS_MOM2D 1   // cell-split free-space kernel: moments in both directions (0: per-row expansion)
+#endif
 #ifndef BS_QX_UNROLL
 #define BS_QX_UNROLL 2
 #endif
@@ -121,7 +124,37 @@ __global__ void k_cell_geometry(int ncell, int nq, int nq_pad, int nam, const in
   o8[4] = s6 * nx;
   o8[5] = s6 * ny;
   o8[6] = s6 * nz;
-  o8[7] = 0.0;
+  // Pad slot of point q: constant number q of a bilinear (Q1-mapped) cell y = y00 + xi a + eta b + xi eta c, read by the
+  // 2-D moment formulation of K1 (integrate_free_lin2d): 0-11 = y00, a, b, c; 12 + 6 v + t for the value v = (i,j) of the
+  // symmetric 6-vector: t = 0 a_i b_j + b_i a_j, 1 a_i a_j, 2 b_i b_j, 3 a_i c_j + c_i a_j, 4 b_i c_j + c_i b_j, 5 c_i c_j.
+  double cst = 0.0;
+  if (nam == 4 && q < 48) {
+    double X[4][3];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) X[a][d] = map_nodes[(size_t)3 * conn_map[(size_t)cell * 4 + a] + d];
+    double A[3], B[3], C[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      A[d] = X[1][d] - X[0][d];
+      B[d] = X[2][d] - X[0][d];
+      C[d] = (X[3][d] - X[2][d]) - (X[1][d] - X[0][d]);
+    }
+    if (q < 12) {
+      const int d = q % 3;
+      cst = q < 3 ? X[0][d] : (q < 6 ? A[d] : (q < 9 ? B[d] : C[d]));
+    } else {
+      const int v = (q - 12) / 6, tt = (q - 12) % 6;
+      const int i = v < 3 ? 0 : (v < 5 ? 1 : 2), j = v < 3 ? v : (v < 5 ? v - 2 : 2);
+      cst = tt == 0 ? fma(A[i], B[j], B[i] * A[j])
+          : tt == 1 ? A[i] * A[j]
+          : tt == 2 ? B[i] * B[j]
+          : tt == 3 ? fma(A[i], C[j], C[i] * A[j])
+          : tt == 4 ? fma(B[i], C[j], C[i] * B[j]) : C[i] * C[j];
+    }
+  }
+  o8[7] = cst;
 }
 
 void launch_cell_geometry(Context &c) {
@@ -581,6 +614,147 @@ __device__ __forceinline__ void integrate_free_lin(const double *__restrict__ c8
   }
 }
 
+// Cell-split mode (one thread integrates the whole cell): the moment formulation in both directions.  On a bilinear cell
+// R = R00 + xi a + eta b + xi eta c, so every product R_i R_j is a polynomial with 9 coefficients P_km (k, m <= 2) in
+// (xi, eta), and with the bilinear shape functions the cell integrals are contractions of P with the 16 scalar moments
+// M_km = sum_q c_q xi_q^k eta_q^m (k, m <= 3) per layer.  Per rule row: the four xi-moments of integrate_free_lin, then
+// 16 FMAs per layer into M (instead of the 60-FMA expansion of the row); per cell: one expansion, 9 FMAs per value and
+// shape function, added to the thread's tile entries.  Cell constants come from the pad slots of the record (K0).
+template <int MODE>
+__device__ __forceinline__ void integrate_free_lin2d(const double *__restrict__ c8, const double *__restrict__ xi_s,
+                                                     const double (&x)[3], double *const (&dst)[4], int vs) {
+  constexpr int N1 = 8;
+  constexpr int KO = (MODE == 2) ? 6 : 0;  // first tile plane (relative to dst) of the double layer
+  double Mg[4][4], Mk[4][4], Mi[2][2];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int m = 0; m < 4; ++m) Mg[k][m] = Mk[k][m] = 0.0;
+  Mi[0][0] = Mi[0][1] = Mi[1][0] = Mi[1][1] = 0.0;
+  FreeA sa;
+  FreeB sb;
+  {
+    FreeA a0;
+    free_stage_a<MODE>(c8, x, a0);
+    free_stage_b<MODE>(a0, sb);
+    free_stage_a<MODE>(c8 + 8, x, sa);
+  }
+  for (int qy = 0; qy < N1; ++qy) {
+    double mg[4] = {0.0, 0.0, 0.0, 0.0}, mk[4] = {0.0, 0.0, 0.0, 0.0}, mi[2] = {0.0, 0.0};
+    const double *crow = c8 + (size_t)8 * qy * N1;
+    const double *nrow = c8 + (size_t)8 * ((qy + 1 < N1) ? qy + 1 : qy) * N1;  // next row (harmless re-read at the end)
+#pragma unroll
+    for (int qx = 0; qx < N1; ++qx) {
+      FreeB nb;
+      free_stage_b<MODE>(sa, nb);                                                                  // point qx+1
+      FreeA na;
+      free_stage_a<MODE>(qx + 2 < N1 ? crow + 8 * (qx + 2) : nrow + 8 * (qx + 2 - N1), x, na);      // point qx+2
+      free_stage_c_lin<MODE>(sb, xi_s + 4 * qx, mg, mk, mi);                                       // point qx
+      sb = nb;
+      sa = na;
+    }
+    const double2 e12 = *reinterpret_cast<const double2 *>(xi_s + 4 * qy);  // eta, eta^2 (same 1-D rule)
+    const double e3 = xi_s[4 * qy + 2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (MODE != 1) {
+        Mg[k][0] += mg[k];
+        Mg[k][1] = fma(mg[k], e12.x, Mg[k][1]);
+        Mg[k][2] = fma(mg[k], e12.y, Mg[k][2]);
+        Mg[k][3] = fma(mg[k], e3, Mg[k][3]);
+      }
+      if (MODE != 0) {
+        Mk[k][0] += mk[k];
+        Mk[k][1] = fma(mk[k], e12.x, Mk[k][1]);
+        Mk[k][2] = fma(mk[k], e12.y, Mk[k][2]);
+        Mk[k][3] = fma(mk[k], e3, Mk[k][3]);
+      }
+    }
+    if (MODE != 1) {
+      Mi[0][0] += mi[0];
+      Mi[0][1] = fma(mi[0], e12.x, Mi[0][1]);
+      Mi[1][0] += mi[1];
+      Mi[1][1] = fma(mi[1], e12.x, Mi[1][1]);
+    }
+  }
+  // ---- expansion: shape function a = ix + 2 iy, phi_a = l_ix(xi) l_iy(eta), l_0 = 1 - t, l_1 = t
+  auto cst = [&](int k) { return c8[8 * k + 7]; };
+  double R00[3], A[3], B[3], C[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    R00[d] = cst(d) - x[d];
+    A[d] = cst(3 + d);
+    B[d] = cst(6 + d);
+    C[d] = cst(9 + d);
+  }
+  double Ni[4] = {0.0, 0.0, 0.0, 0.0};
+  if (MODE != 1) {
+    Ni[3] = Mi[1][1];
+    Ni[2] = Mi[0][1] - Mi[1][1];
+    Ni[1] = Mi[1][0] - Mi[1][1];
+    Ni[0] = (Mi[0][0] - Mi[1][0]) - Ni[2];
+  }
+  // The sums of a layer are formed in registers (24 independent chains of 9 FMAs, the cell constants are plain loads with
+  // no store in between) and added to the tile entries in one pass at the end.
+  auto expand = [&](const double (&M)[4][4], int plane0, bool iso) {
+    // N[a][k][m] = sum_q c_q phi_a xi^k eta^m, k, m <= 2
+    double N[4][3][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double X0[4], X1[4];  // l_0(xi) xi^k, l_1(xi) xi^k against eta^m, m <= 3
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        X1[m] = M[k + 1][m];
+        X0[m] = M[k][m] - M[k + 1][m];
+      }
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        N[2][k][m] = X0[m + 1];
+        N[0][k][m] = X0[m] - X0[m + 1];
+        N[3][k][m] = X1[m + 1];
+        N[1][k][m] = X1[m] - X1[m + 1];
+      }
+    }
+    double out[4][6];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = i; j < 3; ++j) {
+        const int v = (i == 0) ? j : (i == 1 ? 2 + j : 5);
+        double P[3][3];
+        P[0][0] = R00[i] * R00[j];
+        P[1][0] = (i == j) ? 2.0 * (R00[i] * A[i]) : fma(R00[i], A[j], A[i] * R00[j]);
+        P[0][1] = (i == j) ? 2.0 * (R00[i] * B[i]) : fma(R00[i], B[j], B[i] * R00[j]);
+        P[1][1] = fma(R00[i], C[j], fma(C[i], R00[j], cst(12 + 6 * v)));
+        P[2][0] = cst(12 + 6 * v + 1);
+        P[0][2] = cst(12 + 6 * v + 2);
+        P[2][1] = cst(12 + 6 * v + 3);
+        P[1][2] = cst(12 + 6 * v + 4);
+        P[2][2] = cst(12 + 6 * v + 5);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          // three partial chains over k: shorter dependent chains, two extra adds
+          double o0 = P[0][0] * N[a][0][0], o1 = P[1][0] * N[a][1][0], o2 = P[2][0] * N[a][2][0];
+#pragma unroll
+          for (int m = 1; m < 3; ++m) {
+            o0 = fma(P[0][m], N[a][0][m], o0);
+            o1 = fma(P[1][m], N[a][1][m], o1);
+            o2 = fma(P[2][m], N[a][2][m], o2);
+          }
+          double o = (o0 + o1) + o2;
+          if (iso && i == j) o += Ni[a];
+          out[a][v] = o;
+        }
+      }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int v = 0; v < 6; ++v) dst[a][(size_t)(plane0 + v) * vs] += out[a][v];
+  };
+  if (MODE != 1) expand(Mg, 0, true);
+  if (MODE != 0) expand(Mk, KO, false);
+}
+
 // Free-surface image system on the same fast path: G_fs = G(R) + s_i G(R_im), K likewise, with s_i = -1 on the row of
 // the wall normal and +1 otherwise (ref: source/free_surface_kernel.cc:19-72, 135-209).  Both terms are free-space
 // kernels, so one layer at a time (MODE 0 or 1, the layer-split launches) is accumulated as two symmetric 6-vectors
@@ -806,6 +980,18 @@ __device__ __forceinline__ void cell_pass(const double *__restrict__ cq, const d
   double *dst[NA];
   // the free-surface integrators keep their own partial sums and combine them into acc at the end: preloading acc would
   // only lengthen its live range there, so that kernel adds to the tile after the cell
+  // 2-D moment formulation (free space, cell-split): the expansion at the end of the cell adds to the tile itself
+  constexpr bool MOM2D = TILE_ACC && KT == BS_KERNEL_FREE && N1C == -8 && BS_MOM2D;
+  if constexpr (MOM2D) {
+    if (ok) {
+      const int vs = acc_vstride(tj);
+      double *d4[NA];
+#pragma unroll
+      for (int a = 0; a < NA; ++a) d4[a] = acc_s + (size_t)VOFF * vs + (size_t)slot[a] * ACC_LD + rl;
+      integrate_free_lin2d<MODE>(cq, l1d_s + 32, x, d4, vs);
+    }
+    return;
+  }
   constexpr bool PRELOAD = TILE_ACC && KT != BS_KERNEL_FREE_SURFACE;
   if constexpr (PRELOAD) {
     static_assert(QS == 1, "tile accumulators: one thread per node and cell");
