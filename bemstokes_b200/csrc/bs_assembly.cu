@@ -20,6 +20,9 @@
 #ifndef BS_MOM2D
 #define BS_MOM2D 1   // cell-split free-space kernel: moments in both directions (0: per-row expansion)
 #endif
+#ifndef BS_EXPAND_SPLIT
+#define BS_EXPAND_SPLIT 0
+#endif
 #ifndef BS_QX_UNROLL
 #define BS_QX_UNROLL 2
 #endif
@@ -614,6 +617,74 @@ __device__ __forceinline__ void integrate_free_lin(const double *__restrict__ c8
   }
 }
 
+// Expansion of the 2-D moments of one layer (see integrate_free_lin2d): out[a][v] = sum_km P_v[k][m] N_a[k][m] with
+// N_a[k][m] = sum_q c_q phi_a xi^k eta^m (shape function a = ix + 2 iy, phi_a = l_ix(xi) l_iy(eta), l_0 = 1 - t, l_1 = t)
+// and P_v the 9 coefficients of R_i R_j on the bilinear cell, R00 = y00 - x; cell constants from the record's pad slots.
+// iso != nullptr: the 2 x 2 moments of the isotropic part c_1, added to the diagonal values.  The sums are formed in
+// registers (24 independent chains of 9 FMAs; the cell constants are plain loads with no store in between).
+__device__ __forceinline__ void expand_moments2d(const double (&M)[4][4], const double (*iso)[2], const double (&R00)[3],
+                                                 const double *__restrict__ c8, double (&out)[4][6]) {
+  auto cst = [&](int k) { return c8[8 * k + 7]; };
+  double A[3], B[3], C[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    A[d] = cst(3 + d);
+    B[d] = cst(6 + d);
+    C[d] = cst(9 + d);
+  }
+  double Ni[4] = {0.0, 0.0, 0.0, 0.0};
+  if (iso) {
+    Ni[3] = iso[1][1];
+    Ni[2] = iso[0][1] - iso[1][1];
+    Ni[1] = iso[1][0] - iso[1][1];
+    Ni[0] = (iso[0][0] - iso[1][0]) - Ni[2];
+  }
+  double N[4][3][3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    double X0[4], X1[4];  // l_0(xi) xi^k, l_1(xi) xi^k against eta^m, m <= 3
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      X1[m] = M[k + 1][m];
+      X0[m] = M[k][m] - M[k + 1][m];
+    }
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      N[2][k][m] = X0[m + 1];
+      N[0][k][m] = X0[m] - X0[m + 1];
+      N[3][k][m] = X1[m + 1];
+      N[1][k][m] = X1[m] - X1[m + 1];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = i; j < 3; ++j) {
+      const int v = (i == 0) ? j : (i == 1 ? 2 + j : 5);
+      double P[3][3];
+      P[0][0] = R00[i] * R00[j];
+      P[1][0] = (i == j) ? 2.0 * (R00[i] * A[i]) : fma(R00[i], A[j], A[i] * R00[j]);
+      P[0][1] = (i == j) ? 2.0 * (R00[i] * B[i]) : fma(R00[i], B[j], B[i] * R00[j]);
+      P[1][1] = fma(R00[i], C[j], fma(C[i], R00[j], cst(12 + 6 * v)));
+      P[2][0] = cst(12 + 6 * v + 1);
+      P[0][2] = cst(12 + 6 * v + 2);
+      P[2][1] = cst(12 + 6 * v + 3);
+      P[1][2] = cst(12 + 6 * v + 4);
+      P[2][2] = cst(12 + 6 * v + 5);
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        double o = P[0][0] * N[a][0][0];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+          for (int m = 0; m < 3; ++m)
+            if (k + m > 0) o = fma(P[k][m], N[a][k][m], o);
+        if (iso && i == j) o += Ni[a];
+        out[a][v] = o;
+      }
+    }
+}
+
 // Cell-split mode (one thread integrates the whole cell): the moment formulation in both directions.  On a bilinear cell
 // R = R00 + xi a + eta b + xi eta c, so every product R_i R_j is a polynomial with 9 coefficients P_km (k, m <= 2) in
 // (xi, eta), and with the bilinear shape functions the cell integrals are contractions of P with the 16 scalar moments
@@ -677,83 +748,119 @@ __device__ __forceinline__ void integrate_free_lin2d(const double *__restrict__ 
       Mi[1][1] = fma(mi[1], e12.x, Mi[1][1]);
     }
   }
-  // ---- expansion: shape function a = ix + 2 iy, phi_a = l_ix(xi) l_iy(eta), l_0 = 1 - t, l_1 = t
-  auto cst = [&](int k) { return c8[8 * k + 7]; };
-  double R00[3], A[3], B[3], C[3];
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    R00[d] = cst(d) - x[d];
-    A[d] = cst(3 + d);
-    B[d] = cst(6 + d);
-    C[d] = cst(9 + d);
-  }
-  double Ni[4] = {0.0, 0.0, 0.0, 0.0};
+  // ---- expansion, one layer at a time; the sums are added to the thread's tile entries in one pass per layer
+  const double R00[3] = {c8[7] - x[0], c8[15] - x[1], c8[23] - x[2]};
+  double out[4][6];
   if (MODE != 1) {
-    Ni[3] = Mi[1][1];
-    Ni[2] = Mi[0][1] - Mi[1][1];
-    Ni[1] = Mi[1][0] - Mi[1][1];
-    Ni[0] = (Mi[0][0] - Mi[1][0]) - Ni[2];
-  }
-  // The sums of a layer are formed in registers (24 independent chains of 9 FMAs, the cell constants are plain loads with
-  // no store in between) and added to the tile entries in one pass at the end.
-  auto expand = [&](const double (&M)[4][4], int plane0, bool iso) {
-    // N[a][k][m] = sum_q c_q phi_a xi^k eta^m, k, m <= 2
-    double N[4][3][3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      double X0[4], X1[4];  // l_0(xi) xi^k, l_1(xi) xi^k against eta^m, m <= 3
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        X1[m] = M[k + 1][m];
-        X0[m] = M[k][m] - M[k + 1][m];
-      }
-#pragma unroll
-      for (int m = 0; m < 3; ++m) {
-        N[2][k][m] = X0[m + 1];
-        N[0][k][m] = X0[m] - X0[m + 1];
-        N[3][k][m] = X1[m + 1];
-        N[1][k][m] = X1[m] - X1[m + 1];
-      }
-    }
-    double out[4][6];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = i; j < 3; ++j) {
-        const int v = (i == 0) ? j : (i == 1 ? 2 + j : 5);
-        double P[3][3];
-        P[0][0] = R00[i] * R00[j];
-        P[1][0] = (i == j) ? 2.0 * (R00[i] * A[i]) : fma(R00[i], A[j], A[i] * R00[j]);
-        P[0][1] = (i == j) ? 2.0 * (R00[i] * B[i]) : fma(R00[i], B[j], B[i] * R00[j]);
-        P[1][1] = fma(R00[i], C[j], fma(C[i], R00[j], cst(12 + 6 * v)));
-        P[2][0] = cst(12 + 6 * v + 1);
-        P[0][2] = cst(12 + 6 * v + 2);
-        P[2][1] = cst(12 + 6 * v + 3);
-        P[1][2] = cst(12 + 6 * v + 4);
-        P[2][2] = cst(12 + 6 * v + 5);
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          // three partial chains over k: shorter dependent chains, two extra adds
-          double o0 = P[0][0] * N[a][0][0], o1 = P[1][0] * N[a][1][0], o2 = P[2][0] * N[a][2][0];
-#pragma unroll
-          for (int m = 1; m < 3; ++m) {
-            o0 = fma(P[0][m], N[a][0][m], o0);
-            o1 = fma(P[1][m], N[a][1][m], o1);
-            o2 = fma(P[2][m], N[a][2][m], o2);
-          }
-          double o = (o0 + o1) + o2;
-          if (iso && i == j) o += Ni[a];
-          out[a][v] = o;
-        }
-      }
+    expand_moments2d(Mg, Mi, R00, c8, out);
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int v = 0; v < 6; ++v) dst[a][(size_t)(plane0 + v) * vs] += out[a][v];
-  };
-  if (MODE != 1) expand(Mg, 0, true);
-  if (MODE != 0) expand(Mk, KO, false);
+      for (int v = 0; v < 6; ++v) dst[a][(size_t)v * vs] += out[a][v];
+  }
+  if (MODE != 0) {
+    expand_moments2d(Mk, nullptr, R00, c8, out);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int v = 0; v < 6; ++v) dst[a][(size_t)(KO + v) * vs] += out[a][v];
+  }
 }
+
+// Free-surface image system, cell-split mode: the direct part (R = y - x) and the image part (R = y - x_im) are two
+// free-space kernels on the same cell, one layer per launch (MODE 0 or 1): two sets of 2-D moments, two expansions that
+// differ in R00 only, combined with the sign of the image term into the 9 unsymmetric tile values
+// (ref: source/free_surface_kernel.cc:19-72, 135-209).
+template <int MODE>
+__device__ __forceinline__ void integrate_free_surface_lin2d(const double *__restrict__ c8, const double *__restrict__ xi_s,
+                                                             const double (&x)[3], const double (&xim)[3], int o,
+                                                             double *const (&dst)[4], int vs) {
+  static_assert(MODE == 0 || MODE == 1, "one layer per launch");
+  constexpr int N1 = 8;
+  double MA[4][4], MB[4][4], IA[2][2], IB[2][2];
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int m = 0; m < 4; ++m) MA[k][m] = MB[k][m] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+#pragma unroll
+    for (int m = 0; m < 2; ++m) IA[k][m] = IB[k][m] = 0.0;
+  FreeA saA, saB;
+  FreeB sbA, sbB;
+  {
+    FreeA a0;
+    free_stage_a<MODE>(c8, x, a0);
+    free_stage_b<MODE>(a0, sbA);
+    free_stage_a<MODE>(c8, xim, a0);
+    free_stage_b<MODE>(a0, sbB);
+    free_stage_a<MODE>(c8 + 8, x, saA);
+    free_stage_a<MODE>(c8 + 8, xim, saB);
+  }
+  for (int qy = 0; qy < N1; ++qy) {
+    double mA[4] = {0.0, 0.0, 0.0, 0.0}, mB[4] = {0.0, 0.0, 0.0, 0.0}, iA[2] = {0.0, 0.0}, iB[2] = {0.0, 0.0};
+    double dummy[4] = {0.0, 0.0, 0.0, 0.0};
+    const double *crow = c8 + (size_t)8 * qy * N1;
+    const double *nrow = c8 + (size_t)8 * ((qy + 1 < N1) ? qy + 1 : qy) * N1;
+#pragma unroll
+    for (int qx = 0; qx < N1; ++qx) {
+      FreeB nbA, nbB;
+      free_stage_b<MODE>(saA, nbA);
+      free_stage_b<MODE>(saB, nbB);
+      FreeA naA, naB;
+      const double *rec = qx + 2 < N1 ? crow + 8 * (qx + 2) : nrow + 8 * (qx + 2 - N1);
+      free_stage_a<MODE>(rec, x, naA);
+      free_stage_a<MODE>(rec, xim, naB);
+      if (MODE == 0) {
+        free_stage_c_lin<0>(sbA, xi_s + 4 * qx, mA, dummy, iA);
+        free_stage_c_lin<0>(sbB, xi_s + 4 * qx, mB, dummy, iB);
+      } else {
+        free_stage_c_lin<1>(sbA, xi_s + 4 * qx, dummy, mA, iA);
+        free_stage_c_lin<1>(sbB, xi_s + 4 * qx, dummy, mB, iB);
+      }
+      sbA = nbA;
+      sbB = nbB;
+      saA = naA;
+      saB = naB;
+    }
+    const double2 e12 = *reinterpret_cast<const double2 *>(xi_s + 4 * qy);
+    const double e3 = xi_s[4 * qy + 2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      MA[k][0] += mA[k];
+      MA[k][1] = fma(mA[k], e12.x, MA[k][1]);
+      MA[k][2] = fma(mA[k], e12.y, MA[k][2]);
+      MA[k][3] = fma(mA[k], e3, MA[k][3]);
+      MB[k][0] += mB[k];
+      MB[k][1] = fma(mB[k], e12.x, MB[k][1]);
+      MB[k][2] = fma(mB[k], e12.y, MB[k][2]);
+      MB[k][3] = fma(mB[k], e3, MB[k][3]);
+    }
+    if (MODE == 0) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        IA[k][0] += iA[k];
+        IA[k][1] = fma(iA[k], e12.x, IA[k][1]);
+        IB[k][0] += iB[k];
+        IB[k][1] = fma(iB[k], e12.x, IB[k][1]);
+      }
+    }
+  }
+  const double R00a[3] = {c8[7] - x[0], c8[15] - x[1], c8[23] - x[2]};
+  const double R00b[3] = {c8[7] - xim[0], c8[15] - xim[1], c8[23] - xim[2]};
+  double oa[4][6], ob[4][6];
+  expand_moments2d(MA, MODE == 0 ? IA : nullptr, R00a, c8, oa);
+  expand_moments2d(MB, MODE == 0 ? IB : nullptr, R00b, c8, ob);
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double sg = (i == o) ? -1.0 : 1.0;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) dst[a][(size_t)(3 * i + j) * vs] += fma(sg, ob[a][vidx<6>(i, j)], oa[a][vidx<6>(i, j)]);
+    }
+}
+
 
 // Free-surface image system on the same fast path: G_fs = G(R) + s_i G(R_im), K likewise, with s_i = -1 on the row of
 // the wall normal and +1 otherwise (ref: source/free_surface_kernel.cc:19-72, 135-209).  Both terms are free-space
@@ -981,14 +1088,15 @@ __device__ __forceinline__ void cell_pass(const double *__restrict__ cq, const d
   // the free-surface integrators keep their own partial sums and combine them into acc at the end: preloading acc would
   // only lengthen its live range there, so that kernel adds to the tile after the cell
   // 2-D moment formulation (free space, cell-split): the expansion at the end of the cell adds to the tile itself
-  constexpr bool MOM2D = TILE_ACC && KT == BS_KERNEL_FREE && N1C == -8 && BS_MOM2D;
+  constexpr bool MOM2D = TILE_ACC && KT != BS_KERNEL_NO_SLIP && N1C == -8 && BS_MOM2D;
   if constexpr (MOM2D) {
     if (ok) {
       const int vs = acc_vstride(tj);
       double *d4[NA];
 #pragma unroll
       for (int a = 0; a < NA; ++a) d4[a] = acc_s + (size_t)VOFF * vs + (size_t)slot[a] * ACC_LD + rl;
-      integrate_free_lin2d<MODE>(cq, l1d_s + 32, x, d4, vs);
+      if constexpr (KT == BS_KERNEL_FREE) integrate_free_lin2d<MODE>(cq, l1d_s + 32, x, d4, vs);
+      else if constexpr (MODE != 2) integrate_free_surface_lin2d<MODE>(cq, l1d_s + 32, x, xim, o, d4, vs);  // layer-split launches
     }
     return;
   }
@@ -1206,13 +1314,32 @@ __global__ void __launch_bounds__(TI *QS *VS *CS, CTAS_PER_SM) k_assemble_regula
       l1d_s[65] = 1.0 / (x7 - x0);
     }
   }
-  for (int i = t; i < (ce - cs) * NA; i += NT) {
-    const int cell = P.blk_cells[cs + i / NA];  // -1: no partner cell in this step (cell-split mode)
-    if (i % NA == 0) s_cells[i / NA] = cell;
-    s_conn[i] = cell >= 0 ? P.conn_pos[(size_t)cell * NA + i % NA] : -1;
-    s_slots[i] = P.blk_slots[(size_t)cs * NA + i];
+  if constexpr (NA == 4) {
+    // a block has at most MAXC * 4 <= NT metadata entries: one per thread, the two dependent global loads are in flight
+    // while the tile is cleared
+    static_assert(MAXC * 4 <= NT, "one metadata entry per thread");
+    const bool has = t < (ce - cs) * NA;
+    const int cell = has ? P.blk_cells[cs + t / NA] : -1;  // -1: no partner cell in this step (cell-split mode)
+    const signed char sl = has ? P.blk_slots[(size_t)cs * NA + t] : (signed char)0;
+    const int ntile = NV2 * acc_vstride(tj), half = (ntile / 2) & ~1;
+    for (int i = 2 * t; i < half; i += 2 * NT) *reinterpret_cast<double2 *>(acc_s + i) = make_double2(0.0, 0.0);
+    const int cn = (has && cell >= 0) ? P.conn_pos[(size_t)cell * NA + t % NA] : -1;
+    for (int i = half + 2 * t; i + 1 < ntile; i += 2 * NT) *reinterpret_cast<double2 *>(acc_s + i) = make_double2(0.0, 0.0);
+    if ((ntile & 1) && t == 0) acc_s[ntile - 1] = 0.0;
+    if (has) {
+      if (t % NA == 0) s_cells[t / NA] = cell;
+      s_conn[t] = cn;
+      s_slots[t] = sl;
+    }
+  } else {
+    for (int i = t; i < (ce - cs) * NA; i += NT) {
+      const int cell = P.blk_cells[cs + i / NA];
+      if (i % NA == 0) s_cells[i / NA] = cell;
+      s_conn[i] = cell >= 0 ? P.conn_pos[(size_t)cell * NA + i % NA] : -1;
+      s_slots[i] = P.blk_slots[(size_t)cs * NA + i];
+    }
+    for (int i = t; i < NV2 * acc_vstride(tj); i += NT) acc_s[i] = 0.0;
   }
-  for (int i = t; i < NV2 * acc_vstride(tj); i += NT) acc_s[i] = 0.0;
   __syncthreads();
   double x[3] = {0, 0, 0};
   if (row_ok) {
@@ -1239,6 +1366,8 @@ __global__ void __launch_bounds__(TI *QS *VS *CS, CTAS_PER_SM) k_assemble_regula
   // block), all warps finish that step first.
   const unsigned sync_mask = (CS == 2) ? P.blk_sync[blk] : 0u;
   for (int step = 0; step < nsteps; ++step) {
+    // (a named barrier per pair of warps owning the same tile rows measured 8 % slower than the CTA barrier: the warps
+    // of a CTA drift apart; a CTA barrier at every step measured the same as this)
     if (CS == 2 && ((sync_mask >> step) & 1u)) __syncthreads();
     if (t == 0 && step + ns - 1 < nsteps) {
       if (step >= 1) {  // the stage was last used by step-1
@@ -1322,6 +1451,20 @@ __global__ void __launch_bounds__(TI *QS *VS *CS, CTAS_PER_SM) k_assemble_regula
 #pragma unroll
     for (int i = 0; i < 3; ++i) soff[sidx][i] = valid ? vidx<NV>(i, j) * vs + sl * ACC_LD + (second[sidx] ? 1 : 0) : 0;
   }
+  // cell-split mode, fused: this thread's share of the panel rows is fetched now and staged after the write-out
+  constexpr int NPF = (CS == 2) ? (3 * tj_cell_split(KT) * MAX_PANEL + NT - 1) / NT : 1;
+  double pf[NPF];
+  constexpr bool prefetch_panel = CS == 2;  // measured + 2 % on the default workload
+  if (prefetch_panel && FUSED && LAYER != 1) {
+#pragma unroll
+    for (int u = 0; u < NPF; ++u) {
+      const int idx = t + u * NT;
+      const int col = idx / MAX_PANEL, q = idx - col * MAX_PANEL;
+      const int sl = col / 3, j = col - 3 * sl;
+      const int node = (sl < tj) ? nodes[sl] : -1;
+      pf[u] = (node >= 0 && q < P.pp) ? P.panel[((size_t)3 * node + j) * P.pp + q] : 0.0;
+    }
+  }
   for (int r_ = 2 * warp; r_ < rows_tile; r_ += 2 * NWARP) {
     const bool has2 = r_ + 1 < rows_tile;
 #pragma unroll
@@ -1350,11 +1493,17 @@ __global__ void __launch_bounds__(TI *QS *VS *CS, CTAS_PER_SM) k_assemble_regula
     const int pp = P.pp;
     constexpr int PS = MAX_PANEL;  // padded panel stride in shared memory (zero filled): fixed-trip inner loops
     double *xs = (LAYER == 0) ? acc_s : cellbuf;  // [3*tj][PS]
-    for (int idx = t; idx < 3 * tj * PS; idx += NT) {
-      const int col = idx / PS, q = idx - col * PS;
-      const int sl = col / 3, j = col - 3 * sl;
-      const int node = nodes[sl];
-      xs[idx] = (node >= 0 && q < pp) ? P.panel[((size_t)3 * node + j) * pp + q] : 0.0;
+    if (prefetch_panel) {
+#pragma unroll
+      for (int u = 0; u < NPF; ++u)
+        if (t + u * NT < 3 * tj * PS) xs[t + u * NT] = pf[u];
+    } else {
+      for (int idx = t; idx < 3 * tj * PS; idx += NT) {
+        const int col = idx / PS, q = idx - col * PS;
+        const int sl = col / 3, j = col - 3 * sl;
+        const int node = nodes[sl];
+        xs[idx] = (node >= 0 && q < pp) ? P.panel[((size_t)3 * node + j) * pp + q] : 0.0;
+      }
     }
     __syncthreads();
     // TPR threads per row node split the panel columns; each keeps the three matrix rows of its node in registers,
