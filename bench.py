@@ -162,10 +162,10 @@ def load_traffic(wl, world):
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 t = json.load(f)
             if t.get("workload_key") == key:
-                return t["k_gemv<2>"]["dram_bytes_per_launch"], t["k_assemble_regular"]["dram_bytes_per_assembly"], name
+                return t["k_gemv<2>"]["dram_bytes_per_launch"], t["k_assemble_regular"]["dram_bytes_per_assembly"], name, t["k_assemble_regular"]
         except Exception:
             pass
-    return None, None, None
+    return None, None, None, {}
 
 
 def f_pair_of(wl):
@@ -577,7 +577,7 @@ def run_ours(args):
         mv_bytes = 8.0 * (n + 6) * (n + 6)                          # whole job: every rank streams its row block
         mv_gbs_job = mv_bytes / (mv_ms * 1e-3) / 1e9
         mv_gbs_gpu = mv_gbs_job / world
-        traffic_mv, traffic_asm, traffic_src = load_traffic(wl, world)
+        traffic_mv, traffic_asm, traffic_src, asm_ncu = load_traffic(wl, world)
         roof_mv = {"kernel": "k_gemv<2>", "bound": "hbm", "achieved": mv_gbs_gpu, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                    "frac": mv_gbs_gpu / peaks["hbm_gbs"], "traffic": traffic_mv, "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)",
                    "algorithmic_bytes_per_launch": 8.0 * rows_loc * (n + 6), "launch_ms": mv_ms}
@@ -587,7 +587,12 @@ def run_ours(args):
                     "peak_source": "measured in this run: 8-chain DFMA microbenchmark sustained for 1 s under the power cap "
                                    "(bs_bench_fp64_sustained); silicon figure 148 SM x 64 DFMA x 2 x max clock in frac_of_silicon_peak",
                     "peak_silicon": fp64_silicon, "frac_of_silicon_peak": asm_tflops / world / fp64_silicon,
-                    "algorithmic_flops_per_pair": f_pair, "pairs_regular": pr, "pairs_singular": ps, "launch_ms": asm_ms}
+                    "algorithmic_flops_per_pair": f_pair, "pairs_regular": pr, "pairs_singular": ps, "launch_ms": asm_ms,
+                    # what the kernel really executes (ncu, profiles/): the moment formulation needs fewer FP64 instructions
+                    # than the convention's 73 FMA-equivalents per pair, so `frac` (algorithmic flops / peak) can exceed the
+                    # FP64-pipe utilisation - and 1
+                    "executed_fp64_instructions_per_pair": asm_ncu.get("fp64_instructions_per_pair"),
+                    "fp64_pipe_active_pct_ncu": asm_ncu.get("fp64_pipe_active_pct")}
         dominant_is_asm = asm_ms >= solve_ms
         parity_ok = par_v <= PARITY_TOL and (par_k or 0.0) <= PARITY_TOL
         parity = {"rows": par_rows, "max_row_rel_err_V": par_v, "max_row_rel_err_K": (par_k if not wl.get("fused") else None),
