@@ -68,3 +68,38 @@ def test_constraint_rows_and_torque_unknown(setup):
     A0, b0 = bo.monolithic(bo.correct_V(V, pre)[0], bo.correct_K(K, N), pre, "Real", 1, 1.0, sv)
     A1, b1 = bo.monolithic(bo.correct_V(V, pre, {})[0], bo.correct_K(K, N, False, {}), pre, "Real", 1, 1.0, sv, None, {}, None)
     assert np.array_equal(A0, A1) and np.array_equal(b0, b1)
+
+
+def test_no_slip_coefficient_tensor_form():
+    """The device's cell-split no-slip kernel (bemstokes_b200/csrc/bs_assembly.cu, integrate_no_slip) sums scalar
+    coefficients times the tensors R(x)R, Q(x)Q, n(x)Q instead of evaluating the nine entries one by one; this restates that
+    form in NumPy and compares it with the literal transcription of the reference (ref: source/no_slip_wall_kernel.cc:23-116,
+    127-199 -> oracle G_ns / W_ns) for the three wall orientations."""
+    import math
+    rng = np.random.default_rng(1)
+    for o in range(3):
+        x = rng.normal(size=3)
+        xim = x.copy()
+        xim[o] = x[o] - 2 * (x[o] + 2.0)
+        y, n = rng.normal(size=(64, 3)), rng.normal(size=(64, 3))
+        R, Q = y - x, y - xim
+        G, S = bo.G_ns(R, Q, o), (bo.W_ns(R, Q, o) * n[:, None, None, :]).sum(-1)
+        ri, qi = 1 / np.sqrt((R * R).sum(-1)), 1 / np.sqrt((Q * Q).sum(-1))
+        h0, Qo = 0.5 * (x[o] - xim[o]), Q[:, o]
+        s = 2 * h0 * (h0 - Qo)
+        e = np.ones(3)
+        e[o] = -1
+        PR, PQ, NQ = R[:, :, None] * R[:, None, :], Q[:, :, None] * Q[:, None, :], n[:, :, None] * Q[:, None, :]
+        Rn, Qn = (R * n).sum(-1), (Q * n).sum(-1)
+        G2, S2 = np.zeros_like(G), np.zeros_like(S)
+        for i in range(3):
+            for j in range(3):
+                anti = (i == o) * Q[:, j] - (j == o) * Q[:, i]
+                G2[:, i, j] = (ri ** 3 * PR[:, i, j] + (-qi ** 3 - 3 * e[i] * s * qi ** 5) * PQ[:, i, j]
+                               + (i == j) * (ri - qi + e[i] * s * qi ** 3) - 2 * h0 * qi ** 3 * e[i] * anti) / (8 * math.pi)
+                br = (-2 * h0 * h0 * NQ[:, i, j] + 2 * h0 * Qo * (NQ[:, i, j] - NQ[:, j, i]) - (i == j) * s * Q[:, i] ** 2 * n[:, i]
+                      + (i == o) * 2 * h0 * Qn * Q[:, j])
+                S2[:, i, j] = (-Rn * ri ** 5 * PR[:, i, j] + Qn * qi ** 5 * (1 + 5 * e[i] * s * qi ** 2) * PQ[:, i, j]
+                               + e[i] * qi ** 5 * br) * 3 / (4 * math.pi)
+        assert np.abs(G - G2).max() <= 1e-14 * np.abs(G).max()
+        assert np.abs(S - S2).max() <= 1e-14 * np.abs(S).max()
