@@ -28,7 +28,9 @@ class BsStats(C.Structure):
                 ("solve_ms", C.c_double), ("vmult_ms_last", C.c_double), ("kernel_launches", C.c_longlong),
                 ("pairs_regular", C.c_longlong), ("pairs_singular", C.c_longlong),
                 ("n_cell_blocks", C.c_longlong), ("n_colours", C.c_longlong), ("node_touch_ratio", C.c_double),
-                ("gmres_stream_ms_last", C.c_double), ("gmres_matvec_ms_last", C.c_double), ("gmres_sweeps_last", C.c_longlong)]
+                ("gmres_stream_ms_last", C.c_double), ("gmres_matvec_ms_last", C.c_double), ("gmres_sweeps_last", C.c_longlong),
+                ("cell_sets", C.c_longlong), ("cell_steps", C.c_longlong), ("unpaired_cells", C.c_longlong),
+                ("sync_steps", C.c_longlong)]
 
 
 ALLGATHERV_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, c_int_p, c_int_p, C.c_void_p)

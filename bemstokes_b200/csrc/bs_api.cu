@@ -1246,6 +1246,10 @@ int bs_get_stats(bs_context *h, bs_stats *out) {
   c.stats.n_cell_blocks = c.blocks.nblocks;
   c.stats.n_colours = c.blocks.colour_start.empty() ? 0 : (long long)c.blocks.colour_start.size() - 1;
   c.stats.node_touch_ratio = c.blocks.node_touch_ratio;
+  c.stats.cell_sets = c.blocks.cs;
+  c.stats.cell_steps = c.blocks.steps;
+  c.stats.unpaired_cells = c.blocks.unpaired;
+  c.stats.sync_steps = c.blocks.sync_steps;
   *out = c.stats;
   BS_API_END
 }

@@ -711,6 +711,7 @@ void build_cell_blocks(Context &c) {
       B.steps += (long long)order.size() / 2;
       for (unsigned m = sync; m; m &= m - 1) ++B.sync_steps;
     }
+    if (B.cs != 2) B.steps += (long long)order.size();
     for (int cell : order) {
       B.cells.push_back(cell);
       for (int a = 0; a < na; ++a) {

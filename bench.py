@@ -651,7 +651,9 @@ def run_ours(args):
             "roofline": roof_asm if dominant_is_asm else roof_mv,
             "roofline_secondary": roof_mv if dominant_is_asm else roof_asm,
             "tiling": {"cell_blocks": int(st["n_cell_blocks"]), "colours": int(st["n_colours"]),
-                       "node_touch_ratio": st["node_touch_ratio"]},
+                       "node_touch_ratio": st["node_touch_ratio"], "cell_sets": int(st["cell_sets"]),
+                       "cell_steps": int(st["cell_steps"]), "unpaired_cells": int(st["unpaired_cells"]),
+                       "steps_behind_a_barrier": int(st["sync_steps"])},
             "fp64_peak_tflops_measured": fp64.value, "fp64_peak_tflops_silicon": fp64_silicon,
             "frames": frames,
             "clocks": clocks,

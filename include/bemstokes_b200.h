@@ -249,6 +249,9 @@ typedef struct {
   /* last device-resident GMRES solve: time on the stream, of which in the sweeps over the matrix (CUDA events around each) */
   double gmres_stream_ms_last, gmres_matvec_ms_last;
   long long gmres_sweeps_last;
+  /* regular pass, cell-split mode (Q1 unknowns, Gauss 8, no regularisation): thread sets working on different cells of a
+   * block (2, else 1), steps of all blocks (pairs of cells), cells without a partner, steps that start with a barrier */
+  long long cell_sets, cell_steps, unpaired_cells, sync_steps;
 } bs_stats;
 int bs_get_stats(bs_context *ctx, bs_stats *out);
 int bs_reset_stats(bs_context *ctx);

@@ -124,6 +124,28 @@ def test_assembly_entries_Q1(half, kern, goldens):
     p.close()
 
 
+@pytest.mark.parametrize("kern", ["free", "free_surface", "no_slip"])
+def test_cell_split_kernel_against_thread_pair_kernel(half, kern, monkeypatch):
+    """K1 has two variants for Q1 unknowns with Gauss 8: the cell-split mode (one thread per node and cell, pairs of cells
+    without a common node, 2-D moment formulation / coefficient x tensor sums; the default) and the thread-pair mode of
+    round 1 (two threads per node share the rows of the rule; BS_NO_CELLSPLIT=1).  Different cell blocks, different
+    arithmetic, same matrices (ref: bem_stokes.cc:2905-2951); the oracle comparison of both is test_assembly_entries_Q1
+    and this one."""
+    kw = dict(reflect_kernel=(kern == "free_surface"), no_slip_kernel=(kern == "no_slip"), wall_spans_0=(80, 0, 80),
+              wall_position_0=(0, 1.4, 0))
+    p = make_problem(half, **kw)
+    V2, K2 = raw_VK(p)
+    assert p.stats()["cell_sets"] == 2
+    p.close()
+    monkeypatch.setenv("BS_NO_CELLSPLIT", "1")
+    p = make_problem(half, **kw)
+    V1, K1 = raw_VK(p)
+    assert p.stats()["cell_sets"] == 1
+    p.close()
+    assert rel_rows(V2, V1) < ENTRY_TOL, rel_rows(V2, V1)
+    assert rel_rows(K2, K1) < ENTRY_TOL, rel_rows(K2, K1)
+
+
 @pytest.mark.parametrize("kind", ["Telles", "Duffy"])
 def test_assembly_singular_kinds(half, kind):
     p = make_problem(half, singular_quadrature_type=kind, singular_quadrature_order=6)

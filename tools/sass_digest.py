@@ -11,12 +11,14 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "bemstokes_b200", "libbemstokes_b200.so")
 HOT = [
-    ("K1 free space, Q1, Gauss 8, linear rows, fused (default bench)", r"k_assemble_regularILi4ELi0ELi0ELi2ELi1ELb0ELb1ELin8E"),
-    ("K1 free space, Q1, Gauss 8, linear rows, V and K stored", r"k_assemble_regularILi4ELi0ELi0ELi2ELi1ELb0ELb0ELin8E"),
+    ("K1 free space, Q1, Gauss 8, cell-split, 2-D moments, fused (default bench)", r"k_assemble_regularILi4ELi0ELi0ELi1ELi1ELb0ELb1ELin8ELi2E"),
+    ("K1 free space, Q1, Gauss 8, cell-split, 2-D moments, V and K stored", r"k_assemble_regularILi4ELi0ELi0ELi1ELi1ELb0ELb0ELin8ELi2E"),
+    ("K1 free space, Q1, Gauss 8, thread pairs, linear rows, fused (BS_NO_CELLSPLIT=1: the kernel before the cell-split mode)", r"k_assemble_regularILi4ELi0ELi0ELi2ELi1ELb0ELb1ELin8ELi1E"),
     ("K1 free space, Q2 (V warps / K warps)", r"k_assemble_regularILi9ELi0ELi0ELi1ELi2ELb0ELb0ELi8E"),
-    ("K1 free surface, Q1, single layer launch", r"k_assemble_regularILi4ELi1ELi1ELi2ELi1ELb0ELb0ELi0E"),
-    ("K1 free surface, Q1, double layer launch", r"k_assemble_regularILi4ELi1ELi2ELi2ELi1ELb0ELb0ELi0E"),
-    ("K1 no-slip, Q1, single layer launch", r"k_assemble_regularILi4ELi2ELi1ELi2ELi1ELb0ELb0ELi0E"),
+    ("K1 free surface, Q1, cell-split, 2-D moments, single layer launch", r"k_assemble_regularILi4ELi1ELi1ELi1ELi1ELb0ELb0ELin8ELi2E"),
+    ("K1 free surface, Q1, cell-split, 2-D moments, double layer launch", r"k_assemble_regularILi4ELi1ELi2ELi1ELi1ELb0ELb0ELin8ELi2E"),
+    ("K1 no-slip, Q1, cell-split, coefficient x tensor sums, single layer launch", r"k_assemble_regularILi4ELi2ELi1ELi1ELi1ELb0ELb0ELi0ELi2E"),
+    ("K1 no-slip, Q1, cell-split, coefficient x tensor sums, double layer launch", r"k_assemble_regularILi4ELi2ELi2ELi1ELi1ELb0ELb0ELi0ELi2E"),
     ("K5 k_gemv<2>", r"k_gemvILi2E"),
     ("K6 k_gemm_dmma<2,4> (multi-RHS sweep)", r"k_gemm_dmmaILi2ELi4E"),
     ("K8 k_lu_gemm_dmma (LU trailing update)", r"k_lu_gemm_dmma"),
