@@ -996,6 +996,9 @@ int gmres_batched(Context &c, int which, int nrhs, const double *d_B, double *d_
                   int max_tmp, int *iters, double *final_res) {
   BS_REQUIRE(max_tmp >= 3, "max_n_tmp_vectors must be >= 3");
   BS_REQUIRE(nrhs >= 1, "nrhs must be positive");
+  // the identity "preconditioner" has no matrix of its own: it acts on the system being solved (after a solve with another
+  // matrix - the DN route solves with V - the vector length of apply_precond would otherwise be that matrix's)
+  if (c.prec_kind == BS_PREC_NONE) c.prec_which = which;
   // default: the device-resident iteration (bs_gmres.cu).  This host-driven loop remains for deal.II's modified
   // Gram-Schmidt verbatim (host decisions every 5th iteration) and for callback communicators.
   if (gmres_device_eligible(c, nrhs, max_tmp))

@@ -174,6 +174,28 @@ def test_device_gmres_restart_and_max_steps(prob):
     assert np.abs(x1 - x2).max() <= 1e-9 * np.abs(x2).max()
 
 
+def test_identity_preconditioner_follows_the_system(prob):
+    """After a solve with V (the DN route, ref: bem_stokes.cc:4072-4129) an unpreconditioned solve of the monolithic system
+    must act on all 3N + 6 unknowns: the right-hand sides of the resistance problem live in the rigid rows only, so an
+    identity 'preconditioner' sized for V returned x = 0 after 0 iterations.  Host-driven loop (the one callback
+    communicators use) and device-resident loop."""
+    p, A = prob
+    n = A.shape[0]
+    B = np.zeros((6, n))
+    for r in range(6):
+        B[r, n - 6 + r] = 1.0
+    Xo = np.linalg.solve(A, B.T).T
+    for ortho in ("MGS", "CGS2"):
+        p.preconditioner_type = "None"
+        p.gmres_orthogonalization = ortho
+        p.dirichlet_to_neumann_operator(p.N_rigid[0])
+        X = np.zeros_like(B)
+        its = p.gmres_multi(_lib.MAT_A, X, B)
+        assert min(its) > 5, its
+        assert np.abs(X - Xo).max() <= 1e-7 * np.abs(Xo).max()
+    p.gmres_orthogonalization = "CGS2"
+
+
 @pytest.mark.parametrize("meshname,grid_type", [("sphere_half_refined_0.inp", "Real"),
                                                 ("prolate_spheroid_lambda_2_ref_0.msh", "ImposedForce")])
 def test_dn_route_batched(meshname, grid_type):
