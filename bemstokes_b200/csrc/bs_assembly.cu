@@ -734,42 +734,49 @@ __device__ __forceinline__ void integrate_free_lin2d(const double *__restrict__ 
     }
   };
 #if BS_ROWS2
-  // two rule rows at a time: two independent point pipelines per thread (twice the instruction-level parallelism for the
-  // dependent chains of stage A / B; one warp per scheduler and CTA cannot rely on its neighbour for that)
-  FreeA saA, saB;
-  FreeB sbA, sbB;
-  {
+  // BS_ROWS2 + 1... rule rows at a time (NR): independent point pipelines per thread (more instruction-level parallelism
+  // for the dependent chains of stage A / B; one warp per scheduler and CTA cannot rely on its neighbour for that)
+  constexpr int NR = (BS_ROWS2 == 1) ? 2 : BS_ROWS2;
+  static_assert(N1 % NR == 0, "rows in flight must divide the rule size");
+  FreeA sa[NR];
+  FreeB sb[NR];
+#pragma unroll
+  for (int u = 0; u < NR; ++u) {
     FreeA a0;
-    free_stage_a<MODE>(c8, x, a0);
-    free_stage_b<MODE>(a0, sbA);
-    free_stage_a<MODE>(c8 + 8, x, saA);
-    free_stage_a<MODE>(c8 + 8 * N1, x, a0);
-    free_stage_b<MODE>(a0, sbB);
-    free_stage_a<MODE>(c8 + 8 * N1 + 8, x, saB);
+    free_stage_a<MODE>(c8 + 8 * N1 * u, x, a0);
+    free_stage_b<MODE>(a0, sb[u]);
+    free_stage_a<MODE>(c8 + 8 * N1 * u + 8, x, sa[u]);
   }
-  for (int qy = 0; qy < N1; qy += 2) {
-    double mgA[4] = {0.0, 0.0, 0.0, 0.0}, mkA[4] = {0.0, 0.0, 0.0, 0.0}, miA[2] = {0.0, 0.0};
-    double mgB[4] = {0.0, 0.0, 0.0, 0.0}, mkB[4] = {0.0, 0.0, 0.0, 0.0}, miB[2] = {0.0, 0.0};
-    const double *crowA = c8 + (size_t)8 * qy * N1, *crowB = crowA + 8 * N1;
-    const int qn = (qy + 2 < N1) ? qy + 2 : qy;  // this pipeline's next row (harmless re-read at the end)
-    const double *nrowA = c8 + (size_t)8 * qn * N1, *nrowB = nrowA + 8 * N1;
+  for (int qy = 0; qy < N1; qy += NR) {
+    double mg[NR][4], mk[NR][4], mi[NR][2];
+#pragma unroll
+    for (int u = 0; u < NR; ++u) {
+      mi[u][0] = mi[u][1] = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mg[u][k] = mk[u][k] = 0.0;
+    }
+    const double *crow = c8 + (size_t)8 * qy * N1;
+    const int qn = (qy + NR < N1) ? qy + NR : qy;  // the pipelines' next rows (harmless re-read at the end)
+    const double *nrow = c8 + (size_t)8 * qn * N1;
 #pragma unroll
     for (int qx = 0; qx < N1; ++qx) {
-      FreeB nbA, nbB;
-      free_stage_b<MODE>(saA, nbA);
-      free_stage_b<MODE>(saB, nbB);
-      FreeA naA, naB;
-      free_stage_a<MODE>(qx + 2 < N1 ? crowA + 8 * (qx + 2) : nrowA + 8 * (qx + 2 - N1), x, naA);
-      free_stage_a<MODE>(qx + 2 < N1 ? crowB + 8 * (qx + 2) : nrowB + 8 * (qx + 2 - N1), x, naB);
-      free_stage_c_lin<MODE>(sbA, xi_s + 4 * qx, mgA, mkA, miA);
-      free_stage_c_lin<MODE>(sbB, xi_s + 4 * qx, mgB, mkB, miB);
-      sbA = nbA;
-      sbB = nbB;
-      saA = naA;
-      saB = naB;
+      FreeB nb[NR];
+      FreeA na[NR];
+#pragma unroll
+      for (int u = 0; u < NR; ++u) free_stage_b<MODE>(sa[u], nb[u]);
+#pragma unroll
+      for (int u = 0; u < NR; ++u)
+        free_stage_a<MODE>((qx + 2 < N1 ? crow + 8 * (qx + 2) : nrow + 8 * (qx + 2 - N1)) + 8 * N1 * u, x, na[u]);
+#pragma unroll
+      for (int u = 0; u < NR; ++u) free_stage_c_lin<MODE>(sb[u], xi_s + 4 * qx, mg[u], mk[u], mi[u]);
+#pragma unroll
+      for (int u = 0; u < NR; ++u) {
+        sb[u] = nb[u];
+        sa[u] = na[u];
+      }
     }
-    add_row(mgA, mkA, miA, qy);
-    add_row(mgB, mkB, miB, qy + 1);
+#pragma unroll
+    for (int u = 0; u < NR; ++u) add_row(mg[u], mk[u], mi[u], qy + u);
   }
 #else
   FreeA sa;
