@@ -26,9 +26,6 @@
 #ifndef BS_ROWS2
 #define BS_ROWS2 1   // cell-split free-space kernel: two rule rows per thread in flight (measured +2-3 %)
 #endif
-#ifndef BS_EXPAND_SPLIT
-#define BS_EXPAND_SPLIT 0
-#endif
 #ifndef BS_QX_UNROLL
 #define BS_QX_UNROLL 2
 #endif
