@@ -146,6 +146,21 @@ def test_cell_split_kernel_against_thread_pair_kernel(half, kern, monkeypatch):
     assert rel_rows(K2, K1) < ENTRY_TOL, rel_rows(K2, K1)
 
 
+@pytest.mark.parametrize("kern", ["free", "free_surface", "no_slip"])
+def test_assembly_is_bitwise_reproducible(kern):
+    """The stored matrices have a fixed summation order (colours are separate launches; within a block every tile entry
+    belongs to one thread at a time - in the cell-split mode the two thread sets of a CTA work on cells without a common
+    node, with a barrier where consecutive steps would collide): repeated assemblies must agree bit for bit.  A race
+    between the thread sets would show up here as a difference in the last digits."""
+    p = make_problem(bb.cubesphere(m=12), reflect_kernel=(kern == "free_surface"), no_slip_kernel=(kern == "no_slip"),
+                     wall_spans_0=(80, 0, 80), wall_position_0=(0, 1.4, 0))   # 866 nodes: 14 row tiles x ~110 blocks
+    V0, K0 = raw_VK(p)
+    for _ in range(4):
+        V, K = raw_VK(p)
+        assert np.array_equal(V, V0) and np.array_equal(K, K0)
+    p.close()
+
+
 @pytest.mark.parametrize("kind", ["Telles", "Duffy"])
 def test_assembly_singular_kinds(half, kind):
     p = make_problem(half, singular_quadrature_type=kind, singular_quadrature_order=6)
