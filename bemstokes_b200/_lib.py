@@ -57,6 +57,8 @@ SIGNATURES = {
                              C.POINTER(C.c_double), c_double_p, c_double_p, c_double_p, C.POINTER(C.c_int)]),
     "bs_host_prepass": (C.c_int, [C.c_int, C.c_int, C.c_int, c_double_p, C.c_int, c_int_p, C.c_int, c_int_p, C.c_int, c_double_p,
                                   c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
+    "bs_host_cell_blocks": (C.c_int, [C.c_int, c_double_p, C.c_int, c_int_p, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p,
+                                      C.POINTER(C.c_uint), c_int_p, C.POINTER(C.c_ubyte), c_int_p, c_int_p]),
     "bs_set_constraints": (C.c_int, [ctx_p, C.c_int, c_int_p, c_int_p, c_int_p, c_double_p]),
     "bs_set_torque_mode": (C.c_int, [ctx_p, c_double_p, c_double_p, C.c_double]),
     "bs_assemble_VK": (C.c_int, [ctx_p]),

@@ -1175,6 +1175,44 @@ int bs_host_prepass(int fe_degree, int map_degree, int n_map_nodes, const double
   BS_API_END
 }
 
+int bs_host_cell_blocks(int n_nodes, const double *nodes, int ncell, const int *conn, int kernel_type, int n1d,
+                        int *sizes_out, int *cell_ptr, int *cells, unsigned *sync_mask, int *block_nodes,
+                        unsigned char *first_touch, int *colour_start, int *pos_of_node) {
+  BS_API_BEGIN
+  BS_REQUIRE(n_nodes > 0 && ncell > 0 && nodes && conn && sizes_out && n1d >= 1, "bad arguments");
+  BS_REQUIRE(kernel_type >= 0 && kernel_type <= 2, "unknown kernel type");
+  Context c;  // host members only: nothing below touches the device
+  c.N = c.Nmap = n_nodes;
+  c.ncell = ncell;
+  c.na = c.na_map = 4;
+  c.map_nodes.assign(nodes, nodes + (size_t)3 * n_nodes);
+  c.conn.assign(conn, conn + (size_t)4 * ncell);
+  c.conn_map = c.conn;
+  c.kp.type = kernel_type;
+  c.kp.eps = 0.0;
+  c.x1d.assign(n1d, 0.0);
+  c.nq = n1d * n1d;
+  c.nq_pad = (c.nq + 1) & ~1;
+  compute_node_order(c);
+  build_cell_blocks(c);
+  const ColumnBlocks &B = c.blocks;
+  sizes_out[0] = B.nblocks;
+  sizes_out[1] = B.tj;
+  sizes_out[2] = B.cs;
+  sizes_out[3] = (int)B.colour_start.size() - 1;
+  sizes_out[4] = (int)B.cells.size();
+  sizes_out[5] = B.unpaired;
+  BS_REQUIRE(B.tj <= 32 && B.colour_start.size() <= 65, "tiling exceeds the documented output sizes");
+  if (cell_ptr) std::copy(B.cell_ptr.begin(), B.cell_ptr.end(), cell_ptr);
+  if (cells) std::copy(B.cells.begin(), B.cells.end(), cells);
+  if (sync_mask) std::copy(B.sync.begin(), B.sync.end(), sync_mask);
+  if (block_nodes) std::copy(B.nodes.begin(), B.nodes.end(), block_nodes);
+  if (first_touch) std::copy(B.first.begin(), B.first.end(), first_touch);
+  if (colour_start) std::copy(B.colour_start.begin(), B.colour_start.end(), colour_start);
+  if (pos_of_node) std::copy(c.pos_of_node.begin(), c.pos_of_node.end(), pos_of_node);
+  BS_API_END
+}
+
 int bs_set_comm(bs_context *h, bs_allgatherv_fn ag, bs_allreduce_sum_fn ar, void *user) {
   BS_API_BEGIN
   Context &c = ctx_of(h);

@@ -95,6 +95,18 @@ int bs_set_kernel(bs_context *ctx, int type, double epsilon, int wall_orientatio
 int bs_make_gauss_1d(int n, double *x, double *w);
 int bs_make_singular_rule(int kind, int order, int fe_degree, int local_index, int capacity, double *xi, double *w);
 
+/* Host helper, no device needed: the tiling of the regular assembly pass (K1) for a Q1 mesh - cell blocks, colours and,
+ * in the cell-split mode (Gauss 8, no regularisation), the pairs of cells the two thread sets of a CTA integrate
+ * concurrently with the steps that start with a barrier - exactly as bs_set_geometry / bs_set_quadrature build it
+ * (the loop nest it tiles: ref bem_stokes.cc:2871-2998).  For tests and tooling.  nodes [N][3], conn [ncell][4].
+ * sizes_out[6] = n_blocks, nodes per block (stride of block_nodes / first_touch), cell sets (1 or 2), n_colours,
+ * length of `cells`, cells without partner.  Arrays sized by the caller (NULL = skip): cell_ptr [ncell + 1],
+ * cells [2 ncell] (-1 = no partner in this step), sync_mask [ncell] (bit s: step s of the block starts with a barrier),
+ * block_nodes / first_touch [32 ncell] (node POSITION per slot, -1 unused), colour_start [65], pos_of_node [N]. */
+int bs_host_cell_blocks(int n_nodes, const double *nodes, int ncell, const int *conn, int kernel_type, int n1d,
+                        int *sizes_out, int *cell_ptr, int *cells, unsigned *sync_mask, int *block_nodes,
+                        unsigned char *first_touch, int *colour_start, int *pos_of_node);
+
 /* Host pre-pass with the reference's semantics (compute_center_of_mass_and_rigid_modes bem_stokes.cc:2440-2788,
  * compute_normal_vector 3922-4011) for hosts without deal.II: scalar mass matrix, L2-projected unit normals nhat
  * (= normal_vector_pure for a body-only mesh), Mnhat = M nhat, l2gamma = nhat^T M nhat, the six rigid modes about
