@@ -671,7 +671,11 @@ def run_ours(args):
         line["tail_summary"] = {"value": line["value"], "tts_s": summary["time_to_solution_s"], "gmres_its": its,
                                 "ms_per_it": summary["gmres_ms_per_iteration"], "non_matvec_ms_per_it": summary["gmres_non_matvec_ms_per_iteration"],
                                 "drag_over_6pi": summary["drag_over_6pi"], "parity_rows": par_rows, "parity_err_V": par_v,
-                                "parity_ok": bool(parity_ok), "allreduce_calls": n_ar, "allgather_calls": n_ag}
+                                "parity_ok": bool(parity_ok), "allreduce_calls": n_ar, "allgather_calls": n_ag,
+                                "e2e": line["e2e"]["value"], "assembly_ms": asm_ms, "gemv_tbs_per_gpu": mv_gbs_gpu / 1e3,
+                                "gemv_frac_of_measured_copy_peak": roof_mv["frac"], "k1_frac_algorithmic": roof_asm["frac"],
+                                "k1_fp64_instr_per_pair_ncu": roof_asm["executed_fp64_instructions_per_pair"],
+                                "k1_fp64_pipe_active_pct_ncu": roof_asm["fp64_pipe_active_pct_ncu"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
