@@ -4,13 +4,17 @@
 //   K0  k_cell_geometry      FEValues::reinit for every cell with the regular rule: y_q, n_q*JxW_q, JxW_q (and a
 //                            point-major copy with the constants folded in for the free-space fast path)
 //   K1  k_assemble_regular   CTA tile = TI (64) collocation nodes x one cell block (<= tj nodes, disjoint cells,
-//                            coloured); QS threads per node split the rows of the tensor rule; the block's cells are
-//                            streamed through shared memory by bulk-async copies (TMA engine) in a full/empty
-//                            mbarrier ring; per-thread sum-factorised register accumulators over q (free-space
-//                            kernel: software-pipelined 55-instruction formulation), per-CTA shared-memory tile over
-//                            cells, one coalesced write-out per CTA: plain stores where this colour is the first to
-//                            touch a node column, RED.ADD.F64 otherwise (colours are separate launches -> fixed
-//                            summation order); fused variant multiplies the K tile with the panel instead of storing it
+//                            coloured); the block's cells are streamed through shared memory by bulk-async copies (TMA
+//                            engine) in a full/empty mbarrier ring; per-CTA shared-memory tile over cells, one coalesced
+//                            write-out per CTA: plain stores where this colour is the first to touch a node column,
+//                            RED.ADD.F64 otherwise (colours are separate launches -> fixed summation order); fused
+//                            variant multiplies the K tile with the panel instead of storing it.
+//                            Cell-split mode (Q1 unknowns, Gauss 8, no regularisation; cell_sets()): one thread per
+//                            (node, cell), the CTA's two thread sets on two cells of the block without a common node;
+//                            free space / free surface: 2-D moment formulation (integrate_free_lin2d,
+//                            integrate_free_surface_lin2d), no slip: coefficient x tensor sums (integrate_no_slip).
+//                            Otherwise: QS threads per node split the rows of the tensor rule (or V warps / K warps for
+//                            Q2), per-thread sum-factorised register accumulators over q, partner exchange by shuffles.
 //   K2  k_assemble_singular  one warp per owned collocation node: the cells containing the node are
 //                            integrated with the singular rule of that local index (geometry evaluated on
 //                            the fly) and added to the node's three rows.
@@ -24,7 +28,7 @@
 #define BS_NOSLIP_FAST 1   // cell-split no-slip kernel: coefficient x tensor sums (0: entry-by-entry green_eval)
 #endif
 #ifndef BS_ROWS2
-#define BS_ROWS2 1   // cell-split free-space kernel: two rule rows per thread in flight (measured +2-3 %)
+#define BS_ROWS2 1   // cell-split free-space kernel: 0 one rule row per thread in flight, 1 two rows (measured +2-3 %), n > 1: n rows
 #endif
 #ifndef BS_QX_UNROLL
 #define BS_QX_UNROLL 2
@@ -731,7 +735,7 @@ __device__ __forceinline__ void integrate_free_lin2d(const double *__restrict__ 
     }
   };
 #if BS_ROWS2
-  // BS_ROWS2 + 1... rule rows at a time (NR): independent point pipelines per thread (more instruction-level parallelism
+  // NR rule rows at a time: independent point pipelines per thread (more instruction-level parallelism
   // for the dependent chains of stage A / B; one warp per scheduler and CTA cannot rely on its neighbour for that)
   constexpr int NR = (BS_ROWS2 == 1) ? 2 : BS_ROWS2;
   static_assert(N1 % NR == 0, "rows in flight must divide the rule size");
